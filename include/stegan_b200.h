@@ -1,0 +1,192 @@
+/*
+ * stegan_b200.h - C ABI of libstegan_b200.so: hand-written sm_100a kernels for the
+ * STE-GAN hot path (generator + discriminator stacks + TD / LSGAN / feature-matching
+ * losses, forward and backward).
+ *
+ * The reference (scheck-k/ste-gan) is 100 % Python and defines no FFI of its own: on
+ * this path it dispatches into PyTorch (torch==2.0.1 + cuDNN 8.5, requirements.txt:51,97).
+ * Each entry point below therefore cites the reference *call site* whose library
+ * dispatch it replaces.  Plain pointers + sizes only; no torch types.  The caller
+ * (PyTorch on the host side) owns every buffer; the library allocates nothing
+ * persistent and never frees caller memory.  Every function enqueues work on
+ * `stream` and returns 0, or a negative STG_E* code (see stg_strerror); the host
+ * wrapper turns non-zero into a Python exception.  There is no CPU fallback.
+ *
+ * Layout convention: activations are CHANNELS-LAST, [B][T][C] with C contiguous
+ * (the reference is [B][C][T]; the host wrapper converts at the module boundary).
+ * A "period view" (DiscriminatorP's [B,C,T/p,p] Conv2d with (k,1) kernels,
+ * models/discriminator.py:34-43,84-93) is the same memory addressed as B*p virtual
+ * samples whose rows are p*C elements apart: `phases = p`.
+ */
+#ifndef STEGAN_B200_H_
+#define STEGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* stg_stream_t; /* cudaStream_t */
+
+enum { STG_F32 = 0, STG_BF16 = 1 };
+enum { STG_ACT_NONE = 0, STG_ACT_RELU = 1, STG_ACT_LEAKY = 2, STG_ACT_TANH = 3 };
+enum {
+  STG_OK = 0,
+  STG_EINVAL = -1,      /* bad argument / unsupported shape */
+  STG_ECUDA = -2,       /* CUDA runtime error (see stg_last_cuda_error) */
+  STG_EUNSUPPORTED = -3 /* shape not supported by the requested engine */
+};
+enum { STG_ENGINE_AUTO = 0, STG_ENGINE_SIMT = 1, STG_ENGINE_TCGEN05 = 2 };
+
+#define STG_MAX_TAPS 48
+
+/*
+ * One convolution-shaped contraction, used for forward, data-gradient and (with
+ * stg_conv_wgrad) weight-gradient:
+ *
+ *   acc[n][r][c] = sum_{j<k} sum_{q<c_src/groups} src[n][row(r,j)][g(c)*c_src/groups + q] * w[j][c][q]
+ *     forward   : row(r,j) = r*stride + j*dilation - pad
+ *     transposed: row(r,j) = (r + pad - j*dilation) / stride  (tap skipped unless divisible)
+ *   v = acc + bias[c]
+ *   if pair_sum : v[r'] = v[2r'] + v[2r'+1]                 (backward of nearest-upsample x2)
+ *   v = (v + add_pre[r][c]) * dact(mask[r][c]) + add_post[r >> post_shift][c]
+ *   y_raw[r][c] = v ;  y_act[r (and 2r,2r+1 if dup_rows)][c] = act(v)
+ *
+ * Replaces: nn.Conv1d / nn.Conv2d((k,1)) dispatch at layers/conv.py:16-17,89-101 with the
+ * elementwise neighbours of layers/conv.py:38-84 (ReLU, nn.Upsample, residual sums),
+ * models/generator.py:133-137,160 (ReLU, tanh) and models/discriminator.py:40,64,90,116
+ * (leaky_relu 0.1) fused in; `transposed` is the autograd conv backward-data of the same.
+ */
+typedef struct StgConv {
+  int32_t dtype;      /* STG_F32 | STG_BF16 : storage type of src, w, add_*, mask, y_*; accumulation is fp32 */
+  int32_t engine;     /* STG_ENGINE_* */
+  int32_t n_samples;  /* B */
+  int32_t phases;     /* period p (virtual samples = B*p), 1 for plain conv1d */
+  int32_t t_src;      /* rows per virtual sample of src */
+  int32_t t_dst;      /* rows per virtual sample of the accumulator (before pair_sum) */
+  int32_t c_src;      /* channels of src (total) */
+  int32_t c_dst;      /* channels of dst (total) */
+  int32_t groups;
+  int32_t k, dilation, stride, pad;
+  int32_t transposed; /* 0 forward, 1 data-gradient */
+  int32_t pair_sum;   /* 1: sum accumulator rows 2r,2r+1 -> output row r */
+  int32_t post_shift; /* add_post row index = r >> post_shift */
+  int32_t mask_mode;  /* STG_ACT_* whose derivative (as a function of its OUTPUT) multiplies v */
+  int32_t act;        /* STG_ACT_* applied for y_act */
+  int32_t dup_rows;   /* 1: y_act row r is written to rows 2r and 2r+1 (nearest-upsample x2) */
+  int32_t raw_f32;    /* 1: y_raw is float32 regardless of dtype */
+  const void* src;
+  const void* w;        /* packed [k][c_dst][c_src/groups] (see stg_weightnorm_fold) */
+  const float* bias;    /* [c_dst] or NULL */
+  const void* add_pre;  /* [B][rows][c_dst] or NULL */
+  const void* mask;     /* [B][rows][c_dst] or NULL */
+  const void* add_post; /* [B][rows >> post_shift][c_dst] or NULL */
+  void* y_raw;          /* or NULL */
+  void* y_act;          /* or NULL */
+} StgConv;
+
+int stg_conv(const StgConv* d, stg_stream_t stream);
+
+/*
+ * Weight gradient: dw[c][j][q] += sum_{n,r} dy[n][r][c] * x[n][r*stride + j*dilation - pad][g(c)*cin_g + q]
+ * dw is float32 [c_out][k][c_in/groups] and is ACCUMULATED into (caller zeroes it).
+ * Replaces the autograd conv backward-weight of the call sites listed for StgConv.
+ */
+typedef struct StgWgrad {
+  int32_t dtype, engine;
+  int32_t n_samples, phases, t_in, t_out, c_in, c_out, groups, k, dilation, stride, pad;
+  const void* x;   /* [B][t_in*phases][c_in]  */
+  const void* dy;  /* [B][t_out*phases][c_out] */
+  float* dw;       /* [c_out][k][c_in/groups] */
+  float* dbias;    /* [c_out] accumulated column sums of dy, or NULL */
+} StgWgrad;
+
+int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream);
+
+/*
+ * weight_norm (torch.nn.utils.weight_norm, dim 0; layers/conv.py:16-17,92,99):
+ *   w = g * v / ||v||  per output channel; v is the torch layout [c_out][c_in/groups][k].
+ * Emits the forward pack wf [k][c_out][cin_g] and the data-gradient pack
+ * wd [k][c_in][c_out/groups] in `dtype`, and scale[c_out] = g/||v|| (fp32) for the backward.
+ */
+int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups,
+                        int dtype, void* wf, void* wd, float* scale, stg_stream_t stream);
+/* dw [c_out][k][cin_g] fp32 -> dv (torch layout) and dg; ACCUMULATES into dv/dg when accumulate != 0. */
+int stg_weightnorm_fold_bwd(const float* dw, const float* v, const float* g, int c_out, int cin_g, int k,
+                            float* dv, float* dg, int accumulate, stg_stream_t stream);
+
+/*
+ * spectral_norm (legacy torch.nn.utils.spectral_norm, layers/conv.py:94,101): when
+ * `training`, one power iteration updating u[c_out], v[cin_g*k] in place (eps 1e-12), then
+ * sigma = u^T W v, packs of W/sigma as above.  `sigma_out[0]` receives sigma.
+ * scratch: float[c_out + cin_g*k + 8].
+ */
+int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
+                          int training, int dtype, void* wf, void* wd, float* sigma_out, float* scratch,
+                          stg_stream_t stream);
+/* d w_orig = dw/sigma - (sum(dw .* w_orig)/sigma^2) u v^T ; u, v, sigma are the values used by that forward. */
+int stg_spectralnorm_fold_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
+                              const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
+                              float* scratch, stg_stream_t stream);
+
+/* models/generator.py:143-146,154: x0[b][t] = concat(units[b][t][0:d_units], emb[ids[b]][0:d_emb]) in `dtype`. */
+int stg_embed_concat(const float* units, const float* emb, const int64_t* ids, int B, int T, int d_units, int d_emb,
+                     int dtype, void* x0, stg_stream_t stream);
+/* backward of the embedding branch: demb[ids[b]] += sum_t dx0[b][t][d_units:] (dx0 in `dtype`). */
+int stg_embed_concat_bwd(const void* dx0, const int64_t* ids, int B, int T, int d_units, int d_emb, int dtype,
+                         float* demb, stg_stream_t stream);
+
+/*
+ * Discriminator input preparation (models/discriminator.py:36,86 reflect pad right by p - T%p;
+ * :140,153 AvgPool1d(4,2,1), count_include_pad).  x is float32 [B][T][C].
+ */
+int stg_reflect_pad_right(const float* x, int B, int T, int C, int T_pad, int dtype, void* out, stg_stream_t stream);
+int stg_reflect_pad_right_bwd(const void* dout, int B, int T, int C, int T_pad, int dtype, float* dx, stg_stream_t stream);
+int stg_avgpool4(const float* x, int B, int T, int C, float* out, stg_stream_t stream);           /* out [B][T/2][C] */
+int stg_avgpool4_bwd(const float* dout, int B, int T, int C, float* dx, stg_stream_t stream);     /* dx += */
+int stg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, stg_stream_t stream);
+/* out[r] = in[2r] + in[2r+1] over rows of C elements (backward of nearest-upsample x2). */
+int stg_pair_sum_rows(const void* in, int64_t rows_out, int C, int dtype, void* out, stg_stream_t stream);
+int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, int64_t n, stg_stream_t stream); /* y += alpha*x */
+
+/*
+ * Multi-resolution time-domain feature loss (losses/time_domain_loss.py:13-107,
+ * layers/average_filter.py:10-28).  x_real, x_gen float32 [B][T][C].  Writes
+ * losses[0..2] (one per (win,shift) in {(20,8),(51,13),(80,16)}) and, if dx_gen != NULL,
+ * ACCUMULATES grad_scale * d(sum of the three)/d x_gen into dx_gen.
+ * scratch: float[ 6*B*T*C + 3 ].
+ */
+int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, float grad_scale,
+                float* dx_gen, float* scratch, stg_stream_t stream);
+
+/*
+ * LSGAN terms (ste_gan/train.py:192-196,209-211): out[slot] += mean((x - target)^2);
+ * if dx != NULL, dx = grad_scale * 2 (x - target) / n   (written, `dtype`).
+ */
+int stg_mse_const(const void* x, int dtype, int64_t n, float target, float* out_slot, float grad_scale, void* dx,
+                  stg_stream_t stream);
+/*
+ * Feature matching (ste_gan/train.py:257-264): out[slot] += mean(|a - b|); if da != NULL,
+ * da = grad_scale * sign(a - b) / n (written, `dtype`).
+ */
+int stg_l1_mean(const void* a, const void* b, int dtype, int64_t n, float* out_slot, float grad_scale, void* da,
+                stg_stream_t stream);
+
+/* torch.optim.AdamW (ste_gan/constants.py:57; train.py:80-81,199,267) over one flat fp32 buffer.
+ * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable. */
+int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream);
+
+/* diagnostics */
+const char* stg_strerror(int code);
+const char* stg_last_cuda_error(void);
+int stg_version(void);
+/* 1 if the tcgen05 engine can take this contraction (shape/alignment rules in DESIGN.md), else 0. */
+int stg_conv_tc_supported(const StgConv* d);
+int stg_wgrad_tc_supported(const StgWgrad* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEGAN_B200_H_ */

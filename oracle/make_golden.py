@@ -1,0 +1,173 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules.
+
+Run in the authoring container only (needs /root/reference):
+    python oracle/make_golden.py
+The reference imports `omegaconf` (absent here) for type annotations only, so a
+3-line in-memory stub is installed first.  Nothing from the
+reference is copied; only its *outputs* on seeded inputs are stored.
+
+Fixtures (all fp32, seed 0):
+  init_checksums.pt   per-key checksums of the seed-0 random init of G, small D and
+                      full D - pins that the drop-in modules initialise identically,
+                      so the large weights never need to be committed.
+  generator_tiny.pt   channels=64 generator: full state_dict + inputs + output.
+  td_loss.pt          inputs + features + the three loss values.
+  disc_small.pt / disc_full.pt   seed-0 discriminators on a seeded input: per-fmap
+                      shape, checksum and strided samples (two consecutive training
+                      forwards, so the spectral-norm power iteration is pinned).
+  train_step_b1.pt    BASELINE.json configs[0]: G + small D fwd/bwd, B=1, T=100:
+                      losses, G output, per-parameter gradient norms and samples.
+"""
+import os
+import sys
+import types
+import warnings
+
+import torch
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+m = types.ModuleType("omegaconf"); m.OmegaConf = object; m.DictConfig = dict
+sys.modules["omegaconf"] = m
+sys.path.insert(0, "/root/reference")
+
+import torch.nn.functional as F  # noqa: E402
+from ste_gan.losses.time_domain_loss import MultiTimeDomainFeatureLoss  # noqa: E402
+from ste_gan.models.discriminator import Discriminator, DiscriminatorSmall  # noqa: E402
+from ste_gan.models.generator import EMGGeneratorGanTTS  # noqa: E402
+
+from oracle import ste_gan_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(os.cpu_count())
+
+
+def checksum(t: torch.Tensor):
+    t = t.detach().double().flatten()
+    n = t.numel()
+    idx = torch.linspace(0, n - 1, min(n, 16)).long()
+    return dict(shape=list(t.shape) if False else None, numel=n, sum=t.sum().item(), abssum=t.abs().sum().item(),
+                l2=t.norm().item(), samples=t[idx].float().clone(), idx=idx)
+
+
+def tensor_summary(t: torch.Tensor):
+    c = checksum(t)
+    c["shape"] = list(t.shape)
+    return c
+
+
+def seeded(ctor, seed=0):
+    torch.manual_seed(seed)
+    return ctor()
+
+
+def main():
+    # ---- init checksums -------------------------------------------------
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8))
+    ds = seeded(lambda: DiscriminatorSmall(8))
+    df = seeded(lambda: Discriminator(8))
+    gm = seeded(lambda: EMGGeneratorGanTTS("MFCCS", 25, 17, 8))
+    init = {name: {k: tensor_summary(v) for k, v in mod.state_dict().items()}
+            for name, mod in [("generator", g), ("disc_small", ds), ("disc_full", df), ("generator_mfcc", gm)]}
+    init["param_order"] = {name: [n for n, _ in mod.named_parameters()]
+                           for name, mod in [("generator", g), ("disc_small", ds), ("disc_full", df)]}
+    torch.save(init, os.path.join(OUT, "init_checksums.pt"))
+
+    # ---- tiny generator with stored weights ----------------------------
+    gt = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, channels=64), seed=1)
+    su, sess, _ = O.synthetic_batch(2, 12, seed=3)
+    with torch.no_grad():
+        y = gt(su, sess, torch.zeros(2, dtype=torch.long))
+    sd = {k: v.detach().clone() for k, v in gt.state_dict().items()}
+    assert O.rel_l2(O.generator_forward(sd, su, sess), y) < 1e-6
+    torch.save(dict(state_dict=sd, speech_units=su, session_ids=sess, output=y, channels=64),
+               os.path.join(OUT, "generator_tiny.pt"))
+
+    # ---- TD loss ---------------------------------------------------------
+    gen = torch.Generator().manual_seed(5)
+    xr = torch.tanh(torch.randn(2, 160, 8, generator=gen))
+    xg = torch.tanh(torch.randn(2, 160, 8, generator=gen)).requires_grad_(True)
+    mtd = MultiTimeDomainFeatureLoss(8)
+    loss, parts = mtd.time_domain_loss(xr, xg)
+    (grad,) = torch.autograd.grad(loss, xg)
+    feats = [l.calculate_time_domain_features(xr).detach() for l in mtd.time_domain_losses]
+    torch.save(dict(x_real=xr, x_gen=xg.detach(), loss=loss.detach(), parts=[p.detach() for p in parts],
+                    grad_x_gen=grad, feats_real=feats), os.path.join(OUT, "td_loss.pt"))
+    ol, op = O.multi_td_loss(xr, xg.detach())
+    assert abs(float(ol) - float(loss)) < 1e-6, (float(ol), float(loss))
+
+    # ---- discriminators: two consecutive training forwards ---------------
+    for name, mod, small in [("disc_small", ds, True), ("disc_full", df, False)]:
+        gen = torch.Generator().manual_seed(7)
+        x = torch.tanh(torch.randn(2, 400, 8, generator=gen))
+        sd0 = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+        passes = []
+        for _ in range(2):
+            with torch.no_grad():
+                res = mod(x)
+            passes.append([[tensor_summary(f) for f in fm] for fm in res])
+        # oracle agreement (functional restatement, same two forwards)
+        sdo = {k: v.clone() for k, v in sd0.items()}
+        for p in range(2):
+            with torch.no_grad():
+                ores = O.discriminator_forward(sdo, x, small=small, training=True)
+            for a, b in zip(ores, passes[p]):
+                for fa, fb in zip(a, b):
+                    assert list(fa.shape) == fb["shape"]
+                    assert abs(fa.double().sum().item() - fb["sum"]) <= 1e-4 * max(1.0, fb["abssum"]), name
+        torch.save(dict(x=x, passes=passes, names=mod.discriminator_names), os.path.join(OUT, f"{name}.pt"))
+
+    # ---- configs[0]: B=1 T=100 G + small D fwd/bwd ------------------------
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8))
+    ds = seeded(lambda: DiscriminatorSmall(8))
+    sd_g = {k: v.detach().clone() for k, v in g.state_dict().items()}
+    sd_d = {k: v.detach().clone() for k, v in ds.state_dict().items()}
+    su, sess, x_real = O.synthetic_batch(1, 100, seed=0)
+    mtd = MultiTimeDomainFeatureLoss(8)
+    g.train(); ds.train()
+    x_pred = g(su, sess, torch.zeros(1, dtype=torch.long))
+    d_fake_det = ds(x_pred.detach()); d_real = ds(x_real)
+    loss_d = 0
+    for sc in d_fake_det:
+        loss_d = loss_d + F.mse_loss(sc[-1], torch.zeros_like(sc[-1]))
+    for sc in d_real:
+        loss_d = loss_d + F.mse_loss(sc[-1], torch.ones_like(sc[-1]))
+    ds.zero_grad(); loss_d.backward()
+    grad_d = {n: p.grad.detach().clone() for n, p in ds.named_parameters()}
+    ds.zero_grad()
+    d_fake = ds(x_pred); d_real = ds(x_real)
+    loss_adv = 0
+    for sc in d_fake:
+        loss_adv = loss_adv + F.mse_loss(sc[-1], torch.ones_like(sc[-1]))
+    td = mtd(x_real, x_pred)
+    fm = 0
+    for i in range(len(d_fake)):
+        for j in range(len(d_fake[i]) - 1):
+            fm = fm + F.l1_loss(d_fake[i][j], d_real[i][j].detach())
+    loss_g = loss_adv + 15.0 * td + 7.0 * fm
+    x_pred.retain_grad()
+    loss_g.backward()
+    grad_g = {n: p.grad.detach().clone() for n, p in g.named_parameters()}
+    ref = dict(loss_d=loss_d.detach(), loss_g=loss_g.detach(), loss_adv=loss_adv.detach(), loss_td=td.detach(),
+               loss_fm=fm.detach(), x_pred=x_pred.detach().clone(), grad_x_pred=x_pred.grad.detach().clone(),
+               grad_g={k: tensor_summary(v) for k, v in grad_g.items()},
+               grad_d={k: tensor_summary(v) for k, v in grad_d.items()},
+               d_fake_det=[[tensor_summary(f) for f in fm_] for fm_ in d_fake_det])
+    torch.save(ref, os.path.join(OUT, "train_step_b1.pt"))
+    # oracle agreement on the same step (no D update between the phases, as above)
+    o = O.losses_and_grads(sd_g, sd_d, su, sess, x_real, small=True)
+    for k in ("loss_d", "loss_g", "loss_adv", "loss_td", "loss_fm"):
+        assert abs(float(o[k]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), (k, float(o[k]), float(ref[k]))
+    assert O.rel_l2(o["x_pred"], ref["x_pred"]) < 1e-6
+    worst = max(O.rel_l2(o["grad_g"][k], grad_g[k]) for k in grad_g)
+    worst_d = max(O.rel_l2(o["grad_d"][k], grad_d[k]) for k in grad_d)
+    print("oracle vs reference: worst grad_g rel-L2 %.3e, worst grad_d rel-L2 %.3e" % (worst, worst_d))
+    assert worst < 1e-4 and worst_d < 1e-4
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

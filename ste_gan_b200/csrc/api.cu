@@ -1,0 +1,78 @@
+// extern "C" entry points that dispatch between the engines, plus diagnostics.
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace stg {
+
+static thread_local std::string g_last_error;
+
+void set_cuda_error(cudaError_t e, const char* where) {
+  g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
+}
+
+int colsum(const void* dy, int dtype, int64_t rows, int C, float* out, cudaStream_t s);
+
+static int validate_conv(const StgConv* d) {
+  if (!d || !d->src || !d->w) return STG_EINVAL;
+  if (d->dtype != STG_F32 && d->dtype != STG_BF16) return STG_EINVAL;
+  if (d->n_samples < 1 || d->phases < 1 || d->t_src < 1 || d->t_dst < 1) return STG_EINVAL;
+  if (d->groups < 1 || d->c_src % d->groups || d->c_dst % d->groups) return STG_EINVAL;
+  if (d->k < 1 || d->dilation < 1 || d->stride < 1 || d->pad < 0) return STG_EINVAL;
+  if (d->post_shift < 0 || d->post_shift > 1) return STG_EINVAL;
+  if (d->dup_rows && d->pair_sum) return STG_EINVAL;
+  if (!d->y_raw && !d->y_act) return STG_EINVAL;
+  return STG_OK;
+}
+
+}  // namespace stg
+
+using namespace stg;
+
+extern "C" int stg_conv(const StgConv* d, stg_stream_t stream) {
+  int r = validate_conv(d);
+  if (r) return r;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d->engine) {
+    case STG_ENGINE_SIMT: return conv_simt(d, s);
+    case STG_ENGINE_TCGEN05: return conv_tc(d, s);
+    case STG_ENGINE_AUTO:
+      if (conv_tc_supported(d)) return conv_tc(d, s);
+      return conv_simt(d, s);
+    default: return STG_EINVAL;
+  }
+}
+
+extern "C" int stg_conv_tc_supported(const StgConv* d) { return (d && validate_conv(d) == STG_OK && conv_tc_supported(d)) ? 1 : 0; }
+extern "C" int stg_wgrad_tc_supported(const StgWgrad* d) { return (d && wgrad_tc_supported(d)) ? 1 : 0; }
+
+extern "C" int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream) {
+  if (!d || !d->x || !d->dy) return STG_EINVAL;
+  if (d->dtype != STG_F32 && d->dtype != STG_BF16) return STG_EINVAL;
+  if (d->groups < 1 || d->c_in % d->groups || d->c_out % d->groups) return STG_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int r = STG_OK;
+  if (d->dw) {
+    if (d->engine == STG_ENGINE_TCGEN05) r = wgrad_tc(d, s);
+    else if (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d)) r = wgrad_tc(d, s);
+    else if (d->engine == STG_ENGINE_AUTO || d->engine == STG_ENGINE_SIMT) r = wgrad_simt(d, s);
+    else r = STG_EINVAL;
+    if (r) return r;
+  }
+  if (d->dbias) r = colsum(d->dy, d->dtype, (int64_t)d->n_samples * d->phases * d->t_out, d->c_out, d->dbias, s);
+  return r;
+}
+
+extern "C" const char* stg_strerror(int code) {
+  switch (code) {
+    case STG_OK: return "ok";
+    case STG_EINVAL: return "invalid argument or unsupported shape";
+    case STG_ECUDA: return "CUDA error";
+    case STG_EUNSUPPORTED: return "shape not supported by the requested engine";
+    default: return "unknown error";
+  }
+}
+extern "C" const char* stg_last_cuda_error(void) { return g_last_error.c_str(); }
+extern "C" int stg_version(void) { return 100; }

@@ -1,0 +1,335 @@
+// tcgen05 implicit-GEMM convolution (forward and data-gradient), bf16 in / fp32 accumulate.
+//
+// GEMM view (channels-last activations):   D[t][c_dst] = sum_taps sum_{c_src} A_tap[t][c_src] * W_tap[c_dst][c_src]
+//   M = 128 time rows of one (virtual) sample   -> TMEM lanes
+//   N = BN output channels                      -> TMEM columns
+//   K = 64-channel chunks, one per (tap, chunk) -> one pipeline stage each
+// A tiles come straight from the activation tensor by TMA: the row coordinate is
+// r0*stride + tap_offset, may be negative or run past the sample and is zero-filled by
+// the TMA unit, which implements zero padding, dilation and per-sample boundaries with
+// no im2col buffer.  Period views (DiscriminatorP) are a 4-D tensor map (C, rows, phase, B).
+// W tiles come from the packed [k][c_dst][c_src] weights.  Both operands are K-major
+// with 128-byte swizzle.  One elected thread issues tcgen05.mma; accumulators live in
+// TMEM; four epilogue warps read them back with tcgen05.ld and apply the fused
+// epilogue of StgConv (bias, pair-sum, add_pre, activation mask, residual, activation,
+// row duplication).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (TMEM sub-partition = warp_id % 4).
+#include "tc_common.cuh"
+
+namespace stg {
+
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;        // rows per CTA tile
+constexpr int KC = 64;         // channels per K chunk (128 B of bf16)
+constexpr int A_BYTES = TM * KC * 2;
+constexpr int MAX_STAGES = 6;
+
+struct TcEpi {
+  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, raw_f32, pair_sum;
+  const float* bias;
+  const bf16 *add_pre, *mask, *add_post;
+  void* y_raw;
+  bf16* y_act;
+};
+
+struct TcP {
+  int phases, t_dst, stride, n_taps, k_chunks, bn, stages, a_boxes, tmem_cols;
+  int tap_off[STG_MAX_TAPS];
+  int tap_w[STG_MAX_TAPS];
+  TcEpi e;
+};
+
+__device__ __forceinline__ void ld16(const bf16* p, float (&o)[16]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint4 b = *reinterpret_cast<const uint4*>(p + 8);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    o[2 * i] = __low2float(h);
+    o[2 * i + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ void st16(bf16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void st16f(float* p, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// one output row, 16 consecutive channels starting at `col`
+__device__ __forceinline__ void tc_epilogue16(const TcEpi& e, int b, int ph, int row, int col, float (&v)[16]) {
+  const int64_t pitch = (int64_t)e.phases * e.c_dst;
+  const int64_t off = ((int64_t)b * e.t_out + row) * pitch + (int64_t)ph * e.c_dst + col;
+  const int ncols = min(16, e.c_dst - col);
+  const bool vec = (ncols == 16) && ((e.c_dst & 7) == 0);
+  if (e.add_pre) {
+    float t[16];
+    if (vec) ld16(e.add_pre + off, t); else for (int i = 0; i < 16; ++i) t[i] = i < ncols ? to_f(e.add_pre[off + i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  if (e.mask) {
+    float t[16];
+    if (vec) ld16(e.mask + off, t); else for (int i = 0; i < 16; ++i) t[i] = i < ncols ? to_f(e.mask[off + i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= act_grad_from_output(e.mask_mode, t[i]);
+  }
+  if (e.add_post) {
+    const int t_post = e.t_out >> e.post_shift;
+    const int64_t o2 = ((int64_t)b * t_post + (row >> e.post_shift)) * pitch + (int64_t)ph * e.c_dst + col;
+    float t[16];
+    if (vec) ld16(e.add_post + o2, t); else for (int i = 0; i < 16; ++i) t[i] = i < ncols ? to_f(e.add_post[o2 + i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  if (e.y_raw) {
+    if (e.raw_f32) {
+      float* p = static_cast<float*>(e.y_raw) + off;
+      if (vec) st16f(p, v); else for (int i = 0; i < ncols; ++i) p[i] = v[i];
+    } else {
+      bf16* p = static_cast<bf16*>(e.y_raw) + off;
+      if (vec) st16(p, v); else for (int i = 0; i < ncols; ++i) p[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+  if (e.y_act) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = act_apply(e.act, v[i]);
+    if (e.dup_rows) {
+      bf16* p0 = e.y_act + ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col;
+      bf16* p1 = p0 + pitch;
+      if (vec) { st16(p0, a); st16(p1, a); }
+      else for (int i = 0; i < ncols; ++i) { p0[i] = __float2bfloat16_rn(a[i]); p1[i] = p0[i]; }
+    } else {
+      bf16* p = e.y_act + off;
+      if (vec) st16(p, a); else for (int i = 0; i < ncols; ++i) p[i] = __float2bfloat16_rn(a[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_bytes = p.bn * KC * 2;
+  const int stage_bytes = A_BYTES + b_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // 8-byte aligned (multiple of 1024)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, b = n / p.phases, ph = n % p.phases;
+  const int r0 = blockIdx.x * TM;
+  const int col0 = blockIdx.y * p.bn;
+  const int n_iters = p.n_taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int rows_per_box = TM / p.a_boxes;
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.stages, phs = (it / p.stages) & 1;
+        const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
+        mbar_wait(empty_bar(s), phs ^ 1);
+        mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+        const uint32_t a_dst = smem_base + s * stage_bytes;
+        for (int bx = 0; bx < p.a_boxes; ++bx)
+          tma_load_4d(a_dst + bx * rows_per_box * KC * 2, &tmA, full_bar(s), chunk * KC,
+                      (r0 + bx * rows_per_box) * p.stride + p.tap_off[tap], ph, b);
+        tma_load_3d(a_dst + A_BYTES, &tmW, full_bar(s), chunk * KC, col0, p.tap_w[tap]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % p.stages, phs = (it / p.stages) & 1;
+      mbar_wait(full_bar(s), phs);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_base + s * stage_bytes;
+        const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
+        const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks)  // +32 bytes (16 bf16) along K inside the swizzle atom
+          umma_bf16(tmem_base, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(empty_bar(s));
+        if (it == n_iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue =====
+    const int sub = warp & 3;  // TMEM sub-partition this warp may read
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int arow = r0 + sub * 32 + lane;  // accumulator row of this thread
+    const TcEpi& e = p.e;
+    for (int c = 0; c < p.bn; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+      const int col = col0 + c;
+      if (col >= e.c_dst) continue;  // warp-uniform
+      if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += (col + i < e.c_dst) ? e.bias[col + i] : 0.f;
+      }
+      if (e.pair_sum) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+        if ((lane & 1) == 0 && arow < p.t_dst) tc_epilogue16(e, b, ph, arow >> 1, col, v);
+      } else if (arow < p.t_dst) {
+        tc_epilogue16(e, b, ph, arow, col, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return STG_ECUDA; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed");
+    return STG_ECUDA;
+  }
+  return STG_OK;
+}
+
+static int pick_bn(int c_dst) {
+  if (c_dst <= 16) return 16;
+  if (c_dst <= 256 && (c_dst % 16) == 0) return c_dst;
+  if (c_dst % 128 == 0) return 128;
+  if (c_dst % 192 == 0) return 192;
+  if (c_dst % 64 == 0) return 64;
+  return 128;
+}
+
+bool conv_tc_supported(const StgConv* d) {
+  if (d->dtype != STG_BF16 || d->groups != 1) return false;
+  if (d->k > STG_MAX_TAPS || d->k < 1) return false;
+  if ((d->c_src % 8) != 0) return false;                 // 16-byte global strides for TMA
+  if (d->transposed && d->stride != 1) return false;     // phase-decomposed strided dgrad: not in this engine yet
+  if (!d->transposed && d->stride > 4) return false;     // A box rows = 64*stride <= 256
+  if (d->pair_sum && (d->t_dst & 1)) return false;
+  if (d->add_pre == nullptr && d->mask == nullptr && d->add_post == nullptr && d->y_raw == nullptr && d->y_act == nullptr)
+    return false;
+  return true;
+}
+
+int conv_tc(const StgConv* d, cudaStream_t s) {
+  if (!conv_tc_supported(d)) return STG_EUNSUPPORTED;
+  TcP p;
+  p.phases = d->phases; p.t_dst = d->t_dst; p.stride = d->transposed ? 1 : d->stride;
+  p.n_taps = d->k; p.k_chunks = ceil_div(d->c_src, KC);
+  p.bn = pick_bn(d->c_dst);
+  p.a_boxes = (p.stride * TM <= 256) ? 1 : 2;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  for (int j = 0; j < d->k; ++j) {
+    p.tap_off[j] = d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad);
+    p.tap_w[j] = j;
+  }
+  const int stage_bytes = A_BYTES + p.bn * KC * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.n_taps * p.k_chunks) stages = p.n_taps * p.k_chunks;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 2);
+
+  TcEpi& e = p.e;
+  e.phases = d->phases; e.t_out = d->pair_sum ? d->t_dst / 2 : d->t_dst; e.c_dst = d->c_dst;
+  e.post_shift = d->post_shift; e.mask_mode = d->mask_mode; e.act = d->act; e.dup_rows = d->dup_rows;
+  e.raw_f32 = d->raw_f32; e.pair_sum = d->pair_sum; e.bias = d->bias;
+  e.add_pre = static_cast<const bf16*>(d->add_pre); e.mask = static_cast<const bf16*>(d->mask);
+  e.add_post = static_cast<const bf16*>(d->add_post); e.y_raw = d->y_raw; e.y_act = static_cast<bf16*>(d->y_act);
+
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t C = d->c_src, P = d->phases, T = d->t_src, B = d->n_samples;
+    const uint64_t dims[4] = {C, T, P, B};
+    const uint64_t strides[3] = {P * C * 2, C * 2, T * P * C * 2};
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)((TM / p.a_boxes) * p.stride), 1, 1};
+    const uint32_t es[4] = {1, (uint32_t)p.stride, 1, 1};
+    int r = make_tmap_bf16(&tmA, d->src, 4, dims, strides, box, es);
+    if (r) return r;
+  }
+  {
+    const uint64_t C = d->c_src, N = d->c_dst, K = d->k;
+    const uint64_t dims[3] = {C, N, K};
+    const uint64_t strides[2] = {C * 2, N * C * 2};
+    const uint32_t box[3] = {(uint32_t)KC, (uint32_t)p.bn, 1};
+    int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr);
+    if (r) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(d->t_dst, TM), ceil_div(d->c_dst, p.bn), d->n_samples * d->phases);
+  if (grid.z > 65535 || grid.y > 65535) return STG_EINVAL;
+  conv_tc_kernel<<<grid, 192, smem, s>>>(tmA, tmW, p);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+}  // namespace stg

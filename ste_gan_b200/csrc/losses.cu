@@ -1,0 +1,209 @@
+// Loss kernels: multi-resolution time-domain feature loss (fwd + bwd), LSGAN MSE-to-constant
+// and feature-matching L1 reductions (fwd + bwd).  HBM-bound; vectorised loads where the
+// layout allows, warp-shuffle + one atomic per block reductions, fp32 arithmetic throughout.
+#include "common.cuh"
+
+namespace stg {
+namespace {
+
+__device__ __forceinline__ int reflect(int t, int T_) {
+  t = t < 0 ? -t : t;
+  return t >= T_ ? 2 * (T_ - 1) - t : t;
+}
+__device__ __forceinline__ float sgn(float d) { return (float)((d > 0.f) - (d < 0.f)); }
+
+// low = avg9(avg9(x)) with reflect padding at each stage; hi = |x - low|     (time_domain_loss.py:51-60)
+__global__ void td_filter_kernel(const float* __restrict__ x, int T_, int C, int64_t total, float* __restrict__ low,
+                                 float* __restrict__ hi) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bt = i / C;
+    const int t = (int)(bt % T_);
+    const float* xs = x + (bt - t) * C + c;  // sample base, channel c; element t at xs[t*C]
+    float s2 = 0.f;
+    for (int a = -4; a <= 4; ++a) {
+      const int u = reflect(t + a, T_);
+      float s1 = 0.f;
+#pragma unroll
+      for (int q = -4; q <= 4; ++q) s1 += xs[(int64_t)reflect(u + q, T_) * C];
+      s2 += s1 * (1.f / 9.f);
+    }
+    const float lw = s2 * (1.f / 9.f);
+    low[i] = lw;
+    hi[i] = fabsf(xs[(int64_t)t * C] - lw);
+  }
+}
+
+struct TdRes { int win, shift, frames; };
+
+// one thread per (b, f, c): 4 features of real and generated, L1, optional scatter of d/dlow, d/dhi
+__global__ void __launch_bounds__(256) td_feature_kernel(const float* __restrict__ low_r, const float* __restrict__ hi_r,
+                                                         const float* __restrict__ low_g, const float* __restrict__ hi_g,
+                                                         int B, int T_, int C, TdRes r, float* __restrict__ loss_slot,
+                                                         float gscale, float* __restrict__ dlow, float* __restrict__ dhi) {
+  __shared__ float red[32];
+  const int64_t total = (int64_t)B * r.frames * C;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv_n = 1.f / (float)(total * 4);
+  float acc = 0.f;
+  if (i < total) {
+    const int c = (int)(i % C);
+    const int64_t bf = i / C;
+    const int f = (int)(bf % r.frames), b = (int)(bf / r.frames);
+    const int64_t base = (int64_t)b * T_ * C + c;
+    const int start = f * r.shift - r.win / 2;
+    float ml_r = 0, pl_r = 0, ph_r = 0, mh_r = 0, ml_g = 0, pl_g = 0, ph_g = 0, mh_g = 0;
+    for (int j = 0; j < r.win; ++j) {
+      const int64_t o = base + (int64_t)reflect(start + j, T_) * C;
+      const float a = low_r[o], h = hi_r[o], a2 = low_g[o], h2 = hi_g[o];
+      ml_r += a; pl_r = fmaf(a, a, pl_r); ph_r = fmaf(h, h, ph_r); mh_r += h;
+      ml_g += a2; pl_g = fmaf(a2, a2, pl_g); ph_g = fmaf(h2, h2, ph_g); mh_g += h2;
+    }
+    const float iw = 1.f / (float)r.win;
+    const float d0 = (ml_g - ml_r) * iw, d1 = pl_g - pl_r, d2 = ph_g - ph_r, d3 = (mh_g - mh_r) * iw;
+    acc = fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+    if (dlow) {
+      const float s0 = sgn(d0) * inv_n * gscale * iw, s1 = sgn(d1) * inv_n * gscale * 2.f;
+      const float s2 = sgn(d2) * inv_n * gscale * 2.f, s3 = sgn(d3) * inv_n * gscale * iw;
+      for (int j = 0; j < r.win; ++j) {
+        const int64_t o = base + (int64_t)reflect(start + j, T_) * C;
+        atomicAdd(dlow + o, s0 + s1 * low_g[o]);
+        atomicAdd(dhi + o, s3 + s2 * hi_g[o]);
+      }
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_slot, acc * inv_n);
+}
+
+// z = dlow - dhi*sgn(x-low) (in place over dlow) ; dx += dhi*sgn(x-low)
+__global__ void td_bwd_split_kernel(const float* __restrict__ x, const float* __restrict__ low, float* __restrict__ dlow,
+                                    const float* __restrict__ dhi, int64_t total, float* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = dhi[i] * sgn(x[i] - low[i]);
+    dlow[i] -= d;
+    dx[i] += d;
+  }
+}
+// transpose of the reflect-padded 9-tap mean: out[reflect(t+a)] += z[t]/9
+__global__ void td_avg9_t_kernel(const float* __restrict__ z, int T_, int C, int64_t total, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bt = i / C;
+    const int t = (int)(bt % T_);
+    const int64_t base = (bt - t) * C + c;
+    const float v = z[i] * (1.f / 9.f);
+#pragma unroll
+    for (int a = -4; a <= 4; ++a) atomicAdd(out + base + (int64_t)reflect(t + a, T_) * C, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mse_const_kernel(const T* __restrict__ x, int64_t n, float target,
+                                                        float* __restrict__ slot, float gcoef, T* __restrict__ dx) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = to_f(x[i]) - target;
+    acc = fmaf(d, d, acc);
+    if (dx) dx[i] = from_f<T>(gcoef * d);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_mean_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n4,
+                                                      int64_t n, float* __restrict__ slot, float gcoef, T* __restrict__ da) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  // vector body (4 elements / thread / iteration)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float va[4], vb[4], g[4];
+    ld4(a + 4 * i, va);
+    ld4(b + 4 * i, vb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float d = va[q] - vb[q];
+      acc += fabsf(d);
+      g[q] = gcoef * sgn(d);
+    }
+    if (da) st4(da + 4 * i, g);
+  }
+  // scalar tail
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = to_f(a[i]) - to_f(b[i]);
+    acc += fabsf(d);
+    if (da) da[i] = from_f<T>(gcoef * sgn(d));
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
+}
+
+inline int grid_for(int64_t n, int per_thread = 1) {
+  int64_t b = ceil_div64(n, 256 * (int64_t)per_thread);
+  const int64_t cap = 148 * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+}  // namespace stg
+
+using namespace stg;
+#define S_ static_cast<cudaStream_t>(stream)
+
+extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, float grad_scale,
+                           float* dx_gen, float* scratch, stg_stream_t stream) {
+  if (!x_real || !x_gen || !losses || !scratch || T < 48) return STG_EINVAL;
+  const int64_t n = (int64_t)B * T * C;
+  float *low_r = scratch, *hi_r = scratch + n, *low_g = scratch + 2 * n, *hi_g = scratch + 3 * n;
+  float *dlow = scratch + 4 * n, *dhi = scratch + 5 * n;
+  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_real, T, C, n, low_r, hi_r);
+  STG_LAUNCH_CHECK();
+  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_gen, T, C, n, low_g, hi_g);
+  STG_LAUNCH_CHECK();
+  STG_CUDA_CHECK(cudaMemsetAsync(losses, 0, 3 * sizeof(float), S_));
+  if (dx_gen) STG_CUDA_CHECK(cudaMemsetAsync(dlow, 0, 2 * n * sizeof(float), S_));
+  const int wins[3] = {20, 51, 80}, shifts[3] = {8, 13, 16};  // time_domain_loss.py:88-93
+  for (int i = 0; i < 3; ++i) {
+    TdRes r;
+    r.win = wins[i]; r.shift = shifts[i];
+    r.frames = (T + 2 * (r.win / 2) - r.win) / r.shift + 1;
+    const int64_t total = (int64_t)B * r.frames * C;
+    td_feature_kernel<<<(int)ceil_div64(total, 256), 256, 0, S_>>>(low_r, hi_r, low_g, hi_g, B, T, C, r, losses + i,
+                                                                   grad_scale, dx_gen ? dlow : nullptr, dhi);
+    STG_LAUNCH_CHECK();
+  }
+  if (dx_gen) {
+    td_bwd_split_kernel<<<grid_for(n), 256, 0, S_>>>(x_gen, low_g, dlow, dhi, n, dx_gen);
+    STG_LAUNCH_CHECK();
+    STG_CUDA_CHECK(cudaMemsetAsync(dhi, 0, n * sizeof(float), S_));
+    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dlow, T, C, n, dhi);  // dhi <- A^T z
+    STG_LAUNCH_CHECK();
+    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dhi, T, C, n, dx_gen);  // dx += A^T A^T z
+    STG_LAUNCH_CHECK();
+  }
+  return STG_OK;
+}
+
+extern "C" int stg_mse_const(const void* x, int dtype, int64_t n, float target, float* out_slot, float grad_scale,
+                             void* dx, stg_stream_t stream) {
+  if (!x || n < 1) return STG_EINVAL;
+  const float gcoef = grad_scale * 2.f / (float)n;
+  if (dtype == STG_F32) mse_const_kernel<float><<<grid_for(n), 256, 0, S_>>>((const float*)x, n, target, out_slot, gcoef, (float*)dx);
+  else mse_const_kernel<bf16><<<grid_for(n), 256, 0, S_>>>((const bf16*)x, n, target, out_slot, gcoef, (bf16*)dx);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_l1_mean(const void* a, const void* b, int dtype, int64_t n, float* out_slot, float grad_scale,
+                           void* da, stg_stream_t stream) {
+  if (!a || !b || n < 1) return STG_EINVAL;
+  const float gcoef = grad_scale / (float)n;
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+  const int64_t n4 = al ? n / 4 : 0;
+  if (dtype == STG_F32) l1_mean_kernel<float><<<grid_for(n, 4), 256, 0, S_>>>((const float*)a, (const float*)b, n4, n, out_slot, gcoef, (float*)da);
+  else l1_mean_kernel<bf16><<<grid_for(n, 4), 256, 0, S_>>>((const bf16*)a, (const bf16*)b, n4, n, out_slot, gcoef, (bf16*)da);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}

@@ -1,0 +1,248 @@
+// weight_norm / spectral_norm re-parametrisation kernels: fold (v,g) or (W,u,v) into the
+// packed operand layouts the conv engines read, and the matching backward.
+//   forward pack  wf [k][c_out][cin_g]      (K-major rows for the forward GEMM)
+//   dgrad pack    wd [k][c_in][cout_g]      (K-major rows for the data-gradient GEMM)
+// All reductions in fp32.  HBM-bound: each launch reads v once and writes each pack once.
+#include "common.cuh"
+
+namespace stg {
+namespace {
+
+// scale[co] = g[co] / ||v[co]||   (one block per output channel)
+__global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int n,
+                                                       float* __restrict__ scale) {
+  __shared__ float red[32];
+  const int co = blockIdx.x;
+  const float* row = v + (int64_t)co * n;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float x = row[i]; s = fmaf(x, x, s); }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) scale[co] = g[co] / sqrtf(s);
+}
+
+// wf[j][co][ci] = v[co][ci][j] * scale[co]   grid: (ceil(cin_g*k/256), c_out)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                                                       int c_out, int cin_g, int k, T* __restrict__ wf) {
+  const int co = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;  // j*cin_g + ci
+  if (idx >= cin_g * k) return;
+  const int j = idx / cin_g, ci = idx - j * cin_g;
+  const float w = v[((int64_t)co * cin_g + ci) * k + j] * scale[co];
+  wf[((int64_t)j * c_out + co) * cin_g + ci] = from_f<T>(w);
+}
+
+// wd[j][gi*cin_g + ci][co_l] = v[gi*cout_g + co_l][ci][j] * scale[co]   32x32 smem transpose
+// grid: (ceil(cout_g/32), ceil(cin_g/32), k*groups)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                                                         int cin_g, int cout_g, int k, int groups, T* __restrict__ wd) {
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z % k, gi = blockIdx.z / k;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int c_in = cin_g * groups;
+  for (int r = ty; r < 32; r += 8) {  // r: co_l, tx: ci
+    const int co_l = co0 + r, ci = ci0 + tx;
+    float w = 0.f;
+    if (co_l < cout_g && ci < cin_g) {
+      const int co = gi * cout_g + co_l;
+      w = v[((int64_t)co * cin_g + ci) * k + j] * scale[co];
+    }
+    tile[r][tx] = w;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {  // r: ci, tx: co_l
+    const int ci = ci0 + r, co_l = co0 + tx;
+    if (ci < cin_g && co_l < cout_g)
+      wd[((int64_t)j * c_in + gi * cin_g + ci) * cout_g + co_l] = from_f<T>(tile[tx][r]);
+  }
+}
+
+// dv[co][ci][j] (+)= scale*dw[co][j][ci] - (g*dot/norm^3) v ; dg[co] (+)= dot/norm
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                     const float* __restrict__ g, int cin_g, int k,
+                                                     float* __restrict__ dv, float* __restrict__ dg, int accumulate) {
+  __shared__ float red[32];
+  const int co = blockIdx.x, n = cin_g * k;
+  const float* vr = v + (int64_t)co * n;
+  const float* dr = dw + (int64_t)co * n;
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const float x = vr[i];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(x, dr[j * cin_g + ci], dot);
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float norm = sqrtf(ss), gg = g[co];
+  const float a = gg / norm, bcoef = gg * dot / (norm * ss);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const float val = a * dr[j * cin_g + ci] - bcoef * vr[i];
+    float* o = dv + (int64_t)co * n + i;
+    *o = accumulate ? (*o + val) : val;
+  }
+  if (threadIdx.x == 0) dg[co] = accumulate ? (dg[co] + dot / norm) : dot / norm;
+}
+
+// ---- spectral norm
+// out[col] += sum_{row in chunk} W[row][col] * u[row]     grid (ceil(n/256), ceil(rows/32))
+__global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int rows,
+                                                      int n, float* __restrict__ out) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= n) return;
+  const int r0 = blockIdx.y * 32, r1 = min(rows, r0 + 32);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s = fmaf(W[(int64_t)r * n + col], u[r], s);
+  atomicAdd(out + col, s);
+}
+// x <- x / max(||x||, eps) ; optionally dst = normalized, and sigma = <normalized, raw>
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restrict__ raw, int n, float eps,
+                                                            float* __restrict__ dst, float* __restrict__ sigma) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(raw[i], raw[i], s);
+  s = block_sum(s, red);
+  const float nrm = fmaxf(sqrtf(s), eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = raw[i] / nrm;
+  if (sigma && threadIdx.x == 0) *sigma = s / nrm;
+}
+// out[row] = sum_col W[row][col] * v[col]   (block per row)
+__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ v, int n,
+                                                     float* __restrict__ out) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(W[(int64_t)row * n + i], v[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[row] = s;
+}
+__global__ void __launch_bounds__(1024) sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
+                                                      float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(a[i], b[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s;
+}
+__global__ void sn_fill_scale_kernel(const float* __restrict__ sigma, int c_out, float* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c_out) scale[i] = 1.f / sigma[0];
+}
+// acc += sum dw[co][j][ci] * W[co][ci][j]
+__global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ dw, const float* __restrict__ W,
+                                                         int cin_g, int k, float* __restrict__ acc) {
+  __shared__ float red[32];
+  const int co = blockIdx.x, n = cin_g * k;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    s = fmaf(W[(int64_t)co * n + i], dw[(int64_t)co * n + j * cin_g + ci], s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+__global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ u,
+                                                     const float* __restrict__ v, const float* __restrict__ sigma,
+                                                     const float* __restrict__ dot, int cin_g, int k,
+                                                     float* __restrict__ dW, int accumulate) {
+  const int co = blockIdx.x, n = cin_g * k;
+  const float sg = sigma[0], coef = dot[0] / (sg * sg) * u[co], inv = 1.f / sg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const float val = dw[(int64_t)co * n + j * cin_g + ci] * inv - coef * v[i];
+    float* o = dW + (int64_t)co * n + i;
+    *o = accumulate ? (*o + val) : val;
+  }
+}
+
+template <typename T>
+int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, T* wf, T* wd, cudaStream_t s) {
+  const int cout_g = c_out / groups;
+  if (wf) {
+    dim3 g1(ceil_div(cin_g * k, 256), c_out);
+    pack_fwd_kernel<T><<<g1, 256, 0, s>>>(v, scale, c_out, cin_g, k, wf);
+    STG_LAUNCH_CHECK();
+  }
+  if (wd) {
+    dim3 g2(ceil_div(cout_g, 32), ceil_div(cin_g, 32), k * groups);
+    pack_dgrad_kernel<T><<<g2, 256, 0, s>>>(v, scale, cin_g, cout_g, k, groups, wd);
+    STG_LAUNCH_CHECK();
+  }
+  return STG_OK;
+}
+
+}  // namespace
+}  // namespace stg
+
+using namespace stg;
+
+extern "C" int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups, int dtype,
+                                   void* wf, void* wd, float* scale, stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!v || !g || !scale || c_out < 1 || cin_g < 1 || k < 1 || groups < 1 || c_out % groups) return STG_EINVAL;
+  wn_scale_kernel<<<c_out, 256, 0, s>>>(v, g, cin_g * k, scale);
+  STG_LAUNCH_CHECK();
+  if (dtype == STG_F32) return launch_packs<float>(v, scale, c_out, cin_g, k, groups, (float*)wf, (float*)wd, s);
+  if (dtype == STG_BF16) return launch_packs<bf16>(v, scale, c_out, cin_g, k, groups, (bf16*)wf, (bf16*)wd, s);
+  return STG_EINVAL;
+}
+
+extern "C" int stg_weightnorm_fold_bwd(const float* dw, const float* v, const float* g, int c_out, int cin_g, int k,
+                                       float* dv, float* dg, int accumulate, stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!dw || !v || !g || !dv || !dg) return STG_EINVAL;
+  wn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, v, g, cin_g, k, dv, dg, accumulate);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
+                                     int training, int dtype, void* wf, void* wd, float* sigma_out, float* scratch,
+                                     stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w_orig || !u || !v || !sigma_out || !scratch) return STG_EINVAL;
+  const int n = cin_g * k;
+  float* raw_u = scratch;          // [c_out]
+  float* raw_v = scratch + c_out;  // [n]
+  float* scale = raw_u;            // reused after u is final
+  const float eps = 1e-12f;
+  if (training) {
+    STG_CUDA_CHECK(cudaMemsetAsync(raw_v, 0, sizeof(float) * n, s));
+    dim3 g1(ceil_div(n, 256), ceil_div(c_out, 32));
+    sn_wt_u_kernel<<<g1, 256, 0, s>>>(w_orig, u, c_out, n, raw_v);
+    STG_LAUNCH_CHECK();
+    sn_normalize_kernel<<<1, 1024, 0, s>>>(raw_v, n, eps, v, nullptr);
+    STG_LAUNCH_CHECK();
+    sn_w_v_kernel<<<c_out, 256, 0, s>>>(w_orig, v, n, raw_u);
+    STG_LAUNCH_CHECK();
+    // u = raw/max(||raw||,eps) ; sigma = <u, W v> = ||raw||^2 / max(||raw||, eps)
+    sn_normalize_kernel<<<1, 1024, 0, s>>>(raw_u, c_out, eps, u, sigma_out);
+    STG_LAUNCH_CHECK();
+  } else {
+    sn_w_v_kernel<<<c_out, 256, 0, s>>>(w_orig, v, n, raw_u);
+    STG_LAUNCH_CHECK();
+    sn_dot_kernel<<<1, 1024, 0, s>>>(u, raw_u, c_out, sigma_out);
+    STG_LAUNCH_CHECK();
+  }
+  sn_fill_scale_kernel<<<ceil_div(c_out, 256), 256, 0, s>>>(sigma_out, c_out, scale);
+  STG_LAUNCH_CHECK();
+  if (dtype == STG_F32) return launch_packs<float>(w_orig, scale, c_out, cin_g, k, groups, (float*)wf, (float*)wd, s);
+  if (dtype == STG_BF16) return launch_packs<bf16>(w_orig, scale, c_out, cin_g, k, groups, (bf16*)wf, (bf16*)wd, s);
+  return STG_EINVAL;
+}
+
+extern "C" int stg_spectralnorm_fold_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
+                                         const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
+                                         float* scratch, stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!dw || !w_orig || !u || !v || !sigma || !dw_orig || !scratch) return STG_EINVAL;
+  STG_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), s));
+  sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, scratch);
+  STG_LAUNCH_CHECK();
+  sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_orig, accumulate);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}

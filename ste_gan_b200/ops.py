@@ -1,0 +1,250 @@
+"""Host-side wrappers: torch tensors in, C-ABI calls out (raw pointers + current stream).
+
+PyTorch is used for device memory and streams only.  Every wrapper checks buffer sizes
+before handing raw pointers to the library (an out-of-bounds write on the device is a
+fault, not an exception).  No CPU fallback exists: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, BF16, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, F32,
+                   StgConv, StgWgrad, check)
+
+Tensor = torch.Tensor
+_engine_override: Optional[int] = None  # tests force an engine through this
+
+
+def set_engine(engine: Optional[int]) -> None:
+    global _engine_override
+    _engine_override = engine
+
+
+def code_of(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: Optional[Tensor], numel: int, dtype: Optional[torch.dtype], name: str) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.StgError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.StgError(f"{name}: expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.StgError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.numel() < numel:
+        raise _lib.StgError(f"{name}: buffer too small ({t.numel()} < {numel})")
+
+
+def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_src: int, c_dst: int, k: int,
+         phases: int = 1, groups: int = 1, dilation: int = 1, stride: int = 1, pad: int = 0, transposed: bool = False,
+         pair_sum: bool = False, post_shift: int = 0, mask: Optional[Tensor] = None, mask_mode: int = ACT_NONE,
+         act: int = ACT_NONE, dup_rows: bool = False, bias: Optional[Tensor] = None, add_pre: Optional[Tensor] = None,
+         add_post: Optional[Tensor] = None, y_raw: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
+         engine: int = ENGINE_AUTO) -> None:
+    """One StgConv launch (see include/stegan_b200.h for the exact contraction + epilogue)."""
+    dt = src.dtype
+    nv = n_samples * phases
+    t_out = t_dst // 2 if pair_sum else t_dst
+    _need(src, nv * t_src * c_src, None, "src")
+    _need(w, k * c_dst * (c_src // groups), dt, "w")
+    _need(bias, c_dst, torch.float32, "bias")
+    _need(add_pre, nv * t_out * c_dst, dt, "add_pre")
+    _need(mask, nv * t_out * c_dst, dt, "mask")
+    _need(add_post, nv * (t_out >> post_shift) * c_dst, dt, "add_post")
+    raw_f32 = y_raw is not None and y_raw.dtype == torch.float32 and dt != torch.float32
+    _need(y_raw, nv * t_out * c_dst, torch.float32 if raw_f32 else dt, "y_raw")
+    _need(y_act, nv * t_out * c_dst * (2 if dup_rows else 1), dt, "y_act")
+    d = StgConv(dtype=code_of(dt), engine=_engine_override if _engine_override is not None else engine,
+                n_samples=n_samples, phases=phases, t_src=t_src, t_dst=t_dst, c_src=c_src, c_dst=c_dst, groups=groups,
+                k=k, dilation=dilation, stride=stride, pad=pad, transposed=int(transposed), pair_sum=int(pair_sum),
+                post_shift=post_shift, mask_mode=mask_mode, act=act, dup_rows=int(dup_rows), raw_f32=int(raw_f32),
+                src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
+                add_post=_ptr(add_post), y_raw=_ptr(y_raw), y_act=_ptr(y_act))
+    check(_lib.load().stg_conv(C.byref(d), _stream()), "stg_conv")
+
+
+def conv_tc_supported(**kw) -> bool:
+    d = StgConv(**kw)
+    return bool(_lib.load().stg_conv_tc_supported(C.byref(d)))
+
+
+def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], *, n_samples: int, t_in: int,
+          t_out: int, c_in: int, c_out: int, k: int, phases: int = 1, groups: int = 1, dilation: int = 1,
+          stride: int = 1, pad: int = 0, engine: int = ENGINE_AUTO) -> None:
+    """dw[c_out][k][c_in/groups] += ..., dbias[c_out] += column sums of dy (fp32, accumulated)."""
+    nv = n_samples * phases
+    _need(x, nv * t_in * c_in, None, "x")
+    _need(dy, nv * t_out * c_out, x.dtype, "dy")
+    _need(dw, c_out * k * (c_in // groups), torch.float32, "dw")
+    _need(dbias, c_out, torch.float32, "dbias")
+    d = StgWgrad(dtype=code_of(x.dtype), engine=_engine_override if _engine_override is not None else engine,
+                 n_samples=n_samples, phases=phases, t_in=t_in, t_out=t_out, c_in=c_in, c_out=c_out, groups=groups,
+                 k=k, dilation=dilation, stride=stride, pad=pad, x=_ptr(x), dy=_ptr(dy), dw=_ptr(dw), dbias=_ptr(dbias))
+    check(_lib.load().stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
+
+
+def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True):
+    """v [c_out, cin_g, k(,1)], g [c_out,1,1(,1)] -> (wf [k,c_out,cin_g], wd [k,c_in,cout_g] | None, scale [c_out])."""
+    c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
+    _need(v, c_out * cin_g * k, torch.float32, "v"); _need(g, c_out, torch.float32, "g")
+    wf = torch.empty((k, c_out, cin_g), device=v.device, dtype=dtype)
+    wd = torch.empty((k, cin_g * groups, c_out // groups), device=v.device, dtype=dtype) if want_dgrad else None
+    scale = torch.empty((c_out,), device=v.device, dtype=torch.float32)
+    check(_lib.load().stg_weightnorm_fold(_ptr(v), _ptr(g), c_out, cin_g, k, groups, code_of(dtype), _ptr(wf), _ptr(wd),
+                                          _ptr(scale), _stream()), "stg_weightnorm_fold")
+    return wf, wd, scale
+
+
+def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor, accumulate: bool) -> None:
+    c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
+    _need(dw, c_out * cin_g * k, torch.float32, "dw"); _need(dv, c_out * cin_g * k, torch.float32, "dv")
+    _need(dg, c_out, torch.float32, "dg")
+    check(_lib.load().stg_weightnorm_fold_bwd(_ptr(dw), _ptr(v), _ptr(g), c_out, cin_g, k, _ptr(dv), _ptr(dg),
+                                              int(accumulate), _stream()), "stg_weightnorm_fold_bwd")
+
+
+def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, training: bool, dtype: torch.dtype,
+                      want_dgrad: bool = True):
+    """In-place power iteration on u, v when training.  Returns (wf, wd, sigma[1])."""
+    c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
+    n = cin_g * k
+    _need(w_orig, c_out * n, torch.float32, "w_orig"); _need(u, c_out, torch.float32, "u"); _need(v, n, torch.float32, "v")
+    wf = torch.empty((k, c_out, cin_g), device=u.device, dtype=dtype)
+    wd = torch.empty((k, cin_g * groups, c_out // groups), device=u.device, dtype=dtype) if want_dgrad else None
+    sigma = torch.empty((1,), device=u.device, dtype=torch.float32)
+    scratch = torch.empty((c_out + n + 8,), device=u.device, dtype=torch.float32)
+    check(_lib.load().stg_spectralnorm_fold(_ptr(w_orig), _ptr(u), _ptr(v), c_out, cin_g, k, groups, int(training),
+                                            code_of(dtype), _ptr(wf), _ptr(wd), _ptr(sigma), _ptr(scratch), _stream()),
+          "stg_spectralnorm_fold")
+    return wf, wd, sigma
+
+
+def spectralnorm_fold_bwd(dw: Tensor, w_orig: Tensor, u: Tensor, v: Tensor, sigma: Tensor, dw_orig: Tensor,
+                          accumulate: bool) -> None:
+    c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
+    _need(dw, c_out * cin_g * k, torch.float32, "dw"); _need(dw_orig, c_out * cin_g * k, torch.float32, "dw_orig")
+    scratch = torch.empty((8,), device=u.device, dtype=torch.float32)
+    check(_lib.load().stg_spectralnorm_fold_bwd(_ptr(dw), _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), c_out, cin_g, k,
+                                                _ptr(dw_orig), int(accumulate), _ptr(scratch), _stream()),
+          "stg_spectralnorm_fold_bwd")
+
+
+def embed_concat(units: Tensor, emb: Optional[Tensor], ids: Optional[Tensor], dtype: torch.dtype) -> Tensor:
+    B, T, du = units.shape
+    de = 0 if emb is None else emb.shape[1]
+    _need(units, B * T * du, torch.float32, "units")
+    if emb is not None:
+        _need(emb, emb.shape[0] * de, torch.float32, "emb"); _need(ids, B, torch.int64, "ids")
+    x0 = torch.empty((B, T, du + de), device=units.device, dtype=dtype)
+    check(_lib.load().stg_embed_concat(_ptr(units), _ptr(emb), _ptr(ids), B, T, du, de, code_of(dtype), _ptr(x0),
+                                       _stream()), "stg_embed_concat")
+    return x0
+
+
+def embed_concat_bwd(dx0: Tensor, ids: Tensor, d_units: int, demb: Tensor) -> None:
+    B, T, Cc = dx0.shape
+    de = Cc - d_units
+    _need(ids, B, torch.int64, "ids"); _need(demb, de, torch.float32, "demb")
+    check(_lib.load().stg_embed_concat_bwd(_ptr(dx0), _ptr(ids), B, T, d_units, de, code_of(dx0.dtype), _ptr(demb),
+                                           _stream()), "stg_embed_concat_bwd")
+
+
+def reflect_pad_right(x: Tensor, t_pad: int, dtype: torch.dtype) -> Tensor:
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    out = torch.empty((B, t_pad, Cc), device=x.device, dtype=dtype)
+    check(_lib.load().stg_reflect_pad_right(_ptr(x), B, T, Cc, t_pad, code_of(dtype), _ptr(out), _stream()),
+          "stg_reflect_pad_right")
+    return out
+
+
+def reflect_pad_right_bwd(dout: Tensor, T: int, dx: Tensor) -> None:
+    B, t_pad, Cc = dout.shape
+    _need(dx, B * T * Cc, torch.float32, "dx"); _need(dout, B * t_pad * Cc, None, "dout")
+    check(_lib.load().stg_reflect_pad_right_bwd(_ptr(dout), B, T, Cc, t_pad, code_of(dout.dtype), _ptr(dx), _stream()),
+          "stg_reflect_pad_right_bwd")
+
+
+def avgpool4(x: Tensor) -> Tensor:
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    out = torch.empty((B, (T + 2 - 4) // 2 + 1, Cc), device=x.device, dtype=torch.float32)
+    check(_lib.load().stg_avgpool4(_ptr(x), B, T, Cc, _ptr(out), _stream()), "stg_avgpool4")
+    return out
+
+
+def avgpool4_bwd(dout: Tensor, T: int, dx: Tensor) -> None:
+    B, To, Cc = dout.shape
+    _need(dout, B * To * Cc, torch.float32, "dout"); _need(dx, B * T * Cc, torch.float32, "dx")
+    check(_lib.load().stg_avgpool4_bwd(_ptr(dout), B, T, Cc, _ptr(dx), _stream()), "stg_avgpool4_bwd")
+
+
+def cast(src: Tensor, dtype: torch.dtype) -> Tensor:
+    _need(src, src.numel(), None, "src")
+    dst = torch.empty(src.shape, device=src.device, dtype=dtype)
+    check(_lib.load().stg_cast(_ptr(src), code_of(src.dtype), _ptr(dst), code_of(dtype), src.numel(), _stream()), "stg_cast")
+    return dst
+
+
+def pair_sum_rows(x: Tensor, rows_out: int, Cc: int) -> Tensor:
+    _need(x, 2 * rows_out * Cc, None, "x")
+    out = torch.empty((rows_out, Cc), device=x.device, dtype=x.dtype)
+    check(_lib.load().stg_pair_sum_rows(_ptr(x), rows_out, Cc, code_of(x.dtype), _ptr(out), _stream()), "stg_pair_sum_rows")
+    return out
+
+
+def axpy_f32(y: Tensor, x: Tensor, alpha: float) -> None:
+    _need(y, x.numel(), torch.float32, "y"); _need(x, x.numel(), None, "x")
+    check(_lib.load().stg_axpy_f32(_ptr(y), _ptr(x), code_of(x.dtype), float(alpha), x.numel(), _stream()), "stg_axpy_f32")
+
+
+def td_loss(x_real: Tensor, x_gen: Tensor, losses: Tensor, grad_scale: float = 0.0, dx_gen: Optional[Tensor] = None) -> None:
+    """losses[0:3] <- the three resolutions; dx_gen += grad_scale * d(sum)/d x_gen when given."""
+    B, T, Cc = x_gen.shape
+    n = B * T * Cc
+    _need(x_real, n, torch.float32, "x_real"); _need(x_gen, n, torch.float32, "x_gen")
+    _need(losses, 3, torch.float32, "losses"); _need(dx_gen, n, torch.float32, "dx_gen")
+    scratch = torch.empty((6 * n + 8,), device=x_gen.device, dtype=torch.float32)
+    check(_lib.load().stg_td_loss(_ptr(x_real), _ptr(x_gen), B, T, Cc, _ptr(losses), float(grad_scale), _ptr(dx_gen),
+                                  _ptr(scratch), _stream()), "stg_td_loss")
+
+
+def mse_const(x: Tensor, target: float, out_slot: Optional[Tensor], grad_scale: float = 0.0, dx: Optional[Tensor] = None) -> None:
+    _need(x, x.numel(), None, "x"); _need(dx, x.numel(), x.dtype, "dx"); _need(out_slot, 1, torch.float32, "out_slot")
+    check(_lib.load().stg_mse_const(_ptr(x), code_of(x.dtype), x.numel(), float(target), _ptr(out_slot), float(grad_scale),
+                                    _ptr(dx), _stream()), "stg_mse_const")
+
+
+def l1_mean(a: Tensor, b: Tensor, out_slot: Optional[Tensor], grad_scale: float = 0.0, da: Optional[Tensor] = None) -> None:
+    _need(a, a.numel(), None, "a"); _need(b, a.numel(), a.dtype, "b"); _need(da, a.numel(), a.dtype, "da")
+    _need(out_slot, 1, torch.float32, "out_slot")
+    check(_lib.load().stg_l1_mean(_ptr(a), _ptr(b), code_of(a.dtype), a.numel(), _ptr(out_slot), float(grad_scale), _ptr(da),
+                                  _stream()), "stg_l1_mean")
+
+
+def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, lr: float, beta1: float = 0.8, beta2: float = 0.99,
+          eps: float = 1e-8, weight_decay: float = 0.01, grad_scale: float = 1.0) -> None:
+    n = p.numel()
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _need(t, n, torch.float32, nm)
+    _need(step, 1, torch.int64, "step")
+    check(_lib.load().stg_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, beta1, beta2, eps, weight_decay, _ptr(step),
+                                grad_scale, _stream()), "stg_adamw")

@@ -1,0 +1,215 @@
+"""Kernel-level parity (GPU): every conv engine through the C ABI against a CPU fp64 conv.
+
+fp32 (CUDA-core engine): relative L2 <= 1e-5.  bf16 tcgen05 engine: inputs are rounded to
+bf16 on the host first and the accumulator is read back as fp32, so the only difference
+from the fp64 reference is the fp32 accumulation order: relative L2 <= 1e-4 (2e-2 is the
+north_star tolerance for bf16 *storage*, checked in the model-level tests).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.refconv import conv_ref, pack_dgrad, pack_fwd, rel_l2, to_virtual, from_virtual
+
+pytestmark = pytest.mark.gpu
+
+# name, B, phases, T, c_in, c_out, k, dil, stride, pad, groups
+CASES = [
+    ("g_k3d1", 2, 1, 100, 64, 128, 3, 1, 1, 1, 1),
+    ("g_k3d27", 2, 1, 100, 128, 64, 3, 27, 1, 27, 1),
+    ("g_k3d9_192", 2, 1, 300, 192, 192, 3, 9, 1, 9, 1),
+    ("g_k1_320", 2, 1, 37, 320, 64, 1, 1, 1, 0, 1),
+    ("g_k3_768", 1, 1, 100, 768, 384, 3, 3, 1, 3, 1),
+    ("s_k15_c8", 2, 1, 200, 8, 128, 15, 1, 1, 7, 1),
+    ("s_k37_g4", 2, 1, 200, 128, 256, 37, 1, 2, 18, 4),
+    ("s_k37_g16", 2, 1, 100, 256, 512, 37, 1, 2, 18, 16),
+    ("s_k41_s4_g16", 1, 1, 128, 256, 512, 41, 1, 4, 20, 16),
+    ("s_k5", 1, 1, 50, 512, 128, 5, 1, 1, 2, 1),
+    ("s_out", 2, 1, 50, 128, 1, 3, 1, 1, 1, 1),
+    ("p3_l1", 2, 3, 67, 8, 32, 3, 1, 1, 2, 1),
+    ("p3_l2", 2, 3, 69, 32, 256, 3, 1, 3, 2, 1),
+    ("p2_l3", 2, 2, 140, 256, 128, 3, 1, 3, 2, 1),
+    ("p5_k5s3", 2, 5, 40, 32, 128, 5, 1, 3, 2, 1),
+    ("last", 2, 1, 160, 192, 8, 3, 1, 1, 1, 1),
+]
+
+
+def t_out_of(T, k, d, s, pad):
+    return (T + 2 * pad - d * (k - 1) - 1) // s + 1
+
+
+def make_case(case, seed=0):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T * p, ci, generator=gen)
+    w = torch.randn(co, ci // g, k, generator=gen) / (ci // g * k) ** 0.5
+    bias = torch.randn(co, generator=gen)
+    To = t_out_of(T, k, d, s, pad)
+    dy = torch.randn(B, To * p, co, generator=gen)
+    return x, w, bias, dy, To
+
+
+def run_fwd(ops, case, dtype, engine, x, w, bias, To):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    dev = "cuda"
+    xd = x.to(dev, dtype)
+    wf = pack_fwd(w).to(dev, dtype)
+    y = torch.empty(B, To * p, co, device=dev, dtype=torch.float32)
+    ya = torch.empty(B, To * p, co, device=dev, dtype=dtype)
+    ops.conv(xd, wf, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k, dilation=d,
+             stride=s, pad=pad, bias=bias.to(dev), act=ops.ACT_LEAKY, y_raw=y, y_act=ya, engine=engine)
+    torch.cuda.synchronize()
+    return y.cpu(), ya.float().cpu()
+
+
+def run_dgrad(ops, case, dtype, engine, dy, w, To):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    dev = "cuda"
+    wd = pack_dgrad(w, g).to(dev, dtype)
+    dx = torch.empty(B, T * p, ci, device=dev, dtype=torch.float32)
+    ops.conv(dy.to(dev, dtype), wd, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
+             dilation=d, stride=s, pad=pad, transposed=True, y_raw=dx, engine=engine)
+    torch.cuda.synchronize()
+    return dx.cpu()
+
+
+def run_wgrad(ops, case, dtype, engine, x, dy, To):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    dev = "cuda"
+    dw = torch.zeros(co, k, ci // g, device=dev)
+    db = torch.zeros(co, device=dev)
+    ops.wgrad(x.to(dev, dtype), dy.to(dev, dtype), dw, db, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=co,
+              groups=g, k=k, dilation=d, stride=s, pad=pad, engine=engine)
+    torch.cuda.synchronize()
+    return dw.cpu(), db.cpu()
+
+
+def reference(case, x, w, bias, dy):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y = conv_ref(xr, wr, bias, phases=p, stride=s, dilation=d, pad=pad, groups=g)
+    gx, gw = torch.autograd.grad(y, [xr, wr], dy.double())
+    return y.detach(), gx, gw.permute(0, 2, 1).contiguous(), dy.double().sum(dim=(0, 1))  # gw -> [co][k][cin_g]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_simt_f32(case):
+    from ste_gan_b200 import ops
+    x, w, bias, dy, To = make_case(case)
+    y_ref, gx_ref, gw_ref, gb_ref = reference(case, x, w, bias, dy)
+    y, ya = run_fwd(ops, case, torch.float32, ops.ENGINE_SIMT, x, w, bias, To)
+    assert rel_l2(y, y_ref) < 1e-5
+    assert rel_l2(ya, F.leaky_relu(y_ref, 0.1)) < 1e-5
+    dx = run_dgrad(ops, case, torch.float32, ops.ENGINE_SIMT, dy, w, To)
+    assert rel_l2(dx, gx_ref) < 1e-5
+    dw, db = run_wgrad(ops, case, torch.float32, ops.ENGINE_SIMT, x, dy, To)
+    assert rel_l2(dw, gw_ref) < 1e-5
+    assert rel_l2(db, gb_ref) < 1e-5
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_simt_bf16(case):
+    from ste_gan_b200 import ops
+    x, w, bias, dy, To = make_case(case, seed=1)
+    x, w, dy = _bf(x), _bf(w), _bf(dy)
+    y_ref, gx_ref, gw_ref, gb_ref = reference(case, x, w, bias, dy)
+    y, ya = run_fwd(ops, case, torch.bfloat16, ops.ENGINE_SIMT, x, w, bias, To)
+    assert rel_l2(y, y_ref) < 1e-4
+    assert rel_l2(ya, F.leaky_relu(y_ref, 0.1)) < 1e-2
+    assert rel_l2(run_dgrad(ops, case, torch.bfloat16, ops.ENGINE_SIMT, dy, w, To), gx_ref) < 1e-4
+    dw, db = run_wgrad(ops, case, torch.bfloat16, ops.ENGINE_SIMT, x, dy, To)
+    assert rel_l2(dw, gw_ref) < 1e-4 and rel_l2(db, gb_ref) < 1e-4
+
+
+def _tc_conv_desc(ops, case, transposed):
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    To = t_out_of(T, k, d, s, pad)
+    if transposed:
+        return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
+                    dilation=d, stride=s, pad=pad, transposed=1, src=1, w=1, y_raw=1)
+    return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k,
+                dilation=d, stride=s, pad=pad, transposed=0, src=1, w=1, y_raw=1)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tcgen05_fwd(case):
+    from ste_gan_b200 import ops
+    if not ops.conv_tc_supported(**_tc_conv_desc(ops, case, False)):
+        pytest.skip("shape not taken by the tcgen05 engine")
+    x, w, bias, dy, To = make_case(case, seed=2)
+    x, w = _bf(x), _bf(w)
+    y_ref = conv_ref(x, w, bias, phases=case[2], stride=case[8], dilation=case[7], pad=case[9], groups=case[10])
+    y, ya = run_fwd(ops, case, torch.bfloat16, ops.ENGINE_TCGEN05, x, w, bias, To)
+    assert rel_l2(y, y_ref) < 1e-4
+    assert rel_l2(ya, F.leaky_relu(y_ref, 0.1)) < 1e-2
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tcgen05_dgrad(case):
+    from ste_gan_b200 import ops
+    if not ops.conv_tc_supported(**_tc_conv_desc(ops, case, True)):
+        pytest.skip("shape not taken by the tcgen05 engine")
+    x, w, bias, dy, To = make_case(case, seed=3)
+    w, dy = _bf(w), _bf(dy)
+    _, gx_ref, _, _ = reference(case, x, w, bias, dy)
+    assert rel_l2(run_dgrad(ops, case, torch.bfloat16, ops.ENGINE_TCGEN05, dy, w, To), gx_ref) < 1e-4
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tcgen05_wgrad(case):
+    from ste_gan_b200 import ops, _lib
+    import ctypes as C
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    To = t_out_of(T, k, d, s, pad)
+    wd = _lib.StgWgrad(dtype=1, engine=2, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=co, groups=g, k=k,
+                       dilation=d, stride=s, pad=pad)
+    if not _lib.load().stg_wgrad_tc_supported(C.byref(wd)):
+        pytest.skip("shape not taken by the tcgen05 engine")
+    x, w, bias, dy, To = make_case(case, seed=4)
+    x, dy = _bf(x), _bf(dy)
+    _, _, gw_ref, gb_ref = reference(case, x, w, bias, dy)
+    dw, db = run_wgrad(ops, case, torch.bfloat16, ops.ENGINE_TCGEN05, x, dy, To)
+    assert rel_l2(dw, gw_ref) < 1e-4
+    assert rel_l2(db, gb_ref) < 1e-4
+
+
+@pytest.mark.parametrize("engine_dtype", [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)],
+                         ids=["simt-f32", "simt-bf16", "tc-bf16"])
+def test_fused_epilogue(engine_dtype):
+    """pair_sum + add_pre + mask + add_post(shifted) on a data-gradient, and dup_rows + residual on a forward."""
+    from ste_gan_b200 import ops
+    eng, dtype = engine_dtype
+    engine = ops.ENGINE_SIMT if eng == "simt" else ops.ENGINE_TCGEN05
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    dev = "cuda"
+    gen = torch.Generator().manual_seed(11)
+    B, T, ci, co, k, d = 2, 96, 64, 128, 3, 3
+    q = (lambda t: t) if dtype == torch.float32 else _bf
+    x = q(torch.randn(B, T, ci, generator=gen)); w = q(torch.randn(co, ci, k, generator=gen) / 14)
+    bias = torch.randn(co, generator=gen)
+    res = q(torch.randn(B, T // 2, co, generator=gen))
+    # forward: y = conv(x) + bias + res[t>>1]; y_act = relu(y) duplicated
+    y = torch.empty(B, T, co, device=dev, dtype=dtype); ya = torch.empty(B, 2 * T, co, device=dev, dtype=dtype)
+    ops.conv(x.to(dev, dtype), pack_fwd(w).to(dev, dtype), n_samples=B, t_src=T, t_dst=T, c_src=ci, c_dst=co, k=k,
+             dilation=d, pad=d, bias=bias.to(dev), add_post=res.to(dev, dtype), post_shift=1, act=ops.ACT_RELU,
+             dup_rows=True, y_raw=y, y_act=ya, engine=engine)
+    y_ref = conv_ref(x, w, bias, dilation=d, pad=d) + res.double().repeat_interleave(2, dim=1)
+    assert rel_l2(y.float().cpu(), y_ref) < tol
+    assert rel_l2(ya.float().cpu(), F.relu(y_ref).repeat_interleave(2, dim=1)) < tol
+    # data-gradient with pair-sum: dx[t] = (g[2t] + g[2t+1] + pre[t]) * relu'(m[t]) + post[t]
+    dy = q(torch.randn(B, T, co, generator=gen))
+    pre = q(torch.randn(B, T // 2, ci, generator=gen)); post = q(torch.randn(B, T // 2, ci, generator=gen))
+    m = q(torch.randn(B, T // 2, ci, generator=gen))
+    dx = torch.empty(B, T // 2, ci, device=dev, dtype=dtype)
+    ops.conv(dy.to(dev, dtype), pack_dgrad(w, 1).to(dev, dtype), n_samples=B, t_src=T, t_dst=T, c_src=co, c_dst=ci, k=k,
+             dilation=d, pad=d, transposed=True, pair_sum=True, add_pre=pre.to(dev, dtype), mask=m.to(dev, dtype),
+             mask_mode=ops.ACT_RELU, add_post=post.to(dev, dtype), y_raw=dx, engine=engine)
+    xr = x.double().requires_grad_(True)
+    (g,) = torch.autograd.grad(conv_ref(xr, w, None, dilation=d, pad=d), xr, dy.double())
+    ref = (g[:, 0::2] + g[:, 1::2] + pre.double()) * (m.double() > 0) + post.double()
+    assert rel_l2(dx.float().cpu(), ref) < tol
