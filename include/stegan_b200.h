@@ -75,7 +75,7 @@ typedef struct StgConv {
   int32_t mask_mode;  /* STG_ACT_* whose derivative (as a function of its OUTPUT) multiplies v */
   int32_t act;        /* STG_ACT_* applied for y_act */
   int32_t dup_rows;   /* 1: y_act row r is written to rows 2r and 2r+1 (nearest-upsample x2) */
-  int32_t raw_f32;    /* 1: y_raw is float32 regardless of dtype */
+  int32_t out_f32;    /* 1: y_raw and y_act are float32 regardless of dtype */
   const void* src;
   const void* w;        /* packed [k][c_dst][c_src/groups] (see stg_weightnorm_fold) */
   const float* bias;    /* [c_dst] or NULL */
@@ -146,6 +146,9 @@ int stg_reflect_pad_right_bwd(const void* dout, int B, int T, int C, int T_pad, 
 int stg_avgpool4(const float* x, int B, int T, int C, float* out, stg_stream_t stream);           /* out [B][T/2][C] */
 int stg_avgpool4_bwd(const float* dout, int B, int T, int C, float* dx, stg_stream_t stream);     /* dx += */
 int stg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, stg_stream_t stream);
+/* out = dy * act'(y), the derivative expressed through the activation OUTPUT y (tanh of models/generator.py:160);
+ * dy, y float32, out in `dtype`. */
+int stg_act_bwd(const float* dy, const float* y, int mode, int64_t n, int dtype, void* out, stg_stream_t stream);
 /* out[r] = in[2r] + in[2r+1] over rows of C elements (backward of nearest-upsample x2). */
 int stg_pair_sum_rows(const void* in, int64_t rows_out, int C, int dtype, void* out, stg_stream_t stream);
 int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, int64_t n, stg_stream_t stream); /* y += alpha*x */
@@ -154,18 +157,21 @@ int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, int64_t n, s
  * Multi-resolution time-domain feature loss (losses/time_domain_loss.py:13-107,
  * layers/average_filter.py:10-28).  x_real, x_gen float32 [B][T][C].  Writes
  * losses[0..2] (one per (win,shift) in {(20,8),(51,13),(80,16)}) and, if dx_gen != NULL,
- * ACCUMULATES grad_scale * d(sum of the three)/d x_gen into dx_gen.
+ * ACCUMULATES sum_i grad_scale[i] * d losses[i] / d x_gen into dx_gen (grad_scale: 3 host floats).
  * scratch: float[ 6*B*T*C + 3 ].
  */
-int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, float grad_scale,
+int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, const float* grad_scale,
                 float* dx_gen, float* scratch, stg_stream_t stream);
+/* AverageFilter (layers/average_filter.py:10-28) on `rows` independent series of length T (float32):
+ * reflect pad window/2 (if pad) then mean over `window`, stride 1. */
+int stg_average_filter(const float* x, int64_t rows, int T, int window, int pad, float* out, stg_stream_t stream);
 
 /*
  * LSGAN terms (ste_gan/train.py:192-196,209-211): out[slot] += mean((x - target)^2);
- * if dx != NULL, dx = grad_scale * 2 (x - target) / n   (written, `dtype`).
+ * if dx != NULL, dx = grad_scale * 2 (x - target) / n   (written, `dx_dtype`).
  */
 int stg_mse_const(const void* x, int dtype, int64_t n, float target, float* out_slot, float grad_scale, void* dx,
-                  stg_stream_t stream);
+                  int dx_dtype, stg_stream_t stream);
 /*
  * Feature matching (ste_gan/train.py:257-264): out[slot] += mean(|a - b|); if da != NULL,
  * da = grad_scale * sign(a - b) / n (written, `dtype`).

@@ -22,7 +22,7 @@ MAX_TAPS = 48
 class StgConv(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dtype", "engine", "n_samples", "phases", "t_src", "t_dst", "c_src", "c_dst", "groups", "k", "dilation",
-        "stride", "pad", "transposed", "pair_sum", "post_shift", "mask_mode", "act", "dup_rows", "raw_f32")] + [
+        "stride", "pad", "transposed", "pair_sum", "post_shift", "mask_mode", "act", "dup_rows", "out_f32")] + [
         (n, C.c_void_p) for n in ("src", "w", "bias", "add_pre", "mask", "add_post", "y_raw", "y_act")]
 
 
@@ -49,10 +49,12 @@ _SIGS = {
     "stg_avgpool4": [_P, _I, _I, _I, _P, _P],
     "stg_avgpool4_bwd": [_P, _I, _I, _I, _P, _P],
     "stg_cast": [_P, _I, _P, _I, _L, _P],
+    "stg_act_bwd": [_P, _P, _I, _L, _I, _P, _P],
     "stg_pair_sum_rows": [_P, _L, _I, _I, _P, _P],
     "stg_axpy_f32": [_P, _P, _I, _F, _L, _P],
-    "stg_td_loss": [_P, _P, _I, _I, _I, _P, _F, _P, _P, _P],
-    "stg_mse_const": [_P, _I, _L, _F, _P, _F, _P, _P],
+    "stg_td_loss": [_P, _P, _I, _I, _I, _P, C.POINTER(C.c_float), _P, _P, _P],
+    "stg_average_filter": [_P, _L, _I, _I, _I, _P, _P],
+    "stg_mse_const": [_P, _I, _L, _F, _P, _F, _P, _I, _P],
     "stg_l1_mean": [_P, _P, _I, _L, _P, _F, _P, _P],
     "stg_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _F, _P],
 }

@@ -11,7 +11,7 @@ namespace {
 constexpr int BM = 64, BN = 64, BK = 16, LDS = 68;  // LDS: padded leading dim (floats)
 
 struct EpiP {
-  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, raw_f32, pair_sum;
+  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, out_f32, pair_sum;
   const float* bias;
   const void *add_pre, *mask, *add_post;
   void *y_raw, *y_act;
@@ -45,7 +45,7 @@ __device__ __forceinline__ void epilogue_row(const EpiP& e, int b, int ph, int r
     v[i] = x + post[i];
   }
   if (e.y_raw) {
-    if (e.raw_f32) {
+    if (e.out_f32) {
       float* p = static_cast<float*>(e.y_raw) + off;
       if (vec) st4(p, v); else for (int i = 0; i < ncols; ++i) p[i] = v[i];
     } else {
@@ -57,15 +57,15 @@ __device__ __forceinline__ void epilogue_row(const EpiP& e, int b, int ph, int r
     float a[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = act_apply(e.act, v[i]);
-    if (e.dup_rows) {
-      const int64_t o0 = ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col;
-      T* p0 = static_cast<T*>(e.y_act) + o0;
-      T* p1 = p0 + pitch;
-      if (vec) { st4(p0, a); st4(p1, a); }
-      else for (int i = 0; i < ncols; ++i) { p0[i] = from_f<T>(a[i]); p1[i] = from_f<T>(a[i]); }
+    const int64_t o0 = e.dup_rows ? ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col : off;
+    if (e.out_f32) {
+      float* p0 = static_cast<float*>(e.y_act) + o0;
+      if (vec) st4(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = a[i];
+      if (e.dup_rows) { float* p1 = p0 + pitch; if (vec) st4(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = a[i]; }
     } else {
-      T* p = static_cast<T*>(e.y_act) + off;
-      if (vec) st4(p, a); else for (int i = 0; i < ncols; ++i) p[i] = from_f<T>(a[i]);
+      T* p0 = static_cast<T*>(e.y_act) + o0;
+      if (vec) st4(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = from_f<T>(a[i]);
+      if (e.dup_rows) { T* p1 = p0 + pitch; if (vec) st4(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = from_f<T>(a[i]); }
     }
   }
 }
@@ -101,25 +101,48 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
 
   const int lrow = tid >> 2, lk = (tid & 3) * 4;
   const int drow = r0 + lrow;
+  const bool vec4 = (p.csrc_g & 3) == 0;
   const bool col_ok = (cl0 + lrow) < p.cdst_g;
 
   for (int k0 = 0; k0 < K; k0 += BK) {
     const int kg = k0 + lk;
     float a[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0};
-    if (kg < K) {
-      const int j = kg / p.csrc_g, q = kg - j * p.csrc_g;
-      int srow;
-      bool ok = drow < p.t_dst;
-      if (!p.transposed) {
-        srow = drow * p.stride + j * p.dilation - p.pad;
-      } else {
-        const int num = drow + p.pad - j * p.dilation;
-        srow = num / p.stride;
-        ok = ok && (num >= 0) && (srow * p.stride == num);
+    if (vec4) {
+      if (kg < K) {
+        const int j = kg / p.csrc_g, q = kg - j * p.csrc_g;
+        int srow;
+        bool ok = drow < p.t_dst;
+        if (!p.transposed) {
+          srow = drow * p.stride + j * p.dilation - p.pad;
+        } else {
+          const int num = drow + p.pad - j * p.dilation;
+          srow = num / p.stride;
+          ok = ok && (num >= 0) && (srow * p.stride == num);
+        }
+        ok = ok && srow >= 0 && srow < p.t_src;
+        if (ok) ld4(src + src_base + (int64_t)srow * src_pitch + q, a);
+        if (col_ok) ld4(w + ((int64_t)j * p.c_dst + col0 + lrow) * p.csrc_g + q, bb);
       }
-      ok = ok && srow >= 0 && srow < p.t_src;
-      if (ok) ld4(src + src_base + (int64_t)srow * src_pitch + q, a);
-      if (col_ok) ld4(w + ((int64_t)j * p.c_dst + col0 + lrow) * p.csrc_g + q, bb);
+    } else {
+      // channel counts that are not a multiple of 4 (C = 1 logits): element-wise gather
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ke = kg + i;
+        if (ke >= K) break;
+        const int j = ke / p.csrc_g, q = ke - j * p.csrc_g;
+        int srow;
+        bool ok = drow < p.t_dst;
+        if (!p.transposed) {
+          srow = drow * p.stride + j * p.dilation - p.pad;
+        } else {
+          const int num = drow + p.pad - j * p.dilation;
+          srow = num / p.stride;
+          ok = ok && (num >= 0) && (srow * p.stride == num);
+        }
+        ok = ok && srow >= 0 && srow < p.t_src;
+        if (ok) a[i] = to_f(src[src_base + (int64_t)srow * src_pitch + q]);
+        if (col_ok) bb[i] = to_f(w[((int64_t)j * p.c_dst + col0 + lrow) * p.csrc_g + q]);
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -280,12 +303,11 @@ int conv_simt(const StgConv* d, cudaStream_t s) {
   p.csrc_g = d->c_src / d->groups; p.cdst_g = d->c_dst / d->groups;
   p.tiles_per_group = ceil_div(p.cdst_g, BN);
   p.src = d->src; p.w = d->w;
-  if ((p.csrc_g & 3) != 0) return STG_EINVAL;
   if (d->pair_sum && (d->t_dst & 1)) return STG_EINVAL;
   EpiP& e = p.e;
   e.phases = d->phases; e.t_out = d->pair_sum ? d->t_dst / 2 : d->t_dst; e.c_dst = d->c_dst;
   e.post_shift = d->post_shift; e.mask_mode = d->mask_mode; e.act = d->act; e.dup_rows = d->dup_rows;
-  e.raw_f32 = d->raw_f32; e.pair_sum = d->pair_sum; e.bias = d->bias; e.add_pre = d->add_pre; e.mask = d->mask;
+  e.out_f32 = d->out_f32; e.pair_sum = d->pair_sum; e.bias = d->bias; e.add_pre = d->add_pre; e.mask = d->mask;
   e.add_post = d->add_post; e.y_raw = d->y_raw; e.y_act = d->y_act;
   dim3 grid(ceil_div(d->t_dst, BM), d->groups * p.tiles_per_group, p.n_vs);
   if (grid.z > 65535 || grid.y > 65535) return STG_EINVAL;

@@ -30,11 +30,11 @@ constexpr int A_BYTES = TM * KC * 2;
 constexpr int MAX_STAGES = 6;
 
 struct TcEpi {
-  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, raw_f32, pair_sum;
+  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, out_f32, pair_sum;
   const float* bias;
   const bf16 *add_pre, *mask, *add_post;
   void* y_raw;
-  bf16* y_act;
+  void* y_act;
 };
 
 struct TcP {
@@ -97,7 +97,7 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& e, int b, int ph, int
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
   if (e.y_raw) {
-    if (e.raw_f32) {
+    if (e.out_f32) {
       float* p = static_cast<float*>(e.y_raw) + off;
       if (vec) st16f(p, v); else for (int i = 0; i < ncols; ++i) p[i] = v[i];
     } else {
@@ -109,14 +109,15 @@ __device__ __forceinline__ void tc_epilogue16(const TcEpi& e, int b, int ph, int
     float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = act_apply(e.act, v[i]);
-    if (e.dup_rows) {
-      bf16* p0 = e.y_act + ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col;
-      bf16* p1 = p0 + pitch;
-      if (vec) { st16(p0, a); st16(p1, a); }
-      else for (int i = 0; i < ncols; ++i) { p0[i] = __float2bfloat16_rn(a[i]); p1[i] = p0[i]; }
+    const int64_t o0 = e.dup_rows ? ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col : off;
+    if (e.out_f32) {
+      float* p0 = static_cast<float*>(e.y_act) + o0;
+      if (vec) st16f(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = a[i];
+      if (e.dup_rows) { float* p1 = p0 + pitch; if (vec) st16f(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = a[i]; }
     } else {
-      bf16* p = e.y_act + off;
-      if (vec) st16(p, a); else for (int i = 0; i < ncols; ++i) p[i] = __float2bfloat16_rn(a[i]);
+      bf16* p0 = static_cast<bf16*>(e.y_act) + o0;
+      if (vec) st16(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = __float2bfloat16_rn(a[i]);
+      if (e.dup_rows) { bf16* p1 = p0 + pitch; if (vec) st16(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = __float2bfloat16_rn(a[i]); }
     }
   }
 }
@@ -298,9 +299,9 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   TcEpi& e = p.e;
   e.phases = d->phases; e.t_out = d->pair_sum ? d->t_dst / 2 : d->t_dst; e.c_dst = d->c_dst;
   e.post_shift = d->post_shift; e.mask_mode = d->mask_mode; e.act = d->act; e.dup_rows = d->dup_rows;
-  e.raw_f32 = d->raw_f32; e.pair_sum = d->pair_sum; e.bias = d->bias;
+  e.out_f32 = d->out_f32; e.pair_sum = d->pair_sum; e.bias = d->bias;
   e.add_pre = static_cast<const bf16*>(d->add_pre); e.mask = static_cast<const bf16*>(d->mask);
-  e.add_post = static_cast<const bf16*>(d->add_post); e.y_raw = d->y_raw; e.y_act = static_cast<bf16*>(d->y_act);
+  e.add_post = static_cast<const bf16*>(d->add_post); e.y_raw = d->y_raw; e.y_act = d->y_act;
 
   CUtensorMap tmA, tmW;
   {

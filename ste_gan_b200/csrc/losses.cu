@@ -98,15 +98,15 @@ __global__ void td_avg9_t_kernel(const float* __restrict__ z, int T_, int C, int
   }
 }
 
-template <typename T>
+template <typename T, typename TD>
 __global__ void __launch_bounds__(256) mse_const_kernel(const T* __restrict__ x, int64_t n, float target,
-                                                        float* __restrict__ slot, float gcoef, T* __restrict__ dx) {
+                                                        float* __restrict__ slot, float gcoef, TD* __restrict__ dx) {
   __shared__ float red[32];
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = to_f(x[i]) - target;
     acc = fmaf(d, d, acc);
-    if (dx) dx[i] = from_f<T>(gcoef * d);
+    if (dx) dx[i] = from_f<TD>(gcoef * d);
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
@@ -140,6 +140,20 @@ __global__ void __launch_bounds__(256) l1_mean_kernel(const T* __restrict__ a, c
   if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
 }
 
+// reflect-padded moving average over the last axis of [rows][T]
+__global__ void average_filter_kernel(const float* __restrict__ x, int64_t rows, int T_, int window, int pad, int To,
+                                      float* __restrict__ out) {
+  const int64_t total = rows * To;
+  const int half = pad ? window / 2 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / To;
+    const int t = (int)(i - r * To);
+    float s = 0.f;
+    for (int j = 0; j < window; ++j) s += x[r * T_ + reflect(t - half + j, T_)];
+    out[i] = s / (float)window;
+  }
+}
+
 inline int grid_for(int64_t n, int per_thread = 1) {
   int64_t b = ceil_div64(n, 256 * (int64_t)per_thread);
   const int64_t cap = 148 * 8;
@@ -152,9 +166,9 @@ inline int grid_for(int64_t n, int per_thread = 1) {
 using namespace stg;
 #define S_ static_cast<cudaStream_t>(stream)
 
-extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, float grad_scale,
-                           float* dx_gen, float* scratch, stg_stream_t stream) {
-  if (!x_real || !x_gen || !losses || !scratch || T < 48) return STG_EINVAL;
+extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses,
+                           const float* grad_scale, float* dx_gen, float* scratch, stg_stream_t stream) {
+  if (!x_real || !x_gen || !losses || !scratch || T < 48 || (dx_gen && !grad_scale)) return STG_EINVAL;
   const int64_t n = (int64_t)B * T * C;
   float *low_r = scratch, *hi_r = scratch + n, *low_g = scratch + 2 * n, *hi_g = scratch + 3 * n;
   float *dlow = scratch + 4 * n, *dhi = scratch + 5 * n;
@@ -171,7 +185,7 @@ extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T
     r.frames = (T + 2 * (r.win / 2) - r.win) / r.shift + 1;
     const int64_t total = (int64_t)B * r.frames * C;
     td_feature_kernel<<<(int)ceil_div64(total, 256), 256, 0, S_>>>(low_r, hi_r, low_g, hi_g, B, T, C, r, losses + i,
-                                                                   grad_scale, dx_gen ? dlow : nullptr, dhi);
+                                                                   dx_gen ? grad_scale[i] : 0.f, dx_gen ? dlow : nullptr, dhi);
     STG_LAUNCH_CHECK();
   }
   if (dx_gen) {
@@ -186,12 +200,23 @@ extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T
   return STG_OK;
 }
 
+extern "C" int stg_average_filter(const float* x, int64_t rows, int T, int window, int pad, float* out, stg_stream_t stream) {
+  if (!x || !out || window < 1 || window > T) return STG_EINVAL;
+  const int To = pad ? T : T - window + 1;
+  average_filter_kernel<<<grid_for(rows * To), 256, 0, S_>>>(x, rows, T, window, pad, To, out);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
 extern "C" int stg_mse_const(const void* x, int dtype, int64_t n, float target, float* out_slot, float grad_scale,
-                             void* dx, stg_stream_t stream) {
+                             void* dx, int dx_dtype, stg_stream_t stream) {
   if (!x || n < 1) return STG_EINVAL;
   const float gcoef = grad_scale * 2.f / (float)n;
-  if (dtype == STG_F32) mse_const_kernel<float><<<grid_for(n), 256, 0, S_>>>((const float*)x, n, target, out_slot, gcoef, (float*)dx);
-  else mse_const_kernel<bf16><<<grid_for(n), 256, 0, S_>>>((const bf16*)x, n, target, out_slot, gcoef, (bf16*)dx);
+  const int g = grid_for(n);
+  if (dtype == STG_F32 && dx_dtype == STG_F32) mse_const_kernel<float, float><<<g, 256, 0, S_>>>((const float*)x, n, target, out_slot, gcoef, (float*)dx);
+  else if (dtype == STG_F32) mse_const_kernel<float, bf16><<<g, 256, 0, S_>>>((const float*)x, n, target, out_slot, gcoef, (bf16*)dx);
+  else if (dx_dtype == STG_F32) mse_const_kernel<bf16, float><<<g, 256, 0, S_>>>((const bf16*)x, n, target, out_slot, gcoef, (float*)dx);
+  else mse_const_kernel<bf16, bf16><<<g, 256, 0, S_>>>((const bf16*)x, n, target, out_slot, gcoef, (bf16*)dx);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

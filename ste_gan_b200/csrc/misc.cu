@@ -95,6 +95,13 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int6
 }
 
 template <typename T>
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int mode, int64_t n,
+                               T* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(dy[i] * act_grad_from_output(mode, y[i]));
+}
+
+template <typename T>
 __global__ void pair_sum_kernel(const T* __restrict__ in, int64_t rows_out, int C, T* __restrict__ out) {
   const int64_t total = rows_out * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -204,6 +211,14 @@ extern "C" int stg_cast(const void* src, int sd, void* dst, int dd, int64_t n, s
   else if (sd == STG_F32 && dd == STG_F32) cast_kernel<float, float><<<g, 256, 0, S_>>>((const float*)src, (float*)dst, n);
   else if (sd == STG_BF16 && dd == STG_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, S_>>>((const bf16*)src, (bf16*)dst, n);
   else return STG_EINVAL;
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_act_bwd(const float* dy, const float* y, int mode, int64_t n, int dtype, void* out, stg_stream_t stream) {
+  if (!dy || !y || !out) return STG_EINVAL;
+  if (dtype == STG_F32) act_bwd_kernel<float><<<grid_for(n), 256, 0, S_>>>(dy, y, mode, n, (float*)out);
+  else act_bwd_kernel<bf16><<<grid_for(n), 256, 0, S_>>>(dy, y, mode, n, (bf16*)out);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

@@ -69,13 +69,15 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
     _need(add_pre, nv * t_out * c_dst, dt, "add_pre")
     _need(mask, nv * t_out * c_dst, dt, "mask")
     _need(add_post, nv * (t_out >> post_shift) * c_dst, dt, "add_post")
-    raw_f32 = y_raw is not None and y_raw.dtype == torch.float32 and dt != torch.float32
-    _need(y_raw, nv * t_out * c_dst, torch.float32 if raw_f32 else dt, "y_raw")
-    _need(y_act, nv * t_out * c_dst * (2 if dup_rows else 1), dt, "y_act")
+    outs = [t for t in (y_raw, y_act) if t is not None]
+    out_f32 = dt != torch.float32 and len(outs) > 0 and all(t.dtype == torch.float32 for t in outs)
+    odt = torch.float32 if out_f32 else dt
+    _need(y_raw, nv * t_out * c_dst, odt, "y_raw")
+    _need(y_act, nv * t_out * c_dst * (2 if dup_rows else 1), odt, "y_act")
     d = StgConv(dtype=code_of(dt), engine=_engine_override if _engine_override is not None else engine,
                 n_samples=n_samples, phases=phases, t_src=t_src, t_dst=t_dst, c_src=c_src, c_dst=c_dst, groups=groups,
                 k=k, dilation=dilation, stride=stride, pad=pad, transposed=int(transposed), pair_sum=int(pair_sum),
-                post_shift=post_shift, mask_mode=mask_mode, act=act, dup_rows=int(dup_rows), raw_f32=int(raw_f32),
+                post_shift=post_shift, mask_mode=mask_mode, act=act, dup_rows=int(dup_rows), out_f32=int(out_f32),
                 src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
                 add_post=_ptr(add_post), y_raw=_ptr(y_raw), y_act=_ptr(y_act))
     check(_lib.load().stg_conv(C.byref(d), _stream()), "stg_conv")
@@ -101,13 +103,18 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
     check(_lib.load().stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
 
 
-def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True):
-    """v [c_out, cin_g, k(,1)], g [c_out,1,1(,1)] -> (wf [k,c_out,cin_g], wd [k,c_in,cout_g] | None, scale [c_out])."""
+def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True, out=None):
+    """v [c_out, cin_g, k(,1)], g [c_out,1,1(,1)] -> (wf [k,c_out,cin_g], wd [k,c_in,cout_g] | None, scale [c_out]).
+    `out` = (wf, wd, scale) re-uses persistent buffers (fixed addresses for CUDA-graph replay)."""
     c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
     _need(v, c_out * cin_g * k, torch.float32, "v"); _need(g, c_out, torch.float32, "g")
-    wf = torch.empty((k, c_out, cin_g), device=v.device, dtype=dtype)
-    wd = torch.empty((k, cin_g * groups, c_out // groups), device=v.device, dtype=dtype) if want_dgrad else None
-    scale = torch.empty((c_out,), device=v.device, dtype=torch.float32)
+    if out is not None:
+        wf, wd, scale = out
+        _need(wf, k * c_out * cin_g, dtype, "wf"); _need(wd, k * c_out * cin_g, dtype, "wd"); _need(scale, c_out, torch.float32, "scale")
+    else:
+        wf = torch.empty((k, c_out, cin_g), device=v.device, dtype=dtype)
+        wd = torch.empty((k, cin_g * groups, c_out // groups), device=v.device, dtype=dtype) if want_dgrad else None
+        scale = torch.empty((c_out,), device=v.device, dtype=torch.float32)
     check(_lib.load().stg_weightnorm_fold(_ptr(v), _ptr(g), c_out, cin_g, k, groups, code_of(dtype), _ptr(wf), _ptr(wd),
                                           _ptr(scale), _stream()), "stg_weightnorm_fold")
     return wf, wd, scale
@@ -204,6 +211,24 @@ def cast(src: Tensor, dtype: torch.dtype) -> Tensor:
     return dst
 
 
+def act_bwd(dy: Tensor, y: Tensor, mode: int, dtype: torch.dtype) -> Tensor:
+    """out = dy * act'(y) with the derivative expressed through the activation OUTPUT y (both fp32)."""
+    _need(dy, y.numel(), torch.float32, "dy"); _need(y, y.numel(), torch.float32, "y")
+    out = torch.empty(y.shape, device=y.device, dtype=dtype)
+    check(_lib.load().stg_act_bwd(_ptr(dy), _ptr(y), mode, y.numel(), code_of(dtype), _ptr(out), _stream()), "stg_act_bwd")
+    return out
+
+
+def average_filter(x: Tensor, window: int, pad: bool) -> Tensor:
+    """AverageFilter.forward on [B, C, T] fp32 (layers/average_filter.py:22-28)."""
+    xc = x.contiguous().float()
+    rows, T = xc.numel() // xc.shape[-1], xc.shape[-1]
+    t_out = T if pad else T - window + 1
+    out = torch.empty(xc.shape[:-1] + (t_out,), device=x.device, dtype=torch.float32)
+    check(_lib.load().stg_average_filter(_ptr(xc), rows, T, window, int(pad), _ptr(out), _stream()), "stg_average_filter")
+    return out
+
+
 def pair_sum_rows(x: Tensor, rows_out: int, Cc: int) -> Tensor:
     _need(x, 2 * rows_out * Cc, None, "x")
     out = torch.empty((rows_out, Cc), device=x.device, dtype=x.dtype)
@@ -216,21 +241,22 @@ def axpy_f32(y: Tensor, x: Tensor, alpha: float) -> None:
     check(_lib.load().stg_axpy_f32(_ptr(y), _ptr(x), code_of(x.dtype), float(alpha), x.numel(), _stream()), "stg_axpy_f32")
 
 
-def td_loss(x_real: Tensor, x_gen: Tensor, losses: Tensor, grad_scale: float = 0.0, dx_gen: Optional[Tensor] = None) -> None:
-    """losses[0:3] <- the three resolutions; dx_gen += grad_scale * d(sum)/d x_gen when given."""
+def td_loss(x_real: Tensor, x_gen: Tensor, losses: Tensor, grad_scale=None, dx_gen: Optional[Tensor] = None) -> None:
+    """losses[0:3] <- the three resolutions; dx_gen += sum_i grad_scale[i] * d loss_i / d x_gen when given."""
     B, T, Cc = x_gen.shape
     n = B * T * Cc
     _need(x_real, n, torch.float32, "x_real"); _need(x_gen, n, torch.float32, "x_gen")
     _need(losses, 3, torch.float32, "losses"); _need(dx_gen, n, torch.float32, "dx_gen")
     scratch = torch.empty((6 * n + 8,), device=x_gen.device, dtype=torch.float32)
-    check(_lib.load().stg_td_loss(_ptr(x_real), _ptr(x_gen), B, T, Cc, _ptr(losses), float(grad_scale), _ptr(dx_gen),
+    gs = (C.c_float * 3)(*([0.0] * 3 if grad_scale is None else [float(g) for g in grad_scale]))
+    check(_lib.load().stg_td_loss(_ptr(x_real), _ptr(x_gen), B, T, Cc, _ptr(losses), gs, _ptr(dx_gen),
                                   _ptr(scratch), _stream()), "stg_td_loss")
 
 
 def mse_const(x: Tensor, target: float, out_slot: Optional[Tensor], grad_scale: float = 0.0, dx: Optional[Tensor] = None) -> None:
-    _need(x, x.numel(), None, "x"); _need(dx, x.numel(), x.dtype, "dx"); _need(out_slot, 1, torch.float32, "out_slot")
+    _need(x, x.numel(), None, "x"); _need(dx, x.numel(), None, "dx"); _need(out_slot, 1, torch.float32, "out_slot")
     check(_lib.load().stg_mse_const(_ptr(x), code_of(x.dtype), x.numel(), float(target), _ptr(out_slot), float(grad_scale),
-                                    _ptr(dx), _stream()), "stg_mse_const")
+                                    _ptr(dx), code_of(dx.dtype) if dx is not None else 0, _stream()), "stg_mse_const")
 
 
 def l1_mean(a: Tensor, b: Tensor, out_slot: Optional[Tensor], grad_scale: float = 0.0, da: Optional[Tensor] = None) -> None:

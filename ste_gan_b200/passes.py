@@ -1,0 +1,430 @@
+"""Whole-network forward / backward passes over the C-ABI kernels.
+
+This is the host side of the hot path: explicit (autograd-free) forward and backward
+schedules for the generator (models/generator.py:140-162 + layers/conv.py:82-84 of the
+reference) and the discriminator stacks (models/discriminator.py), in channels-last
+layout, with every elementwise neighbour of a convolution folded into that convolution's
+epilogue (see include/stegan_b200.h, StgConv).  torch.autograd.Function wrappers in
+ste_gan_b200/autograd.py expose the same passes to `loss.backward()` users.
+
+Gradient flow conventions
+  * activations / activation-gradients: `dtype` (bf16 or fp32) channels-last [B, T(*p), C]
+  * parameter gradients: fp32, ACCUMULATED into `param.grad` (allocated on first use)
+  * weight gradients are first produced in the packed [c_out][k][cin_g] layout by the
+    wgrad engines and then pulled back through the weight_norm / spectral_norm fold.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# folded (re-parametrised + packed) weights
+# --------------------------------------------------------------------------------------
+@dataclass
+class Folded:
+    mod: torch.nn.Module
+    wf: Tensor
+    wd: Optional[Tensor]
+    dtype: torch.dtype
+    scale: Optional[Tensor] = None          # weight-norm: g/||v||
+    u: Optional[Tensor] = None              # spectral-norm: u, v, sigma used by THIS forward
+    v: Optional[Tensor] = None
+    sigma: Optional[Tensor] = None
+
+
+def _w3(t: Tensor) -> Tensor:
+    """[c_out, cin_g, k] or [c_out, cin_g, k, 1] -> 3-D view."""
+    return t.view(t.shape[0], t.shape[1], t.shape[2])
+
+
+def fold(mod, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True,
+         persist: Optional[Dict[int, "Folded"]] = None) -> Folded:
+    """Re-parametrise one conv module into the packed operand layouts (one fold = one
+    power iteration for spectral-norm layers in training mode, as in the reference's
+    forward pre-hook).  `persist` keeps the weight-norm packs of a module in the same
+    buffers across calls (fixed addresses, so CUDA graphs that read them stay valid)."""
+    if mod.norm == "weight_norm":
+        prev = persist.get(id(mod)) if persist is not None else None
+        out = (prev.wf, prev.wd, prev.scale) if prev is not None and prev.dtype == dtype and prev.wd is not None else None
+        wf, wd, scale = ops.weightnorm_fold(_w3(mod.weight_v.data), mod.weight_g.data, mod.groups, dtype,
+                                            want_dgrad or persist is not None, out=out)
+        f = Folded(mod, wf, wd, dtype, scale=scale)
+        if persist is not None:
+            persist[id(mod)] = f
+        return f
+    wf, wd, sigma = ops.spectralnorm_fold(_w3(mod.weight_orig.data), mod.weight_u, mod.weight_v, mod.groups, training,
+                                          dtype, want_dgrad)
+    return Folded(mod, wf, wd, dtype, u=mod.weight_u.clone(), v=mod.weight_v.clone(), sigma=sigma)
+
+
+def _grad_of(p: torch.nn.Parameter) -> Tensor:
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def fold_backward(f: Folded, dw: Tensor) -> None:
+    m = f.mod
+    if m.norm == "weight_norm":
+        ops.weightnorm_fold_bwd(dw, _w3(m.weight_v.data), m.weight_g.data, _grad_of(m.weight_v), _grad_of(m.weight_g), True)
+    else:
+        ops.spectralnorm_fold_bwd(dw, _w3(m.weight_orig.data), f.u, f.v, f.sigma, _grad_of(m.weight_orig), True)
+
+
+class _Workspace:
+    """Zero-initialised fp32 arena for packed weight gradients (one memset per pass)."""
+
+    def __init__(self, convs: Sequence, device):
+        n = sum(c.out_channels * c.kernel * (c.in_channels // c.groups) for c in convs)
+        self.buf = torch.zeros(n, device=device, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, m) -> Tensor:
+        n = m.out_channels * m.kernel * (m.in_channels // m.groups)
+        t = self.buf[self.off:self.off + n]
+        self.off += n
+        return t
+
+
+def _fwd(f: Folded, src: Tensor, B: int, t_src: int, *, phases: int = 1, act: int = ACT_NONE, want_raw: bool = False,
+         want_act: bool = False, dup: bool = False, add_post: Optional[Tensor] = None, post_shift: int = 0,
+         out_f32: bool = False) -> Tuple[Optional[Tensor], Optional[Tensor], int]:
+    m = f.mod
+    t_dst = m.t_out(t_src)
+    odt = torch.float32 if out_f32 else f.dtype
+    y_raw = torch.empty((B, t_dst * phases, m.out_channels), device=src.device, dtype=odt) if want_raw else None
+    y_act = torch.empty((B, t_dst * phases * (2 if dup else 1), m.out_channels), device=src.device, dtype=odt) if want_act else None
+    ops.conv(src, f.wf, n_samples=B, phases=phases, t_src=t_src, t_dst=t_dst, c_src=m.in_channels, c_dst=m.out_channels,
+             groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, bias=m.bias.data, act=act,
+             dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act)
+    return y_raw, y_act, t_dst
+
+
+def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 1, mask: Optional[Tensor] = None,
+           mask_mode: int = ACT_NONE, add_pre: Optional[Tensor] = None, add_post: Optional[Tensor] = None,
+           pair_sum: bool = False, out_f32: bool = False) -> Tensor:
+    m = f.mod
+    rows = t_x // 2 if pair_sum else t_x
+    dx = torch.empty((B, rows * phases, m.in_channels), device=dy.device, dtype=torch.float32 if out_f32 else f.dtype)
+    ops.conv(dy, f.wd, n_samples=B, phases=phases, t_src=t_dy, t_dst=t_x, c_src=m.out_channels, c_dst=m.in_channels,
+             groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, transposed=True,
+             pair_sum=pair_sum, mask=mask, mask_mode=mask_mode, add_pre=add_pre, add_post=add_post, y_raw=dx)
+    return dx
+
+
+def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _Workspace, phases: int = 1) -> None:
+    m = f.mod
+    dw = ws.take(m)
+    ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_x, t_out=t_dy, c_in=m.in_channels,
+              c_out=m.out_channels, groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad)
+    fold_backward(f, dw)
+
+
+# --------------------------------------------------------------------------------------
+# generator
+# --------------------------------------------------------------------------------------
+def generator_convs(model) -> List:
+    convs = [model.gblocks[0]]
+    for blk in list(model.gblocks)[1:]:
+        c = blk.convs()
+        convs += [c["c1"], c["c2"], c["res"], c["c3"], c["c4"]]
+    convs.append(model.last_conv[1])
+    return convs
+
+
+def gblock_fwd(blk, folds: Dict[int, Folded], x_raw: Tensor, x_act: Tensor, B: int, t: int, *, want_raw: bool,
+               want_act: bool, dup_next: bool):
+    """GBlock.forward (layers/conv.py:82-84) on channels-last tensors.
+    x_raw [B,t,C_in]: block input; x_act [B,t*up,C_in]: relu(x) with rows duplicated when the block upsamples.
+    Returns (y_raw|None, relu(y) (rows duplicated if dup_next)|None, saved)."""
+    c = blk.convs()
+    up = blk.upsample
+    t_hi = t * up
+    # conv1: ReLU -> [Up] -> conv(d1) -> ReLU -> conv(d3);  res1: [Up] -> conv(k1) on the raw input   (conv.py:38-56,83)
+    _, a1, _ = _fwd(folds[id(c["c1"])], x_act, B, t_hi, act=ACT_RELU, want_act=True)
+    r, _, _ = _fwd(folds[id(c["res"])], x_raw, B, t, want_raw=True)          # 1x1 commutes with nearest upsampling
+    h_raw, h_act, _ = _fwd(folds[id(c["c2"])], a1, B, t_hi, act=ACT_RELU, want_raw=True, want_act=True,
+                           add_post=r, post_shift=1 if up > 1 else 0)
+    # conv2: ReLU -> conv(d9) -> ReLU -> conv(d27);  y = h + conv2(h)                                (conv.py:61-75,84)
+    _, a3, _ = _fwd(folds[id(c["c3"])], h_act, B, t_hi, act=ACT_RELU, want_act=True)
+    y_raw, y_act, _ = _fwd(folds[id(c["c4"])], a3, B, t_hi, act=ACT_RELU, want_raw=want_raw, want_act=want_act,
+                           add_post=h_raw, dup=dup_next)
+    saved = dict(x_raw=x_raw, x_act=x_act, a1=a1, h_act=h_act, a3=a3, t_lo=t, t_hi=t_hi, up=up)
+    return y_raw, y_act, saved
+
+
+def gblock_bwd(blk, folds: Dict[int, Folded], s: dict, dy: Tensor, B: int, ws: _Workspace, out_f32: bool = False) -> Tensor:
+    """Backward of gblock_fwd: dy = d/d(y raw) [B,t_hi,C_out] -> d/d(x raw) [B,t_lo,C_in]; accumulates weight grads."""
+    c = blk.convs()
+    t_lo, t_hi, up = s["t_lo"], s["t_hi"], s["up"]
+    f1, f2, fr, f3, f4 = (folds[id(c[k])] for k in ("c1", "c2", "res", "c3", "c4"))
+    # y = h + conv_d27(relu(conv_d9(relu h)))
+    _wgrad(f4, s["a3"], dy, B, t_hi, t_hi, ws)
+    da3 = _dgrad(f4, dy, B, t_hi, t_hi, mask=s["a3"], mask_mode=ACT_RELU)
+    _wgrad(f3, s["h_act"], da3, B, t_hi, t_hi, ws)
+    dh = _dgrad(f3, da3, B, t_hi, t_hi, mask=s["h_act"], mask_mode=ACT_RELU, add_post=dy)
+    # h = conv_d3(relu(conv_d1(up(relu x)))) + up(res1(x))
+    _wgrad(f2, s["a1"], dh, B, t_hi, t_hi, ws)
+    da1 = _dgrad(f2, dh, B, t_hi, t_hi, mask=s["a1"], mask_mode=ACT_RELU)
+    dr = dh if up == 1 else ops.pair_sum_rows(dh, B * t_lo, fr.mod.out_channels).view(B, t_lo, -1)
+    _wgrad(fr, s["x_raw"], dr, B, t_lo, t_lo, ws)
+    dx_res = _dgrad(fr, dr, B, t_lo, t_lo)
+    _wgrad(f1, s["x_act"], da1, B, t_hi, t_hi, ws)
+    return _dgrad(f1, da1, B, t_hi, t_hi, pair_sum=up > 1, mask=s["x_raw"], mask_mode=ACT_RELU, add_post=dx_res,
+                  out_f32=out_f32)
+
+
+def fold_generator(model, dtype: torch.dtype, want_dgrad: bool = True) -> Dict[int, Folded]:
+    return {id(c): fold(c, dtype, want_dgrad=want_dgrad) for c in generator_convs(model)}
+
+
+@dataclass
+class GenCtx:
+    B: int = 0
+    T: int = 0
+    dtype: torch.dtype = torch.float32
+    folds: Dict[int, Folded] = field(default_factory=dict)
+    x0: Optional[Tensor] = None
+    ids: List[Optional[Tensor]] = field(default_factory=list)
+    emb_dims: List[int] = field(default_factory=list)
+    blocks: List[dict] = field(default_factory=list)
+    y_last_act: Optional[Tensor] = None
+    x_pred: Optional[Tensor] = None
+
+
+def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor], speaking_mode_ids: Optional[Tensor],
+                      dtype: torch.dtype, need_ctx: bool, folds: Optional[Dict[int, Folded]] = None):
+    """EMGGeneratorGanTTS.forward (generator.py:140-162).  Returns (x_pred fp32 [B,16T,C], ctx|None)."""
+    su = speech_units.contiguous().float()
+    B, T, du = su.shape
+    if folds is None:
+        folds = fold_generator(model, dtype, want_dgrad=need_ctx)
+    # units ++ session embedding ++ speaking-mode embedding  (generator.py:143-151)
+    tables, ids = [], []
+    if model.use_session_embeddings:
+        tables.append(model.session_embeddings.weight); ids.append(session_ids.to(torch.int64).contiguous())
+    if model.use_speaking_mode_embedding:
+        tables.append(model.speaking_mode_embeddings.weight); ids.append(speaking_mode_ids.to(torch.int64).contiguous())
+    if len(tables) == 0:
+        x0 = ops.cast(su, dtype)
+    elif len(tables) == 1:
+        x0 = ops.embed_concat(su, tables[0].data, ids[0], dtype)
+    else:  # two tables: concatenate in two steps (fp32 intermediate)
+        tmp = ops.embed_concat(su, tables[0].data, ids[0], torch.float32)
+        x0 = ops.embed_concat(tmp, tables[1].data, ids[1], dtype)
+    blocks = list(model.gblocks)[1:]
+    ups = [b.upsample for b in blocks]
+    for u in ups:
+        if u not in (1, 2):
+            raise ValueError("GBlock upsample must be 1 or 2 on this path")
+    # gblocks.0 (1x1): raw output feeds res1 of the first GBlock, relu(.) feeds its conv1 (duplicated rows = Upsample)
+    x_raw, x_act, t = _fwd(folds[id(model.gblocks[0])], x0, B, T, act=ACT_RELU, want_raw=True, want_act=True,
+                           dup=ups[0] > 1)
+    saved = []
+    for i, blk in enumerate(blocks):
+        last = i + 1 == len(blocks)
+        nxt_dup = (not last) and ups[i + 1] > 1
+        y_raw, y_act, s = gblock_fwd(blk, folds, x_raw, x_act, B, t, want_raw=not last, want_act=True, dup_next=nxt_dup)
+        if need_ctx:
+            saved.append(s)
+        x_raw, x_act, t = y_raw, y_act, s["t_hi"]
+    # last_conv: ReLU -> conv(k3) ; tanh after the channel-last transpose (generator.py:133-137,157-160)
+    _, x_pred, _ = _fwd(folds[id(model.last_conv[1])], x_act, B, t, act=ACT_TANH, want_act=True, out_f32=True)
+    if not need_ctx:
+        return x_pred, None
+    ctx = GenCtx(B=B, T=T, dtype=dtype, folds=folds, x0=x0, ids=ids, emb_dims=[tb.shape[1] for tb in tables],
+                 blocks=saved, y_last_act=x_act, x_pred=x_pred)
+    ctx.tables = tables
+    ctx.d_units = du
+    ctx.t_out = t
+    return x_pred, ctx
+
+
+def generator_backward(model, ctx: GenCtx, dx_pred: Tensor) -> None:
+    """Backward of generator_forward: accumulates into the .grad of every generator parameter.
+    dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output."""
+    B, dtype, folds = ctx.B, ctx.dtype, ctx.folds
+    ws = _Workspace(generator_convs(model), dx_pred.device)
+    blocks = list(model.gblocks)[1:]
+    t = ctx.t_out
+    # tanh' from the output, then last_conv
+    dpre = ops.act_bwd(dx_pred.contiguous(), ctx.x_pred, ACT_TANH, dtype)
+    f = folds[id(model.last_conv[1])]
+    _wgrad(f, ctx.y_last_act, dpre, B, t, t, ws)
+    dy = _dgrad(f, dpre, B, t, t, mask=ctx.y_last_act, mask_mode=ACT_RELU)        # d(y8 raw)
+    for i in reversed(range(len(blocks))):
+        dy = gblock_bwd(blocks[i], folds, ctx.blocks[i], dy, B, ws)
+    # gblocks.0 and the embeddings
+    f0 = folds[id(model.gblocks[0])]
+    _wgrad(f0, ctx.x0, dy, B, ctx.T, ctx.T, ws)
+    if ctx.tables:
+        dx0 = _dgrad(f0, dy, B, ctx.T, ctx.T)
+        off = ctx.d_units
+        if len(ctx.tables) == 1:
+            ops.embed_concat_bwd(dx0, ctx.ids[0], off, _grad_of(ctx.tables[0]))
+        else:
+            d0, d1 = ctx.emb_dims
+            # [units | emb0 | emb1]: slice copies keep the kernel's contiguous-tail contract
+            ops.embed_concat_bwd(dx0[:, :, :off + d0].contiguous(), ctx.ids[0], off, _grad_of(ctx.tables[0]))
+            ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
+
+
+# --------------------------------------------------------------------------------------
+# discriminators
+# --------------------------------------------------------------------------------------
+def disc_subnets(model) -> List[Tuple[str, object]]:
+    return [("P", d) for d in model.multi_pooled_disc] + [("S", d) for d in model.multi_scale_disc]
+
+
+def discriminator_convs(model) -> List:
+    out = []
+    for _, d in disc_subnets(model):
+        out += list(d.layers) + [d.output]
+    return out
+
+
+def fold_discriminator(model, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True,
+                       reuse: Optional[Dict[int, Folded]] = None,
+                       persist: Optional[Dict[int, Folded]] = None) -> Dict[int, Folded]:
+    """Fold every discriminator conv.  Weight-norm folds depend on the weights only and may be
+    reused between forwards (`reuse`); spectral-norm layers are ALWAYS re-folded because every
+    training-mode forward of the reference runs one more power iteration (conv.py:94,101)."""
+    out = {}
+    for c in discriminator_convs(model):
+        if reuse is not None and c.norm == "weight_norm" and id(c) in reuse:
+            out[id(c)] = reuse[id(c)]
+        else:
+            out[id(c)] = fold(c, dtype, training=training, want_dgrad=want_dgrad, persist=persist)
+    return out
+
+
+@dataclass
+class DiscCtx:
+    B: int = 0
+    T: int = 0
+    C: int = 0
+    dtype: torch.dtype = torch.float32
+    folds: Dict[int, Folded] = field(default_factory=dict)
+    subs: List[dict] = field(default_factory=list)
+
+
+def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded]):
+    """DiscriminatorSmall.forward / Discriminator.forward (discriminator.py:144-155,180-191).
+    x: fp32 [B,T,C].  Returns (results, ctx): results[d] = channels-last feature maps
+    [B, H*p, C_j] in `dtype` with the fp32 logits last."""
+    x = x.contiguous().float()
+    B, T, Cc = x.shape
+    ctx = DiscCtx(B=B, T=T, C=Cc, dtype=dtype, folds=folds)
+    results = []
+    xs = x                                   # multi-scale input, fp32, pooled between scales
+    t_scale = T
+    for kind, d in disc_subnets(model):
+        if kind == "P":
+            p = d.period
+            t_pad = T + (p - T % p)          # reflect pad is always >= 1 (discriminator.py:36,86)
+            src = ops.reflect_pad_right(x, t_pad, dtype)
+            phases, t = p, t_pad // p
+        else:
+            src = ops.cast(xs, dtype)
+            phases, t = 1, t_scale
+        sub = dict(kind=kind, phases=phases, inputs=[src], ts=[t], t_in0=t_scale if kind == "S" else T, mod=d)
+        fmaps = []
+        h = src
+        for layer in d.layers:
+            _, h, t = _fwd(folds[id(layer)], h, B, t, phases=phases, act=ACT_LEAKY, want_act=True)
+            fmaps.append(h); sub["inputs"].append(h); sub["ts"].append(t)
+        logits, _, t = _fwd(folds[id(d.output)], h, B, t, phases=phases, want_raw=True, out_f32=True)
+        sub["ts"].append(t)
+        fmaps.append(logits)
+        results.append(fmaps)
+        ctx.subs.append(sub)
+        if kind == "S":
+            sub["x_scale"] = xs
+            xs = ops.avgpool4(xs)            # AvgPool1d(4,2,1) between (and after) the scales (discriminator.py:153)
+            t_scale = xs.shape[1]
+    return results, ctx
+
+
+def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tensor]],
+                           dfmaps: Optional[Sequence[Sequence[Optional[Tensor]]]] = None, want_input_grad: bool = False,
+                           want_weight_grad: bool = True) -> Optional[Tensor]:
+    """Backward through one discriminator forward.
+    dlogits[d]: gradient w.r.t. the logits of sub-discriminator d (`dtype`, same shape) or None;
+    dfmaps[d][j]: gradient w.r.t. feature map j (`dtype`) or None.
+    Returns d/dx fp32 [B,T,C] when want_input_grad."""
+    B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
+    dev = ctx.subs[0]["inputs"][0].device
+    ws = _Workspace(discriminator_convs(model), dev) if want_weight_grad else None
+    dx = torch.zeros((B, T, Cc), device=dev, dtype=torch.float32) if want_input_grad else None
+    scale_grads = []                          # (t_in, d/d x_scale) for the multi-scale chain
+    for di, sub in enumerate(ctx.subs):
+        d, phases, inputs, ts = sub["mod"], sub["phases"], sub["inputs"], sub["ts"]
+        convs = list(d.layers) + [d.output]
+        g = dlogits[di]
+        fm_g = dfmaps[di] if dfmaps is not None else None
+        if g is None and (fm_g is None or all(t is None for t in fm_g)):
+            if sub["kind"] == "S":
+                scale_grads.append((sub["t_in0"], None))
+            continue
+        if g is None:
+            g = torch.zeros((B, ts[-1] * phases, 1), device=dev, dtype=dtype)
+        dxin = None
+        for j in reversed(range(len(convs))):
+            f = folds[id(convs[j])]
+            if want_weight_grad:
+                _wgrad(f, inputs[j], g, B, ts[j], ts[j + 1], ws, phases=phases)
+            if j == 0:
+                if want_input_grad:
+                    dxin = _dgrad(f, g, B, ts[1], ts[0], phases=phases, out_f32=True)
+                break
+            g = _dgrad(f, g, B, ts[j + 1], ts[j], phases=phases, mask=inputs[j], mask_mode=ACT_LEAKY,
+                       add_pre=fm_g[j - 1] if fm_g is not None else None)
+        if want_input_grad:
+            if sub["kind"] == "P":
+                ops.reflect_pad_right_bwd(dxin, T, dx)
+            else:
+                scale_grads.append((sub["t_in0"], dxin))
+    if want_input_grad and scale_grads:
+        # x_s(i+1) = avgpool(x_s(i)): fold the chain from the coarsest scale back to the input
+        carry = None
+        for t_in, gsc in reversed(scale_grads):
+            cur = gsc
+            if carry is not None:
+                if cur is None:
+                    cur = torch.zeros((B, t_in, Cc), device=dev, dtype=torch.float32)
+                ops.avgpool4_bwd(carry, t_in, cur)
+            carry = cur
+        if carry is not None:
+            ops.axpy_f32(dx, carry, 1.0)
+    return dx
+
+
+# --------------------------------------------------------------------------------------
+# layout helpers + per-layer drop-in forwards (reference layouts)
+# --------------------------------------------------------------------------------------
+def to_reference_layout(fm: Tensor, kind: str, phases: int) -> Tensor:
+    """channels-last [B, H*p, C] -> the reference's [B,C,H,p] (period) or [B,C,T] (scale) view."""
+    B, HP, Cc = fm.shape
+    if kind == "P":
+        return fm.view(B, HP // phases, phases, Cc).permute(0, 3, 1, 2)
+    return fm.transpose(1, 2)
+
+
+def single_conv_forward(mod, x: Tensor) -> Tensor:
+    from .autograd import SingleConvFn
+    return SingleConvFn.apply(mod, x, *[p for p in mod.parameters()])
+
+
+def gblock_forward_torch_layout(blk, x: Tensor) -> Tensor:
+    from .autograd import GBlockFn
+    return GBlockFn.apply(blk, x, *[p for p in blk.parameters()])
+

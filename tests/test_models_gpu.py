@@ -1,0 +1,251 @@
+"""Model-level parity (GPU): drop-in modules and the fused train step against the CPU oracle
+(oracle/ste_gan_oracle.py, pinned to the reference by tests/golden/*) and against the
+committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): relative L2 <= 1e-4 in the fp32 validation mode,
+<= 2e-2 in bf16.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import ste_gan_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def seeded(ctor, seed=0):
+    torch.manual_seed(seed)
+    return ctor()
+
+
+def cpu_sd(mod):
+    return {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+
+
+@pytest.fixture(scope="module")
+def nets():
+    from ste_gan_b200.models.discriminator import DiscriminatorSmall
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8))
+    d = seeded(lambda: DiscriminatorSmall(8))
+    return g, d
+
+
+def test_init_matches_reference_checksums(nets):
+    """Seed-0 initialisation is bit-identical to the reference modules (fixture from oracle/make_golden.py)."""
+    init = torch.load(os.path.join(GOLD, "init_checksums.pt"))
+    for name, mod in (("generator", nets[0]), ("disc_small", nets[1])):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(init[name].keys())
+        for k, ref in init[name].items():
+            t = sd[k].detach().double().flatten()
+            assert list(sd[k].shape) == ref["shape"]
+            assert abs(t.sum().item() - ref["sum"]) <= 1e-9 * max(1.0, ref["abssum"]), k
+            assert torch.equal(t[ref["idx"]].float(), ref["samples"]), k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_generator_tiny_golden(prec):
+    """channels=64 generator with the reference's stored weights, input and output."""
+    import ste_gan_b200
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    fx = torch.load(os.path.join(GOLD, "generator_tiny.pt"))
+    g = EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, channels=fx["channels"])
+    g.load_state_dict(fx["state_dict"])
+    g.cuda()
+    with ste_gan_b200.precision(prec):
+        y = g.generate(fx["speech_units"].cuda(), fx["session_ids"].cuda(), torch.zeros(2, dtype=torch.long).cuda())
+    assert y.shape == fx["output"].shape
+    assert O.rel_l2(y, fx["output"]) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_generator_full_vs_oracle(nets, prec):
+    import ste_gan_b200
+    g = nets[0].cuda()
+    su, sess, _ = O.synthetic_batch(2, 100, seed=1)
+    with torch.no_grad():
+        ref = O.generator_forward(cpu_sd(g), su, sess)
+    with ste_gan_b200.precision(prec):
+        y = g.generate(su.cuda(), sess.cuda(), torch.zeros(2, dtype=torch.long).cuda())
+    assert O.rel_l2(y, ref) < TOL[prec]
+    if prec == "fp32":   # configs[0] golden: B=1 T=100 seed-0 weights
+        fx = torch.load(os.path.join(GOLD, "train_step_b1.pt"))
+        su1, sess1, _ = O.synthetic_batch(1, 100, seed=0)
+        with ste_gan_b200.precision("fp32"):
+            y1 = g.generate(su1.cuda(), sess1.cuda(), torch.zeros(1, dtype=torch.long).cuda())
+        assert O.rel_l2(y1, fx["x_pred"]) < 1e-4
+
+
+@pytest.mark.parametrize("small", [True, False], ids=["small", "full"])
+def test_discriminator_golden_two_forwards(small):
+    """Two consecutive training forwards (pins the per-forward spectral-norm power iteration)."""
+    import ste_gan_b200
+    from ste_gan_b200.models.discriminator import Discriminator, DiscriminatorSmall
+    fx = torch.load(os.path.join(GOLD, "disc_small.pt" if small else "disc_full.pt"))
+    d = seeded(lambda: (DiscriminatorSmall if small else Discriminator)(8)).cuda()
+    assert d.discriminator_names == fx["names"]
+    x = fx["x"].cuda()
+    with ste_gan_b200.precision("fp32"):
+        for p in range(2):
+            with torch.no_grad():
+                res = d(x)
+            for fms, refs in zip(res, fx["passes"][p]):
+                assert len(fms) == len(refs)
+                for fm, ref in zip(fms, refs):
+                    assert list(fm.shape) == ref["shape"]
+                    t = fm.detach().double().cpu().contiguous().flatten()
+                    assert abs(t.norm().item() - ref["l2"]) <= 1e-4 * max(ref["l2"], 1e-3)
+                    assert (t[ref["idx"]].float() - ref["samples"]).norm() <= 2e-4 * max(ref["samples"].norm().item(), 1e-3)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_discriminator_vs_oracle(nets, prec):
+    import ste_gan_b200
+    d = seeded(lambda: type(nets[1])(8)).cuda()
+    sd = cpu_sd(d)
+    _, _, x = O.synthetic_batch(2, 100, seed=2)
+    with torch.no_grad():
+        ref = O.discriminator_forward(sd, x, small=True, training=True)
+    with ste_gan_b200.precision(prec), torch.no_grad():
+        res = d(x.cuda())
+    worst = max(O.rel_l2(a, b) for fa, fb in zip(res, ref) for a, b in zip(fa, fb))
+    assert worst < TOL[prec], worst
+    # spectral-norm buffers advanced identically
+    for k in ("multi_scale_disc.0.layers.3.weight_u", "multi_scale_disc.0.layers.0.weight_v"):
+        assert O.rel_l2(d.state_dict()[k], sd[k]) < 1e-4
+
+
+def test_td_loss_golden():
+    from ste_gan_b200.losses.time_domain_loss import MultiTimeDomainFeatureLoss
+    fx = torch.load(os.path.join(GOLD, "td_loss.pt"))
+    mtd = MultiTimeDomainFeatureLoss(8)
+    xg = fx["x_gen"].cuda().requires_grad_(True)
+    loss, parts = mtd.time_domain_loss(fx["x_real"].cuda(), xg)
+    for a, b in zip(parts, fx["parts"]):
+        assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+    loss.backward()
+    assert O.rel_l2(xg.grad, fx["grad_x_gen"]) < 1e-4
+    # forward(x_real, x_generated) argument order (time_domain_loss.py:105-107)
+    assert abs(float(mtd(fx["x_real"].cuda(), fx["x_gen"].cuda())) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+
+
+def _fresh_nets(small=True):
+    from ste_gan_b200.models.discriminator import Discriminator, DiscriminatorSmall
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8))
+    d = seeded(lambda: (DiscriminatorSmall if small else Discriminator)(8))
+    return g, d
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_train_step_losses_and_grads_vs_oracle(prec):
+    """One fused train step (B=2, T=100) against the oracle: G output, every loss term, the gradient w.r.t.
+    every parameter of G (through D, TD and FM) and of D."""
+    from ste_gan_b200.trainer import GanTrainer
+    g, d = _fresh_nets()
+    sd_g, sd_d = cpu_sd(g), cpu_sd(d)
+    su, sess, x_real = O.synthetic_batch(2, 100, seed=3)
+    ref = O.losses_and_grads(sd_g, sd_d, su, sess, x_real, small=True)
+    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
+    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
+    tol = TOL[prec]
+    assert O.rel_l2(tr.x_pred, ref["x_pred"]) < tol
+    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
+    tr._phase_g(x_real.cuda(), update_d=False)
+    L = tr.losses()
+    for mine, theirs in (("loss_d", "loss_d"), ("loss_adv", "loss_adv"), ("loss_fm", "loss_fm"), ("loss_td", "loss_td"),
+                         ("loss_g", "loss_g")):
+        assert abs(L[mine] - float(ref[theirs])) <= tol * max(1.0, abs(float(ref[theirs]))), (mine, L[mine], float(ref[theirs]))
+    bad = {k: O.rel_l2(gd[k], ref["grad_d"][k]) for k in gd}
+    worst_d = max(bad.values())
+    gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
+    bad_g = {k: O.rel_l2(gg[k], ref["grad_g"][k]) for k in gg}
+    worst_g = max(bad_g.values())
+    print(f"[{prec}] worst grad_d {worst_d:.3e} ({max(bad, key=bad.get)}), worst grad_g {worst_g:.3e} ({max(bad_g, key=bad_g.get)})")
+    assert worst_d < tol and worst_g < tol
+
+
+def test_autograd_dropin_matches_fused_step():
+    """The reference-style loop (modules + loss.backward()) gives the same gradients as the fused trainer (fp32)."""
+    import torch.nn.functional as F
+    import ste_gan_b200
+    from ste_gan_b200.losses.time_domain_loss import MultiTimeDomainFeatureLoss
+    from ste_gan_b200.trainer import GanTrainer
+    su, sess, x_real = (t.cuda() for t in O.synthetic_batch(2, 100, seed=4))
+    g1, d1 = _fresh_nets()
+    tr = GanTrainer(g1.cuda(), d1.cuda(), precision="fp32")
+    tr._phase_d(su, sess, None, x_real)
+    gd_ref = {n: p.grad.detach().clone() for n, p in d1.named_parameters()}
+    tr._phase_g(x_real, update_d=False)
+    g2, d2 = _fresh_nets()
+    g2.cuda(); d2.cuda()
+    mtd = MultiTimeDomainFeatureLoss(8)
+    with ste_gan_b200.precision("fp32"):
+        x_pred = g2(su, sess, torch.zeros(2, dtype=torch.long).cuda())                 # train.py:182
+        D_fake_det, D_real = d2(x_pred.detach()), d2(x_real)                          # :190-191
+        loss_D = sum(F.mse_loss(s[-1], torch.zeros_like(s[-1])) for s in D_fake_det) + \
+            sum(F.mse_loss(s[-1], torch.ones_like(s[-1])) for s in D_real)
+        loss_D.backward()                                                              # :198
+        for n, p in d2.named_parameters():
+            assert O.rel_l2(p.grad, gd_ref[n]) < 1e-4, n
+        d2.zero_grad()
+        D_fake, D_real = d2(x_pred), d2(x_real)                                        # :206-207
+        loss_G = sum(F.mse_loss(s[-1], torch.ones_like(s[-1])) for s in D_fake) + 15.0 * mtd(x_real, x_pred)
+        for i in range(len(D_fake)):
+            for j in range(len(D_fake[i]) - 1):
+                loss_G = loss_G + 7.0 * F.l1_loss(D_fake[i][j], D_real[i][j].detach())  # :259-263
+        loss_G.backward()                                                              # :266
+    assert abs(float(loss_G) - tr.losses()["loss_g"]) <= 1e-4 * abs(float(loss_G))
+    for (n, p), (_, q) in zip(g2.named_parameters(), g1.named_parameters()):
+        assert O.rel_l2(p.grad, q.grad) < 1e-4, n
+
+
+def test_multi_step_matches_oracle_trainer():
+    """Three full steps (D update between the phases, AdamW on both nets) track the oracle's loss trajectory."""
+    from ste_gan_b200.trainer import GanTrainer
+    g, d = _fresh_nets()
+    ot = O.OracleTrainer(cpu_sd(g), cpu_sd(d), small=True)
+    tr = GanTrainer(g.cuda(), d.cuda(), precision="fp32")
+    for step in range(3):
+        su, sess, x_real = O.synthetic_batch(2, 100, seed=10 + step)
+        ref = ot.step(su, sess, x_real)
+        tr.step(su.cuda(), sess.cuda(), x_real.cuda())
+        L = tr.losses()
+        for k in ("loss_d", "loss_g", "loss_fm", "loss_td"):
+            assert abs(L[k] - ref[k]) <= 2e-3 * max(1.0, abs(ref[k])), (step, k, L[k], ref[k])
+    # parameters after 3 optimiser steps
+    worst = max(O.rel_l2(p, ot.g[n]) for n, p in g.named_parameters())
+    assert worst < 1e-3, worst
+
+
+def test_cuda_graph_step_matches_eager():
+    from ste_gan_b200.trainer import GanTrainer
+    su, sess, x_real = (t.cuda() for t in O.synthetic_batch(2, 100, seed=5))
+    g1, d1 = _fresh_nets(); g2, d2 = _fresh_nets()
+    t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="bf16")
+    t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="bf16")
+    t2.capture(2, 100)
+    # capture() ran warm-up steps on zero inputs: bring t1 to the same state
+    z = (torch.zeros_like(su), torch.zeros_like(sess), torch.zeros_like(x_real))
+    for _ in range(2):
+        t1.step(z[0], z[1], z[2])
+    for _ in range(2):
+        t1.step(su, sess, x_real)
+        t2.step_graph(su, sess, x_real)
+    a, b = t1.losses(), t2.losses()
+    for k in a:
+        assert abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+def test_no_cpu_fallback():
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, channels=64)
+    su, sess, _ = O.synthetic_batch(1, 8)
+    with pytest.raises(RuntimeError):
+        g(su, sess, torch.zeros(1, dtype=torch.long))
