@@ -188,6 +188,8 @@ int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr,
 const char* stg_strerror(int code);
 const char* stg_last_cuda_error(void);
 int stg_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long stg_launch_count(void);
 /* 1 if the tcgen05 engine can take this contraction (shape/alignment rules in DESIGN.md), else 0. */
 int stg_conv_tc_supported(const StgConv* d);
 int stg_wgrad_tc_supported(const StgWgrad* d);

@@ -8,6 +8,7 @@
 namespace stg {
 
 static thread_local std::string g_last_error;
+unsigned long long g_launch_count = 0;
 
 void set_cuda_error(cudaError_t e, const char* where) {
   g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
@@ -76,3 +77,4 @@ extern "C" const char* stg_strerror(int code) {
 }
 extern "C" const char* stg_last_cuda_error(void) { return g_last_error.c_str(); }
 extern "C" int stg_version(void) { return 100; }
+extern "C" unsigned long long stg_launch_count(void) { return g_launch_count; }

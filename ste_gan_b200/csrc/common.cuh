@@ -19,7 +19,12 @@ void set_cuda_error(cudaError_t e, const char* where);
     }                                                          \
   } while (0)
 
-#define STG_LAUNCH_CHECK() STG_CUDA_CHECK(cudaGetLastError())
+extern unsigned long long g_launch_count;  // kernels launched by this library (process-wide)
+#define STG_LAUNCH_CHECK()                 \
+  do {                                     \
+    ++::stg::g_launch_count;               \
+    STG_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 using bf16 = __nv_bfloat16;
 

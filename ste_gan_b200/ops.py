@@ -17,6 +17,7 @@ from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, BF16, ENGINE_AUTO, E
 
 Tensor = torch.Tensor
 _engine_override: Optional[int] = None  # tests force an engine through this
+profile = None  # bench.py sets this to a list: every conv / wgrad launch is then bracketed by CUDA events
 
 
 def set_engine(engine: Optional[int]) -> None:
@@ -80,7 +81,22 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
                 post_shift=post_shift, mask_mode=mask_mode, act=act, dup_rows=int(dup_rows), out_f32=int(out_f32),
                 src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
                 add_post=_ptr(add_post), y_raw=_ptr(y_raw), y_act=_ptr(y_act))
-    check(_lib.load().stg_conv(C.byref(d), _stream()), "stg_conv")
+    lib = _lib.load()
+    if profile is None:
+        check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
+        return
+    tc = bool(lib.stg_conv_tc_supported(C.byref(d))) and d.engine != ENGINE_SIMT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
+    e1.record()
+    flops = 2.0 * nv * t_src * c_src * k * (c_dst // groups) if transposed else 2.0 * nv * t_dst * c_dst * k * (c_src // groups)
+    esz = 2 if dt == torch.bfloat16 else 4
+    nbytes = esz * (nv * t_src * c_src + k * c_dst * (c_src // groups)) + sum(
+        t.numel() * t.element_size() for t in (add_pre, mask, add_post, y_raw, y_act) if t is not None)
+    profile.append(dict(kind=("dgrad" if transposed else "fwd"), engine="tcgen05" if tc else "simt", flops=flops,
+                        bytes=nbytes, events=(e0, e1),
+                        shape=(n_samples, phases, t_src, t_dst, c_src, c_dst, k, dilation, stride, groups)))
 
 
 def conv_tc_supported(**kw) -> bool:
@@ -100,7 +116,20 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
     d = StgWgrad(dtype=code_of(x.dtype), engine=_engine_override if _engine_override is not None else engine,
                  n_samples=n_samples, phases=phases, t_in=t_in, t_out=t_out, c_in=c_in, c_out=c_out, groups=groups,
                  k=k, dilation=dilation, stride=stride, pad=pad, x=_ptr(x), dy=_ptr(dy), dw=_ptr(dw), dbias=_ptr(dbias))
-    check(_lib.load().stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
+    lib = _lib.load()
+    if profile is None:
+        check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
+        return
+    tc = bool(lib.stg_wgrad_tc_supported(C.byref(d))) and d.engine != ENGINE_SIMT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
+    e1.record()
+    esz = 2 if x.dtype == torch.bfloat16 else 4
+    profile.append(dict(kind="wgrad", engine="tcgen05" if tc else "simt",
+                        flops=2.0 * nv * t_out * c_out * k * (c_in // groups),
+                        bytes=esz * nv * (t_in * c_in + t_out * c_out) + 4 * c_out * k * (c_in // groups),
+                        events=(e0, e1), shape=(n_samples, phases, t_in, t_out, c_in, c_out, k, dilation, stride, groups)))
 
 
 def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True, out=None):

@@ -23,9 +23,8 @@ from __future__ import annotations
 from typing import Dict, List, Optional
 
 import torch
-import torch.distributed as dist
-
 from . import ops, passes
+from .dist import GradReducer
 
 Tensor = torch.Tensor
 
@@ -60,33 +59,11 @@ class FlatParams:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2) -> None:
-        """torch.optim.AdamW(lr=2e-4, betas=(.8,.99)) - ste_gan/constants.py:57."""
-        ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay)
-
-
-class GradReducer:
-    """Bucketed NCCL all-reduce (average) of a flat gradient over the data-parallel group.
-    Buckets are issued back to front (the order backward produces them) on NCCL's stream and
-    waited for before the optimiser kernel."""
-
-    def __init__(self, group=None, bucket_mb: float = 32.0):
-        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-        self.group = group
-        self.bucket = int(bucket_mb * (1 << 20) // 4)
-
-    def all_reduce(self, flat_grad: Tensor) -> None:
-        if not self.enabled:
-            return
-        n = flat_grad.numel()
-        handles = []
-        hi = n
-        while hi > 0:
-            lo = max(0, hi - self.bucket)
-            handles.append(dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
-            hi = lo
-        for h in handles:
-            h.wait()
+    def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2,
+              grad_scale: float = 1.0) -> None:
+        """torch.optim.AdamW(lr=2e-4, betas=(.8,.99)) - ste_gan/constants.py:57.  grad_scale = 1/world
+        turns the all-reduced gradient SUM into the data-parallel mean inside the kernel."""
+        ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay, grad_scale)
 
 
 class GanTrainer:
@@ -138,7 +115,7 @@ class GanTrainer:
         dx_pred = torch.zeros_like(x_pred)
         if self.use_adv:
             if update_d:
-                self.D.adamw(self.lr)                                       # train.py:199
+                self.D.adamw(self.lr, grad_scale=self.reducer.grad_scale)   # train.py:199
             f3 = passes.fold_discriminator(self.net_d, dt, training=True, persist=self._d_persist)
             res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3)
             f4 = passes.fold_discriminator(self.net_d, dt, training=True, reuse=f3)
@@ -164,7 +141,7 @@ class GanTrainer:
         self._gctx = None
 
     def _phase_opt_g(self) -> None:
-        self.G.adamw(self.lr)                                               # train.py:267
+        self.G.adamw(self.lr, grad_scale=self.reducer.grad_scale)           # train.py:267
 
     # ------------------------------------------------------------------ public API
     def step(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,

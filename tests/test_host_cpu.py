@@ -1,0 +1,116 @@
+"""CPU: host-side logic - C-ABI exports, drop-in module surface, data-parallel plumbing (gloo, world 2)."""
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from ste_gan_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "stegan_b200.h")).read()
+    declared = set(re.findall(r"\b(stg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/stegan_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.stg_version() >= 100 and lib.stg_strerror(-3).decode().startswith("shape")
+
+
+def test_ctypes_struct_layout_matches_header():
+    import ctypes as C
+    from ste_gan_b200 import _lib
+    assert C.sizeof(_lib.StgConv) == 20 * 4 + 8 * 8
+    assert C.sizeof(_lib.StgWgrad) == 13 * 4 + 4 + 4 * 8      # 13 ints, padding to 8, 4 pointers
+
+
+def test_init_matches_golden_checksums():
+    """Same seed -> bit-identical parameters / buffers / key order as the reference modules."""
+    from ste_gan_b200.models.discriminator import Discriminator, DiscriminatorSmall
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    init = torch.load(os.path.join(GOLD, "init_checksums.pt"))
+    ctors = {"generator": lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8), "disc_small": lambda: DiscriminatorSmall(8),
+             "disc_full": lambda: Discriminator(8), "generator_mfcc": lambda: EMGGeneratorGanTTS("MFCCS", 25, 17, 8)}
+    for name, ctor in ctors.items():
+        torch.manual_seed(0)
+        mod = ctor()
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(init[name].keys()), name
+        for k, ref in init[name].items():
+            assert list(sd[k].shape) == ref["shape"], (name, k)
+            assert torch.equal(sd[k].double().flatten()[ref["idx"]].float(), ref["samples"]), (name, k)
+        if name in init["param_order"]:
+            assert [n for n, _ in mod.named_parameters()] == init["param_order"][name]
+
+
+def test_module_surface():
+    from ste_gan_b200.losses.time_domain_loss import MultiTimeDomainFeatureLoss
+    from ste_gan_b200.models.discriminator import DiscriminatorSmall, init_emg_discriminators
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS, init_emg_generator
+    class AttrDict(dict):          # stands in for omegaconf.DictConfig: attribute access + `in`
+        __getattr__ = dict.__getitem__
+    cfg = AttrDict(model=AttrDict(speech_feature_type="SPEECH_UNITS", type="EMGGeneratorGanTTS", discriminator_small=True),
+                   data=AttrDict(num_emg_channels=8, num_emg_sessions=17))
+    g = init_emg_generator(cfg)
+    assert isinstance(g, EMGGeneratorGanTTS) and g.input_size == 320 and g.num_output_channels == 8
+    assert g.speech_feature_type == "SPEECH_UNITS" and g.use_session_embeddings and not g.use_speaking_mode_embedding
+    assert sum(p.numel() for p in g.parameters()) == 23546832
+    d = init_emg_discriminators(cfg)
+    assert isinstance(d, DiscriminatorSmall) and sum(p.numel() for p in d.parameters()) == 11856336
+    assert d.discriminator_names == [f"DiscriminatorP-{p}" for p in (2, 3, 5, 7, 11)] + [f"DiscriminatorS-{i}" for i in range(3)]
+    assert len(MultiTimeDomainFeatureLoss(8).time_domain_losses) == 3
+    su = torch.randn(1, 8, 256)
+    with pytest.raises(RuntimeError):            # no CPU fallback
+        g(su, torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+
+
+def test_shard_helpers():
+    from ste_gan_b200.dist import GradReducer, round_robin, shard_range
+    assert [shard_range(r, 3, 10) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    assert sorted(sum((round_robin(r, 4, 10) for r in range(4)), [])) == list(range(10))
+    red = GradReducer(bucket_mb=1.0)
+    assert not red.enabled and red.grad_scale == 1.0
+    b = red.buckets(700000)
+    assert b[0] == (700000 - 262144, 700000) and b[-1][0] == 0 and sum(h - l for l, h in b) == 700000
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from ste_gan_b200.dist import GradReducer, init_from_env, shard_range
+    r, w, _ = init_from_env("gloo")
+    red = GradReducer(bucket_mb=0.001)
+    g = torch.full((1000,), float(r + 1))
+    red.all_reduce(g)
+    flat = torch.arange(8.0) * (r + 1)
+    red.broadcast(flat, src=0)
+    ok = red.enabled and bool((g == 3.0).all()) and red.grad_scale == 0.5 and bool((flat == torch.arange(8.0)).all())
+    lo, hi = shard_range(r, w, 32)
+    out[rank] = (ok, lo, hi)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gloo_world2():
+    """The N>1 exchange step on CPU: bucketed all-reduce (sum) + 1/world scale + initial broadcast."""
+    port = 29500 + os.getpid() % 1000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == (True, 0, 16) and out[1] == (True, 16, 32)
+
+
+def test_precision_context():
+    import ste_gan_b200
+    assert ste_gan_b200.get_precision() == "fp32"
+    with ste_gan_b200.precision("bf16"):
+        assert ste_gan_b200.get_precision() == "bf16"
+    assert ste_gan_b200.get_precision() == "fp32"
+    with pytest.raises(ValueError):
+        ste_gan_b200.set_precision("fp8")

@@ -55,7 +55,7 @@ def run_fwd(ops, case, dtype, engine, x, w, bias, To):
     xd = x.to(dev, dtype)
     wf = pack_fwd(w).to(dev, dtype)
     y = torch.empty(B, To * p, co, device=dev, dtype=torch.float32)
-    ya = torch.empty(B, To * p, co, device=dev, dtype=dtype)
+    ya = torch.empty(B, To * p, co, device=dev, dtype=torch.float32)
     ops.conv(xd, wf, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k, dilation=d,
              stride=s, pad=pad, bias=bias.to(dev), act=ops.ACT_LEAKY, y_raw=y, y_act=ya, engine=engine)
     torch.cuda.synchronize()
@@ -213,3 +213,103 @@ def test_fused_epilogue(engine_dtype):
     (g,) = torch.autograd.grad(conv_ref(xr, w, None, dilation=d, pad=d), xr, dy.double())
     ref = (g[:, 0::2] + g[:, 1::2] + pre.double()) * (m.double() > 0) + post.double()
     assert rel_l2(dx.float().cpu(), ref) < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# weight-norm / spectral-norm folds, input preparation and loss reductions against torch (CPU, fp64)
+# ---------------------------------------------------------------------------------------------
+FOLD_CASES = [(128, 8, 15, 1), (256, 32, 37, 4), (512, 16, 37, 16), (1024, 512, 5, 1), (1, 512, 3, 1), (768, 320, 1, 1)]
+
+
+@pytest.mark.parametrize("shape", FOLD_CASES, ids=[str(s) for s in FOLD_CASES])
+def test_weightnorm_fold_fwd_bwd(shape):
+    from ste_gan_b200 import ops
+    co, cg, k, groups = shape
+    gen = torch.Generator().manual_seed(co + k)
+    v = torch.randn(co, cg, k, generator=gen); g = torch.rand(co, 1, 1, generator=gen) + 0.5
+    dwp = torch.randn(co, k, cg, generator=gen)               # packed-layout upstream gradient
+    vd, gd = v.double().requires_grad_(True), g.double().requires_grad_(True)
+    w = vd * (gd / vd.norm(2, dim=(1, 2), keepdim=True))
+    gv, gg = torch.autograd.grad(w, [vd, gd], dwp.double().permute(0, 2, 1))
+    wf, wd, scale = ops.weightnorm_fold(v.cuda(), g.cuda(), groups, torch.float32)
+    assert rel_l2(wf.cpu(), pack_fwd(w.detach())) < 1e-6
+    assert rel_l2(wd.cpu(), pack_dgrad(w.detach(), groups)) < 1e-6
+    dv = torch.zeros(co, cg, k, device="cuda"); dg = torch.zeros(co, device="cuda")
+    ops.weightnorm_fold_bwd(dwp.cuda(), v.cuda(), g.cuda(), dv, dg, True)
+    assert rel_l2(dv.cpu(), gv) < 1e-5 and rel_l2(dg.cpu(), gg.flatten()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", FOLD_CASES[:4], ids=[str(s) for s in FOLD_CASES[:4]])
+@pytest.mark.parametrize("training", [True, False])
+def test_spectralnorm_fold_fwd_bwd(shape, training):
+    from oracle import ste_gan_oracle as O
+    from ste_gan_b200 import ops
+    co, cg, k, groups = shape
+    gen = torch.Generator().manual_seed(co * 3 + k)
+    w0 = torch.randn(co, cg, k, generator=gen) / (cg * k) ** 0.5
+    u = torch.nn.functional.normalize(torch.randn(co, generator=gen), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(cg * k, generator=gen), dim=0)
+    dwp = torch.randn(co, k, cg, generator=gen)
+    wd_, ud, vd = w0.double().requires_grad_(True), u.double().clone(), v.double().clone()
+    w = O.spectral_norm_weight(wd_, ud, vd, training)         # updates ud, vd in place when training
+    (gw,) = torch.autograd.grad(w, wd_, dwp.double().permute(0, 2, 1))
+    uc, vc = u.cuda(), v.cuda()
+    wf, wdp, sigma = ops.spectralnorm_fold(w0.cuda(), uc, vc, groups, training, torch.float32)
+    assert rel_l2(uc.cpu(), ud) < 1e-5 and rel_l2(vc.cpu(), vd) < 1e-5
+    assert rel_l2(wf.cpu(), pack_fwd(w.detach())) < 1e-5
+    assert rel_l2(wdp.cpu(), pack_dgrad(w.detach(), groups)) < 1e-5
+    dW = torch.zeros(co, cg, k, device="cuda")
+    ops.spectralnorm_fold_bwd(dwp.cuda(), w0.cuda(), uc, vc, sigma, dW, True)
+    assert rel_l2(dW.cpu(), gw) < 1e-5
+
+
+def test_disc_input_prep_and_reductions():
+    from ste_gan_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 101, 8, generator=gen)
+    for p in (2, 3, 5, 7, 11):
+        tp = 101 + (p - 101 % p)
+        ref = F.pad(x.transpose(1, 2), (0, tp - 101), "reflect").transpose(1, 2)
+        out = ops.reflect_pad_right(x.cuda(), tp, torch.float32)
+        assert torch.equal(out.cpu(), ref)
+        g = torch.randn(3, tp, 8, generator=gen)
+        xr = x.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad(F.pad(xr.transpose(1, 2), (0, tp - 101), "reflect").transpose(1, 2), xr, g)
+        dx = torch.zeros(3, 101, 8, device="cuda")
+        ops.reflect_pad_right_bwd(g.cuda(), 101, dx)
+        assert rel_l2(dx.cpu(), gx) < 1e-6
+    for T in (100, 101):
+        xx = torch.randn(2, T, 8, generator=gen)
+        xr = xx.clone().requires_grad_(True)
+        ref = F.avg_pool1d(xr.transpose(1, 2), 4, 2, 1).transpose(1, 2)
+        out = ops.avgpool4(xx.cuda())
+        assert rel_l2(out.cpu(), ref) < 1e-6
+        g = torch.randn(ref.shape, generator=gen)
+        (gx,) = torch.autograd.grad(ref, xr, g)
+        dx = torch.zeros(2, T, 8, device="cuda")
+        ops.avgpool4_bwd(g.cuda(), T, dx)
+        assert rel_l2(dx.cpu(), gx) < 1e-6
+    a, b = torch.randn(5, 333, generator=gen), torch.randn(5, 333, generator=gen)
+    slot = torch.zeros(2, device="cuda"); da = torch.empty(5, 333, device="cuda"); dl = torch.empty(5, 333, device="cuda")
+    ops.l1_mean(a.cuda(), b.cuda(), slot[0:1], 7.0, da)
+    ops.mse_const(a.cuda(), 1.0, slot[1:2], 1.0, dl)
+    assert abs(slot[0].item() - F.l1_loss(a, b).item()) < 1e-6
+    assert abs(slot[1].item() - F.mse_loss(a, torch.ones_like(a)).item()) < 1e-6
+    assert rel_l2(da.cpu(), 7.0 * torch.sign(a - b) / a.numel()) < 1e-6
+    assert rel_l2(dl.cpu(), 2.0 * (a - 1.0) / a.numel()) < 1e-6
+
+
+def test_adamw_matches_torch():
+    from ste_gan_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    p0 = torch.randn(10007, generator=gen)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=2e-4, betas=(0.8, 0.99))
+    p, m, v = p0.cuda(), torch.zeros(10007, device="cuda"), torch.zeros(10007, device="cuda")
+    step = torch.zeros(1, device="cuda", dtype=torch.int64)
+    for i in range(5):
+        g = torch.randn(10007, generator=gen)
+        pr.grad = g.clone(); opt.step()
+        ops.adamw(p, g.cuda(), m, v, step, 2e-4)
+    assert int(step.item()) == 5
+    assert rel_l2(p.cpu(), pr.detach()) < 1e-6
