@@ -277,19 +277,65 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgP p) {
   }
 }
 
+// Column sums (bias gradient): out[c] += sum_r dy[r][c].  Generic path for C that is not a multiple of the vector width.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int64_t rows, int C, int rows_per_block,
                                                      float* __restrict__ out) {
-  // thread -> (column, row lane); rows strided by lanes
-  const int lanes = max(1, 256 / C);
-  const int col = threadIdx.x % C, lane = threadIdx.x / C;
-  if (C <= 256 && lane >= lanes) return;
+  __shared__ float red[32];
   const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
-  for (int c = col; c < C; c += 256) {
+  for (int c = 0; c < C; ++c) {
     float s = 0.f;
-    for (int64_t r = rb + lane; r < re; r += lanes) s += to_f(dy[r * C + c]);
-    atomicAdd(out + c, s);
-    if (C <= 256) break;
+    for (int64_t r = rb + threadIdx.x; r < re; r += 256) s += to_f(dy[r * C + c]);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(out + c, s);
+  }
+}
+
+// Vectorised path: a thread owns VEC consecutive channels (16-byte loads) and walks rows with stride `lanes`;
+// the block reduces its row lanes in shared memory and issues C atomics.  HBM/L2-bound: dy is read once.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, int rows_per_block,
+                                                         float* __restrict__ out) {
+  __shared__ float red[256 * VEC];
+  const int cg = C / VEC, lanes = 256 / cg;
+  const int rl = threadIdx.x / cg, c = threadIdx.x - rl * cg;
+  const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(rows, rb + rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (rl < lanes) {
+    for (int64_t r = rb + rl; r < re; r += lanes) {
+      const T* p = dy + r * C + c * VEC;
+      if constexpr (VEC == 8) {
+        float a[4], b[4];
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint2 lo = make_uint2(q.x, q.y), hi = make_uint2(q.z, q.w);
+        ld4(reinterpret_cast<const bf16*>(&lo), a); ld4(reinterpret_cast<const bf16*>(&hi), b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i] += a[i]; acc[4 + i] += b[i]; }
+      } else {
+        float a[4];
+        ld4(p, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += a[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] = acc[i];
+  __syncthreads();
+  int s = 1;
+  while (s < lanes) s <<= 1;
+  for (s >>= 1; s > 0; s >>= 1) {
+    if (rl < s && rl + s < lanes) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] += red[(threadIdx.x + s * cg) * VEC + i];
+    }
+    __syncthreads();
+  }
+  if (rl == 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(out + c * VEC + i, red[threadIdx.x * VEC + i]);
   }
 }
 
@@ -345,10 +391,21 @@ int wgrad_simt(const StgWgrad* d, cudaStream_t s) {
 }
 
 int colsum(const void* dy, int dtype, int64_t rows, int C, float* out, cudaStream_t s) {
-  const int rows_per_block = 512;
-  const int blocks = (int)ceil_div64(rows, rows_per_block);
-  if (dtype == STG_F32) colsum_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(dy), rows, C, rows_per_block, out);
-  else colsum_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16*>(dy), rows, C, rows_per_block, out);
+  const int vec = dtype == STG_F32 ? 4 : 8;
+  if (C % vec == 0 && C / vec <= 256) {
+    const int lanes = 256 / (C / vec);
+    int64_t rpb = ceil_div64(rows, 148 * 4);
+    if (rpb < 4 * lanes) rpb = 4 * lanes;
+    const int blocks = (int)ceil_div64(rows, rpb);
+    if (dtype == STG_F32) colsum_vec_kernel<float, 4><<<blocks, 256, 0, s>>>(static_cast<const float*>(dy), rows, C, (int)rpb, out);
+    else colsum_vec_kernel<bf16, 8><<<blocks, 256, 0, s>>>(static_cast<const bf16*>(dy), rows, C, (int)rpb, out);
+  } else {
+    int64_t rpb = ceil_div64(rows, 148 * 2);
+    if (rpb < 1024) rpb = 1024;
+    const int blocks = (int)ceil_div64(rows, rpb);
+    if (dtype == STG_F32) colsum_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(dy), rows, C, (int)rpb, out);
+    else colsum_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16*>(dy), rows, C, (int)rpb, out);
+  }
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

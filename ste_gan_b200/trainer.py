@@ -99,6 +99,7 @@ class GanTrainer:
         res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1)
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, reuse=f1)
         res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
+        self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         dl_f, dl_r = [], []
         for fm_f, fm_r in zip(res_f, res_r):
             gf = torch.empty(fm_f[-1].shape, device=self.device, dtype=dt)
