@@ -107,13 +107,21 @@ int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream);
 /*
  * weight_norm (torch.nn.utils.weight_norm, dim 0; layers/conv.py:16-17,92,99):
  *   w = g * v / ||v||  per output channel; v is the torch layout [c_out][c_in/groups][k].
- * Emits the forward pack wf [k][c_out][cin_g] and the data-gradient pack
- * wd [k][c_in][c_out/groups] in `dtype`, and scale[c_out] = g/||v|| (fp32) for the backward.
+ * Emits the forward pack wf [k][c_out][c_in/pack_groups] and the data-gradient pack
+ * wd [k][c_in][c_out/pack_groups] in `dtype`, and scale[c_out] = g/||v|| (fp32) for the backward.
+ * pack_groups (0 = groups) divides groups: the packs then describe the same convolution with only
+ * pack_groups groups whose per-group matrices are block-diagonal - this widens narrow groups to the
+ * 64-channel K chunks of the tcgen05 engine (see stg_tc_pack_groups); pass the same number as
+ * StgConv.groups.  flags & STG_PACK_UNFOLD (groups == 1): taps and channels form one K axis of
+ * Kp = roundup8(k*c_in) elements, wf [c_out][Kp], wd [Kp][c_out] - the operand layouts of a 1-tap
+ * convolution over stg_unfold rows (tiny-channel first layers).
  */
-int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups,
-                        int dtype, void* wf, void* wd, float* scale, stg_stream_t stream);
-/* dw [c_out][k][cin_g] fp32 -> dv (torch layout) and dg; ACCUMULATES into dv/dg when accumulate != 0. */
-int stg_weightnorm_fold_bwd(const float* dw, const float* v, const float* g, int c_out, int cin_g, int k,
+enum { STG_PACK_UNFOLD = 1 };
+int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups, int pack_groups,
+                        int flags, int dtype, void* wf, void* wd, float* scale, stg_stream_t stream);
+/* dw [c_out][dw_ld] fp32 with element (co, j, ci) at co*dw_ld + j*cin_g + ci (dw_ld 0 = k*cin_g) -> dv (torch layout)
+ * and dg; ACCUMULATES into dv/dg when accumulate != 0. */
+int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, const float* v, const float* g, int c_out, int cin_g, int k,
                             float* dv, float* dg, int accumulate, stg_stream_t stream);
 
 /*
@@ -123,12 +131,26 @@ int stg_weightnorm_fold_bwd(const float* dw, const float* v, const float* g, int
  * scratch: float[c_out + cin_g*k + 8].
  */
 int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
-                          int training, int dtype, void* wf, void* wd, float* sigma_out, float* scratch,
-                          stg_stream_t stream);
+                          int pack_groups, int flags, int training, int dtype, void* wf, void* wd, float* sigma_out,
+                          float* scratch, stg_stream_t stream);
 /* d w_orig = dw/sigma - (sum(dw .* w_orig)/sigma^2) u v^T ; u, v, sigma are the values used by that forward. */
-int stg_spectralnorm_fold_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
+int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, const float* w_orig, const float* u, const float* v,
                               const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
                               float* scratch, stg_stream_t stream);
+/* Number of groups the tcgen05 engine wants the packs of a (c_in, c_out, groups) convolution in (== groups
+ * when no widening is needed or possible). */
+int stg_tc_pack_groups(int c_in, int c_out, int groups);
+
+/*
+ * im2col rows for tiny-channel first layers (C_in = 8: models/discriminator.py:26,55,77,104): src [B][t_src*phases][C]
+ * in `dtype` -> out [B][t_dst*phases][Kp], out[b][t*phases+ph][j*C + c] = src[b][(t*stride + j*dilation - pad)*phases + ph][c]
+ * (0 outside the sample or for j*C + c >= k*C), Kp = roundup8(k*C).  stg_unfold_bwd is the adjoint:
+ * dsrc (float32, ACCUMULATED) [B][t_src*phases][C] from dout [B][t_dst*phases][Kp] in `dtype`.
+ */
+int stg_unfold(const void* src, int dtype, int B, int phases, int t_src, int t_dst, int C, int k, int dilation, int stride,
+               int pad, void* out, stg_stream_t stream);
+int stg_unfold_bwd(const void* dout, int dtype, int B, int phases, int t_src, int t_dst, int C, int k, int dilation,
+                   int stride, int pad, float* dsrc, stg_stream_t stream);
 
 /* models/generator.py:143-146,154: x0[b][t] = concat(units[b][t][0:d_units], emb[ids[b]][0:d_emb]) in `dtype`. */
 int stg_embed_concat(const float* units, const float* emb, const int64_t* ids, int B, int T, int d_units, int d_emb,

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libstegan_b200.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+PACK_UNFOLD = 1
 MAX_TAPS = 48
 
 
@@ -38,10 +39,13 @@ _SIGS = {
     "stg_conv_wgrad": [C.POINTER(StgWgrad), _P],
     "stg_conv_tc_supported": [C.POINTER(StgConv)],
     "stg_wgrad_tc_supported": [C.POINTER(StgWgrad)],
-    "stg_weightnorm_fold": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    "stg_weightnorm_fold_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P],
-    "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-    "stg_spectralnorm_fold_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P],
+    "stg_weightnorm_fold": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "stg_weightnorm_fold_bwd": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P],
+    "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "stg_spectralnorm_fold_bwd": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P],
+    "stg_tc_pack_groups": [_I, _I, _I],
+    "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_embed_concat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "stg_embed_concat_bwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "stg_reflect_pad_right": [_P, _I, _I, _I, _I, _I, _P, _P],

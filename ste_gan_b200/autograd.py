@@ -137,6 +137,8 @@ class SingleConvFn(torch.autograd.Function):
             xcl = x.transpose(1, 2).contiguous().to(dtype)
             phases, t = 1, T
         f = passes.fold(mod, dtype, training=mod.training)
+        if f.unfold:
+            xcl = passes.unfold_input(f, xcl, B, t, phases)
         y, _, t_out = passes._fwd(f, xcl, B, t, phases=phases, want_raw=True)
         ctx.mod, ctx.f, ctx.xcl, ctx.geom, ctx.in_dtype = mod, f, xcl, (B, t, t_out, phases, two_d), x.dtype
         y = y.to(x.dtype if x.dtype != torch.float64 else torch.float32)

@@ -47,6 +47,10 @@ extern "C" int stg_conv(const StgConv* d, stg_stream_t stream) {
 }
 
 extern "C" int stg_conv_tc_supported(const StgConv* d) { return (d && validate_conv(d) == STG_OK && conv_tc_supported(d)) ? 1 : 0; }
+extern "C" int stg_tc_pack_groups(int c_in, int c_out, int groups) {
+  if (groups < 1 || c_in % groups || c_out % groups) return groups;
+  return tc_pack_groups(c_in, c_out, groups);
+}
 extern "C" int stg_wgrad_tc_supported(const StgWgrad* d) { return (d && wgrad_tc_supported(d)) ? 1 : 0; }
 
 extern "C" int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream) {

@@ -102,5 +102,6 @@ bool conv_tc_supported(const StgConv* d);
 int wgrad_simt(const StgWgrad* d, cudaStream_t s);
 int wgrad_tc(const StgWgrad* d, cudaStream_t s);
 bool wgrad_tc_supported(const StgWgrad* d);
+int tc_pack_groups(int c_in, int c_out, int groups);
 
 }  // namespace stg

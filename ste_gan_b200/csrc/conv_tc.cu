@@ -37,10 +37,15 @@ struct TcEpi {
   void* y_act;
 };
 
+constexpr int MAX_RES = 8;  // residues of a strided data-gradient (= stride)
+
 struct TcP {
-  int phases, t_dst, stride, n_taps, k_chunks, bn, stages, a_boxes, tmem_cols;
-  int tap_off[STG_MAX_TAPS];
-  int tap_w[STG_MAX_TAPS];
+  int phases, t_dst, stride, k_chunks, bn, stages, a_boxes, tmem_cols;
+  int cs_g, cd_g;          // source / destination channels per (packed) group
+  int n_res, tiles_m;      // output-row residues (1 unless transposed && stride > 1), row tiles per residue
+  int res_first[MAX_RES + 1];  // taps of residue r: [res_first[r], res_first[r+1])
+  int tap_off[STG_MAX_TAPS];   // source-row offset of the tap (rows of the A tile start at r0*stride + tap_off)
+  int tap_w[STG_MAX_TAPS];     // tap index into the packed weights
   TcEpi e;
 };
 
@@ -137,9 +142,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, b = n / p.phases, ph = n % p.phases;
-  const int r0 = blockIdx.x * TM;
+  // strided data-gradient: output rows r = r' * n_res + res are produced per residue class `res` from the
+  // taps j with (res + pad - j*dilation) % stride == 0, as a stride-1 correlation over r'
+  const int res = blockIdx.x / p.tiles_m;
+  const int r0 = (blockIdx.x - res * p.tiles_m) * TM;
   const int col0 = blockIdx.y * p.bn;
-  const int n_iters = p.n_taps * p.k_chunks;
+  const int ch0 = (col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
+  const int tap0 = p.res_first[res];
+  const int n_iters = (p.res_first[res + 1] - tap0) * p.k_chunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -164,12 +174,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rows_per_box = TM / p.a_boxes;
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % p.stages, phs = (it / p.stages) & 1;
-        const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
+        const int tl = it / p.k_chunks, chunk = it - tl * p.k_chunks, tap = tap0 + tl;
         mbar_wait(empty_bar(s), phs ^ 1);
         mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
         const uint32_t a_dst = smem_base + s * stage_bytes;
         for (int bx = 0; bx < p.a_boxes; ++bx)
-          tma_load_4d(a_dst + bx * rows_per_box * KC * 2, &tmA, full_bar(s), chunk * KC,
+          tma_load_4d(a_dst + bx * rows_per_box * KC * 2, &tmA, full_bar(s), ch0 + chunk * KC,
                       (r0 + bx * rows_per_box) * p.stride + p.tap_off[tap], ph, b);
         tma_load_3d(a_dst + A_BYTES, &tmW, full_bar(s), chunk * KC, col0, p.tap_w[tap]);
       }
@@ -196,13 +206,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue =====
     const int sub = warp & 3;  // TMEM sub-partition this warp may read
-    mbar_wait(tmem_full_bar, 0);
+    if (n_iters > 0) mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int arow = r0 + sub * 32 + lane;  // accumulator row of this thread
+    const int arow = (r0 + sub * 32 + lane) * p.n_res + res;  // output row of this thread (before pair_sum)
     const TcEpi& e = p.e;
     for (int c = 0; c < p.bn; c += 16) {
       float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+      if (n_iters > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
       const int col = col0 + c;
       if (col >= e.c_dst) continue;  // warp-uniform
       if (e.bias) {
@@ -254,20 +269,30 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return STG_OK;
 }
 
-static int pick_bn(int c_dst) {
-  if (c_dst <= 16) return 16;
-  if (c_dst <= 256 && (c_dst % 16) == 0) return c_dst;
-  if (c_dst % 128 == 0) return 128;
-  if (c_dst % 192 == 0) return 192;
-  if (c_dst % 64 == 0) return 64;
+static int pick_bn(int cd_g, int groups) {
+  if (groups > 1) {  // a column tile must not straddle groups
+    if (cd_g % 128 == 0) return 128;
+    if (cd_g <= 256 && cd_g % 16 == 0) return cd_g;
+    return 0;
+  }
+  if (cd_g <= 16) return 16;
+  if (cd_g <= 256 && (cd_g % 16) == 0) return cd_g;
+  if (cd_g % 128 == 0) return 128;
+  if (cd_g % 192 == 0) return 192;
+  if (cd_g % 64 == 0) return 64;
   return 128;
 }
 
 bool conv_tc_supported(const StgConv* d) {
-  if (d->dtype != STG_BF16 || d->groups != 1) return false;
+  if (d->dtype != STG_BF16) return false;
   if (d->k > STG_MAX_TAPS || d->k < 1) return false;
   if ((d->c_src % 8) != 0) return false;                 // 16-byte global strides for TMA
-  if (d->transposed && d->stride != 1) return false;     // phase-decomposed strided dgrad: not in this engine yet
+  if (d->groups > 1) {
+    if ((d->c_src / d->groups) % KC) return false;       // whole K chunks per group (see stg_tc_pack_groups)
+    if (pick_bn(d->c_dst / d->groups, d->groups) == 0) return false;
+  }
+  if (d->transposed && d->stride > MAX_RES) return false;
+  if (d->transposed && d->stride > 1 && d->pair_sum) return false;
   if (!d->transposed && d->stride > 4) return false;     // A box rows = 64*stride <= 256
   if (d->pair_sum && (d->t_dst & 1)) return false;
   if (d->add_pre == nullptr && d->mask == nullptr && d->add_post == nullptr && d->y_raw == nullptr && d->y_act == nullptr)
@@ -275,23 +300,58 @@ bool conv_tc_supported(const StgConv* d) {
   return true;
 }
 
+int tc_pack_groups(int c_in, int c_out, int groups) {
+  if (groups <= 1) return 1;
+  const int cin_g = c_in / groups, cout_g = c_out / groups;
+  // smallest merge factor f | groups with (cin_g * f) % 64 == 0 and (cout_g * f) % 64 == 0 (dgrad K chunks)
+  for (int f = 1; f <= groups; ++f) {
+    if (groups % f) continue;
+    if ((cin_g * f) % KC == 0 && (cout_g * f) % KC == 0) return groups / f;
+  }
+  return groups;
+}
+
 int conv_tc(const StgConv* d, cudaStream_t s) {
   if (!conv_tc_supported(d)) return STG_EUNSUPPORTED;
   TcP p;
   p.phases = d->phases; p.t_dst = d->t_dst; p.stride = d->transposed ? 1 : d->stride;
-  p.n_taps = d->k; p.k_chunks = ceil_div(d->c_src, KC);
-  p.bn = pick_bn(d->c_dst);
+  p.cs_g = d->c_src / d->groups; p.cd_g = d->c_dst / d->groups;
+  p.k_chunks = ceil_div(p.cs_g, KC);
+  p.bn = pick_bn(p.cd_g, d->groups);
   p.a_boxes = (p.stride * TM <= 256) ? 1 : 2;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
-  for (int j = 0; j < d->k; ++j) {
-    p.tap_off[j] = d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad);
-    p.tap_w[j] = j;
+  int max_taps = 0;
+  if (d->transposed && d->stride > 1) {
+    p.n_res = d->stride;
+    int n = 0;
+    for (int r = 0; r < p.n_res; ++r) {
+      p.res_first[r] = n;
+      for (int j = 0; j < d->k; ++j) {
+        const int num = r + d->pad - j * d->dilation;
+        if (((num % d->stride) + d->stride) % d->stride != 0) continue;
+        p.tap_off[n] = (num >= 0) ? num / d->stride : -((-num) / d->stride);  // exact division
+        p.tap_w[n] = j;
+        ++n;
+      }
+      if (n - p.res_first[r] > max_taps) max_taps = n - p.res_first[r];
+    }
+    p.res_first[p.n_res] = n;
+    p.tiles_m = ceil_div(ceil_div(d->t_dst, p.n_res), TM);
+  } else {
+    p.n_res = 1;
+    for (int j = 0; j < d->k; ++j) {
+      p.tap_off[j] = d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad);
+      p.tap_w[j] = j;
+    }
+    p.res_first[0] = 0; p.res_first[1] = d->k;
+    max_taps = d->k;
+    p.tiles_m = ceil_div(d->t_dst, TM);
   }
   const int stage_bytes = A_BYTES + p.bn * KC * 2;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > p.n_taps * p.k_chunks) stages = p.n_taps * p.k_chunks;
+  if (stages > max_taps * p.k_chunks) stages = max_taps * p.k_chunks;
   if (stages < 1) stages = 1;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 2);
@@ -314,7 +374,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     if (r) return r;
   }
   {
-    const uint64_t C = d->c_src, N = d->c_dst, K = d->k;
+    const uint64_t C = p.cs_g, N = d->c_dst, K = d->k;
     const uint64_t dims[3] = {C, N, K};
     const uint64_t strides[2] = {C * 2, N * C * 2};
     const uint32_t box[3] = {(uint32_t)KC, (uint32_t)p.bn, 1};
@@ -326,7 +386,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-  dim3 grid(ceil_div(d->t_dst, TM), ceil_div(d->c_dst, p.bn), d->n_samples * d->phases);
+  dim3 grid(p.tiles_m * p.n_res, ceil_div(d->c_dst, p.bn), d->n_samples * d->phases);
   if (grid.z > 65535 || grid.y > 65535) return STG_EINVAL;
   conv_tc_kernel<<<grid, 192, smem, s>>>(tmA, tmW, p);
   STG_LAUNCH_CHECK();

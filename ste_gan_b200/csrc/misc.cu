@@ -142,6 +142,47 @@ inline int grid_for(int64_t n) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// im2col rows for tiny-channel first layers: one thread per (row, tap) copies C channels (C = 8 -> one 16-byte move)
+template <typename T>
+__global__ void unfold_kernel(const T* __restrict__ src, int phases, int t_src, int t_dst, int C, int k, int dil, int stride,
+                              int pad, int Kp, int64_t total, T* __restrict__ out) {
+  const int slots = Kp / C + ((Kp % C) ? 1 : 0);  // k real taps (+ one zero slot when Kp > k*C)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % slots);
+    const int64_t row = i / slots;                      // b*t_dst*phases + t*phases + ph
+    const int ph = (int)(row % phases);
+    const int64_t bt = row / phases;
+    const int t = (int)(bt % t_dst);
+    const int64_t b = bt / t_dst;
+    const int ts = t * stride + j * dil - pad;
+    const bool ok = j < k && ts >= 0 && ts < t_src;
+    const T* s = src + ((b * t_src + ts) * phases + ph) * C;
+    T* o = out + row * Kp + (int64_t)j * C;
+    const int n = min(C, Kp - j * C);
+    for (int c = 0; c < n; ++c) o[c] = ok ? s[c] : from_f<T>(0.f);
+  }
+}
+template <typename T>
+__global__ void unfold_bwd_kernel(const T* __restrict__ dout, int phases, int t_src, int t_dst, int C, int k, int dil,
+                                  int stride, int pad, int Kp, int64_t total, float* __restrict__ dsrc) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t row = i / C;                          // b*t_src*phases + ts*phases + ph
+    const int ph = (int)(row % phases);
+    const int64_t bt = row / phases;
+    const int ts = (int)(bt % t_src);
+    const int64_t b = bt / t_src;
+    float g = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int num = ts + pad - j * dil;
+      if (num < 0) break;
+      const int t = num / stride;
+      if (t * stride == num && t < t_dst) g += to_f(dout[((b * t_dst + t) * phases + ph) * Kp + j * C + c]);
+    }
+    dsrc[i] += g;
+  }
+}
+
 }  // namespace
 }  // namespace stg
 
@@ -246,6 +287,37 @@ extern "C" int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n
   step_inc_kernel<<<1, 1, 0, S_>>>(step_count);
   STG_LAUNCH_CHECK();
   adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_count, grad_scale);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_unfold(const void* src, int dtype, int B, int phases, int t_src, int t_dst, int C, int k, int dilation,
+                          int stride, int pad, void* out, stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!src || !out || B < 1 || phases < 1 || C < 1 || k < 1 || stride < 1 || dilation < 1) return STG_EINVAL;
+  const int Kp = (k * C + 7) / 8 * 8;
+  const int slots = Kp / C + ((Kp % C) ? 1 : 0);
+  const int64_t total = (int64_t)B * t_dst * phases * slots;
+  const int64_t nb = ceil_div64(total, 256);
+  const int blocks = (int)(nb < 148 * 16 ? nb : 148 * 16);
+  if (dtype == STG_F32) unfold_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(src), phases, t_src, t_dst, C, k, dilation, stride, pad, Kp, total, static_cast<float*>(out));
+  else if (dtype == STG_BF16) unfold_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16*>(src), phases, t_src, t_dst, C, k, dilation, stride, pad, Kp, total, static_cast<bf16*>(out));
+  else return STG_EINVAL;
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_unfold_bwd(const void* dout, int dtype, int B, int phases, int t_src, int t_dst, int C, int k,
+                              int dilation, int stride, int pad, float* dsrc, stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!dout || !dsrc || B < 1 || phases < 1 || C < 1 || k < 1 || stride < 1 || dilation < 1) return STG_EINVAL;
+  const int Kp = (k * C + 7) / 8 * 8;
+  const int64_t total = (int64_t)B * t_src * phases * C;
+  const int64_t nb = ceil_div64(total, 256);
+  const int blocks = (int)(nb < 148 * 16 ? nb : 148 * 16);
+  if (dtype == STG_F32) unfold_bwd_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(dout), phases, t_src, t_dst, C, k, dilation, stride, pad, Kp, total, dsrc);
+  else if (dtype == STG_BF16) unfold_bwd_kernel<bf16><<<blocks, 256, 0, s>>>(static_cast<const bf16*>(dout), phases, t_src, t_dst, C, k, dilation, stride, pad, Kp, total, dsrc);
+  else return STG_EINVAL;
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

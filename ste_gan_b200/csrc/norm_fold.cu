@@ -20,53 +20,82 @@ __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__
   if (threadIdx.x == 0) scale[co] = g[co] / sqrtf(s);
 }
 
-// wf[j][co][ci] = v[co][ci][j] * scale[co]   grid: (ceil(cin_g*k/256), c_out)
+// Packed operand layouts.  `pg` (pack groups) divides `groups`: the packs describe the convolution as one with
+// only pg groups whose per-group matrices are block-diagonal (zeros between the real groups).  This is how
+// narrow groups (8..32 channels) are widened to the 64-channel K chunks of the tcgen05 engine.
+//   wf[j][co][ci']  ci' in [0, c_in/pg):  input channel c = (co / (c_out/pg)) * (c_in/pg) + ci'
+// grid: (ceil(cin_gp*k/256), c_out)
 template <typename T>
 __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ v, const float* __restrict__ scale,
-                                                       int c_out, int cin_g, int k, T* __restrict__ wf) {
+                                                       int c_out, int cin_g, int k, int groups, int pg,
+                                                       T* __restrict__ wf) {
   const int co = blockIdx.y;
-  const int idx = blockIdx.x * 256 + threadIdx.x;  // j*cin_g + ci
-  if (idx >= cin_g * k) return;
-  const int j = idx / cin_g, ci = idx - j * cin_g;
-  const float w = v[((int64_t)co * cin_g + ci) * k + j] * scale[co];
-  wf[((int64_t)j * c_out + co) * cin_g + ci] = from_f<T>(w);
+  const int c_in = cin_g * groups, cin_gp = c_in / pg, cout_gp = c_out / pg, cout_g = c_out / groups;
+  const int idx = blockIdx.x * 256 + threadIdx.x;  // j*cin_gp + ci'
+  if (idx >= cin_gp * k) return;
+  const int j = idx / cin_gp, cip = idx - j * cin_gp;
+  const int c = (co / cout_gp) * cin_gp + cip;
+  const int gc = c / cin_g;
+  float w = 0.f;
+  if (gc == co / cout_g) w = v[((int64_t)co * cin_g + (c - gc * cin_g)) * k + j] * scale[co];
+  wf[((int64_t)j * c_out + co) * cin_gp + cip] = from_f<T>(w);
 }
 
-// wd[j][gi*cin_g + ci][co_l] = v[gi*cout_g + co_l][ci][j] * scale[co]   32x32 smem transpose
-// grid: (ceil(cout_g/32), ceil(cin_g/32), k*groups)
+//   wd[j][ci][co']  co' in [0, c_out/pg):  output channel co = (ci / (c_in/pg)) * (c_out/pg) + co'
+// 32x32 smem transpose; grid: (ceil(cout_gp/32), ceil(cin_gp/32), k*pg)
 template <typename T>
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ v, const float* __restrict__ scale,
-                                                         int cin_g, int cout_g, int k, int groups, T* __restrict__ wd) {
+                                                         int c_out, int cin_g, int k, int groups, int pg,
+                                                         T* __restrict__ wd) {
   __shared__ float tile[32][33];
-  const int j = blockIdx.z % k, gi = blockIdx.z / k;
+  const int c_in = cin_g * groups, cin_gp = c_in / pg, cout_gp = c_out / pg, cout_g = c_out / groups;
+  const int j = blockIdx.z % k, gp = blockIdx.z / k;
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int c_in = cin_g * groups;
-  for (int r = ty; r < 32; r += 8) {  // r: co_l, tx: ci
-    const int co_l = co0 + r, ci = ci0 + tx;
+  for (int r = ty; r < 32; r += 8) {  // r: co', tx: ci'
+    const int cop = co0 + r, cip = ci0 + tx;
     float w = 0.f;
-    if (co_l < cout_g && ci < cin_g) {
-      const int co = gi * cout_g + co_l;
-      w = v[((int64_t)co * cin_g + ci) * k + j] * scale[co];
+    if (cop < cout_gp && cip < cin_gp) {
+      const int co = gp * cout_gp + cop, c = gp * cin_gp + cip;
+      const int gc = c / cin_g;
+      if (gc == co / cout_g) w = v[((int64_t)co * cin_g + (c - gc * cin_g)) * k + j] * scale[co];
     }
     tile[r][tx] = w;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {  // r: ci, tx: co_l
-    const int ci = ci0 + r, co_l = co0 + tx;
-    if (ci < cin_g && co_l < cout_g)
-      wd[((int64_t)j * c_in + gi * cin_g + ci) * cout_g + co_l] = from_f<T>(tile[tx][r]);
+  for (int r = ty; r < 32; r += 8) {  // r: ci', tx: co'
+    const int cip = ci0 + r, cop = co0 + tx;
+    if (cip < cin_gp && cop < cout_gp)
+      wd[((int64_t)j * c_in + gp * cin_gp + cip) * cout_gp + cop] = from_f<T>(tile[tx][r]);
   }
+}
+
+// "Unfolded" packs for tiny-channel first layers (groups == 1): taps and channels form ONE K axis of Kp >= k*c_in
+// elements (zero padded), matching stg_unfold's im2col rows:  wf[co][j*c_in + c], wd[j*c_in + c][co].
+template <typename T>
+__global__ void __launch_bounds__(256) pack_unfold_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                                                          int c_out, int c_in, int k, int Kp, T* __restrict__ wf,
+                                                          T* __restrict__ wd) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= c_out * Kp) return;
+  const int co = idx / Kp, q = idx - co * Kp;
+  float w = 0.f;
+  if (q < k * c_in) {
+    const int j = q / c_in, c = q - j * c_in;
+    w = v[((int64_t)co * c_in + c) * k + j] * scale[co];
+  }
+  if (wf) wf[(int64_t)co * Kp + q] = from_f<T>(w);
+  if (wd) wd[(int64_t)q * c_out + co] = from_f<T>(w);
 }
 
 // dv[co][ci][j] (+)= scale*dw[co][j][ci] - (g*dot/norm^3) v ; dg[co] (+)= dot/norm
 __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
-                                                     const float* __restrict__ g, int cin_g, int k,
+                                                     const float* __restrict__ g, int cin_g, int k, int dw_ld,
                                                      float* __restrict__ dv, float* __restrict__ dg, int accumulate) {
   __shared__ float red[32];
   const int co = blockIdx.x, n = cin_g * k;
   const float* vr = v + (int64_t)co * n;
-  const float* dr = dw + (int64_t)co * n;
+  const float* dr = dw + (int64_t)co * dw_ld;
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
@@ -133,42 +162,52 @@ __global__ void sn_fill_scale_kernel(const float* __restrict__ sigma, int c_out,
 }
 // acc += sum dw[co][j][ci] * W[co][ci][j]
 __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ dw, const float* __restrict__ W,
-                                                         int cin_g, int k, float* __restrict__ acc) {
+                                                         int cin_g, int k, int dw_ld, float* __restrict__ acc) {
   __shared__ float red[32];
   const int co = blockIdx.x, n = cin_g * k;
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
-    s = fmaf(W[(int64_t)co * n + i], dw[(int64_t)co * n + j * cin_g + ci], s);
+    s = fmaf(W[(int64_t)co * n + i], dw[(int64_t)co * dw_ld + j * cin_g + ci], s);
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc, s);
 }
 __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ u,
                                                      const float* __restrict__ v, const float* __restrict__ sigma,
-                                                     const float* __restrict__ dot, int cin_g, int k,
+                                                     const float* __restrict__ dot, int cin_g, int k, int dw_ld,
                                                      float* __restrict__ dW, int accumulate) {
   const int co = blockIdx.x, n = cin_g * k;
   const float sg = sigma[0], coef = dot[0] / (sg * sg) * u[co], inv = 1.f / sg;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
-    const float val = dw[(int64_t)co * n + j * cin_g + ci] * inv - coef * v[i];
+    const float val = dw[(int64_t)co * dw_ld + j * cin_g + ci] * inv - coef * v[i];
     float* o = dW + (int64_t)co * n + i;
     *o = accumulate ? (*o + val) : val;
   }
 }
 
 template <typename T>
-int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, T* wf, T* wd, cudaStream_t s) {
-  const int cout_g = c_out / groups;
+int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, int pg, int flags, T* wf,
+                 T* wd, cudaStream_t s) {
+  if (flags & STG_PACK_UNFOLD) {
+    if (groups != 1) return STG_EINVAL;
+    const int Kp = (k * cin_g + 7) / 8 * 8;
+    pack_unfold_kernel<T><<<ceil_div(c_out * Kp, 256), 256, 0, s>>>(v, scale, c_out, cin_g, k, Kp, wf, wd);
+    STG_LAUNCH_CHECK();
+    return STG_OK;
+  }
+  if (pg <= 0) pg = groups;
+  if (groups % pg) return STG_EINVAL;
+  const int c_in = cin_g * groups, cin_gp = c_in / pg, cout_gp = c_out / pg;
   if (wf) {
-    dim3 g1(ceil_div(cin_g * k, 256), c_out);
-    pack_fwd_kernel<T><<<g1, 256, 0, s>>>(v, scale, c_out, cin_g, k, wf);
+    dim3 g1(ceil_div(cin_gp * k, 256), c_out);
+    pack_fwd_kernel<T><<<g1, 256, 0, s>>>(v, scale, c_out, cin_g, k, groups, pg, wf);
     STG_LAUNCH_CHECK();
   }
   if (wd) {
-    dim3 g2(ceil_div(cout_g, 32), ceil_div(cin_g, 32), k * groups);
-    pack_dgrad_kernel<T><<<g2, 256, 0, s>>>(v, scale, cin_g, cout_g, k, groups, wd);
+    dim3 g2(ceil_div(cout_gp, 32), ceil_div(cin_gp, 32), k * pg);
+    pack_dgrad_kernel<T><<<g2, 256, 0, s>>>(v, scale, c_out, cin_g, k, groups, pg, wd);
     STG_LAUNCH_CHECK();
   }
   return STG_OK;
@@ -179,29 +218,31 @@ int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k
 
 using namespace stg;
 
-extern "C" int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups, int dtype,
-                                   void* wf, void* wd, float* scale, stg_stream_t stream) {
+extern "C" int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups,
+                                   int pack_groups, int flags, int dtype, void* wf, void* wd, float* scale,
+                                   stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!v || !g || !scale || c_out < 1 || cin_g < 1 || k < 1 || groups < 1 || c_out % groups) return STG_EINVAL;
   wn_scale_kernel<<<c_out, 256, 0, s>>>(v, g, cin_g * k, scale);
   STG_LAUNCH_CHECK();
-  if (dtype == STG_F32) return launch_packs<float>(v, scale, c_out, cin_g, k, groups, (float*)wf, (float*)wd, s);
-  if (dtype == STG_BF16) return launch_packs<bf16>(v, scale, c_out, cin_g, k, groups, (bf16*)wf, (bf16*)wd, s);
+  if (dtype == STG_F32) return launch_packs<float>(v, scale, c_out, cin_g, k, groups, pack_groups, flags, (float*)wf, (float*)wd, s);
+  if (dtype == STG_BF16) return launch_packs<bf16>(v, scale, c_out, cin_g, k, groups, pack_groups, flags, (bf16*)wf, (bf16*)wd, s);
   return STG_EINVAL;
 }
 
-extern "C" int stg_weightnorm_fold_bwd(const float* dw, const float* v, const float* g, int c_out, int cin_g, int k,
-                                       float* dv, float* dg, int accumulate, stg_stream_t stream) {
+extern "C" int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, const float* v, const float* g, int c_out, int cin_g,
+                                       int k, float* dv, float* dg, int accumulate, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!dw || !v || !g || !dv || !dg) return STG_EINVAL;
-  wn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, v, g, cin_g, k, dv, dg, accumulate);
+  if (dw_ld <= 0) dw_ld = cin_g * k;
+  wn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, v, g, cin_g, k, dw_ld, dv, dg, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
 
 extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
-                                     int training, int dtype, void* wf, void* wd, float* sigma_out, float* scratch,
-                                     stg_stream_t stream) {
+                                     int pack_groups, int flags, int training, int dtype, void* wf, void* wd,
+                                     float* sigma_out, float* scratch, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w_orig || !u || !v || !sigma_out || !scratch) return STG_EINVAL;
   const int n = cin_g * k;
@@ -229,20 +270,21 @@ extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, in
   }
   sn_fill_scale_kernel<<<ceil_div(c_out, 256), 256, 0, s>>>(sigma_out, c_out, scale);
   STG_LAUNCH_CHECK();
-  if (dtype == STG_F32) return launch_packs<float>(w_orig, scale, c_out, cin_g, k, groups, (float*)wf, (float*)wd, s);
-  if (dtype == STG_BF16) return launch_packs<bf16>(w_orig, scale, c_out, cin_g, k, groups, (bf16*)wf, (bf16*)wd, s);
+  if (dtype == STG_F32) return launch_packs<float>(w_orig, scale, c_out, cin_g, k, groups, pack_groups, flags, (float*)wf, (float*)wd, s);
+  if (dtype == STG_BF16) return launch_packs<bf16>(w_orig, scale, c_out, cin_g, k, groups, pack_groups, flags, (bf16*)wf, (bf16*)wd, s);
   return STG_EINVAL;
 }
 
-extern "C" int stg_spectralnorm_fold_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
+extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, const float* w_orig, const float* u, const float* v,
                                          const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
                                          float* scratch, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!dw || !w_orig || !u || !v || !sigma || !dw_orig || !scratch) return STG_EINVAL;
+  if (dw_ld <= 0) dw_ld = cin_g * k;
   STG_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), s));
-  sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, scratch);
+  sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, dw_ld, scratch);
   STG_LAUNCH_CHECK();
-  sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_orig, accumulate);
+  sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_ld, dw_orig, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

@@ -24,6 +24,7 @@ constexpr int MAX_STAGES = 6;
 
 struct WgTcP {
   int phases, t_out, c_in, c_out, k, stride;
+  int cin_g, cout_g, ci_span, x_tiles;  // groups: input channels per group, ..., input-channel span of one 128-row co tile
   int n_taps, tap_groups, bnw, nbox_b, stages, tmem_cols;
   int chunks_per_sample, total_chunks, chunks_per_split;
   int tap_off[STG_MAX_TAPS];
@@ -44,9 +45,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ci0 = blockIdx.x * p.bnw;
   const int co_tile = blockIdx.y / p.tap_groups, tg = blockIdx.y - co_tile * p.tap_groups;
   const int co0 = co_tile * 128;
+  // grouped convolution: the 128 output channels of this tile only meet the input channels of their own groups,
+  // a span of ci_span channels starting at the first group's base; the off-diagonal part of the tile is computed
+  // (the MMA is dense) and dropped in the epilogue
+  const int ci0 = (co0 / p.cout_g) * p.cin_g + blockIdx.x * p.bnw;
   const int tap0 = tg * p.n_taps;
   const int ntap = min(p.n_taps, p.k - tap0);
   const int q0 = blockIdx.z * p.chunks_per_split, q1 = min(p.total_chunks, q0 + p.chunks_per_split);
@@ -110,16 +114,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int co = co0 + sub * 32 + lane;
-    const int KK = p.k * p.c_in;
+    const int KK = p.k * p.cin_g;
+    const int cg_lo = (co < p.c_out ? co / p.cout_g : 0) * p.cin_g;  // input channels [cg_lo, cg_lo + cin_g) belong to co's group
     for (int tl = 0; tl < ntap; ++tl) {
       for (int c = 0; c < p.bnw; c += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tl * p.bnw + c), v);
         if (co < p.c_out) {
-          float* dst = p.dw + (int64_t)co * KK + (int64_t)(tap0 + tl) * p.c_in + ci0 + c;
+          float* dst = p.dw + (int64_t)co * KK + (int64_t)(tap0 + tl) * p.cin_g + (ci0 + c - cg_lo);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (ci0 + c + i < p.c_in) atomicAdd(dst + i, v[i]);
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci0 + c + i;
+            if (ci >= cg_lo && ci < cg_lo + p.cin_g) atomicAdd(dst + i, v[i]);
+          }
         }
       }
     }
@@ -132,11 +139,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 }  // namespace
 
 bool wgrad_tc_supported(const StgWgrad* d) {
-  if (d->dtype != STG_BF16 || d->groups != 1) return false;
+  if (d->dtype != STG_BF16) return false;
   if (d->k < 1 || d->k > STG_MAX_TAPS) return false;
   if ((d->c_in % 8) || (d->c_out % 8)) return false;
   if (d->stride > 4) return false;
-  if (d->c_in < 32 || d->c_out < 32) return false;  // tiny-channel layers: CUDA-core engine
+  if (d->c_out < 32) return false;  // 1- and 8-channel outputs: CUDA-core engine
+  if (d->groups > 1) {
+    const int cout_g = d->c_out / d->groups;
+    if (cout_g < 128 ? (128 % cout_g) : (cout_g % 128)) return false;  // co tiles aligned to group boundaries
+  }
   return true;
 }
 
@@ -144,7 +155,10 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
   if (!wgrad_tc_supported(d)) return STG_EUNSUPPORTED;
   WgTcP p;
   p.phases = d->phases; p.t_out = d->t_out; p.c_in = d->c_in; p.c_out = d->c_out; p.k = d->k; p.stride = d->stride;
-  p.bnw = d->c_in > 64 ? 128 : 64;
+  p.cin_g = d->c_in / d->groups; p.cout_g = d->c_out / d->groups;
+  p.ci_span = d->groups == 1 ? d->c_in : (p.cout_g >= 128 ? p.cin_g : (128 / p.cout_g) * p.cin_g);
+  p.bnw = p.ci_span > 64 ? 128 : 64;
+  p.x_tiles = ceil_div(p.ci_span, p.bnw);
   p.nbox_b = p.bnw / 64;
   int taps = 512 / p.bnw;                       // TMEM columns
   const int smem_budget = 200 * 1024;
@@ -160,7 +174,7 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.chunks_per_sample = ceil_div(d->t_out, RK);
   p.total_chunks = d->n_samples * d->phases * p.chunks_per_sample;
-  const int gx = ceil_div(d->c_in, p.bnw), gy = ceil_div(d->c_out, 128) * p.tap_groups;
+  const int gx = p.x_tiles, gy = ceil_div(d->c_out, 128) * p.tap_groups;
   int want = ceil_div(148, gx * gy);
   if (want < 1) want = 1;
   if (want > p.total_chunks) want = p.total_chunks;

@@ -132,55 +132,98 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
                         events=(e0, e1), shape=(n_samples, phases, t_in, t_out, c_in, c_out, k, dilation, stride, groups)))
 
 
-def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True, out=None):
-    """v [c_out, cin_g, k(,1)], g [c_out,1,1(,1)] -> (wf [k,c_out,cin_g], wd [k,c_in,cout_g] | None, scale [c_out]).
+def tc_pack_groups(c_in: int, c_out: int, groups: int) -> int:
+    """Group count the tcgen05 engine wants the packs in (narrow groups merged into block-diagonal ones)."""
+    return int(_lib.load().stg_tc_pack_groups(c_in, c_out, groups))
+
+
+def round_up8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _pack_shapes(c_out: int, cin_g: int, k: int, groups: int, pack_groups: int, unfold: bool):
+    if unfold:
+        kp = round_up8(k * cin_g)
+        return (c_out, kp), (kp, c_out)
+    c_in = cin_g * groups
+    return (k, c_out, c_in // pack_groups), (k, c_in, c_out // pack_groups)
+
+
+def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_dgrad: bool = True, out=None,
+                    pack_groups: Optional[int] = None, unfold: bool = False):
+    """v [c_out, cin_g, k(,1)], g [c_out,1,1(,1)] -> (wf [k,c_out,c_in/pg], wd [k,c_in,c_out/pg] | None, scale [c_out]);
+    unfold: wf [c_out,Kp], wd [Kp,c_out] (see include/stegan_b200.h).
     `out` = (wf, wd, scale) re-uses persistent buffers (fixed addresses for CUDA-graph replay)."""
     c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
+    pg = groups if pack_groups is None else pack_groups
+    sf, sd = _pack_shapes(c_out, cin_g, k, groups, pg, unfold)
+    nf = sf[0] * sf[1] * (sf[2] if len(sf) > 2 else 1)
     _need(v, c_out * cin_g * k, torch.float32, "v"); _need(g, c_out, torch.float32, "g")
     if out is not None:
         wf, wd, scale = out
-        _need(wf, k * c_out * cin_g, dtype, "wf"); _need(wd, k * c_out * cin_g, dtype, "wd"); _need(scale, c_out, torch.float32, "scale")
+        _need(wf, nf, dtype, "wf"); _need(wd, nf, dtype, "wd"); _need(scale, c_out, torch.float32, "scale")
     else:
-        wf = torch.empty((k, c_out, cin_g), device=v.device, dtype=dtype)
-        wd = torch.empty((k, cin_g * groups, c_out // groups), device=v.device, dtype=dtype) if want_dgrad else None
+        wf = torch.empty(sf, device=v.device, dtype=dtype)
+        wd = torch.empty(sd, device=v.device, dtype=dtype) if want_dgrad else None
         scale = torch.empty((c_out,), device=v.device, dtype=torch.float32)
-    check(_lib.load().stg_weightnorm_fold(_ptr(v), _ptr(g), c_out, cin_g, k, groups, code_of(dtype), _ptr(wf), _ptr(wd),
-                                          _ptr(scale), _stream()), "stg_weightnorm_fold")
+    check(_lib.load().stg_weightnorm_fold(_ptr(v), _ptr(g), c_out, cin_g, k, groups, pg, _lib.PACK_UNFOLD if unfold else 0,
+                                          code_of(dtype), _ptr(wf), _ptr(wd), _ptr(scale), _stream()), "stg_weightnorm_fold")
     return wf, wd, scale
 
 
-def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor, accumulate: bool) -> None:
+def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor, accumulate: bool, dw_ld: int = 0) -> None:
     c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
-    _need(dw, c_out * cin_g * k, torch.float32, "dw"); _need(dv, c_out * cin_g * k, torch.float32, "dv")
+    _need(dw, c_out * max(dw_ld, cin_g * k), torch.float32, "dw"); _need(dv, c_out * cin_g * k, torch.float32, "dv")
     _need(dg, c_out, torch.float32, "dg")
-    check(_lib.load().stg_weightnorm_fold_bwd(_ptr(dw), _ptr(v), _ptr(g), c_out, cin_g, k, _ptr(dv), _ptr(dg),
+    check(_lib.load().stg_weightnorm_fold_bwd(_ptr(dw), dw_ld, _ptr(v), _ptr(g), c_out, cin_g, k, _ptr(dv), _ptr(dg),
                                               int(accumulate), _stream()), "stg_weightnorm_fold_bwd")
 
 
 def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, training: bool, dtype: torch.dtype,
-                      want_dgrad: bool = True):
+                      want_dgrad: bool = True, pack_groups: Optional[int] = None, unfold: bool = False):
     """In-place power iteration on u, v when training.  Returns (wf, wd, sigma[1])."""
     c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
     n = cin_g * k
+    pg = groups if pack_groups is None else pack_groups
+    sf, sd = _pack_shapes(c_out, cin_g, k, groups, pg, unfold)
     _need(w_orig, c_out * n, torch.float32, "w_orig"); _need(u, c_out, torch.float32, "u"); _need(v, n, torch.float32, "v")
-    wf = torch.empty((k, c_out, cin_g), device=u.device, dtype=dtype)
-    wd = torch.empty((k, cin_g * groups, c_out // groups), device=u.device, dtype=dtype) if want_dgrad else None
+    wf = torch.empty(sf, device=u.device, dtype=dtype)
+    wd = torch.empty(sd, device=u.device, dtype=dtype) if want_dgrad else None
     sigma = torch.empty((1,), device=u.device, dtype=torch.float32)
     scratch = torch.empty((c_out + n + 8,), device=u.device, dtype=torch.float32)
-    check(_lib.load().stg_spectralnorm_fold(_ptr(w_orig), _ptr(u), _ptr(v), c_out, cin_g, k, groups, int(training),
-                                            code_of(dtype), _ptr(wf), _ptr(wd), _ptr(sigma), _ptr(scratch), _stream()),
-          "stg_spectralnorm_fold")
+    check(_lib.load().stg_spectralnorm_fold(_ptr(w_orig), _ptr(u), _ptr(v), c_out, cin_g, k, groups, pg,
+                                            _lib.PACK_UNFOLD if unfold else 0, int(training), code_of(dtype), _ptr(wf),
+                                            _ptr(wd), _ptr(sigma), _ptr(scratch), _stream()), "stg_spectralnorm_fold")
     return wf, wd, sigma
 
 
 def spectralnorm_fold_bwd(dw: Tensor, w_orig: Tensor, u: Tensor, v: Tensor, sigma: Tensor, dw_orig: Tensor,
-                          accumulate: bool) -> None:
+                          accumulate: bool, dw_ld: int = 0) -> None:
     c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
-    _need(dw, c_out * cin_g * k, torch.float32, "dw"); _need(dw_orig, c_out * cin_g * k, torch.float32, "dw_orig")
+    _need(dw, c_out * max(dw_ld, cin_g * k), torch.float32, "dw"); _need(dw_orig, c_out * cin_g * k, torch.float32, "dw_orig")
     scratch = torch.empty((8,), device=u.device, dtype=torch.float32)
-    check(_lib.load().stg_spectralnorm_fold_bwd(_ptr(dw), _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), c_out, cin_g, k,
-                                                _ptr(dw_orig), int(accumulate), _ptr(scratch), _stream()),
+    check(_lib.load().stg_spectralnorm_fold_bwd(_ptr(dw), dw_ld, _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), c_out, cin_g,
+                                                k, _ptr(dw_orig), int(accumulate), _ptr(scratch), _stream()),
           "stg_spectralnorm_fold_bwd")
+
+
+def unfold(src: Tensor, *, n_samples: int, phases: int, t_src: int, t_dst: int, channels: int, k: int, dilation: int,
+           stride: int, pad: int) -> Tensor:
+    """im2col rows [B, t_dst*phases, roundup8(k*C)] of a channels-last (period-view) tensor, same dtype."""
+    _need(src, n_samples * phases * t_src * channels, None, "src")
+    out = torch.empty((n_samples, t_dst * phases, round_up8(k * channels)), device=src.device, dtype=src.dtype)
+    check(_lib.load().stg_unfold(_ptr(src), code_of(src.dtype), n_samples, phases, t_src, t_dst, channels, k, dilation,
+                                 stride, pad, _ptr(out), _stream()), "stg_unfold")
+    return out
+
+
+def unfold_bwd(dout: Tensor, dsrc: Tensor, *, n_samples: int, phases: int, t_src: int, t_dst: int, channels: int, k: int,
+               dilation: int, stride: int, pad: int) -> None:
+    """dsrc (fp32 [B, t_src*phases, C]) += adjoint of `unfold` applied to dout."""
+    _need(dout, n_samples * phases * t_dst * round_up8(k * channels), None, "dout")
+    _need(dsrc, n_samples * phases * t_src * channels, torch.float32, "dsrc")
+    check(_lib.load().stg_unfold_bwd(_ptr(dout), code_of(dout.dtype), n_samples, phases, t_src, t_dst, channels, k,
+                                     dilation, stride, pad, _ptr(dsrc), _stream()), "stg_unfold_bwd")
 
 
 def embed_concat(units: Tensor, emb: Optional[Tensor], ids: Optional[Tensor], dtype: torch.dtype) -> Tensor:

@@ -39,11 +39,25 @@ class Folded:
     u: Optional[Tensor] = None              # spectral-norm: u, v, sigma used by THIS forward
     v: Optional[Tensor] = None
     sigma: Optional[Tensor] = None
+    pg: int = 1                             # groups of the packed operands (narrow groups merged for tcgen05)
+    unfold: bool = False                    # tiny-channel first layer: 1-tap conv over im2col rows
+    kp: int = 0                             # ... whose K axis has kp = roundup8(k * c_in) elements
 
 
 def _w3(t: Tensor) -> Tensor:
     """[c_out, cin_g, k] or [c_out, cin_g, k, 1] -> 3-D view."""
     return t.view(t.shape[0], t.shape[1], t.shape[2])
+
+
+def pack_mode(mod, dtype: torch.dtype) -> Tuple[int, bool]:
+    """(pack groups, unfold?) of a conv module in this precision.  fp32 (CUDA-core validation engine) keeps the
+    reference's own grouping; bf16 widens narrow groups to the tensor engine's 64-channel K chunks and turns
+    the C_in = 8 first layers (discriminator.py:26,55,77,104) into 1-tap convs over im2col rows."""
+    if dtype != torch.bfloat16:
+        return mod.groups, False
+    if mod.groups == 1 and mod.in_channels < 16 and mod.in_channels * mod.kernel <= 256 and mod.out_channels >= 32:
+        return 1, True
+    return ops.tc_pack_groups(mod.in_channels, mod.out_channels, mod.groups), False
 
 
 def fold(mod, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True,
@@ -52,18 +66,20 @@ def fold(mod, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True
     power iteration for spectral-norm layers in training mode, as in the reference's
     forward pre-hook).  `persist` keeps the weight-norm packs of a module in the same
     buffers across calls (fixed addresses, so CUDA graphs that read them stay valid)."""
+    pg, unf = pack_mode(mod, dtype)
+    kp = ops.round_up8(mod.kernel * mod.in_channels) if unf else 0
     if mod.norm == "weight_norm":
         prev = persist.get(id(mod)) if persist is not None else None
         out = (prev.wf, prev.wd, prev.scale) if prev is not None and prev.dtype == dtype and prev.wd is not None else None
         wf, wd, scale = ops.weightnorm_fold(_w3(mod.weight_v.data), mod.weight_g.data, mod.groups, dtype,
-                                            want_dgrad or persist is not None, out=out)
-        f = Folded(mod, wf, wd, dtype, scale=scale)
+                                            want_dgrad or persist is not None, out=out, pack_groups=pg, unfold=unf)
+        f = Folded(mod, wf, wd, dtype, scale=scale, pg=pg, unfold=unf, kp=kp)
         if persist is not None:
             persist[id(mod)] = f
         return f
     wf, wd, sigma = ops.spectralnorm_fold(_w3(mod.weight_orig.data), mod.weight_u, mod.weight_v, mod.groups, training,
-                                          dtype, want_dgrad)
-    return Folded(mod, wf, wd, dtype, u=mod.weight_u.clone(), v=mod.weight_v.clone(), sigma=sigma)
+                                          dtype, want_dgrad, pack_groups=pg, unfold=unf)
+    return Folded(mod, wf, wd, dtype, u=mod.weight_u.clone(), v=mod.weight_v.clone(), sigma=sigma, pg=pg, unfold=unf, kp=kp)
 
 
 def _grad_of(p: torch.nn.Parameter) -> Tensor:
@@ -74,38 +90,56 @@ def _grad_of(p: torch.nn.Parameter) -> Tensor:
 
 def fold_backward(f: Folded, dw: Tensor) -> None:
     m = f.mod
+    ld = f.kp if f.unfold else 0            # im2col layers: dw rows are kp long, (tap, channel) order = packed order
     if m.norm == "weight_norm":
-        ops.weightnorm_fold_bwd(dw, _w3(m.weight_v.data), m.weight_g.data, _grad_of(m.weight_v), _grad_of(m.weight_g), True)
+        ops.weightnorm_fold_bwd(dw, _w3(m.weight_v.data), m.weight_g.data, _grad_of(m.weight_v), _grad_of(m.weight_g), True,
+                                dw_ld=ld)
     else:
-        ops.spectralnorm_fold_bwd(dw, _w3(m.weight_orig.data), f.u, f.v, f.sigma, _grad_of(m.weight_orig), True)
+        ops.spectralnorm_fold_bwd(dw, _w3(m.weight_orig.data), f.u, f.v, f.sigma, _grad_of(m.weight_orig), True, dw_ld=ld)
 
 
 class _Workspace:
     """Zero-initialised fp32 arena for packed weight gradients (one memset per pass)."""
 
+    @staticmethod
+    def _size(m) -> int:
+        return m.out_channels * ops.round_up8(m.kernel * (m.in_channels // m.groups))
+
     def __init__(self, convs: Sequence, device):
-        n = sum(c.out_channels * c.kernel * (c.in_channels // c.groups) for c in convs)
+        n = sum(self._size(c) for c in convs)
         self.buf = torch.zeros(n, device=device, dtype=torch.float32)
         self.off = 0
 
     def take(self, m) -> Tensor:
-        n = m.out_channels * m.kernel * (m.in_channels // m.groups)
+        n = self._size(m)
         t = self.buf[self.off:self.off + n]
         self.off += n
         return t
 
 
+def unfold_input(f: Folded, src: Tensor, B: int, t_src: int, phases: int = 1) -> Tensor:
+    """im2col rows of a tiny-channel first layer's input (what _fwd / _wgrad of an `unfold` layer consume)."""
+    m = f.mod
+    return ops.unfold(src, n_samples=B, phases=phases, t_src=t_src, t_dst=m.t_out(t_src), channels=m.in_channels,
+                      k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad)
+
+
 def _fwd(f: Folded, src: Tensor, B: int, t_src: int, *, phases: int = 1, act: int = ACT_NONE, want_raw: bool = False,
          want_act: bool = False, dup: bool = False, add_post: Optional[Tensor] = None, post_shift: int = 0,
          out_f32: bool = False) -> Tuple[Optional[Tensor], Optional[Tensor], int]:
+    """One conv forward.  For an `unfold` layer `src` is the im2col tensor from unfold_input()."""
     m = f.mod
     t_dst = m.t_out(t_src)
     odt = torch.float32 if out_f32 else f.dtype
     y_raw = torch.empty((B, t_dst * phases, m.out_channels), device=src.device, dtype=odt) if want_raw else None
     y_act = torch.empty((B, t_dst * phases * (2 if dup else 1), m.out_channels), device=src.device, dtype=odt) if want_act else None
-    ops.conv(src, f.wf, n_samples=B, phases=phases, t_src=t_src, t_dst=t_dst, c_src=m.in_channels, c_dst=m.out_channels,
-             groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, bias=m.bias.data, act=act,
-             dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act)
+    if f.unfold:
+        ops.conv(src, f.wf, n_samples=B, phases=phases, t_src=t_dst, t_dst=t_dst, c_src=f.kp, c_dst=m.out_channels, k=1,
+                 bias=m.bias.data, act=act, dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act)
+    else:
+        ops.conv(src, f.wf, n_samples=B, phases=phases, t_src=t_src, t_dst=t_dst, c_src=m.in_channels, c_dst=m.out_channels,
+                 groups=f.pg, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, bias=m.bias.data, act=act,
+                 dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act)
     return y_raw, y_act, t_dst
 
 
@@ -113,19 +147,34 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
            mask_mode: int = ACT_NONE, add_pre: Optional[Tensor] = None, add_post: Optional[Tensor] = None,
            pair_sum: bool = False, out_f32: bool = False) -> Tensor:
     m = f.mod
+    if f.unfold:
+        # gradient w.r.t. the im2col rows, then its adjoint back onto the [B, t_x*phases, C_in] input (fp32)
+        assert mask is None and add_pre is None and add_post is None and not pair_sum
+        du = torch.empty((B, t_dy * phases, f.kp), device=dy.device, dtype=f.dtype)
+        ops.conv(dy, f.wd, n_samples=B, phases=phases, t_src=t_dy, t_dst=t_dy, c_src=m.out_channels, c_dst=f.kp, k=1,
+                 transposed=True, y_raw=du)
+        dx = torch.zeros((B, t_x * phases, m.in_channels), device=dy.device, dtype=torch.float32)
+        ops.unfold_bwd(du, dx, n_samples=B, phases=phases, t_src=t_x, t_dst=t_dy, channels=m.in_channels, k=m.kernel,
+                       dilation=m.dilation, stride=m.stride, pad=m.pad)
+        return dx if out_f32 else ops.cast(dx, f.dtype)
     rows = t_x // 2 if pair_sum else t_x
     dx = torch.empty((B, rows * phases, m.in_channels), device=dy.device, dtype=torch.float32 if out_f32 else f.dtype)
     ops.conv(dy, f.wd, n_samples=B, phases=phases, t_src=t_dy, t_dst=t_x, c_src=m.out_channels, c_dst=m.in_channels,
-             groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, transposed=True,
+             groups=f.pg, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, transposed=True,
              pair_sum=pair_sum, mask=mask, mask_mode=mask_mode, add_pre=add_pre, add_post=add_post, y_raw=dx)
     return dx
 
 
 def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _Workspace, phases: int = 1) -> None:
+    """Weight + bias gradient of one conv.  For an `unfold` layer `x` is the im2col tensor from unfold_input()."""
     m = f.mod
     dw = ws.take(m)
-    ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_x, t_out=t_dy, c_in=m.in_channels,
-              c_out=m.out_channels, groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad)
+    if f.unfold:
+        ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_dy, t_out=t_dy, c_in=f.kp,
+                  c_out=m.out_channels, k=1)
+    else:
+        ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_x, t_out=t_dy, c_in=m.in_channels,
+                  c_out=m.out_channels, groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad)
     fold_backward(f, dw)
 
 
@@ -336,6 +385,9 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
         else:
             src = ops.cast(xs, dtype)
             phases, t = 1, t_scale
+        f0 = folds[id(d.layers[0])]
+        if f0.unfold:                         # im2col rows replace the raw input (kept for the first layer's wgrad)
+            src = unfold_input(f0, src, B, t, phases)
         sub = dict(kind=kind, phases=phases, inputs=[src], ts=[t], t_in0=t_scale if kind == "S" else T, mod=d)
         fmaps = []
         h = src

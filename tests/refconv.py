@@ -15,6 +15,36 @@ def pack_dgrad(w, groups):
     return w.view(groups, cout_g, cin_g, k).permute(3, 0, 2, 1).reshape(k, groups * cin_g, cout_g).contiguous()
 
 
+def expand_groups(w, groups, pg):
+    """torch weight [c_out, c_in/groups, k] of a `groups`-grouped conv -> the block-diagonal weight
+    [c_out, c_in/pg, k] of the same conv written with pg | groups groups (zeros between the real groups)."""
+    if pg == groups:
+        return w
+    c_out, cin_g, k = w.shape
+    f = groups // pg
+    cout_g = c_out // groups
+    out = torch.zeros(c_out, cin_g * f, k, dtype=w.dtype)
+    for g in range(groups):
+        lo = (g % f) * cin_g
+        out[g * cout_g:(g + 1) * cout_g, lo:lo + cin_g] = w[g * cout_g:(g + 1) * cout_g]
+    return out
+
+
+def unfold_ref(x_cl, *, phases, k, dilation, stride, pad, t_out):
+    """im2col rows [B, t_out*phases, roundup8(k*C)] of a channels-last period view (host reference of stg_unfold)."""
+    B, TP, Cc = x_cl.shape
+    T = TP // phases
+    x = x_cl.view(B, T, phases, Cc)
+    kp = (k * Cc + 7) // 8 * 8
+    out = torch.zeros(B, t_out, phases, kp, dtype=x_cl.dtype)
+    for j in range(k):
+        for t in range(t_out):
+            ts = t * stride + j * dilation - pad
+            if 0 <= ts < T:
+                out[:, t, :, j * Cc:(j + 1) * Cc] = x[:, ts]
+    return out.view(B, t_out * phases, kp)
+
+
 def to_virtual(x_cl, phases):
     """[B, T*p, C] channels-last period view -> [B*p, C, T] torch conv1d layout."""
     B, TP, Cc = x_cl.shape

@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.refconv import conv_ref, pack_dgrad, pack_fwd, rel_l2, to_virtual, from_virtual
+from tests.refconv import conv_ref, expand_groups, pack_dgrad, pack_fwd, rel_l2, to_virtual, from_virtual, unfold_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +31,9 @@ CASES = [
     ("p2_l3", 2, 2, 140, 256, 128, 3, 1, 3, 2, 1),
     ("p5_k5s3", 2, 5, 40, 32, 128, 5, 1, 3, 2, 1),
     ("last", 2, 1, 160, 192, 8, 3, 1, 1, 1, 1),
+    ("s_k41_s2_g4_full", 2, 1, 150, 128, 128, 41, 1, 2, 20, 4),
+    ("s_k41_g16_full", 1, 1, 60, 1024, 1024, 41, 1, 1, 20, 16),
+    ("s_k37_s2_big", 2, 1, 530, 128, 256, 37, 1, 2, 18, 4),
 ]
 
 
@@ -49,11 +52,19 @@ def make_case(case, seed=0):
     return x, w, bias, dy, To
 
 
+def _pack_groups(ops, case, engine):
+    """tcgen05 engine: narrow groups are merged into block-diagonal ones of >= 64 channels."""
+    name, B, p, T, ci, co, k, d, s, pad, g = case
+    return ops.tc_pack_groups(ci, co, g) if engine == ops.ENGINE_TCGEN05 else g
+
+
 def run_fwd(ops, case, dtype, engine, x, w, bias, To):
     name, B, p, T, ci, co, k, d, s, pad, g = case
     dev = "cuda"
     xd = x.to(dev, dtype)
-    wf = pack_fwd(w).to(dev, dtype)
+    pg = _pack_groups(ops, case, engine)
+    wf = pack_fwd(expand_groups(w, g, pg)).to(dev, dtype)
+    g = pg
     y = torch.empty(B, To * p, co, device=dev, dtype=torch.float32)
     ya = torch.empty(B, To * p, co, device=dev, dtype=torch.float32)
     ops.conv(xd, wf, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k, dilation=d,
@@ -65,7 +76,9 @@ def run_fwd(ops, case, dtype, engine, x, w, bias, To):
 def run_dgrad(ops, case, dtype, engine, dy, w, To):
     name, B, p, T, ci, co, k, d, s, pad, g = case
     dev = "cuda"
-    wd = pack_dgrad(w, g).to(dev, dtype)
+    pg = _pack_groups(ops, case, engine)
+    wd = pack_dgrad(expand_groups(w, g, pg), pg).to(dev, dtype)
+    g = pg
     dx = torch.empty(B, T * p, ci, device=dev, dtype=torch.float32)
     ops.conv(dy.to(dev, dtype), wd, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
              dilation=d, stride=s, pad=pad, transposed=True, y_raw=dx, engine=engine)
@@ -128,6 +141,7 @@ def test_simt_bf16(case):
 
 def _tc_conv_desc(ops, case, transposed):
     name, B, p, T, ci, co, k, d, s, pad, g = case
+    g = ops.tc_pack_groups(ci, co, g)
     To = t_out_of(T, k, d, s, pad)
     if transposed:
         return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
@@ -237,6 +251,56 @@ def test_weightnorm_fold_fwd_bwd(shape):
     dv = torch.zeros(co, cg, k, device="cuda"); dg = torch.zeros(co, device="cuda")
     ops.weightnorm_fold_bwd(dwp.cuda(), v.cuda(), g.cuda(), dv, dg, True)
     assert rel_l2(dv.cpu(), gv) < 1e-5 and rel_l2(dg.cpu(), gg.flatten()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(256, 32, 37, 4), (512, 16, 37, 16), (256, 8, 41, 16), (1024, 64, 41, 16)],
+                         ids=["g4", "g16", "g16_c8", "g16_c64"])
+def test_fold_pack_groups(shape):
+    """Narrow groups merged into block-diagonal packs of >= 64 channels (what the tcgen05 engine reads)."""
+    from ste_gan_b200 import ops
+    co, cg, k, groups = shape
+    gen = torch.Generator().manual_seed(co + k)
+    v = torch.randn(co, cg, k, generator=gen); g = torch.rand(co, 1, 1, generator=gen) + 0.5
+    w = v * (g / v.norm(2, dim=(1, 2), keepdim=True))
+    pg = ops.tc_pack_groups(cg * groups, co, groups)
+    assert groups % pg == 0 and (cg * groups // pg) % 64 == 0 and (co // pg) % 64 == 0
+    wf, wd, _ = ops.weightnorm_fold(v.cuda(), g.cuda(), groups, torch.bfloat16, pack_groups=pg)
+    we = expand_groups(w, groups, pg)
+    for mine, ref in ((wf, pack_fwd(we)), (wd, pack_dgrad(we, pg))):
+        mine = mine.float().cpu()
+        assert mine.shape == ref.shape and rel_l2(mine, ref) < 4e-3               # bf16 rounding of the packs
+        assert torch.equal(mine == 0, ref == 0)                                     # exact block-diagonal structure
+
+
+@pytest.mark.parametrize("geom", [(2, 1, 200, 8, 128, 15, 1, 1, 7), (2, 3, 67, 8, 32, 3, 1, 1, 2), (2, 5, 41, 8, 32, 5, 1, 3, 2)],
+                         ids=["s_k15", "p3_k3", "p5_k5s3"])
+def test_unfold_first_layer(geom):
+    """C_in = 8 first layers as a 1-tap conv over im2col rows: unfold, unfolded packs, fwd / wgrad / input gradient."""
+    from ste_gan_b200 import ops
+    B, p, T, ci, co, k, d, s, pad = geom
+    case = ("u", B, p, T, ci, co, k, d, s, pad, 1)
+    x, w, bias, dy, To = make_case(case, seed=7)
+    x, w, dy = _bf(x), _bf(w), _bf(dy)
+    y_ref, gx_ref, gw_ref, _ = reference(case, x, w, bias, dy)
+    xu = ops.unfold(x.cuda().to(torch.bfloat16), n_samples=B, phases=p, t_src=T, t_dst=To, channels=ci, k=k, dilation=d,
+                    stride=s, pad=pad)
+    assert torch.equal(xu.float().cpu(), unfold_ref(x, phases=p, k=k, dilation=d, stride=s, pad=pad, t_out=To))
+    kp = xu.shape[-1]
+    g1 = torch.ones(co, 1, 1)
+    wf, wd, _ = ops.weightnorm_fold(w.cuda(), w.norm(2, dim=(1, 2), keepdim=True).cuda(), 1, torch.bfloat16, unfold=True)
+    assert wf.shape == (co, kp) and wd.shape == (kp, co)
+    y = torch.empty(B, To * p, co, device="cuda", dtype=torch.float32)
+    ops.conv(xu, wf, n_samples=B, phases=p, t_src=To, t_dst=To, c_src=kp, c_dst=co, k=1, bias=bias.cuda(), y_raw=y)
+    assert rel_l2(y.cpu(), y_ref) < 5e-3          # weights re-rounded to bf16 by the fold
+    dw = torch.zeros(co, kp, device="cuda")
+    ops.wgrad(xu, dy.cuda().to(torch.bfloat16), dw, None, n_samples=B, phases=p, t_in=To, t_out=To, c_in=kp, c_out=co, k=1)
+    assert rel_l2(dw[:, :k * ci].reshape(co, k, ci).cpu(), gw_ref) < 1e-4
+    du = torch.empty(B, To * p, kp, device="cuda", dtype=torch.bfloat16)
+    ops.conv(dy.cuda().to(torch.bfloat16), wd, n_samples=B, phases=p, t_src=To, t_dst=To, c_src=co, c_dst=kp, k=1,
+             transposed=True, y_raw=du)
+    dx = torch.zeros(B, T * p, ci, device="cuda")
+    ops.unfold_bwd(du, dx, n_samples=B, phases=p, t_src=T, t_dst=To, channels=ci, k=k, dilation=d, stride=s, pad=pad)
+    assert rel_l2(dx.cpu(), gx_ref) < 1e-2        # du is stored in bf16
 
 
 @pytest.mark.parametrize("shape", FOLD_CASES[:4], ids=[str(s) for s in FOLD_CASES[:4]])
