@@ -103,6 +103,12 @@ typedef struct StgWgrad {
 } StgWgrad;
 
 int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream);
+/* Layout of dw the selected engine writes for this contraction: element (co, j, ci) at co*ld + j*span + goff(co) + ci.
+ * CUDA-core engine and ungrouped convs: span = c_in/groups, ld = k*span, goff = 0 (compact).  tcgen05 engine on a
+ * grouped conv: span = the input channels a 128-row output-channel tile meets ((128/cout_g)*cin_g, or cin_g when
+ * cout_g >= 128), goff(co) = ((co/cout_g) % (128/cout_g))*cin_g; entries outside a row's own group are scratch.
+ * dw must hold c_out*ld floats. */
+int stg_wgrad_layout(const StgWgrad* d, int* ld, int* span);
 
 /*
  * weight_norm (torch.nn.utils.weight_norm, dim 0; layers/conv.py:16-17,92,99):
@@ -119,10 +125,11 @@ int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream);
 enum { STG_PACK_UNFOLD = 1 };
 int stg_weightnorm_fold(const float* v, const float* g, int c_out, int cin_g, int k, int groups, int pack_groups,
                         int flags, int dtype, void* wf, void* wd, float* scale, stg_stream_t stream);
-/* dw [c_out][dw_ld] fp32 with element (co, j, ci) at co*dw_ld + j*cin_g + ci (dw_ld 0 = k*cin_g) -> dv (torch layout)
- * and dg; ACCUMULATES into dv/dg when accumulate != 0. */
-int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, const float* v, const float* g, int c_out, int cin_g, int k,
-                            float* dv, float* dg, int accumulate, stg_stream_t stream);
+/* dw fp32 in the layout reported by stg_wgrad_layout: element (co, j, ci) at co*dw_ld + j*dw_span + goff(co) + ci
+ * (dw_span 0 = cin_g, dw_ld 0 = k*dw_span: the compact [c_out][k][cin_g]) -> dv (torch layout) and dg;
+ * ACCUMULATES into dv/dg when accumulate != 0. */
+int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* v, const float* g, int c_out, int cin_g,
+                            int k, int groups, float* dv, float* dg, int accumulate, stg_stream_t stream);
 
 /*
  * spectral_norm (legacy torch.nn.utils.spectral_norm, layers/conv.py:94,101): when
@@ -134,8 +141,8 @@ int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, in
                           int pack_groups, int flags, int training, int dtype, void* wf, void* wd, float* sigma_out,
                           float* scratch, stg_stream_t stream);
 /* d w_orig = dw/sigma - (sum(dw .* w_orig)/sigma^2) u v^T ; u, v, sigma are the values used by that forward. */
-int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, const float* w_orig, const float* u, const float* v,
-                              const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
+int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* w_orig, const float* u, const float* v,
+                              const float* sigma, int c_out, int cin_g, int k, int groups, float* dw_orig, int accumulate,
                               float* scratch, stg_stream_t stream);
 /* Number of groups the tcgen05 engine wants the packs of a (c_in, c_out, groups) convolution in (== groups
  * when no widening is needed or possible). */

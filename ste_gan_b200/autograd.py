@@ -152,7 +152,7 @@ class SingleConvFn(torch.autograd.Function):
         g = g.reshape(B, -1, g.shape[-1]).to(f.dtype)
         params = list(mod.parameters())
         with _collect_param_grads(params) as col:
-            ws = passes._Workspace([mod], g.device)
+            ws = passes._Workspace([f], g.device)
             passes._wgrad(f, ctx.xcl, g, B, t, t_out, ws, phases=phases)
         dx = None
         if ctx.needs_input_grad[1]:
@@ -187,6 +187,6 @@ class GBlockFn(torch.autograd.Function):
         dy = gy.transpose(1, 2).contiguous().to(next(iter(ctx.folds.values())).dtype)
         params = list(blk.parameters())
         with _collect_param_grads(params) as col:
-            ws = passes._Workspace(list(blk.convs().values()), dy.device)
+            ws = passes._Workspace(list(ctx.folds.values()), dy.device)
             dx = passes.gblock_bwd(blk, ctx.folds, ctx.saved, dy, ctx.B, ws)
         return (None, dx.to(ctx.in_dtype).transpose(1, 2)) + tuple(col.grads)

@@ -60,14 +60,24 @@ extern "C" int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int r = STG_OK;
   if (d->dw) {
-    if (d->engine == STG_ENGINE_TCGEN05) r = wgrad_tc(d, s);
-    else if (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d)) r = wgrad_tc(d, s);
-    else if (d->engine == STG_ENGINE_AUTO || d->engine == STG_ENGINE_SIMT) r = wgrad_simt(d, s);
+    // the tcgen05 engine folds the bias gradient into the same kernel (one extra MMA against an all-ones operand)
+    if (d->engine == STG_ENGINE_TCGEN05) return wgrad_tc(d, s);
+    if (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d)) return wgrad_tc(d, s);
+    if (d->engine == STG_ENGINE_AUTO || d->engine == STG_ENGINE_SIMT) r = wgrad_simt(d, s);
     else r = STG_EINVAL;
     if (r) return r;
   }
   if (d->dbias) r = colsum(d->dy, d->dtype, (int64_t)d->n_samples * d->phases * d->t_out, d->c_out, d->dbias, s);
   return r;
+}
+
+extern "C" int stg_wgrad_layout(const StgWgrad* d, int* ld, int* span) {
+  if (!d || !ld || !span || d->groups < 1 || d->c_in % d->groups) return STG_EINVAL;
+  const bool tc = d->engine == STG_ENGINE_TCGEN05 || (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d));
+  if (tc) { wgrad_tc_layout(d, ld, span); return STG_OK; }
+  *span = d->c_in / d->groups;
+  *ld = d->k * *span;
+  return STG_OK;
 }
 
 extern "C" const char* stg_strerror(int code) {

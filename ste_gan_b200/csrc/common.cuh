@@ -103,5 +103,6 @@ int wgrad_simt(const StgWgrad* d, cudaStream_t s);
 int wgrad_tc(const StgWgrad* d, cudaStream_t s);
 bool wgrad_tc_supported(const StgWgrad* d);
 int tc_pack_groups(int c_in, int c_out, int groups);
+void wgrad_tc_layout(const StgWgrad* d, int* ld, int* span);
 
 }  // namespace stg

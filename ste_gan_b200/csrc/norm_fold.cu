@@ -88,20 +88,29 @@ __global__ void __launch_bounds__(256) pack_unfold_kernel(const float* __restric
   if (wd) wd[(int64_t)q * c_out + co] = from_f<T>(w);
 }
 
+// Gradient layouts: element (co, j, ci) of dw lives at co*dw_ld + j*span + goff(co) + ci.  Compact: span = cin_g,
+// goff = 0.  "Span" layout of the tcgen05 wgrad for grouped convs (wgrad_tc.cu): span = input channels met by a
+// 128-row co tile, goff = offset of co's own group inside that span.
+__device__ __forceinline__ int span_goff(int co, int cin_g, int cout_g, int span) {
+  if (span == cin_g || cout_g >= 128) return 0;
+  return ((co / cout_g) % (128 / cout_g)) * cin_g;
+}
+
 // dv[co][ci][j] (+)= scale*dw[co][j][ci] - (g*dot/norm^3) v ; dg[co] (+)= dot/norm
 __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
-                                                     const float* __restrict__ g, int cin_g, int k, int dw_ld,
-                                                     float* __restrict__ dv, float* __restrict__ dg, int accumulate) {
+                                                     const float* __restrict__ g, int cin_g, int k, int dw_ld, int span,
+                                                     int cout_g, float* __restrict__ dv, float* __restrict__ dg,
+                                                     int accumulate) {
   __shared__ float red[32];
   const int co = blockIdx.x, n = cin_g * k;
   const float* vr = v + (int64_t)co * n;
-  const float* dr = dw + (int64_t)co * dw_ld;
+  const float* dr = dw + (int64_t)co * dw_ld + span_goff(co, cin_g, cout_g, span);
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
     const float x = vr[i];
     ss = fmaf(x, x, ss);
-    dot = fmaf(x, dr[j * cin_g + ci], dot);
+    dot = fmaf(x, dr[j * span + ci], dot);
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ d
   const float a = gg / norm, bcoef = gg * dot / (norm * ss);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
-    const float val = a * dr[j * cin_g + ci] - bcoef * vr[i];
+    const float val = a * dr[j * span + ci] - bcoef * vr[i];
     float* o = dv + (int64_t)co * n + i;
     *o = accumulate ? (*o + val) : val;
   }
@@ -162,13 +171,14 @@ __global__ void sn_fill_scale_kernel(const float* __restrict__ sigma, int c_out,
 }
 // acc += sum dw[co][j][ci] * W[co][ci][j]
 __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ dw, const float* __restrict__ W,
-                                                         int cin_g, int k, int dw_ld, float* __restrict__ acc) {
+                                                         int cin_g, int k, int dw_ld, int span, int cout_g,
+                                                         float* __restrict__ acc) {
   __shared__ float red[32];
   const int co = blockIdx.x, n = cin_g * k;
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
-    s = fmaf(W[(int64_t)co * n + i], dw[(int64_t)co * dw_ld + j * cin_g + ci], s);
+    s = fmaf(W[(int64_t)co * n + i], dw[(int64_t)co * dw_ld + span_goff(co, cin_g, cout_g, span) + j * span + ci], s);
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc, s);
@@ -176,12 +186,12 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ u,
                                                      const float* __restrict__ v, const float* __restrict__ sigma,
                                                      const float* __restrict__ dot, int cin_g, int k, int dw_ld,
-                                                     float* __restrict__ dW, int accumulate) {
+                                                     int span, int cout_g, float* __restrict__ dW, int accumulate) {
   const int co = blockIdx.x, n = cin_g * k;
   const float sg = sigma[0], coef = dot[0] / (sg * sg) * u[co], inv = 1.f / sg;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;
-    const float val = dw[(int64_t)co * dw_ld + j * cin_g + ci] * inv - coef * v[i];
+    const float val = dw[(int64_t)co * dw_ld + span_goff(co, cin_g, cout_g, span) + j * span + ci] * inv - coef * v[i];
     float* o = dW + (int64_t)co * n + i;
     *o = accumulate ? (*o + val) : val;
   }
@@ -230,12 +240,14 @@ extern "C" int stg_weightnorm_fold(const float* v, const float* g, int c_out, in
   return STG_EINVAL;
 }
 
-extern "C" int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, const float* v, const float* g, int c_out, int cin_g,
-                                       int k, float* dv, float* dg, int accumulate, stg_stream_t stream) {
+extern "C" int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* v, const float* g, int c_out,
+                                       int cin_g, int k, int groups, float* dv, float* dg, int accumulate,
+                                       stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!dw || !v || !g || !dv || !dg) return STG_EINVAL;
-  if (dw_ld <= 0) dw_ld = cin_g * k;
-  wn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, v, g, cin_g, k, dw_ld, dv, dg, accumulate);
+  if (!dw || !v || !g || !dv || !dg || groups < 1) return STG_EINVAL;
+  if (dw_span <= 0) dw_span = cin_g;
+  if (dw_ld <= 0) dw_ld = dw_span * k;
+  wn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, v, g, cin_g, k, dw_ld, dw_span, c_out / groups, dv, dg, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
@@ -275,16 +287,17 @@ extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, in
   return STG_EINVAL;
 }
 
-extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, const float* w_orig, const float* u, const float* v,
-                                         const float* sigma, int c_out, int cin_g, int k, float* dw_orig, int accumulate,
-                                         float* scratch, stg_stream_t stream) {
+extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* w_orig, const float* u,
+                                         const float* v, const float* sigma, int c_out, int cin_g, int k, int groups,
+                                         float* dw_orig, int accumulate, float* scratch, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!dw || !w_orig || !u || !v || !sigma || !dw_orig || !scratch) return STG_EINVAL;
-  if (dw_ld <= 0) dw_ld = cin_g * k;
+  if (!dw || !w_orig || !u || !v || !sigma || !dw_orig || !scratch || groups < 1) return STG_EINVAL;
+  if (dw_span <= 0) dw_span = cin_g;
+  if (dw_ld <= 0) dw_ld = dw_span * k;
   STG_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(float), s));
-  sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, dw_ld, scratch);
+  sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, dw_ld, dw_span, c_out / groups, scratch);
   STG_LAUNCH_CHECK();
-  sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_ld, dw_orig, accumulate);
+  sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_ld, dw_span, c_out / groups, dw_orig, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

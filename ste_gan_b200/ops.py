@@ -104,14 +104,26 @@ def conv_tc_supported(**kw) -> bool:
     return bool(_lib.load().stg_conv_tc_supported(C.byref(d)))
 
 
+def wgrad_layout(dtype: torch.dtype, *, c_in: int, c_out: int, k: int, groups: int = 1, stride: int = 1,
+                 engine: int = ENGINE_AUTO) -> tuple:
+    """(ld, span) of the gradient buffer the selected engine writes (include/stegan_b200.h, stg_wgrad_layout)."""
+    d = StgWgrad(dtype=code_of(dtype), engine=_engine_override if _engine_override is not None else engine, n_samples=1,
+                 phases=1, t_in=1, t_out=1, c_in=c_in, c_out=c_out, groups=groups, k=k, dilation=1, stride=stride, pad=0)
+    ld, span = C.c_int(0), C.c_int(0)
+    check(_lib.load().stg_wgrad_layout(C.byref(d), C.byref(ld), C.byref(span)), "stg_wgrad_layout")
+    return ld.value, span.value
+
+
 def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], *, n_samples: int, t_in: int,
           t_out: int, c_in: int, c_out: int, k: int, phases: int = 1, groups: int = 1, dilation: int = 1,
           stride: int = 1, pad: int = 0, engine: int = ENGINE_AUTO) -> None:
-    """dw[c_out][k][c_in/groups] += ..., dbias[c_out] += column sums of dy (fp32, accumulated)."""
+    """dw (layout: wgrad_layout) += ..., dbias[c_out] += column sums of dy (fp32, accumulated)."""
     nv = n_samples * phases
     _need(x, nv * t_in * c_in, None, "x")
     _need(dy, nv * t_out * c_out, x.dtype, "dy")
-    _need(dw, c_out * k * (c_in // groups), torch.float32, "dw")
+    if dw is not None:
+        ld, _ = wgrad_layout(x.dtype, c_in=c_in, c_out=c_out, k=k, groups=groups, stride=stride, engine=engine)
+        _need(dw, c_out * ld, torch.float32, "dw")
     _need(dbias, c_out, torch.float32, "dbias")
     d = StgWgrad(dtype=code_of(x.dtype), engine=_engine_override if _engine_override is not None else engine,
                  n_samples=n_samples, phases=phases, t_in=t_in, t_out=t_out, c_in=c_in, c_out=c_out, groups=groups,
@@ -171,12 +183,14 @@ def weightnorm_fold(v: Tensor, g: Tensor, groups: int, dtype: torch.dtype, want_
     return wf, wd, scale
 
 
-def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor, accumulate: bool, dw_ld: int = 0) -> None:
+def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor, accumulate: bool, dw_ld: int = 0,
+                        dw_span: int = 0, groups: int = 1) -> None:
+    """dw in the layout of `wgrad_layout` (defaults: compact [c_out][k][cin_g])."""
     c_out, cin_g, k = v.shape[0], v.shape[1], v.shape[2]
-    _need(dw, c_out * max(dw_ld, cin_g * k), torch.float32, "dw"); _need(dv, c_out * cin_g * k, torch.float32, "dv")
+    _need(dw, c_out * max(dw_ld, max(dw_span, cin_g) * k), torch.float32, "dw"); _need(dv, c_out * cin_g * k, torch.float32, "dv")
     _need(dg, c_out, torch.float32, "dg")
-    check(_lib.load().stg_weightnorm_fold_bwd(_ptr(dw), dw_ld, _ptr(v), _ptr(g), c_out, cin_g, k, _ptr(dv), _ptr(dg),
-                                              int(accumulate), _stream()), "stg_weightnorm_fold_bwd")
+    check(_lib.load().stg_weightnorm_fold_bwd(_ptr(dw), dw_ld, dw_span, _ptr(v), _ptr(g), c_out, cin_g, k, groups, _ptr(dv),
+                                              _ptr(dg), int(accumulate), _stream()), "stg_weightnorm_fold_bwd")
 
 
 def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, training: bool, dtype: torch.dtype,
@@ -198,12 +212,12 @@ def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, trainin
 
 
 def spectralnorm_fold_bwd(dw: Tensor, w_orig: Tensor, u: Tensor, v: Tensor, sigma: Tensor, dw_orig: Tensor,
-                          accumulate: bool, dw_ld: int = 0) -> None:
+                          accumulate: bool, dw_ld: int = 0, dw_span: int = 0, groups: int = 1) -> None:
     c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
-    _need(dw, c_out * max(dw_ld, cin_g * k), torch.float32, "dw"); _need(dw_orig, c_out * cin_g * k, torch.float32, "dw_orig")
+    _need(dw, c_out * max(dw_ld, max(dw_span, cin_g) * k), torch.float32, "dw"); _need(dw_orig, c_out * cin_g * k, torch.float32, "dw_orig")
     scratch = torch.empty((8,), device=u.device, dtype=torch.float32)
-    check(_lib.load().stg_spectralnorm_fold_bwd(_ptr(dw), dw_ld, _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), c_out, cin_g,
-                                                k, _ptr(dw_orig), int(accumulate), _ptr(scratch), _stream()),
+    check(_lib.load().stg_spectralnorm_fold_bwd(_ptr(dw), dw_ld, dw_span, _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), c_out,
+                                                cin_g, k, groups, _ptr(dw_orig), int(accumulate), _ptr(scratch), _stream()),
           "stg_spectralnorm_fold_bwd")
 
 

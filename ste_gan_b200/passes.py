@@ -88,30 +88,42 @@ def _grad_of(p: torch.nn.Parameter) -> Tensor:
     return p.grad
 
 
+def dw_layout(f: Folded) -> Tuple[int, int, int]:
+    """(floats, ld, span) of the packed weight-gradient buffer of this conv (ops.wgrad_layout); cached per fold mode."""
+    m = f.mod
+    key = (f.dtype, f.unfold, ops._engine_override)
+    cache = m.__dict__.setdefault("_stg_dw_layout", {})
+    if key not in cache:
+        if f.unfold:                        # im2col layers: rows are kp long, (tap, channel) order = packed order
+            ld, span = f.kp, m.in_channels
+        else:
+            ld, span = ops.wgrad_layout(f.dtype, c_in=m.in_channels, c_out=m.out_channels, k=m.kernel, groups=m.groups,
+                                        stride=m.stride)
+        cache[key] = (m.out_channels * ld, ld, span)
+    return cache[key]
+
+
 def fold_backward(f: Folded, dw: Tensor) -> None:
     m = f.mod
-    ld = f.kp if f.unfold else 0            # im2col layers: dw rows are kp long, (tap, channel) order = packed order
+    _, ld, span = dw_layout(f)
     if m.norm == "weight_norm":
         ops.weightnorm_fold_bwd(dw, _w3(m.weight_v.data), m.weight_g.data, _grad_of(m.weight_v), _grad_of(m.weight_g), True,
-                                dw_ld=ld)
+                                dw_ld=ld, dw_span=span, groups=m.groups)
     else:
-        ops.spectralnorm_fold_bwd(dw, _w3(m.weight_orig.data), f.u, f.v, f.sigma, _grad_of(m.weight_orig), True, dw_ld=ld)
+        ops.spectralnorm_fold_bwd(dw, _w3(m.weight_orig.data), f.u, f.v, f.sigma, _grad_of(m.weight_orig), True,
+                                  dw_ld=ld, dw_span=span, groups=m.groups)
 
 
 class _Workspace:
     """Zero-initialised fp32 arena for packed weight gradients (one memset per pass)."""
 
-    @staticmethod
-    def _size(m) -> int:
-        return m.out_channels * ops.round_up8(m.kernel * (m.in_channels // m.groups))
-
-    def __init__(self, convs: Sequence, device):
-        n = sum(self._size(c) for c in convs)
+    def __init__(self, folds: Sequence["Folded"], device):
+        n = sum(dw_layout(f)[0] for f in folds)
         self.buf = torch.zeros(n, device=device, dtype=torch.float32)
         self.off = 0
 
-    def take(self, m) -> Tensor:
-        n = self._size(m)
+    def take(self, f: "Folded") -> Tensor:
+        n = dw_layout(f)[0]
         t = self.buf[self.off:self.off + n]
         self.off += n
         return t
@@ -168,7 +180,7 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
 def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _Workspace, phases: int = 1) -> None:
     """Weight + bias gradient of one conv.  For an `unfold` layer `x` is the im2col tensor from unfold_input()."""
     m = f.mod
-    dw = ws.take(m)
+    dw = ws.take(f)
     if f.unfold:
         ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_dy, t_out=t_dy, c_in=f.kp,
                   c_out=m.out_channels, k=1)
@@ -302,7 +314,7 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
     dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output."""
     B, dtype, folds = ctx.B, ctx.dtype, ctx.folds
-    ws = _Workspace(generator_convs(model), dx_pred.device)
+    ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
     blocks = list(model.gblocks)[1:]
     t = ctx.t_out
     # tanh' from the output, then last_conv
@@ -415,7 +427,7 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
     Returns d/dx fp32 [B,T,C] when want_input_grad."""
     B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
     dev = ctx.subs[0]["inputs"][0].device
-    ws = _Workspace(discriminator_convs(model), dev) if want_weight_grad else None
+    ws = _Workspace([folds[id(c)] for c in discriminator_convs(model)], dev) if want_weight_grad else None
     dx = torch.zeros((B, T, Cc), device=dev, dtype=torch.float32) if want_input_grad else None
     scale_grads = []                          # (t_in, d/d x_scale) for the multi-scale chain
     for di, sub in enumerate(ctx.subs):

@@ -89,12 +89,20 @@ def run_dgrad(ops, case, dtype, engine, dy, w, To):
 def run_wgrad(ops, case, dtype, engine, x, dy, To):
     name, B, p, T, ci, co, k, d, s, pad, g = case
     dev = "cuda"
-    dw = torch.zeros(co, k, ci // g, device=dev)
+    ld, span = ops.wgrad_layout(dtype, c_in=ci, c_out=co, k=k, groups=g, stride=s, engine=engine)
+    dw = torch.zeros(co * ld, device=dev)
     db = torch.zeros(co, device=dev)
     ops.wgrad(x.to(dev, dtype), dy.to(dev, dtype), dw, db, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=co,
               groups=g, k=k, dilation=d, stride=s, pad=pad, engine=engine)
     torch.cuda.synchronize()
-    return dw.cpu(), db.cpu()
+    # element (co, j, ci) at co*ld + j*span + goff(co) + ci  (include/stegan_b200.h, stg_wgrad_layout)
+    cin_g, cout_g = ci // g, co // g
+    dwv = dw.cpu().view(co, k, span)
+    out = torch.empty(co, k, cin_g)
+    for c in range(co):
+        goff = 0 if (span == cin_g or cout_g >= 128) else ((c // cout_g) % (128 // cout_g)) * cin_g
+        out[c] = dwv[c, :, goff:goff + cin_g]
+    return out, db.cpu()
 
 
 def reference(case, x, w, bias, dy):
