@@ -222,6 +222,9 @@ unsigned long long stg_launch_count(void);
 /* 1 if the tcgen05 engine can take this contraction (shape/alignment rules in DESIGN.md), else 0. */
 int stg_conv_tc_supported(const StgConv* d);
 int stg_wgrad_tc_supported(const StgWgrad* d);
+/* debug: device buffer of 1 + 3*4000 int64 that receives a (tag, value, globaltimer ns) timeline of CTA 0 of every
+ * following tcgen05 stg_conv launch (NULL switches it off). */
+int stg_debug_set_trace(void* buf);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,7 @@ _SIGS = {
     "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "stg_spectralnorm_fold_bwd": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
     "stg_tc_pack_groups": [_I, _I, _I],
+    "stg_debug_set_trace": [_P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_embed_concat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],

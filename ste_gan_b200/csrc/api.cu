@@ -92,3 +92,6 @@ extern "C" const char* stg_strerror(int code) {
 extern "C" const char* stg_last_cuda_error(void) { return g_last_error.c_str(); }
 extern "C" int stg_version(void) { return 100; }
 extern "C" unsigned long long stg_launch_count(void) { return g_launch_count; }
+
+/* debug: device buffer of 1 + 3*4000 int64 receiving a timeline of CTA 0 of every following stg_conv tcgen05 launch */
+extern "C" int stg_debug_set_trace(void* buf) { conv_tc_set_trace(static_cast<long long*>(buf)); return STG_OK; }

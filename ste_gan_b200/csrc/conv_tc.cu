@@ -1,24 +1,36 @@
 // tcgen05 implicit-GEMM convolution (forward and data-gradient), bf16 in / fp32 accumulate.
 //
 // GEMM view (channels-last activations):   D[t][c_dst] = sum_taps sum_{c_src} A_tap[t][c_src] * W_tap[c_dst][c_src]
-//   M = 128 time rows of one (virtual) sample   -> TMEM lanes
+//   M = 128 output rows of one sample           -> TMEM lanes
 //   N = BN <= 256 output channels               -> TMEM columns
 //   K = 64-channel chunks, one per (tap, chunk) -> one pipeline stage each
 // A tiles come straight from the activation tensor by TMA: the row coordinate is
-// r0*stride + tap_offset, may be negative or run past the sample and is zero-filled by
+// h0*stride + tap_offset, may be negative or run past the sample and is zero-filled by
 // the TMA unit, which implements zero padding, dilation and per-sample boundaries with
-// no im2col buffer.  Period views (DiscriminatorP) are a 4-D tensor map (C, rows, phase, B).
+// no im2col buffer.  Period views (DiscriminatorP's [B,C,T/p,p] Conv2d) are a 4-D tensor map
+// (C, phase, h, B) and a tile packs ALL p phases of 128/p consecutive h rows, so the M tile stays full
+// however short T/p is and its output rows are contiguous in memory.
 // W tiles come from the packed [k][c_dst][c_src/g] weights.  Both operands are K-major
 // with 128-byte swizzle.
 //
 // PERSISTENT kernel: one CTA per SM walks the tile list (column tile fastest, so CTAs that run
-// together share A rows in L2).  Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM
-// alloc + single-thread tcgen05.mma issuer, warps 2..9 = epilogue.  The shared-memory ring runs
-// continuously across tiles; the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so
-// the epilogue of tile i (tcgen05.ld -> bias / pair-sum / add_pre / activation mask / residual /
-// activation / row duplication -> global stores) overlaps the MMAs of tile i+1.  The eight
-// epilogue warps split the tile by TMEM sub-partition (warp % 4) and column half, and prefetch the
-// epilogue operands of the next 16-column chunk while the current one is processed.
+// together share A rows in L2).  Warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread
+// tcgen05.mma issuer, the rest = epilogue.  The shared-memory ring runs continuously across tiles; the
+// accumulator is DOUBLE-BUFFERED in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the MMAs
+// of tile i+1.
+//
+// Two epilogues (bias, pair-sum, add_pre, activation-derivative mask, residual add, activation, row
+// duplication are fused in both):
+//   STAGED  (bf16 outputs, c_dst % 8 == 0, no residue classes): 4 warps.  Epilogue operands are TMA-loaded
+//           into 128 x 32 shared-memory sub-tiles two sub-tiles ahead, results are written to swizzled
+//           shared memory and leave with TMA stores - no thread touches global memory, so the LSU only
+//           sees conflict-free 16-byte shared accesses (row-per-thread global accesses cost one
+//           wavefront per 16 bytes and made the epilogue, not the MMAs, the critical path).
+//   DIRECT  (fp32 outputs, 1-channel logits, strided data-gradients): 8 warps, row-per-thread global
+//           loads/stores with the next chunk's operands prefetched.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace stg {
@@ -31,71 +43,142 @@ constexpr int TM = 128;        // rows per CTA tile
 constexpr int KC = 64;         // channels per K chunk (128 B of bf16)
 constexpr int A_BYTES = TM * KC * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;
-constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
 constexpr int ACC_COLS = 256;  // TMEM column distance between the two accumulator buffers
+constexpr int SUB = 32;        // staged epilogue: columns per sub-tile (64-byte rows, SWIZZLE_64B)
+constexpr int SLOT = TM * SUB * 2;  // bytes of one 128 x 32 bf16 sub-tile
+constexpr int MAX_RES = 8;     // residues of a strided data-gradient (= stride)
 
 struct TcEpi {
-  int phases, t_out, c_dst, post_shift, mask_mode, act, dup_rows, out_f32, pair_sum;
+  int rows, c_dst, post_shift, mask_mode, act, dup_rows, out_f32, pair_sum;  // rows: output rows per sample (all phases)
+  int n_in, n_out, has_pre, has_mask, has_post, has_raw, has_act;            // staged: slot bookkeeping
+  float act_slope, mask_slope;  // act(v) = max(v, act_slope*v) ; act'(m) = m > 0 ? 1 : mask_slope   (none 1, relu 0, leaky 0.1)
   const float* bias;
   const bf16 *add_pre, *mask, *add_post;
   void* y_raw;
   void* y_act;
 };
 
-constexpr int MAX_RES = 8;  // residues of a strided data-gradient (= stride)
-
 struct TcP {
   int phases, t_dst, stride, k_chunks, bn, stages, a_boxes, tmem_cols;
+  int pack, nh, mrows;     // phases packed per tile, h rows per tile, used accumulator rows = nh * pack
   int cs_g, cd_g;          // source / destination channels per (packed) group
   int n_res, tiles_m;      // output-row residues (1 unless transposed && stride > 1), row tiles per residue
-  int tiles_n, n_tiles;    // column tiles, total tiles = n_vs * n_res * tiles_m * tiles_n
+  int tiles_n, n_tiles;    // column tiles, total tiles = B * n_res * tiles_m * tiles_n
   int res_first[MAX_RES + 1];  // taps of residue r: [res_first[r], res_first[r+1])
-  int tap_off[STG_MAX_TAPS];   // source-row offset of the tap (rows of the A tile start at r0*stride + tap_off)
+  int tap_off[STG_MAX_TAPS];   // source-row offset of the tap (rows of the A tile start at h0*stride + tap_off)
   int tap_w[STG_MAX_TAPS];     // tap index into the packed weights
+  long long* trace;            // debug timeline (stg_debug_set_trace) or nullptr
   TcEpi e;
 };
 
-__device__ __forceinline__ void ld16(const bf16* p, float (&o)[16]) {
-  const uint4 a = *reinterpret_cast<const uint4*>(p);
-  const uint4 b = *reinterpret_cast<const uint4*>(p + 8);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+struct EpiMaps {
+  CUtensorMap pre, mask, post, raw, act;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* o) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
     o[2 * i] = __low2float(h);
     o[2 * i + 1] = __high2float(h);
   }
 }
-__device__ __forceinline__ void st16(bf16* p, const float (&v)[16]) {
-  uint32_t w[8];
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     w[i] = *reinterpret_cast<uint32_t*>(&h);
   }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void ld16(const bf16* p, float (&o)[16]) {
+  unpack8(*reinterpret_cast<const uint4*>(p), o);
+  unpack8(*reinterpret_cast<const uint4*>(p + 8), o + 8);
+}
+__device__ __forceinline__ void st16(bf16* p, const float (&v)[16]) {
+  *reinterpret_cast<uint4*>(p) = pack8(v);
+  *reinterpret_cast<uint4*>(p + 8) = pack8(v + 8);
 }
 __device__ __forceinline__ void st16f(float* p, const float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 q;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+  return q;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& q) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+}
+// Branch-free activation forms keep the unrolled epilogue small enough for the instruction cache (a per-element
+// switch with tanhf inlined 32x made the epilogue body ~50 KB and instruction-fetch bound).
+__device__ __forceinline__ float slope_of(int act) { return act == STG_ACT_RELU ? 0.f : (act == STG_ACT_LEAKY ? 0.1f : 1.f); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - t, 1.f + t), x);
+}
+__device__ __forceinline__ float act_fast(const TcEpi& e, float v) {
+  return e.act == STG_ACT_TANH ? fast_tanh(v) : fmaxf(v, e.act_slope * v);
+}
+__device__ __forceinline__ float dact_fast(const TcEpi& e, float m) {
+  return e.mask_mode == STG_ACT_TANH ? 1.f - m * m : (m > 0.f ? 1.f : e.mask_slope);
+}
+// byte offset of 16-byte chunk j (0..3) of row r inside a SWIZZLE_64B sub-tile
+__device__ __forceinline__ uint32_t sw64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
-// epilogue operands of one output row, 16 consecutive channels starting at `col` (prefetched one chunk ahead)
+// debug timeline of CTA 0: each role thread appends (tag, value, globaltimer) triples to its own region of the
+// buffer (plain stores, no atomics: the probe must not perturb what it measures).  Regions of 1300 events:
+// 0 producer (tag 1 tile start), 1 MMA issuer (2 tile start, 3 tile issued), 2 epilogue leader (10 tile start,
+// 11 accumulator ready, 20..24 sub-tile phases, 12 sub-tile done).  Empty slots keep tag 0.
+struct Tracer {
+  long long* base; int n;
+  __device__ __forceinline__ Tracer(long long* tr, int region) : base(tr && blockIdx.x == 0 ? tr + 1 + 3 * 1300 * region : nullptr), n(0) {}
+  __device__ __forceinline__ void ev(int tag, int val) {
+    if (base == nullptr || n >= 1300) return;
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    base[3 * n] = tag; base[3 * n + 1] = val; base[3 * n + 2] = t; ++n;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- tiles
+struct Tile {
+  int b, res, h0, col0, ch0, tap0, n_iters;
+};
+__device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
+  Tile x;
+  const int tn = t % p.tiles_n; int u = t / p.tiles_n;
+  const int tm = u % p.tiles_m; u /= p.tiles_m;
+  // strided data-gradient: output rows h = h' * n_res + res are produced per residue class `res` from the
+  // taps j with (res + pad - j*dilation) % stride == 0, as a stride-1 correlation over h'
+  x.res = u % p.n_res; x.b = u / p.n_res;
+  x.h0 = tm * p.nh;
+  x.col0 = tn * p.bn;
+  x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
+  x.tap0 = p.res_first[x.res];
+  x.n_iters = (p.res_first[x.res + 1] - x.tap0) * p.k_chunks;
+  return x;
+}
+// accumulator row m of a tile -> flat output row of the sample (before pair_sum), or -1
+__device__ __forceinline__ int out_row(const TcP& p, const Tile& x, int m) {
+  if (m >= p.mrows) return -1;
+  const int hl = m / p.pack, ph = m - hl * p.pack;
+  const int h = (x.h0 + hl) * p.n_res + x.res;
+  return h < p.t_dst ? h * p.phases + ph : -1;
+}
+
+// ---------------------------------------------------------------------------------------------- direct epilogue
 struct EpiIn {
   float pre[16], mk[16], post[16];
 };
-
-__device__ __forceinline__ int64_t epi_off(const TcEpi& e, int b, int ph, int row, int col) {
-  return ((int64_t)b * e.t_out + row) * ((int64_t)e.phases * e.c_dst) + (int64_t)ph * e.c_dst + col;
-}
-
-__device__ __forceinline__ void epi_load(const TcEpi& e, int b, int ph, int row, int col, bool row_ok, EpiIn& in) {
+__device__ __forceinline__ void epi_load(const TcEpi& e, int b, int row, int col, bool row_ok, EpiIn& in) {
   if (!row_ok || col >= e.c_dst) return;
   const int ncols = min(16, e.c_dst - col);
   const bool vec = (ncols == 16) && ((e.c_dst & 7) == 0);
-  const int64_t off = epi_off(e, b, ph, row, col);
+  const int64_t off = ((int64_t)b * e.rows + row) * e.c_dst + col;
   if (e.add_pre) {
     if (vec) ld16(e.add_pre + off, in.pre); else for (int i = 0; i < 16; ++i) in.pre[i] = i < ncols ? to_f(e.add_pre[off + i]) : 0.f;
   }
@@ -103,16 +186,13 @@ __device__ __forceinline__ void epi_load(const TcEpi& e, int b, int ph, int row,
     if (vec) ld16(e.mask + off, in.mk); else for (int i = 0; i < 16; ++i) in.mk[i] = i < ncols ? to_f(e.mask[off + i]) : 0.f;
   }
   if (e.add_post) {
-    const int t_post = e.t_out >> e.post_shift;
-    const int64_t o2 = ((int64_t)b * t_post + (row >> e.post_shift)) * ((int64_t)e.phases * e.c_dst) + (int64_t)ph * e.c_dst + col;
+    const int64_t o2 = ((int64_t)b * (e.rows >> e.post_shift) + (row >> e.post_shift)) * e.c_dst + col;
     if (vec) ld16(e.add_post + o2, in.post); else for (int i = 0; i < 16; ++i) in.post[i] = i < ncols ? to_f(e.add_post[o2 + i]) : 0.f;
   }
 }
-
 // v: accumulator (+bias, pair-summed) of one output row, 16 channels
-__device__ __forceinline__ void epi_store(const TcEpi& e, int b, int ph, int row, int col, float (&v)[16], const EpiIn& in) {
-  const int64_t pitch = (int64_t)e.phases * e.c_dst;
-  const int64_t off = epi_off(e, b, ph, row, col);
+__device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int col, float (&v)[16], const EpiIn& in) {
+  const int64_t off = ((int64_t)b * e.rows + row) * e.c_dst + col;
   const int ncols = min(16, e.c_dst - col);
   const bool vec = (ncols == 16) && ((e.c_dst & 7) == 0);
   if (e.add_pre) {
@@ -121,7 +201,7 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int ph, int row
   }
   if (e.mask) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= act_grad_from_output(e.mask_mode, in.mk[i]);
+    for (int i = 0; i < 16; ++i) v[i] *= dact_fast(e, in.mk[i]);
   }
   if (e.add_post) {
 #pragma unroll
@@ -139,52 +219,41 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int ph, int row
   if (e.y_act) {
     float a[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = act_apply(e.act, v[i]);
-    const int64_t o0 = e.dup_rows ? ((int64_t)b * 2 * e.t_out + 2 * row) * pitch + (int64_t)ph * e.c_dst + col : off;
+    for (int i = 0; i < 16; ++i) a[i] = act_fast(e, v[i]);
+    const int64_t o0 = e.dup_rows ? ((int64_t)b * 2 * e.rows + 2 * row) * e.c_dst + col : off;
     if (e.out_f32) {
       float* p0 = static_cast<float*>(e.y_act) + o0;
       if (vec) st16f(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = a[i];
-      if (e.dup_rows) { float* p1 = p0 + pitch; if (vec) st16f(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = a[i]; }
+      if (e.dup_rows) { float* p1 = p0 + e.c_dst; if (vec) st16f(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = a[i]; }
     } else {
       bf16* p0 = static_cast<bf16*>(e.y_act) + o0;
       if (vec) st16(p0, a); else for (int i = 0; i < ncols; ++i) p0[i] = __float2bfloat16_rn(a[i]);
-      if (e.dup_rows) { bf16* p1 = p0 + pitch; if (vec) st16(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = __float2bfloat16_rn(a[i]); }
+      if (e.dup_rows) { bf16* p1 = p0 + e.c_dst; if (vec) st16(p1, a); else for (int i = 0; i < ncols; ++i) p1[i] = __float2bfloat16_rn(a[i]); }
     }
   }
 }
 
-struct Tile {
-  int b, ph, res, r0, col0, ch0, tap0, n_iters;
-};
-__device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
-  Tile x;
-  const int tn = t % p.tiles_n; int u = t / p.tiles_n;
-  const int tm = u % p.tiles_m; u /= p.tiles_m;
-  x.res = u % p.n_res; const int n = u / p.n_res;
-  x.b = n / p.phases; x.ph = n - x.b * p.phases;
-  // strided data-gradient: output rows r = r' * n_res + res are produced per residue class `res` from the
-  // taps j with (res + pad - j*dilation) % stride == 0, as a stride-1 correlation over r'
-  x.r0 = tm * TM;
-  x.col0 = tn * p.bn;
-  x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
-  x.tap0 = p.res_first[x.res];
-  x.n_iters = (p.res_first[x.res + 1] - x.tap0) * p.k_chunks;
-  return x;
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcP p) {
+// ---------------------------------------------------------------------------------------------- kernel
+template <bool kStaged>
+__global__ void __launch_bounds__(kStaged ? 224 : 320, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ EpiMaps em, const TcP p) {
+  constexpr int EPI_WARPS = kStaged ? 4 : 8;   // warps that read the accumulator (arrivals on tmem_empty)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_bytes = p.bn * KC * 2;
   const int stage_bytes = A_BYTES + b_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;  // 8-byte aligned (multiple of 1024)
+  const TcEpi& e = p.e;
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: 2*(n_in+n_out) slots + bias
+  const uint32_t bias_base = epi_base + (kStaged ? (2 * e.n_in + 3 * e.n_out) * SLOT : 0);
+  const uint32_t bar_base = bias_base + (kStaged ? 1024 : 0);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto in_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -192,7 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); mbar_init(in_bar(a), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -208,19 +277,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const int rows_per_box = TM / p.a_boxes;
+      const int hrows_per_box = p.nh / p.a_boxes;
+      Tracer trc(p.trace, 0);
       int itg = 0;  // stage counter, continuous across tiles
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const Tile x = decode_tile(p, t);
+        trc.ev(1, t);
         for (int it = 0; it < x.n_iters; ++it, ++itg) {
           const int s = itg % p.stages, phs = (itg / p.stages) & 1;
           const int tl = it / p.k_chunks, chunk = it - tl * p.k_chunks, tap = x.tap0 + tl;
           mbar_wait(empty_bar(s), phs ^ 1);
-          mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+          mbar_expect_tx(full_bar(s), (uint32_t)(p.mrows * KC * 2 + b_bytes));
           const uint32_t a_dst = smem_base + s * stage_bytes;
           for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_4d(a_dst + bx * rows_per_box * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC,
-                        (x.r0 + bx * rows_per_box) * p.stride + p.tap_off[tap], x.ph, x.b);
+            tma_load_4d(a_dst + bx * hrows_per_box * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+                        (x.h0 + bx * hrows_per_box) * p.stride + p.tap_off[tap], x.b);
           tma_load_3d(a_dst + A_BYTES, &tmW, full_bar(s), chunk * KC, x.col0, p.tap_w[tap]);
         }
       }
@@ -228,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
+    Tracer trc(lane == 0 ? p.trace : nullptr, 1);
     int itg = 0, acc_i = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const Tile x = decode_tile(p, t);
@@ -235,6 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
       mbar_wait(tmem_empty_bar(as), aph ^ 1);  // epilogue has drained this accumulator buffer
       tc_fence_after();
+      trc.ev(2, t);
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
       for (int it = 0; it < x.n_iters; ++it, ++itg) {
         const int s = itg % p.stages, phs = (itg / p.stages) & 1;
@@ -252,14 +325,196 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
+      trc.ev(3, t);
       ++acc_i;
     }
+  } else if constexpr (kStaged) {
+    // ===== staged epilogue: TMEM -> registers -> swizzled smem sub-tiles -> TMA store =====
+    // warps 2..5: math (one accumulator row per thread); warp 6: epilogue DMA (all TMA loads / stores of the
+    // epilogue, so their ~0.1 us issue cost each stays off the math warps' critical path).
+    // Hand-shake per sub-tile q through named barriers (160 = 128 math + 32 DMA threads):
+    //   FULL[q%3]  math arrives after writing the output slots (which implies it has consumed the input slots)
+    //   FREE[q%3]  DMA arrives once the stores that last read output buffer q%3 (sub-tile q-3) have drained
+    const int n_sub = p.bn / SUB;
+    auto in_slot = [&](int buf, int i) { return epi_base + (uint32_t)((buf * e.n_in + i) * SLOT); };
+    auto out_slot = [&](int buf, int o) { return epi_base + (uint32_t)((2 * e.n_in + buf * e.n_out + o) * SLOT); };  // buf: q % 3
+    auto bar_full = [&](int b3) { return 2 + b3; };
+    auto bar_free = [&](int b3) { return 5 + b3; };
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int q_total = my_tiles * n_sub;
+    if (warp == 6) {
+      // ----- epilogue DMA warp -----
+      if (lane == 0) {
+        Tracer trc(p.trace, 3);
+        prefetch_tmap(&em.pre); prefetch_tmap(&em.mask); prefetch_tmap(&em.post); prefetch_tmap(&em.raw); prefetch_tmap(&em.act);
+      }
+      const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
+      const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
+      // iterator over (tile, sub-tile) pairs for the operand loads, which run two sub-tiles ahead of the math
+      int ld_t = blockIdx.x, ld_s = 0, ld_q = 0;
+      auto issue_loads = [&]() {  // lane 0 only
+        if (e.n_in == 0 || ld_t >= p.n_tiles) return;
+        const Tile x = decode_tile(p, ld_t);
+        const int buf = ld_q & 1;
+        const int col = x.col0 + ld_s * SUB;
+        const int r0 = (x.h0 * p.phases) >> (e.pair_sum ? 1 : 0);        // first output row of the tile (n_res == 1)
+        mbar_expect_tx(in_bar(buf), in_bytes);
+        int i = 0;
+        if (e.has_pre) tma_load_3d(in_slot(buf, i++), &em.pre, in_bar(buf), col, r0, x.b);
+        if (e.has_mask) tma_load_3d(in_slot(buf, i++), &em.mask, in_bar(buf), col, r0, x.b);
+        if (e.has_post) tma_load_3d(in_slot(buf, i++), &em.post, in_bar(buf), col, r0 >> e.post_shift, x.b);
+        ++ld_q;
+        if (++ld_s == n_sub) { ld_s = 0; ld_t += gridDim.x; }
+      };
+      if (lane == 0) { issue_loads(); issue_loads(); }
+      int q = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const Tile x = decode_tile(p, t);
+        const int r0_out = (x.h0 * p.phases) >> (e.pair_sum ? 1 : 0);
+        for (int s = 0; s < n_sub; ++s, ++q) {
+          const int obuf = q % 3;
+          asm volatile("bar.sync %0, 160;" ::"r"(bar_full(obuf)) : "memory");   // output slots written, input slots consumed
+          if (lane == 0) {
+            const int col = x.col0 + s * SUB;
+            int o = 0;
+            if (e.has_raw) tma_store_3d(&em.raw, out_slot(obuf, o++), col, r0_out, x.b);
+            if (e.has_act) {
+              tma_store_4d(&em.act, out_slot(obuf, o), col, 0, r0_out, x.b);
+              if (e.dup_rows) tma_store_4d(&em.act, out_slot(obuf, o), col, 1, r0_out, x.b);
+            }
+            bulk_commit();
+            issue_loads();                         // operands of sub-tile q+2 into the input slots just consumed
+            bulk_wait_read<1>();                   // stores of sub-tile q-1 have read their slots -> buffer (q+2)%3 is free
+          }
+          __syncwarp();
+          if (q >= 1 && q + 2 < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free((q + 2) % 3)) : "memory");
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    } else {
+      // ----- math warps -----
+      const int et = threadIdx.x - 64;     // 0..127 = accumulator row m
+      const int sub = warp & 3;            // TMEM sub-partition this warp may read
+      const int m = sub * 32 + lane;
+      Tracer trc(et == 0 ? p.trace : nullptr, 2);
+      int acc_i = 0, q = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const Tile x = decode_tile(p, t);
+        const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
+        trc.ev(10, t);
+        // bias of this column tile -> smem (nobody reads the previous tile's bias any more: every thread has
+        // passed its FULL arrive of the last sub-tile, which comes after its bias reads ... of ITS OWN rows only,
+        // hence the 128-thread barrier below also orders the overwrite against slower warps)
+        if (e.bias) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int c = et; c < p.bn; c += 128) {
+            const int col = x.col0 + c;
+            const float bv = col < e.c_dst ? e.bias[col] : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * c), "f"(bv) : "memory");
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (x.n_iters > 0) {
+          mbar_wait(tmem_full_bar(as), aph);
+          tc_fence_after();
+        }
+        trc.ev(11, t);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * ACC_COLS);
+        const int r_in = e.pair_sum ? (m >> 1) : m;      // my row inside pre / mask / output sub-tiles
+        const bool writer = !e.pair_sum || (lane & 1) == 0;
+#pragma unroll 1
+        for (int s = 0; s < n_sub; ++s, ++q) {
+          const int buf = q & 1;
+          float v[32];
+          if (x.n_iters > 0) {
+            tmem_ld16(t_addr + (uint32_t)(s * SUB), *reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_ld16(t_addr + (uint32_t)(s * SUB + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (s == n_sub - 1 && x.n_iters > 0) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+          }
+          if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 bq;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
+                           : "r"(bias_base + 4u * (s * SUB + i)) : "memory");
+              v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+            }
+          }
+          if (e.pair_sum) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+          }
+          trc.ev(20, s);
+          if (e.n_in > 0) {
+            mbar_wait(in_bar(buf), (q >> 1) & 1);
+            trc.ev(21, s);
+            int i = 0;
+            if (e.has_pre) {
+              const uint32_t sl = in_slot(buf, i++);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float t8[8]; unpack8(lds128(sl + sw64(r_in, j)), t8);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[8 * j + u] += t8[u];
+              }
+            }
+            if (e.has_mask) {
+              const uint32_t sl = in_slot(buf, i++);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float t8[8]; unpack8(lds128(sl + sw64(r_in, j)), t8);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[8 * j + u] *= (t8[u] > 0.f ? 1.f : e.mask_slope);
+              }
+            }
+            if (e.has_post) {
+              const uint32_t sl = in_slot(buf, i++);
+              const int rp = r_in >> e.post_shift;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float t8[8]; unpack8(lds128(sl + sw64(rp, j)), t8);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[8 * j + u] += t8[u];
+              }
+            }
+          }
+          const int obuf = q % 3;
+          if (q >= 3) asm volatile("bar.sync %0, 160;" ::"r"(bar_free(obuf)) : "memory");  // stores of sub-tile q-3 drained
+          trc.ev(23, s);
+          if (writer) {
+            int o = 0;
+            if (e.has_raw) {
+              const uint32_t sl = out_slot(obuf, o++);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sts128(sl + sw64(r_in, j), pack8(&v[8 * j]));
+            }
+            if (e.has_act) {
+              const uint32_t sl = out_slot(obuf, o++);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], e.act_slope * v[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sts128(sl + sw64(r_in, j), pack8(&v[8 * j]));
+            }
+          }
+          fence_proxy_async();
+          asm volatile("bar.arrive %0, 160;" ::"r"(bar_full(obuf)) : "memory");
+          trc.ev(12, s);
+        }
+        if (x.n_iters > 0) ++acc_i;
+      }
+    }
   } else {
-    // ===== epilogue =====
+    // ===== direct epilogue =====
     const int ew = warp - 2;
     const int sub = warp & 3;        // TMEM sub-partition this warp may read
     const int half = ew >> 2;        // column half of the tile
-    const TcEpi& e = p.e;
     // columns of this warp: chunks of 16, split between the two warps of a sub-partition
     const int n_chunks = p.bn / 16;
     const int c_lo = (half == 0) ? 0 : (n_chunks + 1) / 2, c_hi = (half == 0) ? (n_chunks + 1) / 2 : n_chunks;
@@ -267,11 +522,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const Tile x = decode_tile(p, t);
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
-      const int arow = (x.r0 + sub * 32 + lane) * p.n_res + x.res;  // output row of this thread (before pair_sum)
-      const bool row_ok = arow < p.t_dst && (!e.pair_sum || (lane & 1) == 0);
+      const int arow = out_row(p, x, sub * 32 + lane);  // output row of this thread (before pair_sum)
+      const bool row_ok = arow >= 0 && (!e.pair_sum || (lane & 1) == 0);
       const int orow = e.pair_sum ? (arow >> 1) : arow;
       EpiIn inA, inB;
-      if (c_lo < c_hi) epi_load(e, x.b, x.ph, orow, x.col0 + c_lo * 16, row_ok, inA);
+      if (c_lo < c_hi) epi_load(e, x.b, orow, x.col0 + c_lo * 16, row_ok, inA);
       if (x.n_iters > 0) {
         mbar_wait(tmem_full_bar(as), aph);
         tc_fence_after();
@@ -295,14 +550,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
         }
-        if (row_ok) epi_store(e, x.b, x.ph, orow, col, v, in);
+        if (row_ok) epi_store(e, x.b, orow, col, v, in);
       };
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; c += 2) {
-        if (c + 1 < c_hi) epi_load(e, x.b, x.ph, orow, x.col0 + (c + 1) * 16, row_ok, inB);
+        if (c + 1 < c_hi) epi_load(e, x.b, orow, x.col0 + (c + 1) * 16, row_ok, inB);
         process(c, inA);
         if (c + 1 < c_hi) {
-          if (c + 2 < c_hi) epi_load(e, x.b, x.ph, orow, x.col0 + (c + 2) * 16, row_ok, inA);
+          if (c + 2 < c_hi) epi_load(e, x.b, orow, x.col0 + (c + 2) * 16, row_ok, inA);
           process(c + 1, inB);
         }
       }
@@ -334,14 +589,15 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const uint32_t* elem_strides) {
+                   const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) { set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return STG_ECUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed");
@@ -360,33 +616,43 @@ static int sm_count() {
   return n;
 }
 
-static int pick_bn(int cd_g, int groups) {
-  if (groups > 1) {  // a column tile must not straddle groups
-    if (cd_g % 256 == 0) return 256;
-    if (cd_g % 128 == 0) return 128;
-    if (cd_g <= 256 && cd_g % 16 == 0) return cd_g;
-    return 0;
+// Column-tile width: the widest tile that still leaves about one tile per SM (small layers would otherwise run
+// on a fraction of the chip); a column tile never straddles groups.
+static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
+  if (groups == 1 && (cd_g % 16) != 0) return cd_g <= 16 ? 16 : (cd_g <= 128 ? ((cd_g + 15) / 16) * 16 : 128);
+  static const int env_bn = getenv("STG_BN") ? atoi(getenv("STG_BN")) : 0;  // tuning override
+  if (env_bn > 0 && cd_g % env_bn == 0) return env_bn;
+  int best = 0;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    if (cd_g % bn) continue;
+    if (best != 0 && bn < 128) break;              // narrower than 128 only when nothing wider divides
+    best = bn;
+    if (row_tiles * (cd_g / bn) * groups >= 96) break;
   }
-  if (cd_g <= 16) return 16;
-  if (cd_g <= 256 && (cd_g % 16) == 0) return cd_g;
-  if (cd_g % 256 == 0) return 256;
-  if (cd_g % 192 == 0) return 192;
-  if (cd_g % 128 == 0) return 128;
-  if (cd_g % 64 == 0) return 64;
-  return 128;
+  return best;
+}
+
+static void tile_geometry(const StgConv* d, int* pack, int* nh, int* n_res, int* tiles_m) {
+  *pack = d->phases;
+  *nh = TM / d->phases;
+  *n_res = (d->transposed && d->stride > 1) ? d->stride : 1;
+  *tiles_m = ceil_div(ceil_div(d->t_dst, *n_res), *nh);
 }
 
 bool conv_tc_supported(const StgConv* d) {
   if (d->dtype != STG_BF16) return false;
   if (d->k > STG_MAX_TAPS || d->k < 1) return false;
   if ((d->c_src % 8) != 0) return false;                 // 16-byte global strides for TMA
+  if (d->phases > 64) return false;
   if (d->groups > 1) {
     if ((d->c_src / d->groups) % KC) return false;       // whole K chunks per group (see stg_tc_pack_groups)
-    if (pick_bn(d->c_dst / d->groups, d->groups) == 0) return false;
+    if (((d->c_dst / d->groups) % 16) != 0) return false;
   }
   if (d->transposed && d->stride > MAX_RES) return false;
   if (d->transposed && d->stride > 1 && d->pair_sum) return false;
-  if (!d->transposed && d->stride > 4) return false;     // A box rows = 64*stride <= 256
+  if (!d->transposed && d->stride > 4) return false;
+  if (!d->transposed && d->stride > 2 && d->phases > 1 && (TM / d->phases) * d->stride > 256) return false;
+  if ((d->pair_sum || d->dup_rows || d->post_shift) && d->phases != 1) return false;
   if (d->pair_sum && (d->t_dst & 1)) return false;
   if (d->add_pre == nullptr && d->mask == nullptr && d->add_post == nullptr && d->y_raw == nullptr && d->y_act == nullptr)
     return false;
@@ -404,19 +670,38 @@ int tc_pack_groups(int c_in, int c_out, int groups) {
   return groups;
 }
 
+// tensor map of an epilogue operand / output: rows of all phases flattened, [B][rows][C]; `dup`: [B][rows][2][C]
+static int epi_map(CUtensorMap* m, const void* base, int C, int64_t rows, int B, int box_rows, bool dup) {
+  if (dup) {
+    const uint64_t dims[4] = {(uint64_t)C, 2, (uint64_t)rows, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)rows * C * 4};
+    const uint32_t box[4] = {SUB, 1, (uint32_t)box_rows, 1};
+    return make_tmap_bf16(m, base, 4, dims, strides, box, nullptr, 64);
+  }
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)rows, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)rows * C * 2};
+  const uint32_t box[3] = {SUB, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box, nullptr, 64);
+}
+
+static long long* g_trace = nullptr;
+void conv_tc_set_trace(long long* buf) { g_trace = buf; }
+
 int conv_tc(const StgConv* d, cudaStream_t s) {
   if (!conv_tc_supported(d)) return STG_EUNSUPPORTED;
   TcP p;
+  p.trace = g_trace;
   p.phases = d->phases; p.t_dst = d->t_dst; p.stride = d->transposed ? 1 : d->stride;
   p.cs_g = d->c_src / d->groups; p.cd_g = d->c_dst / d->groups;
   p.k_chunks = ceil_div(p.cs_g, KC);
-  p.bn = pick_bn(p.cd_g, d->groups);
-  p.a_boxes = (p.stride * TM <= 256) ? 1 : 2;
-  p.tmem_cols = p.bn <= 128 ? 256 : 512;  // two accumulator buffers ACC_COLS apart (bn <= 32: second one still at +256)
-  p.tmem_cols = 512;
-  int max_taps = 0;
-  if (d->transposed && d->stride > 1) {
-    p.n_res = d->stride;
+  tile_geometry(d, &p.pack, &p.nh, &p.n_res, &p.tiles_m);
+  p.mrows = p.nh * p.pack;
+  p.bn = pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m);
+  if (p.bn <= 0) return STG_EUNSUPPORTED;
+  p.a_boxes = (p.nh * p.stride <= 256) ? 1 : 2;
+  if (p.a_boxes == 2 && (p.pack != 1 || (p.nh & 1))) return STG_EUNSUPPORTED;
+  p.tmem_cols = 512;  // two accumulator buffers ACC_COLS apart
+  if (p.n_res > 1) {
     int n = 0;
     for (int r = 0; r < p.n_res; ++r) {
       p.res_first[r] = n;
@@ -427,42 +712,49 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
         p.tap_w[n] = j;
         ++n;
       }
-      if (n - p.res_first[r] > max_taps) max_taps = n - p.res_first[r];
     }
     p.res_first[p.n_res] = n;
-    p.tiles_m = ceil_div(ceil_div(d->t_dst, p.n_res), TM);
   } else {
-    p.n_res = 1;
     for (int j = 0; j < d->k; ++j) {
       p.tap_off[j] = d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad);
       p.tap_w[j] = j;
     }
     p.res_first[0] = 0; p.res_first[1] = d->k;
-    max_taps = d->k;
-    p.tiles_m = ceil_div(d->t_dst, TM);
   }
-  const int stage_bytes = A_BYTES + p.bn * KC * 2;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 1) stages = 1;
-  p.stages = stages;
-  (void)max_taps;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 6);
 
   TcEpi& e = p.e;
-  e.phases = d->phases; e.t_out = d->pair_sum ? d->t_dst / 2 : d->t_dst; e.c_dst = d->c_dst;
+  const int rows_per_phase = d->pair_sum ? d->t_dst / 2 : d->t_dst;
+  e.rows = rows_per_phase * d->phases; e.c_dst = d->c_dst;
   e.post_shift = d->post_shift; e.mask_mode = d->mask_mode; e.act = d->act; e.dup_rows = d->dup_rows;
   e.out_f32 = d->out_f32; e.pair_sum = d->pair_sum; e.bias = d->bias;
   e.add_pre = static_cast<const bf16*>(d->add_pre); e.mask = static_cast<const bf16*>(d->mask);
   e.add_post = static_cast<const bf16*>(d->add_post); e.y_raw = d->y_raw; e.y_act = d->y_act;
+  e.has_pre = d->add_pre != nullptr; e.has_mask = d->mask != nullptr; e.has_post = d->add_post != nullptr;
+  e.has_raw = d->y_raw != nullptr; e.has_act = d->y_act != nullptr;
+  e.n_in = e.has_pre + e.has_mask + e.has_post; e.n_out = e.has_raw + e.has_act;
+  e.act_slope = d->act == STG_ACT_RELU ? 0.f : (d->act == STG_ACT_LEAKY ? 0.1f : 1.f);
+  e.mask_slope = d->mask_mode == STG_ACT_RELU ? 0.f : (d->mask_mode == STG_ACT_LEAKY ? 0.1f : 1.f);
+  const bool staged = !d->out_f32 && d->act != STG_ACT_TANH && d->mask_mode != STG_ACT_TANH && (d->c_dst % 8) == 0 &&
+                      p.n_res == 1 && (p.bn % SUB) == 0 &&
+                      (!d->post_shift || (rows_per_phase % 2) == 0);
+
+  const int stage_bytes = A_BYTES + p.bn * KC * 2;
+  const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 1024 : 0;
+  int stages = (212 * 1024 - epi_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return STG_EUNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 8);
 
   CUtensorMap tmA, tmW;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
   {
     const uint64_t C = d->c_src, P = d->phases, T = d->t_src, B = d->n_samples;
-    const uint64_t dims[4] = {C, T, P, B};
-    const uint64_t strides[3] = {P * C * 2, C * 2, T * P * C * 2};
-    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)((TM / p.a_boxes) * p.stride), 1, 1};
-    const uint32_t es[4] = {1, (uint32_t)p.stride, 1, 1};
+    const uint64_t dims[4] = {C, P, T, B};
+    const uint64_t strides[3] = {C * 2, P * C * 2, T * P * C * 2};
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.pack, (uint32_t)((p.nh / p.a_boxes) * p.stride), 1};
+    const uint32_t es[4] = {1, 1, (uint32_t)p.stride, 1};
     int r = make_tmap_bf16(&tmA, d->src, 4, dims, strides, box, es);
     if (r) return r;
   }
@@ -474,17 +766,37 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr);
     if (r) return r;
   }
+  if (staged) {
+    const int box_rows = d->pair_sum ? 64 : p.mrows;
+    int r = 0;
+    if (e.has_pre) r |= epi_map(&em.pre, d->add_pre, d->c_dst, e.rows, d->n_samples, box_rows, false);
+    if (e.has_mask) r |= epi_map(&em.mask, d->mask, d->c_dst, e.rows, d->n_samples, box_rows, false);
+    if (e.has_post) r |= epi_map(&em.post, d->add_post, d->c_dst, e.rows >> d->post_shift, d->n_samples, box_rows >> d->post_shift, false);
+    if (e.has_raw) r |= epi_map(&em.raw, d->y_raw, d->c_dst, e.rows, d->n_samples, box_rows, false);
+    if (e.has_act) {
+      if (d->dup_rows) r |= epi_map(&em.act, d->y_act, d->c_dst, e.rows, d->n_samples, box_rows, true);
+      else {  // 4-D with a unit "dup" dimension so the kernel issues the same instruction either way
+        const uint64_t dims[4] = {(uint64_t)d->c_dst, 1, (uint64_t)e.rows, (uint64_t)d->n_samples};
+        const uint64_t strides[3] = {(uint64_t)d->c_dst * 2, (uint64_t)d->c_dst * 2, (uint64_t)e.rows * d->c_dst * 2};
+        const uint32_t box[4] = {SUB, 1, (uint32_t)box_rows, 1};
+        r |= make_tmap_bf16(&em.act, d->y_act, 4, dims, strides, box, nullptr, 64);
+      }
+    }
+    if (r) return STG_ECUDA;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   p.tiles_n = ceil_div(d->c_dst, p.bn);
-  const int64_t n_tiles = (int64_t)d->n_samples * d->phases * p.n_res * p.tiles_m * p.tiles_n;
+  const int64_t n_tiles = (int64_t)d->n_samples * p.n_res * p.tiles_m * p.tiles_n;
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(tmA, tmW, p);
+  if (staged) conv_tc_kernel<true><<<grid, 224, smem, s>>>(tmA, tmW, em, p);
+  else conv_tc_kernel<false><<<grid, 320, smem, s>>>(tmA, tmW, em, p);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
