@@ -144,6 +144,32 @@ int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, in
 int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* w_orig, const float* u, const float* v,
                               const float* sigma, int c_out, int cin_g, int k, int groups, float* dw_orig, int accumulate,
                               float* scratch, stg_stream_t stream);
+/*
+ * Multi-tensor forms: ONE launch sequence for all weight-normed convs of a network (45 in G, 31 in small D; the
+ * per-layer calls above are launch-bound).  `items` is a DEVICE array of n_items entries ordered by row0 / tile0:
+ *   row0  = running sum of c_out (one block per output channel), total_rows = its end value
+ *   tile0 = running sum of pack tiles: k * pack_groups * ceil(c_out/pg/32) * ceil(c_in/pg/32), or for
+ *           STG_PACK_UNFOLD ceil(c_out/32) * ceil(roundup8(k*c_in)/32); total_tiles = its end value
+ * stg_weightnorm_fold_multi fills wf / wd / scale of every item; stg_weightnorm_fold_bwd_multi turns every
+ * item's dw (layout dw_ld / dw_span, see stg_wgrad_layout) into dv / dg.
+ */
+typedef struct StgFoldItem {
+  const float* v;      /* [c_out][cin_g][k] */
+  const float* g;      /* [c_out] */
+  void* wf;
+  void* wd;            /* or NULL */
+  float* scale;        /* [c_out] */
+  const float* dw;     /* backward only */
+  float* dv;
+  float* dg;
+  int32_t c_out, cin_g, k, groups, pg, flags, dw_ld, dw_span;
+  int32_t row0, tile0;
+} StgFoldItem;
+int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, int total_rows, int total_tiles, int dtype,
+                              stg_stream_t stream);
+int stg_weightnorm_fold_bwd_multi(const StgFoldItem* items, int n_items, int total_rows, int accumulate,
+                                  stg_stream_t stream);
+
 /* Number of groups the tcgen05 engine wants the packs of a (c_in, c_out, groups) convolution in (== groups
  * when no widening is needed or possible). */
 int stg_tc_pack_groups(int c_in, int c_out, int groups);

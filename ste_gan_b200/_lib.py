@@ -33,6 +33,11 @@ class StgWgrad(C.Structure):
         "stride", "pad")] + [(n, C.c_void_p) for n in ("x", "dy", "dw", "dbias")]
 
 
+class StgFoldItem(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("v", "g", "wf", "wd", "scale", "dw", "dv", "dg")] + [
+        (n, C.c_int32) for n in ("c_out", "cin_g", "k", "groups", "pg", "flags", "dw_ld", "dw_span", "row0", "tile0")]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _SIGS = {
     "stg_conv": [C.POINTER(StgConv), _P],
@@ -45,6 +50,8 @@ _SIGS = {
     "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "stg_spectralnorm_fold_bwd": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
     "stg_tc_pack_groups": [_I, _I, _I],
+    "stg_weightnorm_fold_multi": [_P, _I, _I, _I, _I, _P],
+    "stg_weightnorm_fold_bwd_multi": [_P, _I, _I, _I, _P],
     "stg_debug_set_trace": [_P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

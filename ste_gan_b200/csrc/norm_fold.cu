@@ -197,6 +197,118 @@ __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ d
   }
 }
 
+// ---------------------------------------------------------------------------------------------- multi-tensor
+// One launch for ALL weight-normed convs of a network: the per-layer kernels above are 5-10 us each and a
+// network has 45 (G) / 31 (D) of them, i.e. more launch gaps than work.  `items` is a device-resident table.
+__device__ __forceinline__ int find_item(const StgFoldItem* __restrict__ items, int n, int idx, bool by_tile) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int first = by_tile ? items[mid].tile0 : items[mid].row0;
+    if (first <= idx) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) wn_scale_multi_kernel(const StgFoldItem* __restrict__ items, int n) {
+  __shared__ float red[32];
+  const int it = find_item(items, n, blockIdx.x, false);
+  const StgFoldItem d = items[it];
+  const int co = blockIdx.x - d.row0, len = d.cin_g * d.k;
+  const float* row = d.v + (int64_t)co * len;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) { const float x = row[i]; s = fmaf(x, x, s); }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) d.scale[co] = d.g[co] / sqrtf(s);
+}
+
+// one 32 x 32 (co' x ci') tile of one tap of one pack group: writes the wf tile and the transposed wd tile
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __restrict__ items, int n) {
+  __shared__ float tile[32][33];
+  const int it = find_item(items, n, blockIdx.x, true);
+  const StgFoldItem d = items[it];
+  int t = blockIdx.x - d.tile0;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  T* wf = static_cast<T*>(d.wf);
+  T* wd = static_cast<T*>(d.wd);
+  if (d.flags & STG_PACK_UNFOLD) {
+    // tiles over (co, q) with q = j*c_in + c in [0, Kp)
+    const int Kp = (d.k * d.cin_g + 7) / 8 * 8, tq = (Kp + 31) / 32;
+    const int co0 = (t / tq) * 32, q0 = (t % tq) * 32;
+    for (int r = ty; r < 32; r += 8) {  // r: co, tx: q
+      const int co = co0 + r, q = q0 + tx;
+      float w = 0.f;
+      if (co < d.c_out && q < d.k * d.cin_g) {
+        const int j = q / d.cin_g, c = q - j * d.cin_g;
+        w = d.v[((int64_t)co * d.cin_g + c) * d.k + j] * d.scale[co];
+      }
+      tile[r][tx] = w;
+      if (wf && co < d.c_out && q < Kp) wf[(int64_t)co * Kp + q] = from_f<T>(w);
+    }
+    __syncthreads();
+    if (wd) {
+      for (int r = ty; r < 32; r += 8) {  // r: q, tx: co
+        const int q = q0 + r, co = co0 + tx;
+        if (q < Kp && co < d.c_out) wd[(int64_t)q * d.c_out + co] = from_f<T>(tile[tx][r]);
+      }
+    }
+    return;
+  }
+  const int pg = d.pg, c_in = d.cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
+  const int tco = (cout_gp + 31) / 32, tci = (cin_gp + 31) / 32;
+  const int ci0 = (t % tci) * 32; t /= tci;
+  const int co0 = (t % tco) * 32; t /= tco;
+  const int j = t % d.k, gp = t / d.k;
+  for (int r = ty; r < 32; r += 8) {  // r: co', tx: ci'
+    const int cop = co0 + r, cip = ci0 + tx;
+    float w = 0.f;
+    if (cop < cout_gp && cip < cin_gp) {
+      const int co = gp * cout_gp + cop, c = gp * cin_gp + cip;
+      const int gc = c / d.cin_g;
+      if (gc == co / cout_g) w = d.v[((int64_t)co * d.cin_g + (c - gc * d.cin_g)) * d.k + j] * d.scale[co];
+      if (wf) wf[((int64_t)j * d.c_out + co) * cin_gp + cip] = from_f<T>(w);
+    }
+    tile[r][tx] = w;
+  }
+  __syncthreads();
+  if (wd) {
+    for (int r = ty; r < 32; r += 8) {  // r: ci', tx: co'
+      const int cip = ci0 + r, cop = co0 + tx;
+      if (cip < cin_gp && cop < cout_gp)
+        wd[((int64_t)j * c_in + gp * cin_gp + cip) * cout_gp + cop] = from_f<T>(tile[tx][r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int accumulate) {
+  __shared__ float red[32];
+  const int it = find_item(items, n_items, blockIdx.x, false);
+  const StgFoldItem d = items[it];
+  const int co = blockIdx.x - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+  const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
+  const float* vr = d.v + (int64_t)co * n;
+  const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const float x = vr[i];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(x, dr[j * span + ci], dot);
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float norm = sqrtf(ss), gg = d.g[co];
+  const float a = gg / norm, bcoef = gg * dot / (norm * ss);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const float val = a * dr[j * span + ci] - bcoef * vr[i];
+    float* o = d.dv + (int64_t)co * n + i;
+    *o = accumulate ? (*o + val) : val;
+  }
+  if (threadIdx.x == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
+}
+
 template <typename T>
 int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, int pg, int flags, T* wf,
                  T* wd, cudaStream_t s) {
@@ -298,6 +410,28 @@ extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span
   sn_bwd_dot_kernel<<<c_out, 256, 0, s>>>(dw, w_orig, cin_g, k, dw_ld, dw_span, c_out / groups, scratch);
   STG_LAUNCH_CHECK();
   sn_bwd_kernel<<<c_out, 256, 0, s>>>(dw, u, v, sigma, scratch, cin_g, k, dw_ld, dw_span, c_out / groups, dw_orig, accumulate);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, int total_rows, int total_tiles, int dtype,
+                                         stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!items || n_items < 1 || total_rows < 1 || total_tiles < 1) return STG_EINVAL;
+  wn_scale_multi_kernel<<<total_rows, 256, 0, s>>>(items, n_items);
+  STG_LAUNCH_CHECK();
+  if (dtype == STG_F32) pack_multi_kernel<float><<<total_tiles, 256, 0, s>>>(items, n_items);
+  else if (dtype == STG_BF16) pack_multi_kernel<bf16><<<total_tiles, 256, 0, s>>>(items, n_items);
+  else return STG_EINVAL;
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_weightnorm_fold_bwd_multi(const StgFoldItem* items, int n_items, int total_rows, int accumulate,
+                                             stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!items || n_items < 1 || total_rows < 1) return STG_EINVAL;
+  wn_bwd_multi_kernel<<<total_rows, 256, 0, s>>>(items, n_items, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

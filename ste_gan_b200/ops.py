@@ -221,6 +221,22 @@ def spectralnorm_fold_bwd(dw: Tensor, w_orig: Tensor, u: Tensor, v: Tensor, sigm
           "stg_spectralnorm_fold_bwd")
 
 
+def fold_table(items: list, device) -> Tensor:
+    """Device-resident StgFoldItem table (uint8 tensor) from a list of _lib.StgFoldItem."""
+    arr = (_lib.StgFoldItem * len(items))(*items)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def weightnorm_fold_multi(table: Tensor, n_items: int, total_rows: int, total_tiles: int, dtype: torch.dtype) -> None:
+    check(_lib.load().stg_weightnorm_fold_multi(_ptr(table), n_items, total_rows, total_tiles, code_of(dtype), _stream()),
+          "stg_weightnorm_fold_multi")
+
+
+def weightnorm_fold_bwd_multi(table: Tensor, n_items: int, total_rows: int, accumulate: bool = True) -> None:
+    check(_lib.load().stg_weightnorm_fold_bwd_multi(_ptr(table), n_items, total_rows, int(accumulate), _stream()),
+          "stg_weightnorm_fold_bwd_multi")
+
+
 def unfold(src: Tensor, *, n_samples: int, phases: int, t_src: int, t_dst: int, channels: int, k: int, dilation: int,
            stride: int, pad: int) -> Tensor:
     """im2col rows [B, t_dst*phases, roundup8(k*C)] of a channels-last (period-view) tensor, same dtype."""

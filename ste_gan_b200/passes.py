@@ -116,6 +116,7 @@ def fold_backward(f: Folded, dw: Tensor) -> None:
 
 class _Workspace:
     """Zero-initialised fp32 arena for packed weight gradients (one memset per pass)."""
+    deferred = False    # weight-norm fold backward runs per layer, right after its wgrad
 
     def __init__(self, folds: Sequence["Folded"], device):
         n = sum(dw_layout(f)[0] for f in folds)
@@ -127,6 +128,95 @@ class _Workspace:
         t = self.buf[self.off:self.off + n]
         self.off += n
         return t
+
+
+class FoldPlan:
+    """Everything the weight-normed convs of ONE network need, at fixed device addresses: packed operands
+    (wf, wd, scale), the fp32 weight-gradient arena, and the device table that lets one launch fold / un-fold all
+    of them (stg_weightnorm_fold_multi / _bwd_multi).  Create it AFTER the parameters and gradients have been
+    re-homed into their flat buffers (trainer.FlatParams): the table stores raw pointers to them.
+    Spectral-norm convs keep their per-forward fold (one power iteration each); they only get gradient scratch here."""
+    deferred = True     # weight-norm fold backward runs once per phase: backward()
+
+    def __init__(self, convs: Sequence, dtype: torch.dtype):
+        from . import _lib
+        self.dtype = dtype
+        self.wn = [c for c in convs if c.norm == "weight_norm"]
+        dev = self.wn[0].bias.device
+        self.device = dev
+        self.folds: Dict[int, Folded] = {}
+        esz = 2 if dtype == torch.bfloat16 else 4
+        metas, n_pack, n_scale, n_dw = [], 0, 0, 0
+        for m in self.wn:
+            pg, unf = pack_mode(m, dtype)
+            cin_g = m.in_channels // m.groups
+            sf, sd = ops._pack_shapes(m.out_channels, cin_g, m.kernel, m.groups, pg, unf)
+            nf = sf[0] * sf[1] * (sf[2] if len(sf) > 2 else 1)
+            nf_al = (nf + 63) // 64 * 64                       # 128-byte aligned packs (TMA base addresses)
+            metas.append((m, pg, unf, sf, sd, nf, nf_al))
+            n_pack += 2 * nf_al; n_scale += (m.out_channels + 3) // 4 * 4
+        self._packs = torch.zeros(n_pack, device=dev, dtype=dtype)
+        self._scales = torch.zeros(n_scale, device=dev, dtype=torch.float32)
+        po = so = 0
+        for (m, pg, unf, sf, sd, nf, nf_al) in metas:
+            wf = self._packs[po:po + nf].view(sf); po += nf_al
+            wd = self._packs[po:po + nf].view(sd); po += nf_al
+            scale = self._scales[so:so + m.out_channels]; so += (m.out_channels + 3) // 4 * 4
+            kp = ops.round_up8(m.kernel * m.in_channels) if unf else 0
+            self.folds[id(m)] = Folded(m, wf, wd, dtype, scale=scale, pg=pg, unfold=unf, kp=kp)
+        # gradient arena (weight-norm convs only; fixed slices)
+        self._dw_off = {}
+        for m in self.wn:
+            n = dw_layout(self.folds[id(m)])[0]
+            self._dw_off[id(m)] = (n_dw, n); n_dw += (n + 3) // 4 * 4
+        self.arena = torch.zeros(n_dw, device=dev, dtype=torch.float32)
+        # device table
+        items, row0, tile0 = [], 0, 0
+        for m in self.wn:
+            f = self.folds[id(m)]
+            cin_g = m.in_channels // m.groups
+            _, ld, span = dw_layout(f)
+            off, n = self._dw_off[id(m)]
+            gv, gg = _grad_of(m.weight_v), _grad_of(m.weight_g)
+            items.append(_lib.StgFoldItem(
+                v=m.weight_v.data.data_ptr(), g=m.weight_g.data.data_ptr(), wf=f.wf.data_ptr(), wd=f.wd.data_ptr(),
+                scale=f.scale.data_ptr(), dw=self.arena[off:off + n].data_ptr(), dv=gv.data_ptr(), dg=gg.data_ptr(),
+                c_out=m.out_channels, cin_g=cin_g, k=m.kernel, groups=m.groups, pg=f.pg,
+                flags=_lib.PACK_UNFOLD if f.unfold else 0, dw_ld=ld, dw_span=span, row0=row0, tile0=tile0))
+            row0 += m.out_channels
+            if f.unfold:
+                tile0 += -(-m.out_channels // 32) * -(-f.kp // 32)
+            else:
+                tile0 += m.kernel * f.pg * -(-(m.out_channels // f.pg) // 32) * -(-(m.in_channels // f.pg) // 32)
+        self.n_items, self.total_rows, self.total_tiles = len(items), row0, tile0
+        self.table = ops.fold_table(items, dev)
+        self._ptrs = [(p.data_ptr(), p.grad.data_ptr()) for m in self.wn for p in (m.weight_v, m.weight_g)]
+
+    def _check_ptrs(self) -> None:
+        cur = [(p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0) for m in self.wn for p in (m.weight_v, m.weight_g)]
+        if cur != self._ptrs:
+            raise RuntimeError("FoldPlan: parameter / gradient storage moved after the plan was built")
+
+    def fold(self) -> Dict[int, Folded]:
+        """Re-parametrise every weight-normed conv from the current weights (2 launches)."""
+        self._check_ptrs()
+        ops.weightnorm_fold_multi(self.table, self.n_items, self.total_rows, self.total_tiles, self.dtype)
+        return self.folds
+
+    # -- gradient arena (the _Workspace interface of _wgrad) -------------------------------------------
+    def zero(self) -> None:
+        self.arena.zero_()
+
+    def take(self, f: Folded) -> Tensor:
+        ent = self._dw_off.get(id(f.mod))
+        if ent is None:                                   # spectral-norm conv: scratch per use
+            return torch.zeros(dw_layout(f)[0], device=self.device, dtype=torch.float32)
+        return self.arena[ent[0]:ent[0] + ent[1]]
+
+    def backward(self) -> None:
+        """dv, dg += fold-backward of everything accumulated in the arena since zero() (1 launch)."""
+        self._check_ptrs()
+        ops.weightnorm_fold_bwd_multi(self.table, self.n_items, self.total_rows, True)
 
 
 def unfold_input(f: Folded, src: Tensor, B: int, t_src: int, phases: int = 1) -> Tensor:
@@ -187,7 +277,8 @@ def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _W
     else:
         ops.wgrad(x, dy, dw, _grad_of(m.bias), n_samples=B, phases=phases, t_in=t_x, t_out=t_dy, c_in=m.in_channels,
                   c_out=m.out_channels, groups=m.groups, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad)
-    fold_backward(f, dw)
+    if not (ws.deferred and m.norm == "weight_norm"):
+        fold_backward(f, dw)
 
 
 # --------------------------------------------------------------------------------------
@@ -244,7 +335,9 @@ def gblock_bwd(blk, folds: Dict[int, Folded], s: dict, dy: Tensor, B: int, ws: _
                   out_f32=out_f32)
 
 
-def fold_generator(model, dtype: torch.dtype, want_dgrad: bool = True) -> Dict[int, Folded]:
+def fold_generator(model, dtype: torch.dtype, want_dgrad: bool = True, plan: Optional[FoldPlan] = None) -> Dict[int, Folded]:
+    if plan is not None:
+        return plan.fold()
     return {id(c): fold(c, dtype, want_dgrad=want_dgrad) for c in generator_convs(model)}
 
 
@@ -310,11 +403,16 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
     return x_pred, ctx
 
 
-def generator_backward(model, ctx: GenCtx, dx_pred: Tensor) -> None:
+def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
-    dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output."""
+    dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output.  With a FoldPlan the packed weight gradients go to
+    its arena and the weight-norm backward of all 45 convs is one launch at the end."""
     B, dtype, folds = ctx.B, ctx.dtype, ctx.folds
-    ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
+    if plan is not None:
+        plan.zero()
+        ws = plan
+    else:
+        ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
     blocks = list(model.gblocks)[1:]
     t = ctx.t_out
     # tanh' from the output, then last_conv
@@ -337,6 +435,8 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor) -> None:
             # [units | emb0 | emb1]: slice copies keep the kernel's contiguous-tail contract
             ops.embed_concat_bwd(dx0[:, :, :off + d0].contiguous(), ctx.ids[0], off, _grad_of(ctx.tables[0]))
             ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
+    if plan is not None:
+        plan.backward()
 
 
 # --------------------------------------------------------------------------------------
@@ -355,10 +455,18 @@ def discriminator_convs(model) -> List:
 
 def fold_discriminator(model, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True,
                        reuse: Optional[Dict[int, Folded]] = None,
-                       persist: Optional[Dict[int, Folded]] = None) -> Dict[int, Folded]:
+                       persist: Optional[Dict[int, Folded]] = None,
+                       plan: Optional[FoldPlan] = None, refold: bool = True) -> Dict[int, Folded]:
     """Fold every discriminator conv.  Weight-norm folds depend on the weights only and may be
     reused between forwards (`reuse`); spectral-norm layers are ALWAYS re-folded because every
     training-mode forward of the reference runs one more power iteration (conv.py:94,101)."""
+    if plan is not None:
+        # weight-norm convs: one multi-tensor launch (when the weights changed), spectral-norm convs one by one
+        out = dict(plan.fold() if refold else plan.folds)
+        for c in discriminator_convs(model):
+            if c.norm != "weight_norm":
+                out[id(c)] = fold(c, dtype, training=training, want_dgrad=want_dgrad)
+        return out
     out = {}
     for c in discriminator_convs(model):
         if reuse is not None and c.norm == "weight_norm" and id(c) in reuse:
@@ -420,14 +528,17 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
 
 def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tensor]],
                            dfmaps: Optional[Sequence[Sequence[Optional[Tensor]]]] = None, want_input_grad: bool = False,
-                           want_weight_grad: bool = True) -> Optional[Tensor]:
+                           want_weight_grad: bool = True, plan: Optional[FoldPlan] = None) -> Optional[Tensor]:
     """Backward through one discriminator forward.
     dlogits[d]: gradient w.r.t. the logits of sub-discriminator d (`dtype`, same shape) or None;
     dfmaps[d][j]: gradient w.r.t. feature map j (`dtype`) or None.
     Returns d/dx fp32 [B,T,C] when want_input_grad."""
     B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
     dev = ctx.subs[0]["inputs"][0].device
-    ws = _Workspace([folds[id(c)] for c in discriminator_convs(model)], dev) if want_weight_grad else None
+    if plan is not None and want_weight_grad:
+        ws = plan                                 # caller zeroes the arena and runs plan.backward() after its passes
+    else:
+        ws = _Workspace([folds[id(c)] for c in discriminator_convs(model)], dev) if want_weight_grad else None
     dx = torch.zeros((B, T, Cc), device=dev, dtype=torch.float32) if want_input_grad else None
     scale_grads = []                          # (t_in, d/d x_scale) for the multi-scale chain
     for di, sub in enumerate(ctx.subs):

@@ -75,6 +75,10 @@ class GanTrainer:
         self.lr, self.w_td, self.w_fm = lr, w_td, w_fm
         self.use_adv, self.use_td, self.use_fm = loss_adversarial, loss_multi_td, loss_feat_match
         self.G, self.D = FlatParams(net_g), FlatParams(net_d)
+        # packed operands, gradient arenas and multi-tensor fold tables at fixed addresses (after the re-homing above)
+        self.g_plan = passes.FoldPlan(passes.generator_convs(net_g), self.dtype)
+        self.d_plan = passes.FoldPlan(passes.discriminator_convs(net_d), self.dtype)
+        self._d_folded = False                  # d_plan packs match the current D weights
         self.reducer = GradReducer(group)
         dev = self.G.flat.device
         self.device = dev
@@ -91,13 +95,14 @@ class GanTrainer:
         self.slots.zero_()
         self.G.zero_grad(); self.D.zero_grad()
         self._gctx = None
-        x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True)
+        x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
         self.x_pred, self._gctx = x_pred, gctx
         if not self.use_adv:
             return
-        f1 = passes.fold_discriminator(self.net_d, dt, training=True, reuse=self.d_folds)
+        f1 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=not self._d_folded)
+        self._d_folded = True
         res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1)
-        f2 = passes.fold_discriminator(self.net_d, dt, training=True, reuse=f1)
+        f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
         res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         dl_f, dl_r = [], []
@@ -107,8 +112,12 @@ class GanTrainer:
             ops.mse_const(fm_f[-1], 0.0, self.slots[0:1], 1.0, gf)          # train.py:193-194
             ops.mse_const(fm_r[-1], 1.0, self.slots[0:1], 1.0, gr)          # train.py:195-196
             dl_f.append(gf); dl_r.append(gr)
-        passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True)
-        passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True)
+        # both passes accumulate their packed weight gradients in the plan's arena; the weight-norm backward is
+        # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
+        self.d_plan.zero()
+        passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
+        passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
+        self.d_plan.backward()
 
     def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
         dt = self.dtype
@@ -117,9 +126,10 @@ class GanTrainer:
         if self.use_adv:
             if update_d:
                 self.D.adamw(self.lr, grad_scale=self.reducer.grad_scale)   # train.py:199
-            f3 = passes.fold_discriminator(self.net_d, dt, training=True, persist=self._d_persist)
+            f3 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=update_d or not self._d_folded)
+            self._d_folded = True
             res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3)
-            f4 = passes.fold_discriminator(self.net_d, dt, training=True, reuse=f3)
+            f4 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
             res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4)
             self.d_folds = f4
             dlog, dfm = [], []
@@ -138,7 +148,7 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        passes.generator_backward(self.net_g, self._gctx, dx_pred)
+        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan)
         self._gctx = None
 
     def _phase_opt_g(self) -> None:
