@@ -40,6 +40,7 @@ extern "C" int stg_conv(const StgConv* d, stg_stream_t stream) {
     case STG_ENGINE_SIMT: return conv_simt(d, s);
     case STG_ENGINE_TCGEN05: return conv_tc(d, s);
     case STG_ENGINE_AUTO:
+      if (conv_c1_supported(d)) return conv_c1(d, s);   // 1-channel logits layers: matrix-vector kernels
       if (conv_tc_supported(d)) return conv_tc(d, s);
       return conv_simt(d, s);
     default: return STG_EINVAL;
@@ -61,6 +62,7 @@ extern "C" int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream) {
   int r = STG_OK;
   if (d->dw) {
     // the tcgen05 engine folds the bias gradient into the same kernel (one extra MMA against an all-ones operand)
+    if (d->engine == STG_ENGINE_AUTO && wgrad_c1_supported(d)) return wgrad_c1(d, s);   // incl. the bias gradient
     if (d->engine == STG_ENGINE_TCGEN05) return wgrad_tc(d, s);
     if (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d)) return wgrad_tc(d, s);
     if (d->engine == STG_ENGINE_AUTO || d->engine == STG_ENGINE_SIMT) r = wgrad_simt(d, s);
@@ -73,7 +75,8 @@ extern "C" int stg_conv_wgrad(const StgWgrad* d, stg_stream_t stream) {
 
 extern "C" int stg_wgrad_layout(const StgWgrad* d, int* ld, int* span) {
   if (!d || !ld || !span || d->groups < 1 || d->c_in % d->groups) return STG_EINVAL;
-  const bool tc = d->engine == STG_ENGINE_TCGEN05 || (d->engine == STG_ENGINE_AUTO && wgrad_tc_supported(d));
+  const bool tc = d->engine == STG_ENGINE_TCGEN05 ||
+                  (d->engine == STG_ENGINE_AUTO && !wgrad_c1_supported(d) && wgrad_tc_supported(d));
   if (tc) { wgrad_tc_layout(d, ld, span); return STG_OK; }
   *span = d->c_in / d->groups;
   *ld = d->k * *span;

@@ -103,6 +103,10 @@ int wgrad_simt(const StgWgrad* d, cudaStream_t s);
 int wgrad_tc(const StgWgrad* d, cudaStream_t s);
 bool wgrad_tc_supported(const StgWgrad* d);
 int tc_pack_groups(int c_in, int c_out, int groups);
+bool conv_c1_supported(const StgConv* d);
+int conv_c1(const StgConv* d, cudaStream_t s);
+bool wgrad_c1_supported(const StgWgrad* d);
+int wgrad_c1(const StgWgrad* d, cudaStream_t s);
 void conv_tc_set_trace(long long* buf);
 void wgrad_tc_layout(const StgWgrad* d, int* ld, int* span);
 

@@ -200,6 +200,35 @@ def test_tcgen05_wgrad(case):
     assert rel_l2(db, gb_ref) < 1e-4
 
 
+@pytest.mark.parametrize("geom", [(2, 1, 50, 128, 3), (2, 3, 61, 512, 3), (3, 11, 18, 512, 3), (2, 1, 100, 1024, 3), (2, 2, 37, 1024, 5)],
+                         ids=["s_c128", "p3_c512", "p11_c512", "s_c1024", "p2_k5"])
+def test_logits_layer_kernels(geom):
+    """C -> 1 `output` layers (matrix-vector kernels picked by ENGINE_AUTO): forward, masked data-gradient with the
+    feature-matching term added, weight + bias gradient."""
+    from ste_gan_b200 import ops
+    B, p, T, ci, k = geom
+    pad = (k - 1) // 2
+    case = ("o", B, p, T, ci, 1, k, 1, 1, pad, 1)
+    x, w, bias, dy, To = make_case(case, seed=12)
+    x, w, dy = _bf(x), _bf(w), _bf(dy)
+    y_ref, gx_ref, gw_ref, gb_ref = reference(case, x, w, bias, dy)
+    dev, bf = "cuda", torch.bfloat16
+    y = torch.empty(B, To * p, 1, device=dev, dtype=torch.float32)
+    ops.conv(x.to(dev, bf), pack_fwd(w).to(dev, bf), n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=1, k=k,
+             pad=pad, bias=bias.to(dev), y_raw=y)
+    assert rel_l2(y.cpu(), y_ref) < 1e-4
+    gen = torch.Generator().manual_seed(5)
+    m = _bf(torch.randn(B, T * p, ci, generator=gen)); pre = _bf(torch.randn(B, T * p, ci, generator=gen) * 0.1)
+    dx = torch.empty(B, T * p, ci, device=dev, dtype=bf)
+    ops.conv(dy.to(dev, bf), pack_dgrad(w, 1).to(dev, bf), n_samples=B, phases=p, t_src=To, t_dst=T, c_src=1, c_dst=ci, k=k,
+             pad=pad, transposed=True, mask=m.to(dev, bf), mask_mode=ops.ACT_LEAKY, add_pre=pre.to(dev, bf), y_raw=dx)
+    ref = (gx_ref + pre.double()) * torch.where(m > 0, 1.0, 0.1).double()
+    assert rel_l2(dx.float().cpu(), ref) < 4e-3        # bf16 output rounding
+    dw = torch.zeros(1, k, ci, device=dev); db = torch.zeros(1, device=dev)
+    ops.wgrad(x.to(dev, bf), dy.to(dev, bf), dw, db, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=1, k=k, pad=pad)
+    assert rel_l2(dw.cpu(), gw_ref) < 1e-4 and rel_l2(db.cpu(), gb_ref) < 1e-4
+
+
 @pytest.mark.parametrize("engine_dtype", [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)],
                          ids=["simt-f32", "simt-bf16", "tc-bf16"])
 def test_fused_epilogue(engine_dtype):
