@@ -223,13 +223,18 @@ def run_ours(args):
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": tr.slots.numel() * 4}
 
     # ---- roofline: instrumented eager step (every conv / wgrad launch bracketed by CUDA events)
+    # (every rank runs these steps - they contain the gradient all-reduce - but only rank 0 keeps the numbers)
     roofline, by_kernel = None, []
+    # A 60 ms device-side sleep ahead of each instrumented step lets the host enqueue the whole step before the GPU
+    # starts it, so the event pairs time back-to-back kernels rather than host launch gaps.
+    tr.step(*devb[0])
+    ops.profile = []
+    for j in (1, 2):
+        torch.cuda._sleep(int(0.06 * 1.9e9))
+        tr.step(*devb[j])
+    torch.cuda.synchronize()
+    prof, ops.profile = ops.profile, None
     if rank == 0:
-        tr.step(*devb[0])
-        ops.profile = []
-        tr.step(*devb[1]); tr.step(*devb[2])
-        torch.cuda.synchronize()
-        prof, ops.profile = ops.profile, None
         groups = {}
         for p in prof:
             key = ("conv_tc_kernel" if p["kind"] != "wgrad" else "wgrad_tc_kernel") if p["engine"] == "tcgen05" else \
