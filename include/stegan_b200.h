@@ -251,6 +251,9 @@ int stg_wgrad_tc_supported(const StgWgrad* d);
 /* debug: device buffer of 1 + 3*4000 int64 that receives a (tag, value, globaltimer ns) timeline of CTA 0 of every
  * following tcgen05 stg_conv launch (NULL switches it off). */
 int stg_debug_set_trace(void* buf);
+/* debug hardware probe (csrc/debug_probe.cu): one 128x64x64 MMA whose A operand starts `shift` rows into a TMA-loaded
+ * [rows_a][64] bf16 tile, descriptor base-offset field = base_off; out = float [128][64]. */
+int stg_debug_rowshift(const void* x, const void* w, int rows_a, int shift, int base_off, float* out, stg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ _SIGS = {
     "stg_weightnorm_fold_multi": [_P, _I, _I, _I, _I, _P],
     "stg_weightnorm_fold_bwd_multi": [_P, _I, _I, _I, _P],
     "stg_debug_set_trace": [_P],
+    "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_embed_concat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],

@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libstegan_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-cudart", "shared"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-cudart", "shared"] + os.environ.get("STG_NVCC_EXTRA", "").split()
 
 
 def _sources():

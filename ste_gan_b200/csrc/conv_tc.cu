@@ -28,6 +28,7 @@
 //           wavefront per 16 bytes and made the epilogue, not the MMAs, the critical path).
 //   DIRECT  (fp32 outputs, 1-channel logits, strided data-gradients): 8 warps, row-per-thread global
 //           loads/stores with the next chunk's operands prefetched.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -58,21 +59,36 @@ struct TcEpi {
   void* y_act;
 };
 
+// Per-group / per-tap tables, read with warp-uniform indices (uniform constant loads) by the producer / MMA warps.
+struct TapTables {
+  short g_off[STG_MAX_TAPS];   // source-row offset of the group's window (its rows start at h0*stride + g_off)
+  short tap_shift[STG_MAX_TAPS];   // h-row shift of the tap inside its group's window
+  unsigned char g_tfirst[STG_MAX_TAPS], g_ntaps[STG_MAX_TAPS];  // taps of group g: [g_tfirst, g_tfirst + g_ntaps)
+  unsigned char tap_w[STG_MAX_TAPS];  // tap index into the packed weights
+};
+
 struct TcP {
   int phases, t_dst, stride, k_chunks, bn, stages, a_boxes, tmem_cols;
   int pack, nh, mrows;     // phases packed per tile, h rows per tile, used accumulator rows = nh * pack
   int cs_g, cd_g;          // source / destination channels per (packed) group
   int n_res, tiles_m;      // output-row residues (1 unless transposed && stride > 1), row tiles per residue
   int tiles_n, n_tiles;    // column tiles, total tiles = B * n_res * tiles_m * tiles_n
-  int res_first[MAX_RES + 1];  // taps of residue r: [res_first[r], res_first[r+1])
-  int tap_off[STG_MAX_TAPS];   // source-row offset of the tap (rows of the A tile start at h0*stride + tap_off)
-  int tap_w[STG_MAX_TAPS];     // tap index into the packed weights
+  // Tap groups ("A windows"): the taps of one group read row-shifted views of ONE TMA-loaded window of
+  // nh + max_shift h rows (UMMA descriptors take any row offset into a 128B-swizzled tile - the swizzle is a
+  // function of the shared-memory address, tools/rowshift_probe.py), so a k-tap conv loads its activations
+  // once per group instead of once per tap.  One pipeline stage = (group, 64-channel chunk).
+  int hb, a_bytes, max_ntaps;  // h rows per A box, bytes reserved for the window (1024-aligned), taps per stage slot
+  int res_gfirst[MAX_RES + 1]; // groups of residue r: [res_gfirst[r], res_gfirst[r+1])
+  TapTables tt;
   long long* trace;            // debug timeline (stg_debug_set_trace) or nullptr
   TcEpi e;
 };
 
+constexpr int MAX_STAGED_RES = 4;   // residue classes the staged epilogue has tensor maps for
+// Epilogue tensors as 4-D maps (C, phase, h, B) - per residue class of a strided data-gradient: class r holds the
+// rows h = h'*s + r, i.e. base + r rows, h stride s rows, extent ceil((T - r)/s) - and y_act as (C, dup, h, B).
 struct EpiMaps {
-  CUtensorMap pre, mask, post, raw, act;
+  CUtensorMap pre[MAX_STAGED_RES], mask[MAX_STAGED_RES], raw[MAX_STAGED_RES], post, act;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* o) {
@@ -146,7 +162,7 @@ struct Tracer {
 
 // ---------------------------------------------------------------------------------------------- tiles
 struct Tile {
-  int b, res, h0, col0, ch0, tap0, n_iters;
+  int b, res, h0, col0, ch0, g0, n_iters;
 };
 __device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
   Tile x;
@@ -158,8 +174,8 @@ __device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
   x.h0 = tm * p.nh;
   x.col0 = tn * p.bn;
   x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
-  x.tap0 = p.res_first[x.res];
-  x.n_iters = (p.res_first[x.res + 1] - x.tap0) * p.k_chunks;
+  x.g0 = p.res_gfirst[x.res];
+  x.n_iters = (p.res_gfirst[x.res + 1] - x.g0) * p.k_chunks;
   return x;
 }
 // accumulator row m of a tile -> flat output row of the sample (before pair_sum), or -1
@@ -243,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // 1024-byte alignment for SWIZZLE_128B tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_bytes = p.bn * KC * 2;
-  const int stage_bytes = A_BYTES + b_bytes;
+  const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
   const TcEpi& e = p.e;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: 2*(n_in+n_out) slots + bias
   const uint32_t bias_base = epi_base + (kStaged ? (2 * e.n_in + 3 * e.n_out) * SLOT : 0);
@@ -274,10 +290,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp == 0 && p.max_ntaps == 1) {
+    // ===== TMA producer, one tap per stage (the common case): a single thread runs straight-line code =====
     if (lane == 0) {
-      const int hrows_per_box = p.nh / p.a_boxes;
       Tracer trc(p.trace, 0);
       int itg = 0;  // stage counter, continuous across tiles
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -285,19 +300,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         trc.ev(1, t);
         for (int it = 0; it < x.n_iters; ++it, ++itg) {
           const int s = itg % p.stages, phs = (itg / p.stages) & 1;
-          const int tl = it / p.k_chunks, chunk = it - tl * p.k_chunks, tap = x.tap0 + tl;
+          const int gi = it / p.k_chunks, chunk = it - gi * p.k_chunks, g = x.g0 + gi;
           mbar_wait(empty_bar(s), phs ^ 1);
-          mbar_expect_tx(full_bar(s), (uint32_t)(p.mrows * KC * 2 + b_bytes));
+          mbar_expect_tx(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + b_bytes));
           const uint32_t a_dst = smem_base + s * stage_bytes;
           for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_4d(a_dst + bx * hrows_per_box * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
-                        (x.h0 + bx * hrows_per_box) * p.stride + p.tap_off[tap], x.b);
-          tma_load_3d(a_dst + A_BYTES, &tmW, full_bar(s), chunk * KC, x.col0, p.tap_w[tap]);
+            tma_load_4d(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+                        (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
+          tma_load_3d(a_dst + p.a_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[g]);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 && p.max_ntaps == 1) {
+    // ===== MMA issuer, one tap per stage =====
     const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
     Tracer trc(lane == 0 ? p.trace : nullptr, 1);
     int itg = 0, acc_i = 0;
@@ -316,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t a_addr = smem_base + s * stage_bytes;
           const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + A_BYTES);
+          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes);
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks)  // +32 bytes (16 bf16) along K inside the swizzle atom
             umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
@@ -326,6 +341,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       trc.ev(3, t);
+      ++acc_i;
+    }
+  } else if (warp == 0) {
+    // ===== TMA producer, tap windows (warp-uniform control flow, lane 0's instructions take effect) =====
+    const bool lead = lane == 0;
+    int itg = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const Tile x = decode_tile(p, t);
+      for (int it = 0; it < x.n_iters; ++it, ++itg) {
+        const int s = itg % p.stages, phs = (itg / p.stages) & 1;
+        const int gi = it / p.k_chunks, chunk = it - gi * p.k_chunks, g = x.g0 + gi;
+        const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
+        mbar_wait(empty_bar(s), phs ^ 1);
+        mbar_expect_tx_if(lead, full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
+        const uint32_t a_dst = smem_base + s * stage_bytes;
+#pragma unroll 1
+        for (int bx = 0; bx < p.a_boxes; ++bx)
+          tma_load_4d_if(lead, a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+                         (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
+#pragma unroll 1
+        for (int tl = 0; tl < nt; ++tl)
+          tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer, tap windows (warp-uniform control flow) =====
+    const bool lead = lane == 0;
+    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
+    int itg = 0, acc_i = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const Tile x = decode_tile(p, t);
+      if (x.n_iters == 0) continue;
+      const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
+      mbar_wait(tmem_empty_bar(as), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
+      for (int it = 0; it < x.n_iters; ++it, ++itg) {
+        const int s = itg % p.stages, phs = (itg / p.stages) & 1;
+        const int g = x.g0 + it / p.k_chunks;
+        const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
+        mbar_wait(full_bar(s), phs);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * stage_bytes;
+#pragma unroll 1
+        for (int tl = 0; tl < nt; ++tl) {
+          // tap = the same window, `tap_shift` h rows (x pack phase rows of 128 B) further down
+          const uint64_t adesc = smem_desc_kmajor_sw128(a_addr + (uint32_t)(p.tt.tap_shift[t0 + tl] * p.pack * KC * 2));
+          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes + tl * b_bytes);
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            umma_bf16_if(lead, d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || tl > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit_if(lead, empty_bar(s));
+        umma_commit_if(lead && it == x.n_iters - 1, tmem_full_bar(as));
+        __syncwarp();
+      }
       ++acc_i;
     }
   } else if constexpr (kStaged) {
@@ -346,7 +417,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ----- epilogue DMA warp -----
       if (lane == 0) {
         Tracer trc(p.trace, 3);
-        prefetch_tmap(&em.pre); prefetch_tmap(&em.mask); prefetch_tmap(&em.post); prefetch_tmap(&em.raw); prefetch_tmap(&em.act);
+        for (int r = 0; r < p.n_res; ++r) { prefetch_tmap(&em.pre[r]); prefetch_tmap(&em.mask[r]); prefetch_tmap(&em.raw[r]); }
+        prefetch_tmap(&em.post); prefetch_tmap(&em.act);
       }
       const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
       const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
@@ -357,12 +429,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const Tile x = decode_tile(p, ld_t);
         const int buf = ld_q & 1;
         const int col = x.col0 + ld_s * SUB;
-        const int r0 = (x.h0 * p.phases) >> (e.pair_sum ? 1 : 0);        // first output row of the tile (n_res == 1)
+        const int r0 = x.h0 >> (e.pair_sum ? 1 : 0);                     // first h row of the tile in its residue class
         mbar_expect_tx(in_bar(buf), in_bytes);
         int i = 0;
-        if (e.has_pre) tma_load_3d(in_slot(buf, i++), &em.pre, in_bar(buf), col, r0, x.b);
-        if (e.has_mask) tma_load_3d(in_slot(buf, i++), &em.mask, in_bar(buf), col, r0, x.b);
-        if (e.has_post) tma_load_3d(in_slot(buf, i++), &em.post, in_bar(buf), col, r0 >> e.post_shift, x.b);
+        if (e.has_pre) tma_load_4d(in_slot(buf, i++), &em.pre[x.res], in_bar(buf), col, 0, r0, x.b);
+        if (e.has_mask) tma_load_4d(in_slot(buf, i++), &em.mask[x.res], in_bar(buf), col, 0, r0, x.b);
+        if (e.has_post) tma_load_4d(in_slot(buf, i++), &em.post, in_bar(buf), col, 0, r0 >> e.post_shift, x.b);
         ++ld_q;
         if (++ld_s == n_sub) { ld_s = 0; ld_t += gridDim.x; }
       };
@@ -370,14 +442,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int q = 0;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const Tile x = decode_tile(p, t);
-        const int r0_out = (x.h0 * p.phases) >> (e.pair_sum ? 1 : 0);
+        const int r0_out = x.h0 >> (e.pair_sum ? 1 : 0);
         for (int s = 0; s < n_sub; ++s, ++q) {
           const int obuf = q % 3;
           asm volatile("bar.sync %0, 160;" ::"r"(bar_full(obuf)) : "memory");   // output slots written, input slots consumed
           if (lane == 0) {
             const int col = x.col0 + s * SUB;
             int o = 0;
-            if (e.has_raw) tma_store_3d(&em.raw, out_slot(obuf, o++), col, r0_out, x.b);
+            if (e.has_raw) tma_store_4d(&em.raw[x.res], out_slot(obuf, o++), col, 0, r0_out, x.b);
             if (e.has_act) {
               tma_store_4d(&em.act, out_slot(obuf, o), col, 0, r0_out, x.b);
               if (e.dup_rows) tma_store_4d(&em.act, out_slot(obuf, o), col, 1, r0_out, x.b);
@@ -670,18 +742,22 @@ int tc_pack_groups(int c_in, int c_out, int groups) {
   return groups;
 }
 
-// tensor map of an epilogue operand / output: rows of all phases flattened, [B][rows][C]; `dup`: [B][rows][2][C]
-static int epi_map(CUtensorMap* m, const void* base, int C, int64_t rows, int B, int box_rows, bool dup) {
+// tensor map of an epilogue operand / output for residue class `res` of `n_res`: [B][T][P][C] seen as
+// (C, P, h', B) with h = h'*n_res + res; box = (32, pack, box_h, 1).  `dup`: y_act as [B][T][2][C] -> (C, 2, h, B).
+static int epi_map(CUtensorMap* m, const void* base, int C, int P, int T, int B, int res, int n_res, int pack, int box_h,
+                   bool dup) {
   if (dup) {
-    const uint64_t dims[4] = {(uint64_t)C, 2, (uint64_t)rows, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)rows * C * 4};
-    const uint32_t box[4] = {SUB, 1, (uint32_t)box_rows, 1};
+    const uint64_t dims[4] = {(uint64_t)C, 2, (uint64_t)T, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)T * C * 4};
+    const uint32_t box[4] = {SUB, 1, (uint32_t)box_h, 1};
     return make_tmap_bf16(m, base, 4, dims, strides, box, nullptr, 64);
   }
-  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)rows, (uint64_t)B};
-  const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)rows * C * 2};
-  const uint32_t box[3] = {SUB, (uint32_t)box_rows, 1};
-  return make_tmap_bf16(m, base, 3, dims, strides, box, nullptr, 64);
+  const int h_ext = (T - res + n_res - 1) / n_res;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)P, (uint64_t)h_ext, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)n_res * P * C * 2, (uint64_t)T * P * C * 2};
+  const uint32_t box[4] = {SUB, (uint32_t)pack, (uint32_t)box_h, 1};
+  const bf16* b0 = static_cast<const bf16*>(base) + (int64_t)res * P * C;
+  return make_tmap_bf16(m, b0, 4, dims, strides, box, nullptr, 64);
 }
 
 static long long* g_trace = nullptr;
@@ -698,30 +774,23 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   p.mrows = p.nh * p.pack;
   p.bn = pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m);
   if (p.bn <= 0) return STG_EUNSUPPORTED;
-  p.a_boxes = (p.nh * p.stride <= 256) ? 1 : 2;
-  if (p.a_boxes == 2 && (p.pack != 1 || (p.nh & 1))) return STG_EUNSUPPORTED;
   p.tmem_cols = 512;  // two accumulator buffers ACC_COLS apart
+  // ---- taps per residue class, as (source offset, weight index)
+  struct Tap { int off, w; };
+  Tap taps[MAX_RES][STG_MAX_TAPS]; int ntap[MAX_RES];
   if (p.n_res > 1) {
-    int n = 0;
     for (int r = 0; r < p.n_res; ++r) {
-      p.res_first[r] = n;
+      ntap[r] = 0;
       for (int j = 0; j < d->k; ++j) {
         const int num = r + d->pad - j * d->dilation;
         if (((num % d->stride) + d->stride) % d->stride != 0) continue;
-        p.tap_off[n] = (num >= 0) ? num / d->stride : -((-num) / d->stride);  // exact division
-        p.tap_w[n] = j;
-        ++n;
+        taps[r][ntap[r]++] = Tap{(num >= 0) ? num / d->stride : -((-num) / d->stride), j};  // exact division
       }
     }
-    p.res_first[p.n_res] = n;
   } else {
-    for (int j = 0; j < d->k; ++j) {
-      p.tap_off[j] = d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad);
-      p.tap_w[j] = j;
-    }
-    p.res_first[0] = 0; p.res_first[1] = d->k;
+    ntap[0] = d->k;
+    for (int j = 0; j < d->k; ++j) taps[0][j] = Tap{d->transposed ? (d->pad - j * d->dilation) : (j * d->dilation - d->pad), j};
   }
-
   TcEpi& e = p.e;
   const int rows_per_phase = d->pair_sum ? d->t_dst / 2 : d->t_dst;
   e.rows = rows_per_phase * d->phases; e.c_dst = d->c_dst;
@@ -735,16 +804,93 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   e.act_slope = d->act == STG_ACT_RELU ? 0.f : (d->act == STG_ACT_LEAKY ? 0.1f : 1.f);
   e.mask_slope = d->mask_mode == STG_ACT_RELU ? 0.f : (d->mask_mode == STG_ACT_LEAKY ? 0.1f : 1.f);
   const bool staged = !d->out_f32 && d->act != STG_ACT_TANH && d->mask_mode != STG_ACT_TANH && (d->c_dst % 8) == 0 &&
-                      p.n_res == 1 && (p.bn % SUB) == 0 &&
+                      p.n_res <= MAX_STAGED_RES && (p.n_res == 1 || (!d->add_post && !d->y_act)) && (p.bn % SUB) == 0 &&
                       (!d->post_shift || (rows_per_phase % 2) == 0);
 
-  const int stage_bytes = A_BYTES + p.bn * KC * 2;
+  // ---- tap groups (A windows) and pipeline depth.  Taps of a group must lie on one row lattice of the strided
+  // A box (same offset mod stride) and close enough for the window to fit its boxes; candidates: <= ng taps per
+  // group, pick the ng with the least shared-memory ingest per tile among those that leave >= 3 (else 2) stages.
+  const int b_bytes = p.bn * KC * 2;
   const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 1024 : 0;
-  int stages = (212 * 1024 - epi_bytes) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) return STG_EUNSUPPORTED;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 8);
+  const int avail = 212 * 1024 - epi_bytes;
+  struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
+  auto build = [&](int ng, TcP* out) {
+    Plan pl{ng, 0, 0, 0, 0, 0, 0, false};
+    int n_groups = 0, n_taps_out = 0, max_shift = 0;
+    for (int r = 0; r < p.n_res; ++r) {
+      if (out) out->res_gfirst[r] = n_groups;
+      bool used[STG_MAX_TAPS] = {false};
+      for (int i = 0; i < ntap[r]; ++i) {
+        if (used[i]) continue;
+        // new group seeded by tap i: later taps of the same lattice, sorted by offset implicitly (offsets are monotone in j)
+        int lo = taps[r][i].off, members[STG_MAX_TAPS], nm = 0;
+        for (int j2 = i; j2 < ntap[r] && nm < ng; ++j2) {
+          if (used[j2]) continue;
+          const int diff = taps[r][j2].off - taps[r][i].off;
+          if (diff % p.stride != 0) continue;
+          int new_lo = taps[r][j2].off < lo ? taps[r][j2].off : lo, hi = taps[r][i].off;
+          for (int q = 0; q < nm; ++q) { const int o = taps[r][members[q]].off; if (o > hi) hi = o; if (o < new_lo) new_lo = o; }
+          if (taps[r][j2].off > hi) hi = taps[r][j2].off;
+          if ((hi - new_lo) / p.stride > 128) continue;   // window would not fit
+          members[nm++] = j2; used[j2] = true; lo = new_lo;
+        }
+        for (int q = 0; q < nm; ++q) {
+          const int sh = (taps[r][members[q]].off - lo) / p.stride;
+          if (sh > max_shift) max_shift = sh;
+          if (out) { out->tt.tap_shift[n_taps_out] = (short)sh; out->tt.tap_w[n_taps_out] = (unsigned char)taps[r][members[q]].w; }
+          ++n_taps_out;
+        }
+        if (out) { out->tt.g_off[n_groups] = (short)lo; out->tt.g_tfirst[n_groups] = (unsigned char)(n_taps_out - nm); out->tt.g_ntaps[n_groups] = (unsigned char)nm; }
+        ++n_groups;
+      }
+    }
+    if (out) out->res_gfirst[p.n_res] = n_groups;
+    // window boxes: a_boxes boxes of hb h rows (hb * stride <= 256; box starts on 8-row swizzle boundaries)
+    const int win_h = p.nh + max_shift;
+    int a_boxes = ceil_div(win_h * p.stride, 256), hb = ceil_div(win_h, a_boxes);
+    if (a_boxes > 1) {
+      const int align = 8 / (p.pack >= 8 ? 8 : (8 % p.pack == 0 ? p.pack : 1));   // hb * pack % 8 == 0
+      hb = ceil_div(hb, align) * align;
+      if ((hb * p.pack) % 8 != 0) return pl;
+      while (hb * p.stride > 256) { ++a_boxes; hb = ceil_div(ceil_div(win_h, a_boxes), align) * align; }
+    }
+    if (hb * p.stride > 256 || p.pack > 256) return pl;
+    int a_rows = a_boxes * hb * p.pack;
+    if (a_rows < TM + max_shift * p.pack) a_rows = TM + max_shift * p.pack;   // the MMA always reads 128 rows from the shift
+    pl.hb = hb; pl.a_boxes = a_boxes; pl.a_bytes = ceil_div(a_rows * KC * 2, 1024) * 1024; pl.n_groups = n_groups;
+    const int stage_bytes = pl.a_bytes + ng * b_bytes;
+    pl.stages = avail / stage_bytes;
+    if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+    pl.traffic = (long long)n_groups * (a_boxes * hb * p.pack * KC * 2) + (long long)n_taps_out * b_bytes;
+    pl.ok = pl.stages >= 2;
+    return pl;
+  };
+  static const int env_ng = getenv("STG_NG") ? atoi(getenv("STG_NG")) : 0;  // tuning override
+  Plan best{0, 0, 0, 0, 0, 0, 0, false};
+  const long long base_traffic = build(1, nullptr).traffic;
+  const int cands[] = {1, 2, 3, 4, 5, 6, 8, 10};
+  for (int ci = 0; ci < 8; ++ci) {
+    const int ng = cands[ci];
+    if (env_ng > 0 && ng != env_ng) continue;
+    if (ng > d->k && ng != 1) continue;
+    Plan pl = build(ng, nullptr);
+    if (!pl.ok) continue;
+    if (!best.ok) { best = pl; continue; }           // ng = 1 comes first: the baseline
+    // a window plan replaces the one-tap-per-stage baseline only if it still pipelines (>= 3 stages) and moves
+    // at least 35 % fewer bytes: for k = 3 the saving is ~25 % and the coarser stages cost more than that
+    if (pl.stages >= 3 && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
+  }
+  if (!best.ok) return STG_EUNSUPPORTED;
+  build(best.ng, &p);
+  p.hb = best.hb; p.a_boxes = best.a_boxes; p.a_bytes = best.a_bytes; p.max_ntaps = best.ng; p.stages = best.stages;
+  const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
+  const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 8) + sizeof(TapTables) + 16;
+  static const bool dbg_plan = getenv("STG_DEBUG_PLAN") != nullptr;
+  if (dbg_plan)
+    fprintf(stderr, "[conv_tc] c %d->%d k%d s%d d%d g%d ph%d T %d->%d tr%d | bn %d staged %d ng %d stages %d hb %d a_boxes %d a_bytes %d "
+            "groups %d tiles_m %d res %d smem %zu\n", d->c_src, d->c_dst, d->k, d->stride, d->dilation, d->groups, d->phases, d->t_src,
+            d->t_dst, d->transposed, p.bn, (int)staged, p.max_ntaps, p.stages, p.hb, p.a_boxes, p.a_bytes, p.res_gfirst[p.n_res],
+            p.tiles_m, p.n_res, smem);
 
   CUtensorMap tmA, tmW;
   EpiMaps em;
@@ -753,7 +899,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const uint64_t C = d->c_src, P = d->phases, T = d->t_src, B = d->n_samples;
     const uint64_t dims[4] = {C, P, T, B};
     const uint64_t strides[3] = {C * 2, P * C * 2, T * P * C * 2};
-    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.pack, (uint32_t)((p.nh / p.a_boxes) * p.stride), 1};
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.pack, (uint32_t)(p.hb * p.stride), 1};
     const uint32_t es[4] = {1, 1, (uint32_t)p.stride, 1};
     int r = make_tmap_bf16(&tmA, d->src, 4, dims, strides, box, es);
     if (r) return r;
@@ -767,21 +913,16 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     if (r) return r;
   }
   if (staged) {
-    const int box_rows = d->pair_sum ? 64 : p.mrows;
+    const int box_h = d->pair_sum ? 64 : p.nh;          // h rows of one box (x pack phases = rows of the sub-tile)
+    const int t_rows = rows_per_phase;                  // output rows per phase (after pair_sum)
     int r = 0;
-    if (e.has_pre) r |= epi_map(&em.pre, d->add_pre, d->c_dst, e.rows, d->n_samples, box_rows, false);
-    if (e.has_mask) r |= epi_map(&em.mask, d->mask, d->c_dst, e.rows, d->n_samples, box_rows, false);
-    if (e.has_post) r |= epi_map(&em.post, d->add_post, d->c_dst, e.rows >> d->post_shift, d->n_samples, box_rows >> d->post_shift, false);
-    if (e.has_raw) r |= epi_map(&em.raw, d->y_raw, d->c_dst, e.rows, d->n_samples, box_rows, false);
-    if (e.has_act) {
-      if (d->dup_rows) r |= epi_map(&em.act, d->y_act, d->c_dst, e.rows, d->n_samples, box_rows, true);
-      else {  // 4-D with a unit "dup" dimension so the kernel issues the same instruction either way
-        const uint64_t dims[4] = {(uint64_t)d->c_dst, 1, (uint64_t)e.rows, (uint64_t)d->n_samples};
-        const uint64_t strides[3] = {(uint64_t)d->c_dst * 2, (uint64_t)d->c_dst * 2, (uint64_t)e.rows * d->c_dst * 2};
-        const uint32_t box[4] = {SUB, 1, (uint32_t)box_rows, 1};
-        r |= make_tmap_bf16(&em.act, d->y_act, 4, dims, strides, box, nullptr, 64);
-      }
+    for (int res = 0; res < p.n_res; ++res) {
+      if (e.has_pre) r |= epi_map(&em.pre[res], d->add_pre, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
+      if (e.has_mask) r |= epi_map(&em.mask[res], d->mask, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
+      if (e.has_raw) r |= epi_map(&em.raw[res], d->y_raw, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
     }
+    if (e.has_post) r |= epi_map(&em.post, d->add_post, d->c_dst, d->phases, t_rows >> d->post_shift, d->n_samples, 0, 1, p.pack, box_h >> d->post_shift, false);
+    if (e.has_act) r |= epi_map(&em.act, d->y_act, d->c_dst, d->phases, t_rows, d->n_samples, 0, 1, p.pack, box_h, d->dup_rows != 0);
     if (r) return STG_ECUDA;
   }
   static bool attr_set = false;
