@@ -237,8 +237,8 @@ def run_ours(args):
     if rank == 0:
         groups = {}
         for p in prof:
-            key = ("conv_tc_kernel" if p["kind"] != "wgrad" else "wgrad_tc_kernel") if p["engine"] == "tcgen05" else \
-                  ("conv_simt_kernel" if p["kind"] != "wgrad" else "wgrad_simt_kernel")
+            key = {"tcgen05": ("conv_tc_kernel", "wgrad_tc_kernel"), "simt": ("conv_simt_kernel", "wgrad_simt_kernel"),
+                   "matvec": ("c1_conv_kernels", "c1_wgrad_kernel")}[p["engine"]][1 if p["kind"] == "wgrad" else 0]
             gk = groups.setdefault(key, dict(kernel=key, launches=0, ms=0.0, flops=0.0, bytes=0.0))
             gk["launches"] += 1; gk["ms"] += p["events"][0].elapsed_time(p["events"][1]); gk["flops"] += p["flops"]
             gk["bytes"] += p["bytes"]

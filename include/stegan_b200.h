@@ -37,7 +37,7 @@ enum {
   STG_ECUDA = -2,       /* CUDA runtime error (see stg_last_cuda_error) */
   STG_EUNSUPPORTED = -3 /* shape not supported by the requested engine */
 };
-enum { STG_ENGINE_AUTO = 0, STG_ENGINE_SIMT = 1, STG_ENGINE_TCGEN05 = 2 };
+enum { STG_ENGINE_AUTO = 0, STG_ENGINE_SIMT = 1, STG_ENGINE_TCGEN05 = 2, STG_ENGINE_MATVEC = 3 /* routing result only */ };
 
 #define STG_MAX_TAPS 48
 
@@ -234,6 +234,17 @@ int stg_mse_const(const void* x, int dtype, int64_t n, float target, float* out_
 int stg_l1_mean(const void* a, const void* b, int dtype, int64_t n, float* out_slot, float grad_scale, void* da,
                 stg_stream_t stream);
 
+/* Multi-tensor forms of the two above (27 feature-map pairs / 2 x 8 logits tensors per train step): one launch,
+ * `items` is a HOST array (<= STG_MAX_LOSS_ITEMS) copied by value into the kernel parameters.
+ *   l1 : out_slot[0] += sum_i mean|a_i - b_i| ; da_i = grad_scale * sign(a_i - b_i) / n_i
+ *   mse: slots[slot_i] += mean((x_i - target_i)^2) ; dx_i = grad_scale * 2 (x_i - target_i) / n_i */
+#define STG_MAX_LOSS_ITEMS 32
+typedef struct StgL1Item { const void* a; const void* b; void* da; int64_t n; } StgL1Item;
+typedef struct StgMseItem { const void* x; void* dx; int64_t n; float target; int32_t slot; } StgMseItem;
+int stg_l1_mean_multi(const StgL1Item* items, int n_items, int dtype, float* out_slot, float grad_scale, stg_stream_t stream);
+int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int dx_dtype, float* slots, float grad_scale,
+                        stg_stream_t stream);
+
 /* torch.optim.AdamW (ste_gan/constants.py:57; train.py:80-81,199,267) over one flat fp32 buffer.
  * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable. */
 int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
@@ -248,6 +259,9 @@ unsigned long long stg_launch_count(void);
 /* 1 if the tcgen05 engine can take this contraction (shape/alignment rules in DESIGN.md), else 0. */
 int stg_conv_tc_supported(const StgConv* d);
 int stg_wgrad_tc_supported(const StgWgrad* d);
+/* engine a call will run on (STG_ENGINE_SIMT / _TCGEN05 / _MATVEC: the 1-channel logits kernels) */
+int stg_conv_route(const StgConv* d);
+int stg_wgrad_route(const StgWgrad* d);
 /* debug: device buffer of 1 + 3*4000 int64 that receives a (tag, value, globaltimer ns) timeline of CTA 0 of every
  * following tcgen05 stg_conv launch (NULL switches it off). */
 int stg_debug_set_trace(void* buf);

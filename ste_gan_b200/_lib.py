@@ -38,11 +38,22 @@ class StgFoldItem(C.Structure):
         (n, C.c_int32) for n in ("c_out", "cin_g", "k", "groups", "pg", "flags", "dw_ld", "dw_span", "row0", "tile0")]
 
 
+class StgL1Item(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("da", C.c_void_p), ("n", C.c_int64)]
+
+
+class StgMseItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dx", C.c_void_p), ("n", C.c_int64), ("target", C.c_float), ("slot", C.c_int32)]
+
+
+MAX_LOSS_ITEMS = 32
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _SIGS = {
     "stg_conv": [C.POINTER(StgConv), _P],
     "stg_conv_wgrad": [C.POINTER(StgWgrad), _P],
     "stg_conv_tc_supported": [C.POINTER(StgConv)],
+    "stg_conv_route": [C.POINTER(StgConv)],
+    "stg_wgrad_route": [C.POINTER(StgWgrad)],
     "stg_wgrad_tc_supported": [C.POINTER(StgWgrad)],
     "stg_weightnorm_fold": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "stg_weightnorm_fold_bwd": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
@@ -50,6 +61,8 @@ _SIGS = {
     "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "stg_spectralnorm_fold_bwd": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
     "stg_tc_pack_groups": [_I, _I, _I],
+    "stg_l1_mean_multi": [_P, _I, _I, _P, _F, _P],
+    "stg_mse_const_multi": [_P, _I, _I, _I, _P, _F, _P],
     "stg_weightnorm_fold_multi": [_P, _I, _I, _I, _I, _P],
     "stg_weightnorm_fold_bwd_multi": [_P, _I, _I, _I, _P],
     "stg_debug_set_trace": [_P],

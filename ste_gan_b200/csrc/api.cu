@@ -47,6 +47,21 @@ extern "C" int stg_conv(const StgConv* d, stg_stream_t stream) {
   }
 }
 
+/* which engine a call will run on: STG_ENGINE_SIMT, STG_ENGINE_TCGEN05 or STG_ENGINE_MATVEC */
+extern "C" int stg_conv_route(const StgConv* d) {
+  if (!d || validate_conv(d) != STG_OK) return STG_EINVAL;
+  if (d->engine == STG_ENGINE_SIMT) return STG_ENGINE_SIMT;
+  if (d->engine == STG_ENGINE_TCGEN05) return STG_ENGINE_TCGEN05;
+  if (conv_c1_supported(d)) return STG_ENGINE_MATVEC;
+  return conv_tc_supported(d) ? STG_ENGINE_TCGEN05 : STG_ENGINE_SIMT;
+}
+extern "C" int stg_wgrad_route(const StgWgrad* d) {
+  if (!d) return STG_EINVAL;
+  if (d->engine == STG_ENGINE_SIMT) return STG_ENGINE_SIMT;
+  if (d->engine == STG_ENGINE_TCGEN05) return STG_ENGINE_TCGEN05;
+  if (wgrad_c1_supported(d)) return STG_ENGINE_MATVEC;
+  return wgrad_tc_supported(d) ? STG_ENGINE_TCGEN05 : STG_ENGINE_SIMT;
+}
 extern "C" int stg_conv_tc_supported(const StgConv* d) { return (d && validate_conv(d) == STG_OK && conv_tc_supported(d)) ? 1 : 0; }
 extern "C" int stg_tc_pack_groups(int c_in, int c_out, int groups) {
   if (groups < 1 || c_in % groups || c_out % groups) return groups;

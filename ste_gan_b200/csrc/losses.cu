@@ -140,6 +140,69 @@ __global__ void __launch_bounds__(256) l1_mean_kernel(const T* __restrict__ a, c
   if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
 }
 
+// ---- multi-tensor forms (the feature-matching / LSGAN terms are 27 + 24 tiny tensors per step): the item table
+// travels BY VALUE in the kernel parameters, so the launch is CUDA-graph capturable with no device-side table.
+struct L1Table { StgL1Item it[STG_MAX_LOSS_ITEMS]; int block0[STG_MAX_LOSS_ITEMS + 1]; int n; };
+struct MseTable { StgMseItem it[STG_MAX_LOSS_ITEMS]; int block0[STG_MAX_LOSS_ITEMS + 1]; int n; };
+
+template <typename Tab>
+__device__ __forceinline__ int item_of_block(const Tab& t, int blk) {
+  int i = 0;
+  while (i + 1 < t.n && t.block0[i + 1] <= blk) ++i;
+  return i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_mean_multi_kernel(const L1Table tab, float* __restrict__ slot, float grad_scale) {
+  __shared__ float red[32];
+  const int i = item_of_block(tab, blockIdx.x);
+  const StgL1Item d = tab.it[i];
+  const int lb = blockIdx.x - tab.block0[i], nb = tab.block0[i + 1] - tab.block0[i];
+  const T* a = static_cast<const T*>(d.a); const T* b = static_cast<const T*>(d.b); T* da = static_cast<T*>(d.da);
+  const int64_t n = d.n;
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+  const int64_t n4 = al ? n / 4 : 0;
+  const float gcoef = grad_scale / (float)n;
+  float acc = 0.f;
+  for (int64_t j = (int64_t)lb * 256 + threadIdx.x; j < n4; j += (int64_t)nb * 256) {
+    float va[4], vb[4], g[4];
+    ld4(a + 4 * j, va);
+    ld4(b + 4 * j, vb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float df = va[q] - vb[q];
+      acc += fabsf(df);
+      g[q] = gcoef * sgn(df);
+    }
+    if (da) st4(da + 4 * j, g);
+  }
+  for (int64_t j = 4 * n4 + (int64_t)lb * 256 + threadIdx.x; j < n; j += (int64_t)nb * 256) {
+    const float df = to_f(a[j]) - to_f(b[j]);
+    acc += fabsf(df);
+    if (da) da[j] = from_f<T>(gcoef * sgn(df));
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && slot) atomicAdd(slot, acc / (float)n);
+}
+
+template <typename T, typename TD>
+__global__ void __launch_bounds__(256) mse_const_multi_kernel(const MseTable tab, float* __restrict__ slots, float grad_scale) {
+  __shared__ float red[32];
+  const int i = item_of_block(tab, blockIdx.x);
+  const StgMseItem d = tab.it[i];
+  const int lb = blockIdx.x - tab.block0[i], nb = tab.block0[i + 1] - tab.block0[i];
+  const T* x = static_cast<const T*>(d.x); TD* dx = static_cast<TD*>(d.dx);
+  const float gcoef = grad_scale * 2.f / (float)d.n;
+  float acc = 0.f;
+  for (int64_t j = (int64_t)lb * 256 + threadIdx.x; j < d.n; j += (int64_t)nb * 256) {
+    const float df = to_f(x[j]) - d.target;
+    acc = fmaf(df, df, acc);
+    if (dx) dx[j] = from_f<TD>(gcoef * df);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && slots) atomicAdd(slots + d.slot, acc / (float)d.n);
+}
+
 // reflect-padded moving average over the last axis of [rows][T]
 __global__ void average_filter_kernel(const float* __restrict__ x, int64_t rows, int T_, int window, int pad, int To,
                                       float* __restrict__ out) {
@@ -229,6 +292,49 @@ extern "C" int stg_l1_mean(const void* a, const void* b, int dtype, int64_t n, f
   const int64_t n4 = al ? n / 4 : 0;
   if (dtype == STG_F32) l1_mean_kernel<float><<<grid_for(n, 4), 256, 0, S_>>>((const float*)a, (const float*)b, n4, n, out_slot, gcoef, (float*)da);
   else l1_mean_kernel<bf16><<<grid_for(n, 4), 256, 0, S_>>>((const bf16*)a, (const bf16*)b, n4, n, out_slot, gcoef, (bf16*)da);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_l1_mean_multi(const StgL1Item* items, int n_items, int dtype, float* out_slot, float grad_scale,
+                                 stg_stream_t stream) {
+  if (!items || n_items < 1 || n_items > STG_MAX_LOSS_ITEMS) return STG_EINVAL;
+  L1Table t;
+  t.n = n_items;
+  int blocks = 0;
+  for (int i = 0; i < n_items; ++i) {
+    if (!items[i].a || !items[i].b || items[i].n < 1) return STG_EINVAL;
+    t.it[i] = items[i];
+    t.block0[i] = blocks;
+    int64_t b = ceil_div64(items[i].n, 256 * 4 * 4);   // ~4 vector iterations per thread
+    blocks += (int)(b < 1 ? 1 : (b > 148 ? 148 : b));
+  }
+  t.block0[n_items] = blocks;
+  if (dtype == STG_F32) l1_mean_multi_kernel<float><<<blocks, 256, 0, S_>>>(t, out_slot, grad_scale);
+  else if (dtype == STG_BF16) l1_mean_multi_kernel<bf16><<<blocks, 256, 0, S_>>>(t, out_slot, grad_scale);
+  else return STG_EINVAL;
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int dx_dtype, float* slots,
+                                   float grad_scale, stg_stream_t stream) {
+  if (!items || n_items < 1 || n_items > STG_MAX_LOSS_ITEMS) return STG_EINVAL;
+  MseTable t;
+  t.n = n_items;
+  int blocks = 0;
+  for (int i = 0; i < n_items; ++i) {
+    if (!items[i].x || items[i].n < 1) return STG_EINVAL;
+    t.it[i] = items[i];
+    t.block0[i] = blocks;
+    int64_t b = ceil_div64(items[i].n, 256 * 4);
+    blocks += (int)(b < 1 ? 1 : (b > 64 ? 64 : b));
+  }
+  t.block0[n_items] = blocks;
+  if (x_dtype == STG_F32 && dx_dtype == STG_F32) mse_const_multi_kernel<float, float><<<blocks, 256, 0, S_>>>(t, slots, grad_scale);
+  else if (x_dtype == STG_F32) mse_const_multi_kernel<float, bf16><<<blocks, 256, 0, S_>>>(t, slots, grad_scale);
+  else if (dx_dtype == STG_F32) mse_const_multi_kernel<bf16, float><<<blocks, 256, 0, S_>>>(t, slots, grad_scale);
+  else mse_const_multi_kernel<bf16, bf16><<<blocks, 256, 0, S_>>>(t, slots, grad_scale);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __
   const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
   const float* vr = d.v + (int64_t)co * n;
   const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
+  // (a register-cached single-pass variant measured 1.8x SLOWER: the second pass hits L1/L2 anyway)
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci = i / k, j = i - ci * k;

@@ -85,7 +85,7 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
     if profile is None:
         check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
         return
-    tc = bool(lib.stg_conv_tc_supported(C.byref(d))) and d.engine != ENGINE_SIMT
+    route = {1: "simt", 2: "tcgen05", 3: "matvec"}[lib.stg_conv_route(C.byref(d))]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
@@ -94,7 +94,7 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
     esz = 2 if dt == torch.bfloat16 else 4
     nbytes = esz * (nv * t_src * c_src + k * c_dst * (c_src // groups)) + sum(
         t.numel() * t.element_size() for t in (add_pre, mask, add_post, y_raw, y_act) if t is not None)
-    profile.append(dict(kind=("dgrad" if transposed else "fwd"), engine="tcgen05" if tc else "simt", flops=flops,
+    profile.append(dict(kind=("dgrad" if transposed else "fwd"), engine=route, flops=flops,
                         bytes=nbytes, events=(e0, e1),
                         shape=(n_samples, phases, t_src, t_dst, c_src, c_dst, k, dilation, stride, groups)))
 
@@ -132,13 +132,13 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
     if profile is None:
         check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
         return
-    tc = bool(lib.stg_wgrad_tc_supported(C.byref(d))) and d.engine != ENGINE_SIMT
+    route = {1: "simt", 2: "tcgen05", 3: "matvec"}[lib.stg_wgrad_route(C.byref(d))]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
     e1.record()
     esz = 2 if x.dtype == torch.bfloat16 else 4
-    profile.append(dict(kind="wgrad", engine="tcgen05" if tc else "simt",
+    profile.append(dict(kind="wgrad", engine=route,
                         flops=2.0 * nv * t_out * c_out * k * (c_in // groups),
                         bytes=esz * nv * (t_in * c_in + t_out * c_out) + 4 * c_out * k * (c_in // groups),
                         events=(e0, e1), shape=(n_samples, phases, t_in, t_out, c_in, c_out, k, dilation, stride, groups)))
@@ -366,6 +366,45 @@ def l1_mean(a: Tensor, b: Tensor, out_slot: Optional[Tensor], grad_scale: float 
     _need(out_slot, 1, torch.float32, "out_slot")
     check(_lib.load().stg_l1_mean(_ptr(a), _ptr(b), code_of(a.dtype), a.numel(), _ptr(out_slot), float(grad_scale), _ptr(da),
                                   _stream()), "stg_l1_mean")
+
+
+def l1_mean_multi(pairs, out_slot: Tensor, grad_scale: float, want_grad: bool = True):
+    """Feature matching over a list of (a, b) tensor pairs in one launch per 32 pairs:
+    out_slot[0] += sum_i mean|a_i - b_i|; returns [da_i] (= grad_scale * sign(a_i - b_i) / n_i) or None."""
+    _need(out_slot, 1, torch.float32, "out_slot")
+    das = []
+    lib = _lib.load()
+    for lo in range(0, len(pairs), _lib.MAX_LOSS_ITEMS):
+        chunk = pairs[lo:lo + _lib.MAX_LOSS_ITEMS]
+        items = (_lib.StgL1Item * len(chunk))()
+        for i, (a, b) in enumerate(chunk):
+            _need(a, a.numel(), None, "a"); _need(b, a.numel(), a.dtype, "b")
+            if a.dtype != chunk[0][0].dtype:
+                raise _lib.StgError("l1_mean_multi: mixed dtypes")
+            da = torch.empty_like(a) if want_grad else None
+            das.append(da)
+            items[i] = _lib.StgL1Item(_ptr(a), _ptr(b), _ptr(da), a.numel())
+        check(lib.stg_l1_mean_multi(items, len(chunk), code_of(chunk[0][0].dtype), _ptr(out_slot), float(grad_scale), _stream()),
+              "stg_l1_mean_multi")
+    return das if want_grad else None
+
+
+def mse_const_multi(xs, targets, slots: Tensor, slot_idx, grad_scale: float, dx_dtype: torch.dtype):
+    """LSGAN terms over a list of logits tensors in one launch: slots[slot_idx[i]] += mean((x_i - target_i)^2);
+    returns [dx_i] in `dx_dtype`."""
+    n = len(xs)
+    if n > _lib.MAX_LOSS_ITEMS:
+        raise _lib.StgError("mse_const_multi: too many tensors")
+    items = (_lib.StgMseItem * n)()
+    dxs = []
+    for i, x in enumerate(xs):
+        _need(x, x.numel(), xs[0].dtype, "x")
+        dx = torch.empty(x.shape, device=x.device, dtype=dx_dtype)
+        dxs.append(dx)
+        items[i] = _lib.StgMseItem(_ptr(x), _ptr(dx), x.numel(), float(targets[i]), int(slot_idx[i]))
+    check(_lib.load().stg_mse_const_multi(items, n, code_of(xs[0].dtype), code_of(dx_dtype), _ptr(slots), float(grad_scale),
+                                          _stream()), "stg_mse_const_multi")
+    return dxs
 
 
 def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, lr: float, beta1: float = 0.8, beta2: float = 0.99,

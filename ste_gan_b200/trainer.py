@@ -105,13 +105,11 @@ class GanTrainer:
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
         res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
-        dl_f, dl_r = [], []
-        for fm_f, fm_r in zip(res_f, res_r):
-            gf = torch.empty(fm_f[-1].shape, device=self.device, dtype=dt)
-            gr = torch.empty(fm_r[-1].shape, device=self.device, dtype=dt)
-            ops.mse_const(fm_f[-1], 0.0, self.slots[0:1], 1.0, gf)          # train.py:193-194
-            ops.mse_const(fm_r[-1], 1.0, self.slots[0:1], 1.0, gr)          # train.py:195-196
-            dl_f.append(gf); dl_r.append(gr)
+        # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
+        nd = len(res_f)
+        dl = ops.mse_const_multi([fm[-1] for fm in res_f] + [fm[-1] for fm in res_r], [0.0] * nd + [1.0] * nd, self.slots,
+                                 [0] * (2 * nd), 1.0, dt)
+        dl_f, dl_r = dl[:nd], dl[nd:]
         # both passes accumulate their packed weight gradients in the plan's arena; the weight-norm backward is
         # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
         self.d_plan.zero()
@@ -132,18 +130,16 @@ class GanTrainer:
             f4 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
             res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4)
             self.d_folds = f4
-            dlog, dfm = [], []
-            for fm_f, fm_r in zip(res_f, res_r):
-                g = torch.empty(fm_f[-1].shape, device=self.device, dtype=dt)
-                ops.mse_const(fm_f[-1], 1.0, self.slots[1:2], 1.0, g)       # train.py:210-211
-                dlog.append(g)
-                gs = []
-                if self.use_fm:
-                    for a, b in zip(fm_f[:-1], fm_r[:-1]):                  # train.py:259-262
-                        ga = torch.empty_like(a)
-                        ops.l1_mean(a, b, self.slots[2:3], self.w_fm, ga)
-                        gs.append(ga)
-                dfm.append(gs if self.use_fm else [None] * (len(fm_f) - 1))
+            nd = len(res_f)
+            dlog = ops.mse_const_multi([fm[-1] for fm in res_f], [1.0] * nd, self.slots, [1] * nd, 1.0, dt)   # train.py:210-211
+            if self.use_fm:                                                 # train.py:259-262, one launch for all 27 maps
+                pairs = [(a, b) for fm_f, fm_r in zip(res_f, res_r) for a, b in zip(fm_f[:-1], fm_r[:-1])]
+                grads = ops.l1_mean_multi(pairs, self.slots[2:3], self.w_fm)
+                dfm, i = [], 0
+                for fm_f in res_f:
+                    dfm.append(grads[i:i + len(fm_f) - 1]); i += len(fm_f) - 1
+            else:
+                dfm = [[None] * (len(fm_f) - 1) for fm_f in res_f]
             dx_d = passes.discriminator_backward(self.net_d, ctx_f, dlog, dfm, want_input_grad=True, want_weight_grad=False)
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td:

@@ -400,6 +400,28 @@ def test_disc_input_prep_and_reductions():
     assert rel_l2(dl.cpu(), 2.0 * (a - 1.0) / a.numel()) < 1e-6
 
 
+def test_multi_tensor_losses():
+    """One-launch feature matching / LSGAN over lists of tensors against torch."""
+    from ste_gan_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    shapes = [(2, 77, 32), (2, 300, 8), (1, 5, 1024), (3, 33, 1)] * 9          # 36 pairs -> two launches
+    pairs = [(torch.randn(sh, generator=gen), torch.randn(sh, generator=gen)) for sh in shapes]
+    slot = torch.zeros(3, device="cuda")
+    das = ops.l1_mean_multi([(a.cuda().bfloat16(), b.cuda().bfloat16()) for a, b in pairs], slot[2:3], 7.0)
+    ref = sum(F.l1_loss(a.bfloat16().float(), b.bfloat16().float()).item() for a, b in pairs)
+    assert abs(slot[2].item() - ref) < 1e-4 * ref
+    for (a, b), da in zip(pairs, das):
+        d = a.bfloat16().float() - b.bfloat16().float()
+        assert rel_l2(da.float().cpu(), (7.0 * torch.sign(d) / a.numel()).bfloat16().float()) < 1e-6
+    xs = [torch.randn(2, 50 + i, 1, generator=gen) for i in range(16)]
+    tg = [0.0] * 8 + [1.0] * 8
+    dxs = ops.mse_const_multi([x.cuda() for x in xs], tg, slot, [0] * 8 + [1] * 8, 1.0, torch.bfloat16)
+    assert abs(slot[0].item() - sum(F.mse_loss(x, torch.zeros_like(x)).item() for x in xs[:8])) < 1e-5
+    assert abs(slot[1].item() - sum(F.mse_loss(x, torch.ones_like(x)).item() for x in xs[8:])) < 1e-5
+    for x, t, dx in zip(xs, tg, dxs):
+        assert rel_l2(dx.float().cpu(), 2.0 * (x - t) / x.numel()) < 4e-3
+
+
 def test_adamw_matches_torch():
     from ste_gan_b200 import ops
     gen = torch.Generator().manual_seed(4)
