@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ d
     const int ci = i / k, j = i - ci * k;
     const float val = dw[(int64_t)co * dw_ld + span_goff(co, cin_g, cout_g, span) + j * span + ci] * inv - coef * v[i];
     float* o = dW + (int64_t)co * n + i;
-    *o = accumulate ? (*o + val) : val;
+    if (accumulate) atomicAdd(o, val);   // the fake and the real pass may un-fold this layer concurrently (two streams)
+    else *o = val;
   }
 }
 

@@ -88,6 +88,35 @@ class GanTrainer:
         self._graphs = None
         self._static = None
         self.x_pred: Optional[Tensor] = None
+        # the discriminator passes on x_pred and on x_real are independent: they run on two streams (forked from and
+        # joined back into the current stream, also under graph capture), which fills the SMs that the many
+        # sub-148-tile kernels of the small discriminator layers leave idle
+        self._side = torch.cuda.Stream(device=dev)
+        self.concurrent_d = True
+
+    def _fork(self) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side.wait_event(ev)
+
+    def _join(self) -> None:
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        torch.cuda.current_stream().wait_event(ev)
+
+    def _two_passes(self, fn_a, fn_b):
+        """Run fn_a on the side stream and fn_b on the current stream; returns (fn_a(), fn_b()) after the join.
+        Every tensor the two functions create stays referenced until the caller's phase ends, and the side stream
+        always re-synchronises with the current one at the next fork, so the caching allocator's per-stream pools
+        cannot hand a block to the other stream while it is still in use."""
+        if not self.concurrent_d:
+            return fn_a(), fn_b()
+        self._fork()
+        with torch.cuda.stream(self._side):
+            ra = fn_a()
+        rb = fn_b()
+        self._join()
+        return ra, rb
 
     # ------------------------------------------------------------------ phases
     def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor) -> None:
@@ -101,9 +130,10 @@ class GanTrainer:
             return
         f1 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=not self._d_folded)
         self._d_folded = True
-        res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1)
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
-        res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
+        (res_f, ctx_f), (res_r, ctx_r) = self._two_passes(
+            lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f1),
+            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2))
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
         nd = len(res_f)
@@ -113,8 +143,9 @@ class GanTrainer:
         # both passes accumulate their packed weight gradients in the plan's arena; the weight-norm backward is
         # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
         self.d_plan.zero()
-        passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
-        passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
+        self._two_passes(
+            lambda: passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan),
+            lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan))
         self.d_plan.backward()
 
     def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
@@ -126,9 +157,10 @@ class GanTrainer:
                 self.D.adamw(self.lr, grad_scale=self.reducer.grad_scale)   # train.py:199
             f3 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=update_d or not self._d_folded)
             self._d_folded = True
-            res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3)
             f4 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
-            res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4)
+            (res_f, ctx_f), (res_r, _) = self._two_passes(
+                lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f3),
+                lambda: passes.discriminator_forward(self.net_d, x_real, dt, f4))
             self.d_folds = f4
             nd = len(res_f)
             dlog = ops.mse_const_multi([fm[-1] for fm in res_f], [1.0] * nd, self.slots, [1] * nd, 1.0, dt)   # train.py:210-211
