@@ -440,6 +440,29 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
 
 
 # --------------------------------------------------------------------------------------
+# stream-level concurrency
+# --------------------------------------------------------------------------------------
+def fork_join(side: Optional["torch.cuda.Stream"], fn_side, fn_main):
+    """Run fn_side on `side` and fn_main on the current stream, both ordered after everything enqueued so far;
+    returns (fn_side(), fn_main()) once the current stream has been made to wait for `side`.  Works under CUDA
+    graph capture (the side stream joins the capture through the fork event).  Callers keep every tensor the two
+    functions create referenced until their own phase ends; together with the fork ordering this keeps the caching
+    allocator's per-stream pools from recycling a block that the other stream still uses."""
+    if side is None:
+        return fn_side(), fn_main()
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        ra = fn_side()
+    rb = fn_main()
+    ev2 = torch.cuda.Event()
+    ev2.record(side)
+    torch.cuda.current_stream().wait_event(ev2)
+    return ra, rb
+
+
+# --------------------------------------------------------------------------------------
 # discriminators
 # --------------------------------------------------------------------------------------
 def disc_subnets(model) -> List[Tuple[str, object]]:
@@ -486,93 +509,126 @@ class DiscCtx:
     subs: List[dict] = field(default_factory=list)
 
 
-def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded]):
+def _heavy_split(subs: Sequence) -> Tuple[List[int], List[int]]:
+    """Indices of the sub-discriminators that go to the side stream / stay on the current one: the first (full-rate)
+    scale discriminator is about half of the work of a pass, everything else is the other half."""
+    heavy = [i for i, (kind, _) in enumerate(subs) if kind == "S"][:1]
+    return heavy, [i for i in range(len(subs)) if i not in heavy]
+
+
+def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded], side=None):
     """DiscriminatorSmall.forward / Discriminator.forward (discriminator.py:144-155,180-191).
     x: fp32 [B,T,C].  Returns (results, ctx): results[d] = channels-last feature maps
-    [B, H*p, C_j] in `dtype` with the fp32 logits last."""
+    [B, H*p, C_j] in `dtype` with the fp32 logits last.  `side`: optional extra CUDA stream; the sub-discriminators
+    are independent, so the full-rate scale discriminator runs there while the others run on the current stream."""
     x = x.contiguous().float()
     B, T, Cc = x.shape
     ctx = DiscCtx(B=B, T=T, C=Cc, dtype=dtype, folds=folds)
-    results = []
-    xs = x                                   # multi-scale input, fp32, pooled between scales
-    t_scale = T
-    for kind, d in disc_subnets(model):
-        if kind == "P":
-            p = d.period
-            t_pad = T + (p - T % p)          # reflect pad is always >= 1 (discriminator.py:36,86)
-            src = ops.reflect_pad_right(x, t_pad, dtype)
-            phases, t = p, t_pad // p
-        else:
-            src = ops.cast(xs, dtype)
-            phases, t = 1, t_scale
-        f0 = folds[id(d.layers[0])]
-        if f0.unfold:                         # im2col rows replace the raw input (kept for the first layer's wgrad)
-            src = unfold_input(f0, src, B, t, phases)
-        sub = dict(kind=kind, phases=phases, inputs=[src], ts=[t], t_in0=t_scale if kind == "S" else T, mod=d)
-        fmaps = []
-        h = src
-        for layer in d.layers:
-            _, h, t = _fwd(folds[id(layer)], h, B, t, phases=phases, act=ACT_LEAKY, want_act=True)
-            fmaps.append(h); sub["inputs"].append(h); sub["ts"].append(t)
-        logits, _, t = _fwd(folds[id(d.output)], h, B, t, phases=phases, want_raw=True, out_f32=True)
-        sub["ts"].append(t)
-        fmaps.append(logits)
-        results.append(fmaps)
-        ctx.subs.append(sub)
+    subs = disc_subnets(model)
+    # multi-scale inputs: fp32, AvgPool1d(4,2,1) between (and after) the scales (discriminator.py:153)
+    scale_in, xs = {}, x
+    for i, (kind, d) in enumerate(subs):
         if kind == "S":
-            sub["x_scale"] = xs
-            xs = ops.avgpool4(xs)            # AvgPool1d(4,2,1) between (and after) the scales (discriminator.py:153)
-            t_scale = xs.shape[1]
+            scale_in[i] = xs
+            xs = ops.avgpool4(xs)
+    results: List = [None] * len(subs)
+    sub_ctx: List = [None] * len(subs)
+
+    def run(idx: List[int]) -> None:
+        for i in idx:
+            kind, d = subs[i]
+            if kind == "P":
+                p = d.period
+                t_pad = T + (p - T % p)          # reflect pad is always >= 1 (discriminator.py:36,86)
+                src = ops.reflect_pad_right(x, t_pad, dtype)
+                phases, t = p, t_pad // p
+            else:
+                src = ops.cast(scale_in[i], dtype)
+                phases, t = 1, scale_in[i].shape[1]
+            f0 = folds[id(d.layers[0])]
+            if f0.unfold:                         # im2col rows replace the raw input (kept for the first layer's wgrad)
+                src = unfold_input(f0, src, B, t, phases)
+            sub = dict(kind=kind, phases=phases, inputs=[src], ts=[t], t_in0=scale_in[i].shape[1] if kind == "S" else T, mod=d)
+            fmaps = []
+            h = src
+            for layer in d.layers:
+                _, h, t = _fwd(folds[id(layer)], h, B, t, phases=phases, act=ACT_LEAKY, want_act=True)
+                fmaps.append(h); sub["inputs"].append(h); sub["ts"].append(t)
+            logits, _, t = _fwd(folds[id(d.output)], h, B, t, phases=phases, want_raw=True, out_f32=True)
+            sub["ts"].append(t)
+            fmaps.append(logits)
+            if kind == "S":
+                sub["x_scale"] = scale_in[i]
+            results[i], sub_ctx[i] = fmaps, sub
+
+    heavy, rest = _heavy_split(subs)
+    if side is not None and heavy:
+        fork_join(side, lambda: run(heavy), lambda: run(rest))
+    else:
+        run(list(range(len(subs))))
+    ctx.subs = sub_ctx
+    ctx.keep = (scale_in, xs)
     return results, ctx
 
 
 def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tensor]],
                            dfmaps: Optional[Sequence[Sequence[Optional[Tensor]]]] = None, want_input_grad: bool = False,
-                           want_weight_grad: bool = True, plan: Optional[FoldPlan] = None) -> Optional[Tensor]:
+                           want_weight_grad: bool = True, plan: Optional[FoldPlan] = None, side=None) -> Optional[Tensor]:
     """Backward through one discriminator forward.
     dlogits[d]: gradient w.r.t. the logits of sub-discriminator d (`dtype`, same shape) or None;
     dfmaps[d][j]: gradient w.r.t. feature map j (`dtype`) or None.
-    Returns d/dx fp32 [B,T,C] when want_input_grad."""
+    Returns d/dx fp32 [B,T,C] when want_input_grad.  `side`: optional extra stream for the full-rate scale
+    discriminator (see discriminator_forward)."""
     B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
     dev = ctx.subs[0]["inputs"][0].device
     if plan is not None and want_weight_grad:
         ws = plan                                 # caller zeroes the arena and runs plan.backward() after its passes
     else:
         ws = _Workspace([folds[id(c)] for c in discriminator_convs(model)], dev) if want_weight_grad else None
+        if ws is not None:
+            side = None                           # the bump allocator of _Workspace is not safe across branches
     dx = torch.zeros((B, T, Cc), device=dev, dtype=torch.float32) if want_input_grad else None
-    scale_grads = []                          # (t_in, d/d x_scale) for the multi-scale chain
-    for di, sub in enumerate(ctx.subs):
-        d, phases, inputs, ts = sub["mod"], sub["phases"], sub["inputs"], sub["ts"]
-        convs = list(d.layers) + [d.output]
-        g = dlogits[di]
-        fm_g = dfmaps[di] if dfmaps is not None else None
-        if g is None and (fm_g is None or all(t is None for t in fm_g)):
-            if sub["kind"] == "S":
-                scale_grads.append((sub["t_in0"], None))
-            continue
-        if g is None:
-            g = torch.zeros((B, ts[-1] * phases, 1), device=dev, dtype=dtype)
-        dxin = None
-        for j in reversed(range(len(convs))):
-            f = folds[id(convs[j])]
-            if want_weight_grad:
-                _wgrad(f, inputs[j], g, B, ts[j], ts[j + 1], ws, phases=phases)
-            if j == 0:
-                if want_input_grad:
-                    dxin = _dgrad(f, g, B, ts[1], ts[0], phases=phases, out_f32=True)
-                break
-            g = _dgrad(f, g, B, ts[j + 1], ts[j], phases=phases, mask=inputs[j], mask_mode=ACT_LEAKY,
-                       add_pre=fm_g[j - 1] if fm_g is not None else None)
-        if want_input_grad:
-            if sub["kind"] == "P":
-                ops.reflect_pad_right_bwd(dxin, T, dx)
-            else:
-                scale_grads.append((sub["t_in0"], dxin))
-    if want_input_grad and scale_grads:
+    n_sub = len(ctx.subs)
+    scale_grad: List = [None] * n_sub             # d/d x_scale of the scale discriminators
+
+    def run(idx: List[int]) -> None:
+        for di in idx:
+            sub = ctx.subs[di]
+            d, phases, inputs, ts = sub["mod"], sub["phases"], sub["inputs"], sub["ts"]
+            convs = list(d.layers) + [d.output]
+            g = dlogits[di]
+            fm_g = dfmaps[di] if dfmaps is not None else None
+            if g is None and (fm_g is None or all(t is None for t in fm_g)):
+                continue
+            if g is None:
+                g = torch.zeros((B, ts[-1] * phases, 1), device=dev, dtype=dtype)
+            dxin = None
+            for j in reversed(range(len(convs))):
+                f = folds[id(convs[j])]
+                if want_weight_grad:
+                    _wgrad(f, inputs[j], g, B, ts[j], ts[j + 1], ws, phases=phases)
+                if j == 0:
+                    if want_input_grad:
+                        dxin = _dgrad(f, g, B, ts[1], ts[0], phases=phases, out_f32=True)
+                    break
+                g = _dgrad(f, g, B, ts[j + 1], ts[j], phases=phases, mask=inputs[j], mask_mode=ACT_LEAKY,
+                           add_pre=fm_g[j - 1] if fm_g is not None else None)
+            if want_input_grad:
+                if sub["kind"] == "P":
+                    ops.reflect_pad_right_bwd(dxin, T, dx)      # period discriminators all run in the same branch
+                else:
+                    scale_grad[di] = dxin
+
+    heavy, rest = _heavy_split([(sub["kind"], None) for sub in ctx.subs])
+    if side is not None and heavy:
+        fork_join(side, lambda: run(heavy), lambda: run(rest))
+    else:
+        run(list(range(n_sub)))
+    if want_input_grad:
         # x_s(i+1) = avgpool(x_s(i)): fold the chain from the coarsest scale back to the input
         carry = None
-        for t_in, gsc in reversed(scale_grads):
-            cur = gsc
+        for di in reversed([i for i, sub in enumerate(ctx.subs) if sub["kind"] == "S"]):
+            t_in, cur = ctx.subs[di]["t_in0"], scale_grad[di]
             if carry is not None:
                 if cur is None:
                     cur = torch.zeros((B, t_in, Cc), device=dev, dtype=torch.float32)

@@ -92,7 +92,11 @@ class GanTrainer:
         # joined back into the current stream, also under graph capture), which fills the SMs that the many
         # sub-148-tile kernels of the small discriminator layers leave idle
         self._side = torch.cuda.Stream(device=dev)
+        self._side2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # per pass: the heavy sub-discriminator
         self.concurrent_d = True
+
+    def _s2(self, i: int):
+        return self._side2[i] if self.concurrent_d else None
 
     def _fork(self) -> None:
         ev = torch.cuda.Event()
@@ -132,8 +136,8 @@ class GanTrainer:
         self._d_folded = True
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
         (res_f, ctx_f), (res_r, ctx_r) = self._two_passes(
-            lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f1),
-            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2))
+            lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(0)),
+            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(1)))
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
         nd = len(res_f)
@@ -144,8 +148,10 @@ class GanTrainer:
         # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
         self.d_plan.zero()
         self._two_passes(
-            lambda: passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan),
-            lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan))
+            lambda: passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True,
+                                                  plan=self.d_plan, side=self._s2(0)),
+            lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True,
+                                                  plan=self.d_plan, side=self._s2(1)))
         self.d_plan.backward()
 
     def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
@@ -159,8 +165,8 @@ class GanTrainer:
             self._d_folded = True
             f4 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
             (res_f, ctx_f), (res_r, _) = self._two_passes(
-                lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f3),
-                lambda: passes.discriminator_forward(self.net_d, x_real, dt, f4))
+                lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f3, side=self._s2(0)),
+                lambda: passes.discriminator_forward(self.net_d, x_real, dt, f4, side=self._s2(1)))
             self.d_folds = f4
             nd = len(res_f)
             dlog = ops.mse_const_multi([fm[-1] for fm in res_f], [1.0] * nd, self.slots, [1] * nd, 1.0, dt)   # train.py:210-211
@@ -172,7 +178,8 @@ class GanTrainer:
                     dfm.append(grads[i:i + len(fm_f) - 1]); i += len(fm_f) - 1
             else:
                 dfm = [[None] * (len(fm_f) - 1) for fm_f in res_f]
-            dx_d = passes.discriminator_backward(self.net_d, ctx_f, dlog, dfm, want_input_grad=True, want_weight_grad=False)
+            dx_d = passes.discriminator_backward(self.net_d, ctx_f, dlog, dfm, want_input_grad=True, want_weight_grad=False,
+                                                 side=self._s2(0))
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
