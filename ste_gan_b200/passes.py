@@ -137,6 +137,20 @@ class FoldPlan:
     re-homed into their flat buffers (trainer.FlatParams): the table stores raw pointers to them.
     Spectral-norm convs keep their per-forward fold (one power iteration each); they only get gradient scratch here."""
     deferred = True     # weight-norm fold backward runs once per phase: backward()
+    wgrad_stream = None  # while set (async_wgrads), _wgrad launches on this stream, ordered after its operands
+    _keep: list = []
+
+    def async_wgrads(self, stream) -> None:
+        """From now until join_wgrads(), weight-gradient kernels go to `stream`: a conv's wgrad and dgrad both
+        consume dy and are independent, so the backward critical path becomes the dgrad chain alone."""
+        self.wgrad_stream, self._keep = stream, []
+
+    def join_wgrads(self) -> None:
+        if self.wgrad_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.wgrad_stream)
+            torch.cuda.current_stream().wait_event(ev)
+        self.wgrad_stream, self._keep = None, []     # operands were kept alive until the side stream was joined
 
     def __init__(self, convs: Sequence, dtype: torch.dtype):
         from . import _lib
@@ -269,6 +283,20 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
 
 def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _Workspace, phases: int = 1) -> None:
     """Weight + bias gradient of one conv.  For an `unfold` layer `x` is the im2col tensor from unfold_input()."""
+    m = f.mod
+    side = getattr(ws, "wgrad_stream", None)
+    if side is not None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())       # dy (and x) are ready at this point of the current stream
+        side.wait_event(ev)
+        ws._keep.append((x, dy))                     # the current stream must not recycle them before the join
+        with torch.cuda.stream(side):
+            _wgrad_here(f, x, dy, B, t_x, t_dy, ws, phases)
+        return
+    _wgrad_here(f, x, dy, B, t_x, t_dy, ws, phases)
+
+
+def _wgrad_here(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws, phases: int) -> None:
     m = f.mod
     dw = ws.take(f)
     if f.unfold:
@@ -403,7 +431,7 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
     return x_pred, ctx
 
 
-def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None) -> None:
+def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
     dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output.  With a FoldPlan the packed weight gradients go to
     its arena and the weight-norm backward of all 45 convs is one launch at the end."""
@@ -411,6 +439,8 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
     if plan is not None:
         plan.zero()
         ws = plan
+        if side is not None:
+            plan.async_wgrads(side)             # `side`: extra stream for the 46 weight-gradient kernels
     else:
         ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
     blocks = list(model.gblocks)[1:]
@@ -436,6 +466,7 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
             ops.embed_concat_bwd(dx0[:, :, :off + d0].contiguous(), ctx.ids[0], off, _grad_of(ctx.tables[0]))
             ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
     if plan is not None:
+        plan.join_wgrads()
         plan.backward()
 
 

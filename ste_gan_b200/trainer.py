@@ -183,7 +183,7 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan)
+        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1))
         self._gctx = None
 
     def _phase_opt_g(self) -> None:
