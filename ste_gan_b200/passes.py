@@ -137,20 +137,29 @@ class FoldPlan:
     re-homed into their flat buffers (trainer.FlatParams): the table stores raw pointers to them.
     Spectral-norm convs keep their per-forward fold (one power iteration each); they only get gradient scratch here."""
     deferred = True     # weight-norm fold backward runs once per phase: backward()
-    wgrad_stream = None  # while set (async_wgrads), _wgrad launches on this stream, ordered after its operands
+    wgrad_stream = None  # while set (async_wgrads), _wgrad launches on a side stream, ordered after its operands
     _keep: list = []
 
     def async_wgrads(self, stream) -> None:
-        """From now until join_wgrads(), weight-gradient kernels go to `stream`: a conv's wgrad and dgrad both
-        consume dy and are independent, so the backward critical path becomes the dgrad chain alone."""
+        """From now until join_wgrads(), weight-gradient kernels go to a side stream: a conv's wgrad and dgrad both
+        consume dy and are independent, so the backward critical path becomes the dgrad chain alone.
+        `stream`: one CUDA stream, or a dict {id of a compute stream (.cuda_stream): its side stream} when several
+        branches run backward passes concurrently (wgrads launched from a stream that is not in the dict stay inline)."""
         self.wgrad_stream, self._keep = stream, []
 
+    def side_for_current(self):
+        ws = self.wgrad_stream
+        if isinstance(ws, dict):
+            return ws.get(torch.cuda.current_stream().cuda_stream)
+        return ws
+
     def join_wgrads(self) -> None:
-        if self.wgrad_stream is not None:
+        ws = self.wgrad_stream
+        for st in (ws.values() if isinstance(ws, dict) else ([ws] if ws is not None else [])):
             ev = torch.cuda.Event()
-            ev.record(self.wgrad_stream)
+            ev.record(st)
             torch.cuda.current_stream().wait_event(ev)
-        self.wgrad_stream, self._keep = None, []     # operands were kept alive until the side stream was joined
+        self.wgrad_stream, self._keep = None, []     # operands were kept alive until the side streams were joined
 
     def __init__(self, convs: Sequence, dtype: torch.dtype):
         from . import _lib
@@ -284,7 +293,7 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
 def _wgrad(f: Folded, x: Tensor, dy: Tensor, B: int, t_x: int, t_dy: int, ws: _Workspace, phases: int = 1) -> None:
     """Weight + bias gradient of one conv.  For an `unfold` layer `x` is the im2col tensor from unfold_input()."""
     m = f.mod
-    side = getattr(ws, "wgrad_stream", None)
+    side = ws.side_for_current() if getattr(ws, "wgrad_stream", None) is not None else None
     if side is not None:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())       # dy (and x) are ready at this point of the current stream

@@ -93,6 +93,7 @@ class GanTrainer:
         # sub-148-tile kernels of the small discriminator layers leave idle
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # per pass: the heavy sub-discriminator
+        self._wg = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # weight-gradient side streams
         self.concurrent_d = True
 
     def _s2(self, i: int):
@@ -147,11 +148,15 @@ class GanTrainer:
         # both passes accumulate their packed weight gradients in the plan's arena; the weight-norm backward is
         # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
         self.d_plan.zero()
+        if self.concurrent_d:    # every backward branch (2 passes x {scale-0, rest}) sends its wgrads to its own side stream
+            cur = torch.cuda.current_stream()
+            self.d_plan.async_wgrads({st.cuda_stream: w for st, w in zip((cur, self._side, self._side2[0], self._side2[1]), self._wg)})
         self._two_passes(
             lambda: passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True,
                                                   plan=self.d_plan, side=self._s2(0)),
             lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True,
                                                   plan=self.d_plan, side=self._s2(1)))
+        self.d_plan.join_wgrads()
         self.d_plan.backward()
 
     def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
