@@ -129,16 +129,23 @@ class GanTrainer:
         self.slots.zero_()
         self.G.zero_grad(); self.D.zero_grad()
         self._gctx = None
-        x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
-        self.x_pred, self._gctx = x_pred, gctx
         if not self.use_adv:
+            self.x_pred, self._gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
             return
+        # folds first (the spectral-norm power iterations of the fake and the real forward happen in that order, as in
+        # train.py:190-191); then the real pass - which needs neither G nor x_pred - overlaps the generator forward
         f1 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=not self._d_folded)
         self._d_folded = True
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
-        (res_f, ctx_f), (res_r, ctx_r) = self._two_passes(
-            lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(0)),
-            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(1)))
+
+        def fake_side():
+            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
+            self.x_pred, self._gctx = x_pred, gctx
+            return passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(1))
+
+        (res_r, ctx_r), (res_f, ctx_f) = self._two_passes(
+            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(0)), fake_side)
+        x_pred = self.x_pred
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
         nd = len(res_f)
