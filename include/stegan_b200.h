@@ -76,8 +76,11 @@ typedef struct StgConv {
   int32_t act;        /* STG_ACT_* applied for y_act */
   int32_t dup_rows;   /* 1: y_act row r is written to rows 2r and 2r+1 (nearest-upsample x2) */
   int32_t out_f32;    /* 1: y_raw and y_act are float32 regardless of dtype */
+  int32_t w_fwd_pack; /* transposed only: `w` is the FORWARD pack wf [k][c_out][c_in/groups] (= [k][c_src][c_dst/groups]);
+                         the tcgen05 engine reads it as an MN-major operand, so no second (data-gradient) pack is needed.
+                         The CUDA-core engine needs the data-gradient pack wd (w_fwd_pack = 0). */
   const void* src;
-  const void* w;        /* packed [k][c_dst][c_src/groups] (see stg_weightnorm_fold) */
+  const void* w;        /* packed [k][c_dst][c_src/groups] (see stg_weightnorm_fold), or the forward pack if w_fwd_pack */
   const float* bias;    /* [c_dst] or NULL */
   const void* add_pre;  /* [B][rows][c_dst] or NULL */
   const void* mask;     /* [B][rows][c_dst] or NULL */
@@ -150,6 +153,7 @@ int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const flo
  *   row0  = running sum of c_out (one block per output channel), total_rows = its end value
  *   tile0 = running sum of pack tiles: k * pack_groups * ceil(c_out/pg/32) * ceil(c_in/pg/32), or for
  *           STG_PACK_UNFOLD ceil(c_out/32) * ceil(roundup8(k*c_in)/32); total_tiles = its end value
+ * total_tiles = 0 selects the row form, valid when every item has wd == NULL (forward pack only).
  * stg_weightnorm_fold_multi fills wf / wd / scale of every item; stg_weightnorm_fold_bwd_multi turns every
  * item's dw (layout dw_ld / dw_span, see stg_wgrad_layout) into dv / dg.
  */

@@ -23,7 +23,7 @@ MAX_TAPS = 48
 class StgConv(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dtype", "engine", "n_samples", "phases", "t_src", "t_dst", "c_src", "c_dst", "groups", "k", "dilation",
-        "stride", "pad", "transposed", "pair_sum", "post_shift", "mask_mode", "act", "dup_rows", "out_f32")] + [
+        "stride", "pad", "transposed", "pair_sum", "post_shift", "mask_mode", "act", "dup_rows", "out_f32", "w_fwd_pack")] + [
         (n, C.c_void_p) for n in ("src", "w", "bias", "add_pre", "mask", "add_post", "y_raw", "y_act")]
 
 

@@ -25,6 +25,7 @@ static int validate_conv(const StgConv* d) {
   if (d->post_shift < 0 || d->post_shift > 1) return STG_EINVAL;
   if (d->dup_rows && d->pair_sum) return STG_EINVAL;
   if (!d->y_raw && !d->y_act) return STG_EINVAL;
+  if (d->w_fwd_pack && !d->transposed) return STG_EINVAL;
   return STG_OK;
 }
 
@@ -37,12 +38,12 @@ extern "C" int stg_conv(const StgConv* d, stg_stream_t stream) {
   if (r) return r;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (d->engine) {
-    case STG_ENGINE_SIMT: return conv_simt(d, s);
+    case STG_ENGINE_SIMT: return d->w_fwd_pack ? STG_EUNSUPPORTED : conv_simt(d, s);
     case STG_ENGINE_TCGEN05: return conv_tc(d, s);
     case STG_ENGINE_AUTO:
       if (conv_c1_supported(d)) return conv_c1(d, s);   // 1-channel logits layers: matrix-vector kernels
       if (conv_tc_supported(d)) return conv_tc(d, s);
-      return conv_simt(d, s);
+      return d->w_fwd_pack ? STG_EUNSUPPORTED : conv_simt(d, s);
     default: return STG_EINVAL;
   }
 }

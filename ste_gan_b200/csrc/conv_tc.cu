@@ -78,6 +78,8 @@ struct TcP {
   // function of the shared-memory address, tools/rowshift_probe.py), so a k-tap conv loads its activations
   // once per group instead of once per tap.  One pipeline stage = (group, 64-channel chunk).
   int hb, a_bytes, max_ntaps;  // h rows per A box, bytes reserved for the window (1024-aligned), taps per stage slot
+  int b_mn;                    // data-gradient: W tiles are [64 co rows][64 ci] boxes of the FORWARD pack (MN-major B operand);
+                               // 2 = all bn/64 boxes of a tile come from ONE 4-D TMA box (c_dst/g % 64 == 0)
   int res_gfirst[MAX_RES + 1]; // groups of residue r: [res_gfirst[r], res_gfirst[r+1])
   TapTables tt;
   long long* trace;            // debug timeline (stg_debug_set_trace) or nullptr
@@ -162,7 +164,7 @@ struct Tracer {
 
 // ---------------------------------------------------------------------------------------------- tiles
 struct Tile {
-  int b, res, h0, col0, ch0, g0, n_iters;
+  int b, res, h0, col0, ch0, wcol0, g0, n_iters;
 };
 __device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
   Tile x;
@@ -174,6 +176,7 @@ __device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
   x.h0 = tm * p.nh;
   x.col0 = tn * p.bn;
   x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
+  x.wcol0 = x.col0 % p.cd_g;           // column offset inside the group (forward-pack W coordinates)
   x.g0 = p.res_gfirst[x.res];
   x.n_iters = (p.res_gfirst[x.res + 1] - x.g0) * p.k_chunks;
   return x;
@@ -307,13 +310,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int bx = 0; bx < p.a_boxes; ++bx)
             tma_load_4d(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
                         (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
-          tma_load_3d(a_dst + p.a_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[g]);
+          if (!p.b_mn) {
+            tma_load_3d(a_dst + p.a_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[g]);
+          } else if (p.b_mn == 2) {  // forward pack seen as (64, co row, ci/64, tap): one box = the whole [bn/64][64][64] tile
+            tma_load_4d(a_dst + p.a_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64, p.tt.tap_w[g]);
+          } else {  // forward pack [k][c_src][c_dst/g]: bn/64 boxes of (64 destination channels x 64 source-channel rows)
+            for (int nb = 0; nb < p.bn / 64; ++nb)
+              tma_load_3d(a_dst + p.a_bytes + nb * 8192, &tmW, full_bar(s), x.wcol0 + nb * 64, x.ch0 + chunk * KC, p.tt.tap_w[g]);
+          }
         }
       }
     }
   } else if (warp == 1 && p.max_ntaps == 1) {
     // ===== MMA issuer, one tap per stage =====
-    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
+    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
     Tracer trc(lane == 0 ? p.trace : nullptr, 1);
     int itg = 0, acc_i = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -331,10 +341,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t a_addr = smem_base + s * stage_bytes;
           const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes);
+          if (!p.b_mn) {
+            const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes);
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks)  // +32 bytes (16 bf16) along K inside the swizzle atom
-            umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < KC / 16; ++ks)  // +32 bytes (16 bf16) along K inside the swizzle atom
+              umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          } else {
+            const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + p.a_bytes, 8192, 1024);
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks)  // B: 16 K rows = 2048 B further down
+              umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 128 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
           umma_commit(empty_bar(s));
           if (it == x.n_iters - 1) umma_commit(tmem_full_bar(as));
         }
@@ -361,14 +378,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d_if(lead, a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
                          (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
 #pragma unroll 1
-        for (int tl = 0; tl < nt; ++tl)
-          tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
+        for (int tl = 0; tl < nt; ++tl) {
+          if (!p.b_mn) {
+            tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
+          } else if (p.b_mn == 2) {
+            tma_load_4d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64,
+                           p.tt.tap_w[t0 + tl]);
+          } else {
+#pragma unroll 1
+            for (int nb = 0; nb < p.bn / 64; ++nb)
+              tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes + nb * 8192, &tmW, full_bar(s), x.wcol0 + nb * 64,
+                             x.ch0 + chunk * KC, p.tt.tap_w[t0 + tl]);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer, tap windows (warp-uniform control flow) =====
     const bool lead = lane == 0;
-    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, 0);
+    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
     int itg = 0, acc_i = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const Tile x = decode_tile(p, t);
@@ -388,10 +416,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tl = 0; tl < nt; ++tl) {
           // tap = the same window, `tap_shift` h rows (x pack phase rows of 128 B) further down
           const uint64_t adesc = smem_desc_kmajor_sw128(a_addr + (uint32_t)(p.tt.tap_shift[t0 + tl] * p.pack * KC * 2));
-          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes + tl * b_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes + tl * b_bytes;
+          const uint64_t bdesc = p.b_mn ? smem_desc_mnmajor_sw128(b_addr, 8192, 1024) : smem_desc_kmajor_sw128(b_addr);
+          const uint64_t bstep = p.b_mn ? 128 : 2;
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks)
-            umma_bf16_if(lead, d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || tl > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_if(lead, d_tmem, adesc + 2 * ks, bdesc + bstep * ks, idesc, (it > 0 || tl > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit_if(lead, empty_bar(s));
         umma_commit_if(lead && it == x.n_iters - 1, tmem_full_bar(as));
@@ -692,14 +722,28 @@ static int sm_count() {
 // on a fraction of the chip); a column tile never straddles groups.
 static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
   if (groups == 1 && (cd_g % 16) != 0) return cd_g <= 16 ? 16 : (cd_g <= 128 ? ((cd_g + 15) / 16) * 16 : 128);
-  static const int env_bn = getenv("STG_BN") ? atoi(getenv("STG_BN")) : 0;  // tuning override
+  static const int env_bn = getenv("STG_BN") ? atoi(getenv("STG_BN")) : 0;  // tuning overrides
+  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 64;
   if (env_bn > 0 && cd_g % env_bn == 0) return env_bn;
   int best = 0;
   for (int bn = 256; bn >= 16; bn -= 16) {
     if (cd_g % bn) continue;
     if (best != 0 && bn < 128) break;              // narrower than 128 only when nothing wider divides
     best = bn;
-    if (row_tiles * (cd_g / bn) * groups >= 96) break;
+    if (row_tiles * (cd_g / bn) * groups >= min_tiles) break;
+  }
+  return best;
+}
+
+// data-gradient column tiles are whole 64-channel boxes of the forward pack
+static int pick_bn_mn(int cd_g, int groups, int64_t row_tiles) {
+  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 64;
+  if (cd_g % 64 != 0) return groups == 1 ? (cd_g <= 64 ? 64 : 128) : 0;
+  int best = 0;
+  for (int bn = 256; bn >= 64; bn -= 64) {
+    if (cd_g % bn) continue;
+    best = bn;
+    if (row_tiles * (cd_g / bn) * groups >= min_tiles) break;
   }
   return best;
 }
@@ -720,6 +764,9 @@ bool conv_tc_supported(const StgConv* d) {
     if ((d->c_src / d->groups) % KC) return false;       // whole K chunks per group (see stg_tc_pack_groups)
     if (((d->c_dst / d->groups) % 16) != 0) return false;
   }
+  if (d->transposed && !d->w_fwd_pack) return false;     // the data-gradient reads the forward pack (MN-major B operand)
+  if (d->transposed && ((d->c_dst / d->groups) % 8) != 0) return false;
+  if (d->transposed && d->groups > 1 && ((d->c_dst / d->groups) % 64) != 0) return false;
   if (d->transposed && d->stride > MAX_RES) return false;
   if (d->transposed && d->stride > 1 && d->pair_sum) return false;
   if (!d->transposed && d->stride > 4) return false;
@@ -772,7 +819,9 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   p.k_chunks = ceil_div(p.cs_g, KC);
   tile_geometry(d, &p.pack, &p.nh, &p.n_res, &p.tiles_m);
   p.mrows = p.nh * p.pack;
-  p.bn = pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m);
+  p.b_mn = d->transposed ? 1 : 0;
+  p.bn = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m)
+                : pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m);
   if (p.bn <= 0) return STG_EUNSUPPORTED;
   p.tmem_cols = 512;  // two accumulator buffers ACC_COLS apart
   // ---- taps per residue class, as (source offset, weight index)
@@ -904,11 +953,28 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     int r = make_tmap_bf16(&tmA, d->src, 4, dims, strides, box, es);
     if (r) return r;
   }
-  {
+  if (!p.b_mn) {
     const uint64_t C = p.cs_g, N = d->c_dst, K = d->k;
     const uint64_t dims[3] = {C, N, K};
     const uint64_t strides[2] = {C * 2, N * C * 2};
     const uint32_t box[3] = {(uint32_t)KC, (uint32_t)p.bn, 1};
+    int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr);
+    if (r) return r;
+  } else if (p.cd_g % 64 == 0) {
+    // forward pack [k][c_src][cd_g] seen as (64 inner, source-channel row, cd_g/64, tap): ONE box delivers the whole
+    // MN-major tile [bn/64][64 rows][64] (one TMA instruction per stage instead of bn/64 - each costs ~0.12 us to issue)
+    p.b_mn = 2;
+    const uint64_t N = p.cd_g, R = d->c_src, K = d->k;
+    const uint64_t dims[4] = {64, R, N / 64, K};
+    const uint64_t strides[3] = {N * 2, 128, R * N * 2};
+    const uint32_t box[4] = {64, (uint32_t)KC, (uint32_t)(p.bn / 64), 1};
+    int r = make_tmap_bf16(&tmW, d->w, 4, dims, strides, box, nullptr);
+    if (r) return r;
+  } else {  // (destination channel within group, source channel row, tap); bn/64 boxes per tile, partial last box zero-filled
+    const uint64_t N = p.cd_g, R = d->c_src, K = d->k;
+    const uint64_t dims[3] = {N, R, K};
+    const uint64_t strides[2] = {N * 2, R * N * 2};
+    const uint32_t box[3] = {64, (uint32_t)KC, 1};
     int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr);
     if (r) return r;
   }

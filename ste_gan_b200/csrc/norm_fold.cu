@@ -282,7 +282,57 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __re
   }
 }
 
+// Row form of the fold (forward pack only - the tcgen05 data-gradient reads it too): one block per output channel
+// stages the v row in shared memory (one coalesced read), reduces ||v||, and writes scale plus the k rows
+// wf[j][co][:] (coalesced; the transposition (ci, j) -> (j, ci) happens in shared memory).  Replaces the
+// scale + 32x32-tile pack pair, whose v reads were strided by k.
+constexpr int FOLD_ROW_MAX = 4096;
+template <typename T>
+__global__ void __launch_bounds__(256) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items) {
+  __shared__ float row[FOLD_ROW_MAX];
+  __shared__ float red[32];
+  const int it = find_item(items, n_items, blockIdx.x, false);
+  const StgFoldItem d = items[it];
+  const int co = blockIdx.x - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+  const float* vr = d.v + (int64_t)co * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float x = vr[i];
+    if (i < FOLD_ROW_MAX) row[i] = x;
+    ss = fmaf(x, x, ss);
+  }
+  ss = block_sum(ss, red);   // (contains the barrier that publishes row[])
+  const float sc = d.g[co] / sqrtf(ss);
+  if (threadIdx.x == 0) d.scale[co] = sc;
+  T* wf = static_cast<T*>(d.wf);
+  if (d.flags & STG_PACK_UNFOLD) {           // wf[co][q], q = j*c_in + c  (groups == 1)
+    const int Kp = (k * cin_g + 7) / 8 * 8;
+    for (int q = threadIdx.x; q < Kp; q += 256) {
+      float w = 0.f;
+      if (q < k * cin_g) {
+        const int j = q / cin_g, c = q - j * cin_g, i = c * k + j;
+        w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc;
+      }
+      wf[(int64_t)co * Kp + q] = from_f<T>(w);
+    }
+    return;
+  }
+  const int pg = d.pg, c_in = cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
+  // this row's own group occupies columns [off, off + cin_g) of its pack group; the rest of the row is zero
+  const int off = ((co / cout_g) - (co / cout_gp) * (d.groups / pg)) * cin_g;
+  for (int j = 0; j < k; ++j) {
+    T* dst = wf + ((int64_t)j * d.c_out + co) * cin_gp;
+    for (int cip = threadIdx.x; cip < cin_gp; cip += 256) {
+      const int c = cip - off;
+      float w = 0.f;
+      if (c >= 0 && c < cin_g) { const int i = c * k + j; w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc; }
+      dst[cip] = from_f<T>(w);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int accumulate) {
+  __shared__ float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
   __shared__ float red[32];
   const int it = find_item(items, n_items, blockIdx.x, false);
   const StgFoldItem d = items[it];
@@ -290,23 +340,30 @@ __global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __
   const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
   const float* vr = d.v + (int64_t)co * n;
   const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
-  // (a register-cached single-pass variant measured 1.8x SLOWER: the second pass hits L1/L2 anyway)
+  const bool staged = n <= FOLD_ROW_MAX;
+  if (staged) {   // coalesced read of each tap's run of cin_g gradients, scattered (stride k, k odd) into shared memory
+    for (int j = 0; j < k; ++j)
+      for (int ci = threadIdx.x; ci < cin_g; ci += 256) sdw[ci * k + j] = dr[j * span + ci];
+    __syncthreads();
+  }
   float ss = 0.f, dot = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ci = i / k, j = i - ci * k;
+  for (int i = threadIdx.x; i < n; i += 256) {
     const float x = vr[i];
+    float g;
+    if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
     ss = fmaf(x, x, ss);
-    dot = fmaf(x, dr[j * span + ci], dot);
+    dot = fmaf(x, g, dot);
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
   const float norm = sqrtf(ss), gg = d.g[co];
   const float a = gg / norm, bcoef = gg * dot / (norm * ss);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ci = i / k, j = i - ci * k;
-    const float val = a * dr[j * span + ci] - bcoef * vr[i];
-    float* o = d.dv + (int64_t)co * n + i;
-    *o = accumulate ? (*o + val) : val;
+  float* orow = d.dv + (int64_t)co * n;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float g;
+    if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
+    const float val = a * g - bcoef * vr[i];
+    orow[i] = accumulate ? (orow[i] + val) : val;
   }
   if (threadIdx.x == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
 }
@@ -419,7 +476,14 @@ extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span
 extern "C" int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, int total_rows, int total_tiles, int dtype,
                                          stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!items || n_items < 1 || total_rows < 1 || total_tiles < 1) return STG_EINVAL;
+  if (!items || n_items < 1 || total_rows < 1 || total_tiles < 0) return STG_EINVAL;
+  if (total_tiles == 0) {  // row form: every item wants the forward pack only (wd == NULL)
+    if (dtype == STG_F32) wn_fold_rows_kernel<float><<<total_rows, 256, 0, s>>>(items, n_items);
+    else if (dtype == STG_BF16) wn_fold_rows_kernel<bf16><<<total_rows, 256, 0, s>>>(items, n_items);
+    else return STG_EINVAL;
+    STG_LAUNCH_CHECK();
+    return STG_OK;
+  }
   wn_scale_multi_kernel<<<total_rows, 256, 0, s>>>(items, n_items);
   STG_LAUNCH_CHECK();
   if (dtype == STG_F32) pack_multi_kernel<float><<<total_tiles, 256, 0, s>>>(items, n_items);

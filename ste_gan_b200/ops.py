@@ -59,8 +59,9 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
          pair_sum: bool = False, post_shift: int = 0, mask: Optional[Tensor] = None, mask_mode: int = ACT_NONE,
          act: int = ACT_NONE, dup_rows: bool = False, bias: Optional[Tensor] = None, add_pre: Optional[Tensor] = None,
          add_post: Optional[Tensor] = None, y_raw: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
-         engine: int = ENGINE_AUTO) -> None:
-    """One StgConv launch (see include/stegan_b200.h for the exact contraction + epilogue)."""
+         engine: int = ENGINE_AUTO, w_fwd_pack: bool = False) -> None:
+    """One StgConv launch (see include/stegan_b200.h for the exact contraction + epilogue).
+    w_fwd_pack (transposed only): `w` is the forward pack wf - what the tcgen05 engine wants for data-gradients."""
     dt = src.dtype
     nv = n_samples * phases
     t_out = t_dst // 2 if pair_sum else t_dst
@@ -79,7 +80,7 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
                 n_samples=n_samples, phases=phases, t_src=t_src, t_dst=t_dst, c_src=c_src, c_dst=c_dst, groups=groups,
                 k=k, dilation=dilation, stride=stride, pad=pad, transposed=int(transposed), pair_sum=int(pair_sum),
                 post_shift=post_shift, mask_mode=mask_mode, act=act, dup_rows=int(dup_rows), out_f32=int(out_f32),
-                src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
+                w_fwd_pack=int(w_fwd_pack), src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
                 add_post=_ptr(add_post), y_raw=_ptr(y_raw), y_act=_ptr(y_act))
     lib = _lib.load()
     if profile is None:

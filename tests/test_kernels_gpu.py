@@ -77,11 +77,13 @@ def run_dgrad(ops, case, dtype, engine, dy, w, To):
     name, B, p, T, ci, co, k, d, s, pad, g = case
     dev = "cuda"
     pg = _pack_groups(ops, case, engine)
-    wd = pack_dgrad(expand_groups(w, g, pg), pg).to(dev, dtype)
+    fwd_pack = engine == ops.ENGINE_TCGEN05      # the tensor engine reads the forward pack as an MN-major operand
+    we = expand_groups(w, g, pg)
+    wd = (pack_fwd(we) if fwd_pack else pack_dgrad(we, pg)).to(dev, dtype)
     g = pg
     dx = torch.empty(B, T * p, ci, device=dev, dtype=torch.float32)
     ops.conv(dy.to(dev, dtype), wd, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
-             dilation=d, stride=s, pad=pad, transposed=True, y_raw=dx, engine=engine)
+             dilation=d, stride=s, pad=pad, transposed=True, y_raw=dx, engine=engine, w_fwd_pack=fwd_pack)
     torch.cuda.synchronize()
     return dx.cpu()
 
@@ -153,7 +155,7 @@ def _tc_conv_desc(ops, case, transposed):
     To = t_out_of(T, k, d, s, pad)
     if transposed:
         return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
-                    dilation=d, stride=s, pad=pad, transposed=1, src=1, w=1, y_raw=1)
+                    dilation=d, stride=s, pad=pad, transposed=1, w_fwd_pack=1, src=1, w=1, y_raw=1)
     return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k,
                 dilation=d, stride=s, pad=pad, transposed=0, src=1, w=1, y_raw=1)
 
@@ -220,8 +222,9 @@ def test_logits_layer_kernels(geom):
     gen = torch.Generator().manual_seed(5)
     m = _bf(torch.randn(B, T * p, ci, generator=gen)); pre = _bf(torch.randn(B, T * p, ci, generator=gen) * 0.1)
     dx = torch.empty(B, T * p, ci, device=dev, dtype=bf)
-    ops.conv(dy.to(dev, bf), pack_dgrad(w, 1).to(dev, bf), n_samples=B, phases=p, t_src=To, t_dst=T, c_src=1, c_dst=ci, k=k,
-             pad=pad, transposed=True, mask=m.to(dev, bf), mask_mode=ops.ACT_LEAKY, add_pre=pre.to(dev, bf), y_raw=dx)
+    ops.conv(dy.to(dev, bf), pack_fwd(w).to(dev, bf), n_samples=B, phases=p, t_src=To, t_dst=T, c_src=1, c_dst=ci, k=k,
+             pad=pad, transposed=True, mask=m.to(dev, bf), mask_mode=ops.ACT_LEAKY, add_pre=pre.to(dev, bf), y_raw=dx,
+             w_fwd_pack=True)
     ref = (gx_ref + pre.double()) * torch.where(m > 0, 1.0, 0.1).double()
     assert rel_l2(dx.float().cpu(), ref) < 4e-3        # bf16 output rounding
     dw = torch.zeros(1, k, ci, device=dev); db = torch.zeros(1, device=dev)
@@ -257,9 +260,11 @@ def test_fused_epilogue(engine_dtype):
     pre = q(torch.randn(B, T // 2, ci, generator=gen)); post = q(torch.randn(B, T // 2, ci, generator=gen))
     m = q(torch.randn(B, T // 2, ci, generator=gen))
     dx = torch.empty(B, T // 2, ci, device=dev, dtype=dtype)
-    ops.conv(dy.to(dev, dtype), pack_dgrad(w, 1).to(dev, dtype), n_samples=B, t_src=T, t_dst=T, c_src=co, c_dst=ci, k=k,
-             dilation=d, pad=d, transposed=True, pair_sum=True, add_pre=pre.to(dev, dtype), mask=m.to(dev, dtype),
-             mask_mode=ops.ACT_RELU, add_post=post.to(dev, dtype), y_raw=dx, engine=engine)
+    tc = eng == "tc"
+    ops.conv(dy.to(dev, dtype), (pack_fwd(w) if tc else pack_dgrad(w, 1)).to(dev, dtype), n_samples=B, t_src=T, t_dst=T,
+             c_src=co, c_dst=ci, k=k, dilation=d, pad=d, transposed=True, pair_sum=True, add_pre=pre.to(dev, dtype),
+             mask=m.to(dev, dtype), mask_mode=ops.ACT_RELU, add_post=post.to(dev, dtype), y_raw=dx, engine=engine,
+             w_fwd_pack=tc)
     xr = x.double().requires_grad_(True)
     (g,) = torch.autograd.grad(conv_ref(xr, w, None, dilation=d, pad=d), xr, dy.double())
     ref = (g[:, 0::2] + g[:, 1::2] + pre.double()) * (m.double() > 0) + post.double()
@@ -333,8 +338,8 @@ def test_unfold_first_layer(geom):
     ops.wgrad(xu, dy.cuda().to(torch.bfloat16), dw, None, n_samples=B, phases=p, t_in=To, t_out=To, c_in=kp, c_out=co, k=1)
     assert rel_l2(dw[:, :k * ci].reshape(co, k, ci).cpu(), gw_ref) < 1e-4
     du = torch.empty(B, To * p, kp, device="cuda", dtype=torch.bfloat16)
-    ops.conv(dy.cuda().to(torch.bfloat16), wd, n_samples=B, phases=p, t_src=To, t_dst=To, c_src=co, c_dst=kp, k=1,
-             transposed=True, y_raw=du)
+    ops.conv(dy.cuda().to(torch.bfloat16), wf, n_samples=B, phases=p, t_src=To, t_dst=To, c_src=co, c_dst=kp, k=1,
+             transposed=True, y_raw=du, w_fwd_pack=True)
     dx = torch.zeros(B, T * p, ci, device="cuda")
     ops.unfold_bwd(du, dx, n_samples=B, phases=p, t_src=T, t_dst=To, channels=ci, k=k, dilation=d, stride=s, pad=pad)
     assert rel_l2(dx.cpu(), gx_ref) < 1e-2        # du is stored in bf16

@@ -72,9 +72,9 @@ def main():
                                                   k=k, dilation=d, stride=s, pad=pad, bias=bias, act=ops.ACT_RELU,
                                                   add_post=res if co >= 8 else None, y_raw=y, y_act=ya)))
         if which in ("dgrad", "all") and co >= 8:
-            runs.append(("dgrad", lambda: ops.conv(dy, wd, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci,
+            runs.append(("dgrad", lambda: ops.conv(dy, wf, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci,
                                                     groups=pg, k=k, dilation=d, stride=s, pad=pad, transposed=True, mask=x,
-                                                    mask_mode=ops.ACT_RELU, y_raw=dx)))
+                                                    mask_mode=ops.ACT_RELU, y_raw=dx, w_fwd_pack=True)))
         if which in ("wgrad", "all") and co >= 32:
             runs.append(("wgrad", lambda: ops.wgrad(x, dy, dw, db, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=co,
                                                     groups=g, k=k, dilation=d, stride=s, pad=pad)))

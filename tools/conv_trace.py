@@ -19,8 +19,8 @@ def run():
         ops.conv(x, wf, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=pg, k=k, dilation=d, stride=s,
                  pad=pad, bias=bias, act=ops.ACT_RELU, add_post=res, y_raw=y, y_act=ya)
     else:
-        ops.conv(dy, wd, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=pg, k=k, dilation=d, stride=s,
-                 pad=pad, transposed=True, mask=x, mask_mode=ops.ACT_RELU, y_raw=dx)
+        ops.conv(dy, wf, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=pg, k=k, dilation=d, stride=s,
+                 pad=pad, transposed=True, mask=x, mask_mode=ops.ACT_RELU, y_raw=dx, w_fwd_pack=True)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
