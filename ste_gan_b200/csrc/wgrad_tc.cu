@@ -40,6 +40,9 @@ struct WgTcP {
   int n_taps, tap_groups, bnw, nbox_b, stages, tmem_cols;
   int chunks_per_sample, total_chunks, chunks_per_split;
   int bias_tg;                          // tap group whose x-tile-0 CTAs also accumulate the bias gradient (-1: none)
+  // x window (stride 1): the taps of a group read row-shifted views (tap * dilation rows further down) of ONE
+  // TMA-loaded window of 64 + (n_taps-1)*dilation rows per 64-channel box, instead of one 64-row tile per tap
+  int win, win_rows, wb_bytes, dilation;
   int tap_off[STG_MAX_TAPS];
   float* dbias;
 };
@@ -58,7 +61,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int a_bytes = 2 * BOX_BYTES;
   const int b_bytes = p.nbox_b * BOX_BYTES;  // per tap
-  const int stage_bytes = a_bytes + p.n_taps * b_bytes;
+  const int stage_bytes = a_bytes + (p.win ? p.nbox_b * p.wb_bytes : p.n_taps * b_bytes);
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;      // 2 x STAGE_TILE staging + BOX_BYTES of ones
   const uint32_t ones_base = epi_base + 2 * STAGE_TILE;
   const uint32_t bar_base = ones_base + BOX_BYTES;
@@ -100,7 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(a_bytes + ntap * b_bytes);
+      const uint32_t tx_bytes = (uint32_t)(a_bytes + (p.win ? p.nbox_b * p.win_rows * 128 : ntap * b_bytes));
       for (int q = q0; q < q1; ++q) {
         const int it = q - q0, s = it % p.stages, phs = (it / p.stages) & 1;
         const int n = q / p.chunks_per_sample, rc = q - n * p.chunks_per_sample;
@@ -111,10 +114,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const uint32_t a_dst = smem_base + s * stage_bytes;
         tma_load_4d(a_dst, &tmY, full_bar(s), co0, r0, ph, b);
         tma_load_4d(a_dst + BOX_BYTES, &tmY, full_bar(s), co0 + 64, r0, ph, b);
-        for (int tl = 0; tl < ntap; ++tl)
+        if (p.win) {
           for (int bx = 0; bx < p.nbox_b; ++bx)
-            tma_load_4d(a_dst + a_bytes + tl * b_bytes + bx * BOX_BYTES, &tmX, full_bar(s), ci0 + bx * 64,
-                        r0 * p.stride + p.tap_off[tap0 + tl], ph, b);
+            tma_load_4d(a_dst + a_bytes + bx * p.wb_bytes, &tmX, full_bar(s), ci0 + bx * 64, r0 + p.tap_off[tap0], ph, b);
+        } else {
+          for (int tl = 0; tl < ntap; ++tl)
+            for (int bx = 0; bx < p.nbox_b; ++bx)
+              tma_load_4d(a_dst + a_bytes + tl * b_bytes + bx * BOX_BYTES, &tmX, full_bar(s), ci0 + bx * 64,
+                          r0 * p.stride + p.tap_off[tap0 + tl], ph, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -129,7 +137,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const uint32_t a_addr = smem_base + s * stage_bytes;
         const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, BOX_BYTES, 1024);
         for (int tl = 0; tl < ntap; ++tl) {
-          const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + a_bytes + tl * b_bytes, BOX_BYTES, 1024);
+          const uint64_t bdesc = p.win
+              ? smem_desc_mnmajor_sw128(a_addr + a_bytes + (uint32_t)(tl * p.dilation * 128), (uint32_t)p.wb_bytes, 1024)
+              : smem_desc_mnmajor_sw128(a_addr + a_bytes + tl * b_bytes, BOX_BYTES, 1024);
 #pragma unroll
           for (int ks = 0; ks < RK / 16; ++ks)  // 16 rows = 2048 B further along K
             umma_bf16(tmem_base + (uint32_t)(tl * p.bnw), adesc + (uint64_t)(ks * 128), bdesc + (uint64_t)(ks * 128), idesc,
@@ -255,7 +265,11 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
   p.tmem_cols = 32;
   while (p.tmem_cols < taps * p.bnw + BIAS_COLS) p.tmem_cols *= 2;
   for (int j = 0; j < d->k; ++j) p.tap_off[j] = j * d->dilation - d->pad;
-  const int stage_bytes = 2 * BOX_BYTES + taps * p.nbox_b * BOX_BYTES;
+  p.dilation = d->dilation;
+  p.win_rows = RK + (taps - 1) * d->dilation;
+  p.win = (d->stride == 1 && taps > 1 && p.win_rows <= 256) ? 1 : 0;
+  p.wb_bytes = ceil_div(p.win_rows * 128, 1024) * 1024;
+  const int stage_bytes = 2 * BOX_BYTES + (p.win ? p.nbox_b * p.wb_bytes : taps * p.nbox_b * BOX_BYTES);
   int stages = smem_budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.chunks_per_sample = ceil_div(d->t_out, RK);
@@ -285,7 +299,7 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
     const uint64_t C = d->c_in, P = d->phases, T = d->t_in, B = d->n_samples;
     const uint64_t dims[4] = {C, T, P, B};
     const uint64_t strides[3] = {P * C * 2, C * 2, T * P * C * 2};
-    const uint32_t box[4] = {64, (uint32_t)(RK * d->stride), 1, 1};
+    const uint32_t box[4] = {64, (uint32_t)(p.win ? p.win_rows : RK * d->stride), 1, 1};
     const uint32_t es[4] = {1, (uint32_t)d->stride, 1, 1};
     int r = make_tmap_bf16(&tmX, d->x, 4, dims, strides, box, es);
     if (r) return r;
