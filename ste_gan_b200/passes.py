@@ -339,7 +339,7 @@ def generator_convs(model) -> List:
 
 
 def gblock_fwd(blk, folds: Dict[int, Folded], x_raw: Tensor, x_act: Tensor, B: int, t: int, *, want_raw: bool,
-               want_act: bool, dup_next: bool):
+               want_act: bool, dup_next: bool, side=None):
     """GBlock.forward (layers/conv.py:82-84) on channels-last tensors.
     x_raw [B,t,C_in]: block input; x_act [B,t*up,C_in]: relu(x) with rows duplicated when the block upsamples.
     Returns (y_raw|None, relu(y) (rows duplicated if dup_next)|None, saved)."""
@@ -347,8 +347,10 @@ def gblock_fwd(blk, folds: Dict[int, Folded], x_raw: Tensor, x_act: Tensor, B: i
     up = blk.upsample
     t_hi = t * up
     # conv1: ReLU -> [Up] -> conv(d1) -> ReLU -> conv(d3);  res1: [Up] -> conv(k1) on the raw input   (conv.py:38-56,83)
-    _, a1, _ = _fwd(folds[id(c["c1"])], x_act, B, t_hi, act=ACT_RELU, want_act=True)
-    r, _, _ = _fwd(folds[id(c["res"])], x_raw, B, t, want_raw=True)          # 1x1 commutes with nearest upsampling
+    # the residual 1x1 conv is independent of conv1's first conv: optionally on a side stream
+    (r, _, _), (_, a1, _) = fork_join(
+        side, lambda: _fwd(folds[id(c["res"])], x_raw, B, t, want_raw=True),     # 1x1 commutes with nearest upsampling
+        lambda: _fwd(folds[id(c["c1"])], x_act, B, t_hi, act=ACT_RELU, want_act=True))
     h_raw, h_act, _ = _fwd(folds[id(c["c2"])], a1, B, t_hi, act=ACT_RELU, want_raw=True, want_act=True,
                            add_post=r, post_shift=1 if up > 1 else 0)
     # conv2: ReLU -> conv(d9) -> ReLU -> conv(d27);  y = h + conv2(h)                                (conv.py:61-75,84)
@@ -359,7 +361,8 @@ def gblock_fwd(blk, folds: Dict[int, Folded], x_raw: Tensor, x_act: Tensor, B: i
     return y_raw, y_act, saved
 
 
-def gblock_bwd(blk, folds: Dict[int, Folded], s: dict, dy: Tensor, B: int, ws: _Workspace, out_f32: bool = False) -> Tensor:
+def gblock_bwd(blk, folds: Dict[int, Folded], s: dict, dy: Tensor, B: int, ws: _Workspace, out_f32: bool = False,
+               side=None) -> Tensor:
     """Backward of gblock_fwd: dy = d/d(y raw) [B,t_hi,C_out] -> d/d(x raw) [B,t_lo,C_in]; accumulates weight grads."""
     c = blk.convs()
     t_lo, t_hi, up = s["t_lo"], s["t_hi"], s["up"]
@@ -371,10 +374,13 @@ def gblock_bwd(blk, folds: Dict[int, Folded], s: dict, dy: Tensor, B: int, ws: _
     dh = _dgrad(f3, da3, B, t_hi, t_hi, mask=s["h_act"], mask_mode=ACT_RELU, add_post=dy)
     # h = conv_d3(relu(conv_d1(up(relu x)))) + up(res1(x))
     _wgrad(f2, s["a1"], dh, B, t_hi, t_hi, ws)
-    da1 = _dgrad(f2, dh, B, t_hi, t_hi, mask=s["a1"], mask_mode=ACT_RELU)
-    dr = dh if up == 1 else ops.pair_sum_rows(dh, B * t_lo, fr.mod.out_channels).view(B, t_lo, -1)
-    _wgrad(fr, s["x_raw"], dr, B, t_lo, t_lo, ws)
-    dx_res = _dgrad(fr, dr, B, t_lo, t_lo)
+
+    def res_branch():           # gradient through up(res1(x)): independent of the conv1 chain until their sum
+        dr = dh if up == 1 else ops.pair_sum_rows(dh, B * t_lo, fr.mod.out_channels).view(B, t_lo, -1)
+        _wgrad(fr, s["x_raw"], dr, B, t_lo, t_lo, ws)
+        return _dgrad(fr, dr, B, t_lo, t_lo), dr
+
+    (dx_res, dr), da1 = fork_join(side, res_branch, lambda: _dgrad(f2, dh, B, t_hi, t_hi, mask=s["a1"], mask_mode=ACT_RELU))
     _wgrad(f1, s["x_act"], da1, B, t_hi, t_hi, ws)
     return _dgrad(f1, da1, B, t_hi, t_hi, pair_sum=up > 1, mask=s["x_raw"], mask_mode=ACT_RELU, add_post=dx_res,
                   out_f32=out_f32)
@@ -401,7 +407,7 @@ class GenCtx:
 
 
 def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor], speaking_mode_ids: Optional[Tensor],
-                      dtype: torch.dtype, need_ctx: bool, folds: Optional[Dict[int, Folded]] = None):
+                      dtype: torch.dtype, need_ctx: bool, folds: Optional[Dict[int, Folded]] = None, side=None):
     """EMGGeneratorGanTTS.forward (generator.py:140-162).  Returns (x_pred fp32 [B,16T,C], ctx|None)."""
     su = speech_units.contiguous().float()
     B, T, du = su.shape
@@ -432,7 +438,8 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
     for i, blk in enumerate(blocks):
         last = i + 1 == len(blocks)
         nxt_dup = (not last) and ups[i + 1] > 1
-        y_raw, y_act, s = gblock_fwd(blk, folds, x_raw, x_act, B, t, want_raw=not last, want_act=True, dup_next=nxt_dup)
+        y_raw, y_act, s = gblock_fwd(blk, folds, x_raw, x_act, B, t, want_raw=not last, want_act=True, dup_next=nxt_dup,
+                                     side=side)
         if need_ctx:
             saved.append(s)
         x_raw, x_act, t = y_raw, y_act, s["t_hi"]
@@ -448,7 +455,8 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
     return x_pred, ctx
 
 
-def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None) -> None:
+def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None,
+                       res_side=None) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
     dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output.  With a FoldPlan the packed weight gradients go to
     its arena and the weight-norm backward of all 45 convs is one launch at the end."""
@@ -468,7 +476,7 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
     _wgrad(f, ctx.y_last_act, dpre, B, t, t, ws)
     dy = _dgrad(f, dpre, B, t, t, mask=ctx.y_last_act, mask_mode=ACT_RELU)        # d(y8 raw)
     for i in reversed(range(len(blocks))):
-        dy = gblock_bwd(blocks[i], folds, ctx.blocks[i], dy, B, ws)
+        dy = gblock_bwd(blocks[i], folds, ctx.blocks[i], dy, B, ws, side=res_side)
     # gblocks.0 and the embeddings
     f0 = folds[id(model.gblocks[0])]
     _wgrad(f0, ctx.x0, dy, B, ctx.T, ctx.T, ws)

@@ -139,7 +139,8 @@ class GanTrainer:
         f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
 
         def fake_side():
-            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
+            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold(),
+                                                    side=self._s2(1))
             self.x_pred, self._gctx = x_pred, gctx
             return passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(1))
 
@@ -195,7 +196,7 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1))
+        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0))
         self._gctx = None
 
     def _phase_opt_g(self) -> None:
