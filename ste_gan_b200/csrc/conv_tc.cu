@@ -73,6 +73,10 @@ struct TcP {
   int cs_g, cd_g;          // source / destination channels per (packed) group
   int n_res, tiles_m;      // output-row residues (1 unless transposed && stride > 1), row tiles per residue
   int tiles_n, n_tiles;    // column tiles, total tiles = B * n_res * tiles_m * tiles_n
+  // CTA pairs (cta_group::2, kPair kernels): a "tile" is a PAIR tile = 2 row tiles x one column tile; the row tiles of a
+  // residue class are numbered mt = b * tiles_m + tm and the CTA of cluster rank r takes mt = 2 * pair + r.  An odd count
+  // leaves the last pair's rank-1 CTA with b == n_samples: its loads are zero-filled and its stores clipped by the TMA unit.
+  int n_samples, pairs_per_res;
   // Tap groups ("A windows"): the taps of one group read row-shifted views of ONE TMA-loaded window of
   // nh + max_shift h rows (UMMA descriptors take any row offset into a 128B-swizzled tile - the swizzle is a
   // function of the shared-memory address, tools/rowshift_probe.py), so a k-tap conv loads its activations
@@ -166,13 +170,21 @@ struct Tracer {
 struct Tile {
   int b, res, h0, col0, ch0, wcol0, g0, n_iters;
 };
-__device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
+template <bool kPair>
+__device__ __forceinline__ Tile decode_tile(const TcP& p, int t, int rank) {
   Tile x;
   const int tn = t % p.tiles_n; int u = t / p.tiles_n;
-  const int tm = u % p.tiles_m; u /= p.tiles_m;
+  int tm;
   // strided data-gradient: output rows h = h' * n_res + res are produced per residue class `res` from the
   // taps j with (res + pad - j*dilation) % stride == 0, as a stride-1 correlation over h'
-  x.res = u % p.n_res; x.b = u / p.n_res;
+  if constexpr (kPair) {
+    const int pm = u % p.pairs_per_res; x.res = u / p.pairs_per_res;
+    const int mt = 2 * pm + rank;
+    x.b = mt / p.tiles_m; tm = mt - x.b * p.tiles_m;
+  } else {
+    tm = u % p.tiles_m; u /= p.tiles_m;
+    x.res = u % p.n_res; x.b = u / p.n_res;
+  }
   x.h0 = tm * p.nh;
   x.col0 = tn * p.bn;
   x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
@@ -183,7 +195,7 @@ __device__ __forceinline__ Tile decode_tile(const TcP& p, int t) {
 }
 // accumulator row m of a tile -> flat output row of the sample (before pair_sum), or -1
 __device__ __forceinline__ int out_row(const TcP& p, const Tile& x, int m) {
-  if (m >= p.mrows) return -1;
+  if (m >= p.mrows || x.b >= p.n_samples) return -1;
   const int hl = m / p.pack, ph = m - hl * p.pack;
   const int h = (x.h0 + hl) * p.n_res + x.res;
   return h < p.t_dst ? h * p.phases + ph : -1;
@@ -253,7 +265,7 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int co
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <bool kStaged>
+template <bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kStaged ? 224 : 320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ EpiMaps em, const TcP p) {
@@ -261,9 +273,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_bytes = p.bn * KC * 2;
+  const int b_bytes = (kPair ? p.bn / 2 : p.bn) * KC * 2;   // B tile bytes staged by THIS CTA (a pair splits the columns)
   const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
   const TcEpi& e = p.e;
+  // pair kernels: cluster rank (0 = leader: issues the MMAs, owns the full / tmem_empty barriers), pair tile walk
+  const int rank = kPair ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: 2*(n_in+n_out) slots + bias
   const uint32_t bias_base = epi_base + (kStaged ? (2 * e.n_in + 3 * e.n_out) * SLOT : 0);
   const uint32_t bar_base = bias_base + (kStaged ? 1024 : 0);
@@ -274,140 +290,205 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto in_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 6);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast from lane 0: the compiler can prove the warp index (hence every role branch) warp-uniform, so the
+  // single-issuer instructions (TMA, tcgen05.mma / commit) take their operands straight from uniform registers
+  // instead of a per-instruction ELECT + R2UR "waterfall" - that cut the issue loops from ~600 to ~xxx clk per stage
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); mbar_init(in_bar(a), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), kPair ? 2 * EPI_WARPS : EPI_WARPS); mbar_init(in_bar(a), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (kPair) { tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // pair: stage-full barriers and the accumulator-drained barriers that count live in the LEADER's shared memory
+  const uint32_t lead_bars = kPair ? mapa_u32(bar_base, 0) : bar_base;
+  auto lead_full_bar = [&](int s) { return lead_bars + 8u * s; };
+  auto lead_tmem_empty_bar = [&](int a) { return lead_bars + 8u * (2 * MAX_STAGES + 2 + a); };
+  auto arrive_tmem_empty = [&](int a) {
+    if constexpr (kPair) mbar_arrive_cluster(lead_tmem_empty_bar(a)); else mbar_arrive(tmem_empty_bar(a));
+  };
 
   if (warp == 0 && p.max_ntaps == 1) {
-    // ===== TMA producer, one tap per stage (the common case): a single thread runs straight-line code =====
-    if (lane == 0) {
-      Tracer trc(p.trace, 0);
-      int itg = 0;  // stage counter, continuous across tiles
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const Tile x = decode_tile(p, t);
-        trc.ev(1, t);
-        for (int it = 0; it < x.n_iters; ++it, ++itg) {
-          const int s = itg % p.stages, phs = (itg / p.stages) & 1;
-          const int gi = it / p.k_chunks, chunk = it - gi * p.k_chunks, g = x.g0 + gi;
+    // ===== TMA producer, one tap per stage (the common case) =====
+    // Warp-uniform control flow: every lane runs the loop, lane 0's instructions take effect.  The loop body is
+    // kept to a wait, an expect_tx and the TMA issues - ring position and coordinates advance by increments (the
+    // div/mod + table look-ups of the first version cost the issuing thread ~900 clk per stage, more than the
+    // stage's MMAs).
+    const bool lead = lane == 0;
+    Tracer trc(lead ? p.trace : nullptr, 0);
+    const uint32_t a_box_bytes = (uint32_t)(p.hb * p.pack * KC * 2);
+    const uint32_t tx_bytes = (kPair ? 2u : 1u) * ((uint32_t)p.a_boxes * a_box_bytes + (uint32_t)b_bytes);
+    const int row_step = p.hb * p.stride;
+    int s = 0; uint32_t phs = 0;   // ring position, continuous across tiles
+#ifdef STG_PROF_LOOP
+    long long prof[4] = {0, 0, 0, 0};   // clocks in: empty wait | expect_tx + A loads | W loads + advance ; stages
+#endif
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const Tile x = decode_tile<kPair>(p, t, rank);
+      trc.ev(1, t);
+      const int n_groups = p.res_gfirst[x.res + 1] - x.g0;
+      // W coordinate of this CTA's (half) tile along the destination-channel axis
+      const int wc = p.b_mn == 0 ? x.col0 + (kPair ? rank * (p.bn / 2) : 0)
+                   : p.b_mn == 2 ? x.wcol0 / 64 + (kPair ? rank * (p.bn / 128) : 0) : x.wcol0;
+      for (int gi = 0; gi < n_groups; ++gi) {
+        const int g = x.g0 + gi;
+        const int row0 = x.h0 * p.stride + p.tt.g_off[g];
+        const int tap = p.tt.tap_w[g];
+        for (int chunk = 0; chunk < p.k_chunks; ++chunk) {
+#ifdef STG_PROF_LOOP
+          const long long pc0 = clock64();
+#endif
           mbar_wait(empty_bar(s), phs ^ 1);
-          mbar_expect_tx(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + b_bytes));
-          const uint32_t a_dst = smem_base + s * stage_bytes;
+          trc.ev(4, chunk);
+#ifdef STG_PROF_LOOP
+          const long long pc1 = clock64();
+#endif
+          const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+          const uint32_t fb = kPair ? lead_full_bar(s) : full_bar(s);
+          // pair: both CTAs' bytes complete on the leader's barrier, which expects the sum
+          if (rank == 0) mbar_expect_tx_el(full_bar(s), tx_bytes);
+          const int c0 = x.ch0 + chunk * KC;
+#pragma unroll 1
           for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_4d(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
-                        (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
-          if (!p.b_mn) {
-            tma_load_3d(a_dst + p.a_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[g]);
+            tma_load_4d_el<kPair>(a_dst + bx * a_box_bytes, &tmA, fb, c0, 0, row0 + bx * row_step, x.b);
+#ifdef STG_PROF_LOOP
+          const long long pc2 = clock64();
+#endif
+          if (p.b_mn == 0) {
+            tma_load_3d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, chunk * KC, wc, tap);
           } else if (p.b_mn == 2) {  // forward pack seen as (64, co row, ci/64, tap): one box = the whole [bn/64][64][64] tile
-            tma_load_4d(a_dst + p.a_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64, p.tt.tap_w[g]);
+            tma_load_4d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, 0, c0, wc, tap);
           } else {  // forward pack [k][c_src][c_dst/g]: bn/64 boxes of (64 destination channels x 64 source-channel rows)
+#pragma unroll 1
             for (int nb = 0; nb < p.bn / 64; ++nb)
-              tma_load_3d(a_dst + p.a_bytes + nb * 8192, &tmW, full_bar(s), x.wcol0 + nb * 64, x.ch0 + chunk * KC, p.tt.tap_w[g]);
+              tma_load_3d_el<kPair>(a_dst + p.a_bytes + nb * 8192, &tmW, fb, wc + nb * 64, c0, tap);
           }
+          if (++s == p.stages) { s = 0; phs ^= 1u; }
+#ifdef STG_PROF_LOOP
+          const long long pc3 = clock64();
+          prof[0] += pc1 - pc0; prof[1] += pc2 - pc1; prof[2] += pc3 - pc2; prof[3] += 1;
+#endif
         }
       }
     }
+#ifdef STG_PROF_LOOP
+    if (lead && p.trace && blockIdx.x == 0) for (int i = 0; i < 4; ++i) p.trace[1 + 3 * 5200 + i] = prof[i];
+#endif
   } else if (warp == 1 && p.max_ntaps == 1) {
-    // ===== MMA issuer, one tap per stage =====
-    const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
-    Tracer trc(lane == 0 ? p.trace : nullptr, 1);
-    int itg = 0, acc_i = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const Tile x = decode_tile(p, t);
+    // ===== MMA issuer, one tap per stage (warp-uniform control flow; pair: the leader issues for both CTAs) =====
+    const bool lead = lane == 0;
+    const uint32_t idesc = idesc_bf16_f32(kPair ? 2 * TM : TM, p.bn, 0, p.b_mn ? 1 : 0);
+    Tracer trc(lead ? p.trace : nullptr, 1);
+    // descriptors of stage 0; a stage further on adds stage_bytes >> 4 to the 14-bit start-address field (no carry:
+    // every operand address is below 256 KB)
+    const uint64_t adesc0 = smem_desc_kmajor_sw128(smem_base);
+    const uint64_t bdesc0 = p.b_mn ? smem_desc_mnmajor_sw128(smem_base + p.a_bytes, 8192, 1024) : smem_desc_kmajor_sw128(smem_base + p.a_bytes);
+    const uint32_t dstep = (uint32_t)stage_bytes >> 4;
+    const uint32_t bstep = p.b_mn ? 128u : 2u;   // 16 K elements further: +32 B inside the K-major atom / 16 rows (2048 B) of the MN-major tile
+    int s = 0, acc_i = 0; uint32_t phs = 0;
+#ifdef STG_PROF_LOOP
+    long long mprof[3] = {0, 0, 0};     // clocks in: full wait | MMA issue + commits ; stages
+#endif
+    for (int t = tile0; t < p.n_tiles && rank == 0; t += tstep) {
+      const Tile x = decode_tile<kPair>(p, t, rank);
       if (x.n_iters == 0) continue;
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
-      mbar_wait(tmem_empty_bar(as), aph ^ 1);  // epilogue has drained this accumulator buffer
+      mbar_wait(tmem_empty_bar(as), aph ^ 1);  // epilogue(s) have drained this accumulator buffer
       tc_fence_after();
       trc.ev(2, t);
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
-      for (int it = 0; it < x.n_iters; ++it, ++itg) {
-        const int s = itg % p.stages, phs = (itg / p.stages) & 1;
+      for (int it = 0; it < x.n_iters; ++it) {
+#ifdef STG_PROF_LOOP
+        const long long mc0 = clock64();
+#endif
         mbar_wait(full_bar(s), phs);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_base + s * stage_bytes;
-          const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
-          if (!p.b_mn) {
-            const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + p.a_bytes);
+        trc.ev(5, it);
+#ifdef STG_PROF_LOOP
+        const long long mc1 = clock64();
+#endif
+        const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * dstep), bd = bdesc0 + (uint64_t)((uint32_t)s * dstep);
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)  // +32 bytes (16 bf16) along K inside the swizzle atom
-              umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          } else {
-            const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + p.a_bytes, 8192, 1024);
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)  // B: 16 K rows = 2048 B further down
-              umma_bf16(d_tmem, adesc + 2 * ks, bdesc + 128 * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(s));
-          if (it == x.n_iters - 1) umma_commit(tmem_full_bar(as));
-        }
-        __syncwarp();
+        for (int ks = 0; ks < KC / 16; ++ks)
+          umma_bf16_el<kPair>(d_tmem, ad + 2 * ks, bd + bstep * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        umma_commit_el<kPair>(empty_bar(s));
+        if (it == x.n_iters - 1) umma_commit_el<kPair>(tmem_full_bar(as));
+        if (++s == p.stages) { s = 0; phs ^= 1u; }
+#ifdef STG_PROF_LOOP
+        const long long mc2 = clock64();
+        mprof[0] += mc1 - mc0; mprof[1] += mc2 - mc1; mprof[2] += 1;
+#endif
       }
       trc.ev(3, t);
       ++acc_i;
     }
+#ifdef STG_PROF_LOOP
+    if (lead && p.trace && blockIdx.x == 0) for (int i = 0; i < 3; ++i) p.trace[1 + 3 * 5200 + 8 + i] = mprof[i];
+#endif
   } else if (warp == 0) {
     // ===== TMA producer, tap windows (warp-uniform control flow, lane 0's instructions take effect) =====
     const bool lead = lane == 0;
-    int itg = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const Tile x = decode_tile(p, t);
-      for (int it = 0; it < x.n_iters; ++it, ++itg) {
-        const int s = itg % p.stages, phs = (itg / p.stages) & 1;
-        const int gi = it / p.k_chunks, chunk = it - gi * p.k_chunks, g = x.g0 + gi;
-        const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
+    int s = 0; uint32_t phs = 0;
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const Tile x = decode_tile<kPair>(p, t, rank);
+      const int n_groups = p.res_gfirst[x.res + 1] - x.g0;
+      for (int gi = 0; gi < n_groups; ++gi) {
+       const int g = x.g0 + gi;
+       const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
+       for (int chunk = 0; chunk < p.k_chunks; ++chunk) {
         mbar_wait(empty_bar(s), phs ^ 1);
-        mbar_expect_tx_if(lead, full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
+        mbar_expect_tx_el(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
         const uint32_t a_dst = smem_base + s * stage_bytes;
 #pragma unroll 1
         for (int bx = 0; bx < p.a_boxes; ++bx)
-          tma_load_4d_if(lead, a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+          tma_load_4d_el(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
                          (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
 #pragma unroll 1
         for (int tl = 0; tl < nt; ++tl) {
           if (!p.b_mn) {
-            tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
+            tma_load_3d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
           } else if (p.b_mn == 2) {
-            tma_load_4d_if(lead, a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64,
+            tma_load_4d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64,
                            p.tt.tap_w[t0 + tl]);
           } else {
 #pragma unroll 1
             for (int nb = 0; nb < p.bn / 64; ++nb)
-              tma_load_3d_if(lead, a_dst + p.a_bytes + tl * b_bytes + nb * 8192, &tmW, full_bar(s), x.wcol0 + nb * 64,
+              tma_load_3d_el(a_dst + p.a_bytes + tl * b_bytes + nb * 8192, &tmW, full_bar(s), x.wcol0 + nb * 64,
                              x.ch0 + chunk * KC, p.tt.tap_w[t0 + tl]);
           }
         }
+        if (++s == p.stages) { s = 0; phs ^= 1u; }
+       }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer, tap windows (warp-uniform control flow) =====
     const bool lead = lane == 0;
     const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
-    int itg = 0, acc_i = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const Tile x = decode_tile(p, t);
+    int s = 0, acc_i = 0; uint32_t phs = 0;
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const Tile x = decode_tile<kPair>(p, t, rank);
       if (x.n_iters == 0) continue;
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
       mbar_wait(tmem_empty_bar(as), aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
-      for (int it = 0; it < x.n_iters; ++it, ++itg) {
-        const int s = itg % p.stages, phs = (itg / p.stages) & 1;
-        const int g = x.g0 + it / p.k_chunks;
+      int g = x.g0, chunk = 0;
+      for (int it = 0; it < x.n_iters; ++it) {
         const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
         mbar_wait(full_bar(s), phs);
         tc_fence_after();
@@ -421,11 +502,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bstep = p.b_mn ? 128 : 2;
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks)
-            umma_bf16_if(lead, d_tmem, adesc + 2 * ks, bdesc + bstep * ks, idesc, (it > 0 || tl > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_el(d_tmem, adesc + 2 * ks, bdesc + bstep * ks, idesc, (it > 0 || tl > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit_if(lead, empty_bar(s));
-        umma_commit_if(lead && it == x.n_iters - 1, tmem_full_bar(as));
-        __syncwarp();
+        umma_commit_el(empty_bar(s));
+        if (it == x.n_iters - 1) umma_commit_el(tmem_full_bar(as));
+        if (++s == p.stages) { s = 0; phs ^= 1u; }
+        if (++chunk == p.k_chunks) { chunk = 0; ++g; }
       }
       ++acc_i;
     }
@@ -441,7 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto out_slot = [&](int buf, int o) { return epi_base + (uint32_t)((2 * e.n_in + buf * e.n_out + o) * SLOT); };  // buf: q % 3
     auto bar_full = [&](int b3) { return 2 + b3; };
     auto bar_free = [&](int b3) { return 5 + b3; };
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (p.n_tiles - tile0 + tstep - 1) / tstep;
     const int q_total = my_tiles * n_sub;
     if (warp == 6) {
       // ----- epilogue DMA warp -----
@@ -453,10 +535,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
       const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
       // iterator over (tile, sub-tile) pairs for the operand loads, which run two sub-tiles ahead of the math
-      int ld_t = blockIdx.x, ld_s = 0, ld_q = 0;
+      int ld_t = tile0, ld_s = 0, ld_q = 0;
       auto issue_loads = [&]() {  // lane 0 only
         if (e.n_in == 0 || ld_t >= p.n_tiles) return;
-        const Tile x = decode_tile(p, ld_t);
+        const Tile x = decode_tile<kPair>(p, ld_t, rank);
         const int buf = ld_q & 1;
         const int col = x.col0 + ld_s * SUB;
         const int r0 = x.h0 >> (e.pair_sum ? 1 : 0);                     // first h row of the tile in its residue class
@@ -466,12 +548,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (e.has_mask) tma_load_4d(in_slot(buf, i++), &em.mask[x.res], in_bar(buf), col, 0, r0, x.b);
         if (e.has_post) tma_load_4d(in_slot(buf, i++), &em.post, in_bar(buf), col, 0, r0 >> e.post_shift, x.b);
         ++ld_q;
-        if (++ld_s == n_sub) { ld_s = 0; ld_t += gridDim.x; }
+        if (++ld_s == n_sub) { ld_s = 0; ld_t += tstep; }
       };
       if (lane == 0) { issue_loads(); issue_loads(); }
       int q = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const Tile x = decode_tile(p, t);
+      for (int t = tile0; t < p.n_tiles; t += tstep) {
+        const Tile x = decode_tile<kPair>(p, t, rank);
         const int r0_out = x.h0 >> (e.pair_sum ? 1 : 0);
         for (int s = 0; s < n_sub; ++s, ++q) {
           const int obuf = q % 3;
@@ -500,8 +582,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = sub * 32 + lane;
       Tracer trc(et == 0 ? p.trace : nullptr, 2);
       int acc_i = 0, q = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const Tile x = decode_tile(p, t);
+      for (int t = tile0; t < p.n_tiles; t += tstep) {
+        const Tile x = decode_tile<kPair>(p, t, rank);
         const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
         trc.ev(10, t);
         // bias of this column tile -> smem (nobody reads the previous tile's bias any more: every thread has
@@ -538,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (s == n_sub - 1 && x.n_iters > 0) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+            if (lane == 0) arrive_tmem_empty(as);
           }
           if (e.bias) {
 #pragma unroll
@@ -621,8 +703,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_chunks = p.bn / 16;
     const int c_lo = (half == 0) ? 0 : (n_chunks + 1) / 2, c_hi = (half == 0) ? (n_chunks + 1) / 2 : n_chunks;
     int acc_i = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const Tile x = decode_tile(p, t);
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const Tile x = decode_tile<kPair>(p, t, rank);
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
       const int arow = out_row(p, x, sub * 32 + lane);  // output row of this thread (before pair_sum)
       const bool row_ok = arow >= 0 && (!e.pair_sum || (lane & 1) == 0);
@@ -666,14 +748,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (x.n_iters > 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+        if (lane == 0) arrive_tmem_empty(as);
         ++acc_i;
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if constexpr (kPair) {
+    cluster_sync_all();   // the peer may still read this CTA's shared memory / arrive on its barriers until here
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 }  // namespace
@@ -859,7 +946,18 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   // ---- tap groups (A windows) and pipeline depth.  Taps of a group must lie on one row lattice of the strided
   // A box (same offset mod stride) and close enough for the window to fit its boxes; candidates: <= ng taps per
   // group, pick the ng with the least shared-memory ingest per tile among those that leave >= 3 (else 2) stages.
-  const int b_bytes = p.bn * KC * 2;
+  // CTA pairs: two row tiles of one column tile run as ONE cta_group::2 MMA, each CTA staging half of the W columns
+  // (opt-in, see below).  Needs >= 2 row tiles per residue class, whole 16-column (K-major W) / 64-column (MN-major W,
+  // data-gradient) halves, and the one-tap-per-stage pipeline.
+  // Measured (tools/conv_bench.py, profiles/r1c_pair_vs_single.txt): with the issue loops fixed the single-CTA kernel is
+  // no longer operand-feed-bound and pairs are 0-15 % SLOWER (cluster launch + the M = 256 MMA issues at ~100 clk per
+  // instruction), so pairs are opt-in (STG_PAIR=1).
+  static const int env_pair = getenv("STG_PAIR") ? atoi(getenv("STG_PAIR")) : 0;
+  p.n_samples = d->n_samples;
+  const int n_mt = d->n_samples * p.tiles_m;
+  bool pair = env_pair != 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
+  p.pairs_per_res = (n_mt + 1) / 2;
+  int b_bytes = (pair ? p.bn / 2 : p.bn) * KC * 2;
   const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 1024 : 0;
   const int avail = 212 * 1024 - epi_bytes;
   struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
@@ -930,6 +1028,21 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     if (pl.stages >= 3 && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
   }
   if (!best.ok) return STG_EUNSUPPORTED;
+  if (pair && best.ng != 1) {   // tap windows keep the single-CTA pipeline: plan again with whole W tiles
+    pair = false;
+    b_bytes = p.bn * KC * 2;
+    best = Plan{0, 0, 0, 0, 0, 0, 0, false};
+    for (int ci = 0; ci < 8; ++ci) {
+      const int ng = cands[ci];
+      if (env_ng > 0 && ng != env_ng) continue;
+      if (ng > d->k && ng != 1) continue;
+      Plan pl = build(ng, nullptr);
+      if (!pl.ok) continue;
+      if (!best.ok) { best = pl; continue; }
+      if (pl.stages >= 3 && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
+    }
+    if (!best.ok) return STG_EUNSUPPORTED;
+  }
   build(best.ng, &p);
   p.hb = best.hb; p.a_boxes = best.a_boxes; p.a_bytes = best.a_bytes; p.max_ntaps = best.ng; p.stages = best.stages;
   const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
@@ -957,7 +1070,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const uint64_t C = p.cs_g, N = d->c_dst, K = d->k;
     const uint64_t dims[3] = {C, N, K};
     const uint64_t strides[2] = {C * 2, N * C * 2};
-    const uint32_t box[3] = {(uint32_t)KC, (uint32_t)p.bn, 1};
+    const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(pair ? p.bn / 2 : p.bn), 1};
     int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr);
     if (r) return r;
   } else if (p.cd_g % 64 == 0) {
@@ -967,7 +1080,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const uint64_t N = p.cd_g, R = d->c_src, K = d->k;
     const uint64_t dims[4] = {64, R, N / 64, K};
     const uint64_t strides[3] = {N * 2, 128, R * N * 2};
-    const uint32_t box[4] = {64, (uint32_t)KC, (uint32_t)(p.bn / 64), 1};
+    const uint32_t box[4] = {64, (uint32_t)KC, (uint32_t)((pair ? p.bn / 2 : p.bn) / 64), 1};
     int r = make_tmap_bf16(&tmW, d->w, 4, dims, strides, box, nullptr);
     if (r) return r;
   } else {  // (destination channel within group, source channel row, tap); bn/64 boxes per tile, partial last box zero-filled
@@ -993,17 +1106,37 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   p.tiles_n = ceil_div(d->c_dst, p.bn);
+  if (pair) {
+    const int64_t n_tiles = (int64_t)p.n_res * p.pairs_per_res * p.tiles_n;
+    if (n_tiles > 0x7fffffff) return STG_EINVAL;
+    p.n_tiles = (int)n_tiles;
+    const int max_pairs = sm_count() / 2;
+    const int n_pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 224 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmW, em, p));
+    else STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmW, em, p));
+    STG_LAUNCH_CHECK();
+    return STG_OK;
+  }
   const int64_t n_tiles = (int64_t)d->n_samples * p.n_res * p.tiles_m * p.tiles_n;
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  if (staged) conv_tc_kernel<true><<<grid, 224, smem, s>>>(tmA, tmW, em, p);
-  else conv_tc_kernel<false><<<grid, 320, smem, s>>>(tmA, tmW, em, p);
+  if (staged) conv_tc_kernel<true, false><<<grid, 224, smem, s>>>(tmA, tmW, em, p);
+  else conv_tc_kernel<false, false><<<grid, 320, smem, s>>>(tmA, tmW, em, p);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

@@ -70,7 +70,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast from lane 0: the compiler can prove the warp index (hence every role branch) warp-uniform, so the
+  // single-issuer instructions (TMA, tcgen05.mma / commit) take their operands straight from uniform registers
+  // instead of a per-instruction ELECT + R2UR "waterfall" - that cut the issue loops from ~600 to ~xxx clk per stage
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int co_tile = blockIdx.y / p.tap_groups, tg = blockIdx.y - co_tile * p.tap_groups;
   const int co0 = co_tile * 128;
   const int span0 = (co0 / p.cout_g) * p.cin_g;   // first input channel this co tile meets

@@ -53,6 +53,8 @@ def pack_mode(mod, dtype: torch.dtype) -> Tuple[int, bool]:
     """(pack groups, unfold?) of a conv module in this precision.  fp32 (CUDA-core validation engine) keeps the
     reference's own grouping; bf16 widens narrow groups to the tensor engine's 64-channel K chunks and turns
     the C_in = 8 first layers (discriminator.py:26,55,77,104) into 1-tap convs over im2col rows."""
+    if mod.groups == 1 and mod.kernel == 1 and mod.in_channels % 8 != 0 and mod.out_channels >= 32:
+        return 1, True      # e.g. the MFCC generator's 89 -> 768 input conv: channels zero-padded to a multiple of 8
     if dtype != torch.bfloat16:
         return mod.groups, False
     if mod.groups == 1 and mod.in_channels < 16 and mod.in_channels * mod.kernel <= 256 and mod.out_channels >= 32:
@@ -432,8 +434,10 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
         if u not in (1, 2):
             raise ValueError("GBlock upsample must be 1 or 2 on this path")
     # gblocks.0 (1x1): raw output feeds res1 of the first GBlock, relu(.) feeds its conv1 (duplicated rows = Upsample)
-    x_raw, x_act, t = _fwd(folds[id(model.gblocks[0])], x0, B, T, act=ACT_RELU, want_raw=True, want_act=True,
-                           dup=ups[0] > 1)
+    f0 = folds[id(model.gblocks[0])]
+    if f0.unfold:                 # input channels not a multiple of 8 (MFCC variant): zero-padded rows for the tensor engine
+        x0 = unfold_input(f0, x0, B, T)
+    x_raw, x_act, t = _fwd(f0, x0, B, T, act=ACT_RELU, want_raw=True, want_act=True, dup=ups[0] > 1)
     saved = []
     for i, blk in enumerate(blocks):
         last = i + 1 == len(blocks)

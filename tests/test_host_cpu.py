@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_layout_matches_header():
     import ctypes as C
     from ste_gan_b200 import _lib
-    assert C.sizeof(_lib.StgConv) == 20 * 4 + 8 * 8
+    assert C.sizeof(_lib.StgConv) == 21 * 4 + 4 + 8 * 8        # 21 ints, padding to 8, 8 pointers
     assert C.sizeof(_lib.StgWgrad) == 13 * 4 + 4 + 4 * 8      # 13 ints, padding to 8, 4 pointers
 
 

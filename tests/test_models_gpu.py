@@ -213,6 +213,60 @@ def test_train_step_losses_and_grads_vs_oracle(prec):
         assert e < tol, (k, e)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mfcc_generator_variant(prec):
+    """speech_feature_type = MFCCS (generator.py:116,178-179): 25-d input (+64 embedding = 89 channels, not a multiple
+    of 8 - zero-padded rows on the tensor engine), no upsampling in GBlock 6 -> 8T output samples.  Forward vs the oracle
+    and one fused train step (losses + flat gradients)."""
+    import ste_gan_b200
+    from ste_gan_b200.models.discriminator import DiscriminatorSmall
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    from ste_gan_b200.trainer import GanTrainer
+    g = seeded(lambda: EMGGeneratorGanTTS("MFCCS", 25, 17, 8, channels=256))
+    d = seeded(lambda: DiscriminatorSmall(8))
+    sd_g, sd_d = cpu_sd(g), cpu_sd(d)
+    su, sess, x_real = O.synthetic_batch(2, 100, seed=6, unit_dim=25, hop=8)
+    assert x_real.shape[1] == 800
+    f64 = lambda sd: {k: v.double() for k, v in sd.items()}
+    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=True, speech_feature_type="MFCCS")
+    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
+    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
+    tol = TOL[prec]
+    assert tr.x_pred.shape == (2, 800, 8)
+    assert O.rel_l2(tr.x_pred, ref["x_pred"]) < tol
+    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
+    tr._phase_g(x_real.cuda(), update_d=False)
+    L = tr.losses()
+    for k in ("loss_d", "loss_adv", "loss_fm", "loss_td", "loss_g"):
+        assert abs(L[k] - float(ref[k])) <= tol * max(1.0, abs(float(ref[k]))), (k, L[k], float(ref[k]))
+    gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
+    assert _flat_rel_l2(gd, ref["grad_d"]) < tol and _flat_rel_l2(gg, ref["grad_g"]) < tol
+    for k in ("gblocks.0.weight_v", "gblocks.0.weight_g", "gblocks.0.bias", "session_embeddings.weight"):
+        assert O.rel_l2(gg[k], ref["grad_g"][k]) < tol, k
+
+
+def test_full_discriminator_train_step_bf16():
+    """The full CARGAN `Discriminator` (discriminator.py:158-191: k=41 stride-4 grouped scale stacks, (5,1)/(3,1)
+    period stacks) through one fused train step in the tensor-core mode, against the oracle."""
+    from ste_gan_b200.trainer import GanTrainer
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, channels=128))
+    _, d = _fresh_nets(small=False)
+    sd_g, sd_d = cpu_sd(g), cpu_sd(d)
+    su, sess, x_real = O.synthetic_batch(2, 64, seed=8)
+    f64 = lambda sd: {k: v.double() for k, v in sd.items()}
+    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=False)
+    tr = GanTrainer(g.cuda(), d.cuda(), precision="bf16")
+    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
+    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
+    tr._phase_g(x_real.cuda(), update_d=False)
+    L = tr.losses()
+    for k in ("loss_d", "loss_adv", "loss_fm", "loss_td", "loss_g"):
+        assert abs(L[k] - float(ref[k])) <= 2e-2 * max(1.0, abs(float(ref[k]))), (k, L[k], float(ref[k]))
+    gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
+    assert _flat_rel_l2(gd, ref["grad_d"]) < 2e-2 and _flat_rel_l2(gg, ref["grad_g"]) < 2e-2
+
+
 def test_autograd_dropin_matches_fused_step():
     """The reference-style loop (modules + loss.backward()) gives the same gradients as the fused trainer (fp32)."""
     import torch.nn.functional as F

@@ -31,6 +31,12 @@ run(); torch.cuda.synchronize()
 lib.stg_debug_set_trace(None)
 ev = [e for e in buf[1:1 + 3 * 3990].view(-1, 3).cpu().tolist() if e[0] != 0]
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
-names = {1: "producer tile", 2: "mma start", 3: "mma issued", 10: "epi tile start", 11: "epi acc ready", 12: "epi sub done", 20: "  sub: acc in regs", 21: "  sub: inputs landed", 22: "  sub: smem written", 23: "  sub: out slot free", 24: "  sub: barrier passed"}
-for tag, val, t in ev[:120]:
+names = {4: "  stage free (producer)", 5: "  stage landed (mma)", 1: "producer tile", 2: "mma start", 3: "mma issued", 10: "epi tile start", 11: "epi acc ready", 12: "epi sub done", 20: "  sub: acc in regs", 21: "  sub: inputs landed", 22: "  sub: smem written", 23: "  sub: out slot free", 24: "  sub: barrier passed"}
+for tag, val, t in ev[:int(os.environ.get("TRACE_N", "120"))]:
     print(f"{(t - t0) / 1e3:9.2f} us  {names.get(tag, tag):16s} {val}")
+
+pr = buf[1 + 3 * 5200:1 + 3 * 5200 + 12].cpu().tolist()
+if pr[3] or pr[10]:
+    n = max(pr[3], 1); m = max(pr[10], 1)
+    print(f"PROF producer: {n} stages, clk/stage: empty-wait {pr[0]/n:.0f}  expect+A {pr[1]/n:.0f}  W+advance {pr[2]/n:.0f}")
+    print(f"PROF mma     : {m} stages, clk/stage: full-wait {pr[8]/m:.0f}  issue+commit {pr[9]/m:.0f}")
