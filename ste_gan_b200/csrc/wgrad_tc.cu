@@ -72,7 +72,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   // broadcast from lane 0: the compiler can prove the warp index (hence every role branch) warp-uniform, so the
   // single-issuer instructions (TMA, tcgen05.mma / commit) take their operands straight from uniform registers
-  // instead of a per-instruction ELECT + R2UR "waterfall" - that cut the issue loops from ~600 to ~xxx clk per stage
+  // instead of a per-instruction ELECT + R2UR "waterfall"
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int co_tile = blockIdx.y / p.tap_groups, tg = blockIdx.y - co_tile * p.tap_groups;
   const int co0 = co_tile * 128;
@@ -105,59 +105,64 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t bias_tmem = tmem_base + (uint32_t)(p.n_taps * p.bnw);
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(a_bytes + (p.win ? p.nbox_b * p.win_rows * 128 : ntap * b_bytes));
-      for (int q = q0; q < q1; ++q) {
-        const int it = q - q0, s = it % p.stages, phs = (it / p.stages) & 1;
-        const int n = q / p.chunks_per_sample, rc = q - n * p.chunks_per_sample;
-        const int b = n / p.phases, ph = n - b * p.phases;
-        const int r0 = rc * RK;
-        mbar_wait(empty_bar(s), phs ^ 1);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        const uint32_t a_dst = smem_base + s * stage_bytes;
-        tma_load_4d(a_dst, &tmY, full_bar(s), co0, r0, ph, b);
-        tma_load_4d(a_dst + BOX_BYTES, &tmY, full_bar(s), co0 + 64, r0, ph, b);
-        if (p.win) {
+    // ===== TMA producer: warp-uniform loop, elected issue, coordinates advance by increments (see conv_tc.cu) =====
+    const uint32_t tx_bytes = (uint32_t)(a_bytes + (p.win ? p.nbox_b * p.win_rows * 128 : ntap * b_bytes));
+    int s = 0; uint32_t phs = 0;
+    const int n0 = q0 / p.chunks_per_sample;
+    int rc = q0 - n0 * p.chunks_per_sample, b = n0 / p.phases, ph = n0 - b * p.phases;
+    for (int q = q0; q < q1; ++q) {
+      const int r0 = rc * RK;
+      mbar_wait(empty_bar(s), phs ^ 1);
+      mbar_expect_tx_el(full_bar(s), tx_bytes);
+      const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+      tma_load_4d_el(a_dst, &tmY, full_bar(s), co0, r0, ph, b);
+      tma_load_4d_el(a_dst + BOX_BYTES, &tmY, full_bar(s), co0 + 64, r0, ph, b);
+      if (p.win) {
+#pragma unroll 1
+        for (int bx = 0; bx < p.nbox_b; ++bx)
+          tma_load_4d_el(a_dst + a_bytes + bx * p.wb_bytes, &tmX, full_bar(s), ci0 + bx * 64, r0 + p.tap_off[tap0], ph, b);
+      } else {
+#pragma unroll 1
+        for (int tl = 0; tl < ntap; ++tl)
+#pragma unroll 1
           for (int bx = 0; bx < p.nbox_b; ++bx)
-            tma_load_4d(a_dst + a_bytes + bx * p.wb_bytes, &tmX, full_bar(s), ci0 + bx * 64, r0 + p.tap_off[tap0], ph, b);
-        } else {
-          for (int tl = 0; tl < ntap; ++tl)
-            for (int bx = 0; bx < p.nbox_b; ++bx)
-              tma_load_4d(a_dst + a_bytes + tl * b_bytes + bx * BOX_BYTES, &tmX, full_bar(s), ci0 + bx * 64,
-                          r0 * p.stride + p.tap_off[tap0 + tl], ph, b);
-        }
+            tma_load_4d_el(a_dst + a_bytes + tl * b_bytes + bx * BOX_BYTES, &tmX, full_bar(s), ci0 + bx * 64,
+                           r0 * p.stride + p.tap_off[tap0 + tl], ph, b);
       }
+      if (++s == p.stages) { s = 0; phs ^= 1u; }
+      if (++rc == p.chunks_per_sample) { rc = 0; if (++ph == p.phases) { ph = 0; ++b; } }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer: warp-uniform loop, elected issue, descriptors advance by adds =====
     const uint32_t idesc = idesc_bf16_f32(128, p.bnw, 1, 1);
     const uint32_t idesc_b = idesc_bf16_f32(128, 16, 1, 1);
     const uint64_t ones_desc = smem_desc_mnmajor_sw128(ones_base, BOX_BYTES, 1024);
+    const uint64_t adesc0 = smem_desc_mnmajor_sw128(smem_base, BOX_BYTES, 1024);
+    const uint64_t bdesc0 = smem_desc_mnmajor_sw128(smem_base + a_bytes, p.win ? (uint32_t)p.wb_bytes : (uint32_t)BOX_BYTES, 1024);
+    const uint32_t dstep = (uint32_t)stage_bytes >> 4;                                      // next stage (address field units of 16 B)
+    const uint32_t tstep = p.win ? (uint32_t)(p.dilation * 128) >> 4 : (uint32_t)b_bytes >> 4;  // next tap: window row shift / next tile
+    int s = 0; uint32_t phs = 0;
     for (int q = q0; q < q1; ++q) {
-      const int it = q - q0, s = it % p.stages, phs = (it / p.stages) & 1;
       mbar_wait(full_bar(s), phs);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_base + s * stage_bytes;
-        const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, BOX_BYTES, 1024);
-        for (int tl = 0; tl < ntap; ++tl) {
-          const uint64_t bdesc = p.win
-              ? smem_desc_mnmajor_sw128(a_addr + a_bytes + (uint32_t)(tl * p.dilation * 128), (uint32_t)p.wb_bytes, 1024)
-              : smem_desc_mnmajor_sw128(a_addr + a_bytes + tl * b_bytes, BOX_BYTES, 1024);
+      const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * dstep), bd0 = bdesc0 + (uint64_t)((uint32_t)s * dstep);
+      const uint32_t acc0 = q > q0 ? 1u : 0u;
+#pragma unroll 1
+      for (int tl = 0; tl < ntap; ++tl) {
+        const uint64_t bd = bd0 + (uint64_t)((uint32_t)tl * tstep);
 #pragma unroll
-          for (int ks = 0; ks < RK / 16; ++ks)  // 16 rows = 2048 B further along K
-            umma_bf16(tmem_base + (uint32_t)(tl * p.bnw), adesc + (uint64_t)(ks * 128), bdesc + (uint64_t)(ks * 128), idesc,
-                      (it > 0 || ks > 0) ? 1u : 0u);
-        }
-        if (do_bias) {
-#pragma unroll
-          for (int ks = 0; ks < RK / 16; ++ks)
-            umma_bf16(bias_tmem, adesc + (uint64_t)(ks * 128), ones_desc + (uint64_t)(ks * 128), idesc_b,
-                      (it > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(empty_bar(s));
-        if (q == q1 - 1) umma_commit(tmem_full_bar);
+        for (int ks = 0; ks < RK / 16; ++ks)  // 16 rows = 2048 B further along K
+          umma_bf16_el(tmem_base + (uint32_t)(tl * p.bnw), ad + (uint64_t)(ks * 128), bd + (uint64_t)(ks * 128), idesc,
+                       ks > 0 ? 1u : acc0);
       }
-      __syncwarp();
+      if (do_bias) {
+#pragma unroll
+        for (int ks = 0; ks < RK / 16; ++ks)
+          umma_bf16_el(bias_tmem, ad + (uint64_t)(ks * 128), ones_desc + (uint64_t)(ks * 128), idesc_b, ks > 0 ? 1u : acc0);
+      }
+      umma_commit_el(empty_bar(s));
+      if (q == q1 - 1) umma_commit_el(tmem_full_bar);
+      if (++s == p.stages) { s = 0; phs ^= 1u; }
     }
   } else {
     // ===== epilogue: TMEM -> swizzled smem sub-tiles -> TMA reduce-add into dw =====
