@@ -295,6 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // instead of a per-instruction ELECT + R2UR "waterfall" (MMA issue: 410 -> 82 clk per stage)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+  pdl_trigger();   // the next kernel of the stream may start its prologue now (it still waits for this grid to complete)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
@@ -312,6 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   else __syncthreads();
   tc_fence_after();
+  pdl_wait();      // everything above overlapped the previous kernel's tail; no global memory is touched before this line
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   // pair: stage-full barriers and the accumulator-drained barriers that count live in the LEADER's shared memory
@@ -1122,10 +1124,8 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 224 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2];
+    cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, true);
     if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmW, em, p));
     else STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmW, em, p));
     STG_LAUNCH_CHECK();
@@ -1135,8 +1135,13 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  if (staged) conv_tc_kernel<true, false><<<grid, 224, smem, s>>>(tmA, tmW, em, p);
-  else conv_tc_kernel<false, false><<<grid, 320, smem, s>>>(tmA, tmW, em, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 224 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);
+  if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmW, em, p));
+  else STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmW, em, p));
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

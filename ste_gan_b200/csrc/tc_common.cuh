@@ -3,6 +3,7 @@
 // shared-memory and instruction descriptors.  Inline PTX only.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -165,6 +166,13 @@ __device__ __forceinline__ void umma_commit_el(uint32_t bar) {
     asm volatile(STG_EL_BEGIN "@P_el tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
   }
 }
+
+// ---- programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running: its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor grid has COMPLETED and its memory
+// is visible - it must precede every global-memory access; pdl_trigger() lets the successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
@@ -329,6 +337,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 // bf16 tensor, dims[0] contiguous; strides_bytes[i] is the stride of dims[i+1]
+// Launch attribute list for the tcgen05 kernels: PDL (STG_PDL=0 disables) and, for CTA pairs, cluster dimension 2.
+inline int tc_launch_attrs(cudaLaunchAttribute* at, bool pair) {
+  static const bool pdl = !(getenv("STG_PDL") && atoi(getenv("STG_PDL")) == 0);
+  int n = 0;
+  if (pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  if (pair) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
+  return n;
+}
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes = 128);
 

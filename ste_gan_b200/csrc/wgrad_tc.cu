@@ -21,6 +21,8 @@
 // their own groups - a span of ci_span channels; the MMA computes the dense 128 x ci_span
 // product and the gradient is written in the "span" layout dw[co][j][ci_span] whose
 // off-diagonal entries are ignored by the fold backward (stg_wgrad_layout).
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace stg {
@@ -83,6 +85,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int q0 = blockIdx.z * p.chunks_per_split, q1 = min(p.total_chunks, q0 + p.chunks_per_split);
   const bool do_bias = p.dbias != nullptr && tg == p.bias_tg && blockIdx.x == 0;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmY);
     prefetch_tmap(&tmX);
@@ -92,7 +95,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
-  if (do_bias) {  // all-ones B operand (any layout of ones is ones)
+  if (do_bias) {  // all-ones B operand (any layout of ones is ones; shared memory only)
     for (int i = threadIdx.x; i < BOX_BYTES / 4; i += blockDim.x)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
     fence_proxy_async();
@@ -100,6 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // prologue above overlapped the previous kernel; global memory is only touched from here on
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t bias_tmem = tmem_base + (uint32_t)(p.n_taps * p.bnw);
@@ -326,7 +330,12 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(gx, gy, nsplit);
-  wgrad_tc_kernel<<<grid, 192, smem, s>>>(tmY, tmX, tmD, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);
+  STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tmY, tmX, tmD, p));
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
