@@ -266,10 +266,10 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int co
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool kStaged, bool kPair>
-__global__ void __launch_bounds__(kStaged ? 224 : 320, 1)
+__global__ void __launch_bounds__(kStaged ? 352 : 320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ EpiMaps em, const TcP p) {
-  constexpr int EPI_WARPS = kStaged ? 4 : 8;   // warps that read the accumulator (arrivals on tmem_empty)
+  constexpr int EPI_WARPS = 8;   // warps that read the accumulator (arrivals on tmem_empty)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -282,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: 2*(n_in+n_out) slots + bias
   const uint32_t bias_base = epi_base + (kStaged ? (2 * e.n_in + 3 * e.n_out) * SLOT : 0);
-  const uint32_t bar_base = bias_base + (kStaged ? 1024 : 0);
+  const uint32_t bar_base = bias_base + (kStaged ? 2048 : 0);   // one bias copy per epilogue team
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
@@ -515,9 +515,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if constexpr (kStaged) {
     // ===== staged epilogue: TMEM -> registers -> swizzled smem sub-tiles -> TMA store =====
-    // warps 2..5: math (one accumulator row per thread); warp 6: epilogue DMA (all TMA loads / stores of the
-    // epilogue, so their ~0.1 us issue cost each stays off the math warps' critical path).
-    // Hand-shake per sub-tile q through named barriers (160 = 128 math + 32 DMA threads):
+    // warps 2..5 and 6..9: two math TEAMS of 128 threads (one accumulator row per thread; sub-tile q belongs to team
+    // q & 1, so every SM sub-partition has two epilogue warps to interleave - one team took ~930 clk per sub-tile,
+    // instruction-latency-bound); warp 10: epilogue DMA (all TMA loads / stores of the epilogue, so their issue cost
+    // stays off the math warps' critical path).
+    // Hand-shake per sub-tile q through named barriers (160 = the 128 math threads of q's team + 32 DMA threads):
     //   FULL[q%3]  math arrives after writing the output slots (which implies it has consumed the input slots)
     //   FREE[q%3]  DMA arrives once the stores that last read output buffer q%3 (sub-tile q-3) have drained
     const int n_sub = p.bn / SUB;
@@ -527,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto bar_free = [&](int b3) { return 5 + b3; };
     const int my_tiles = (p.n_tiles - tile0 + tstep - 1) / tstep;
     const int q_total = my_tiles * n_sub;
-    if (warp == 6) {
+    if (warp == 10) {
       // ----- epilogue DMA warp -----
       if (lane == 0) {
         Tracer trc(p.trace, 3);
@@ -579,11 +581,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) bulk_wait_all();
     } else {
       // ----- math warps -----
-      const int et = threadIdx.x - 64;     // 0..127 = accumulator row m
+      const int team = (warp - 2) >> 2;                 // 0 / 1: takes the sub-tiles with q & 1 == team
+      const int et = (int)(threadIdx.x - 64) & 127;     // thread of the team
       const int sub = warp & 3;            // TMEM sub-partition this warp may read
-      const int m = sub * 32 + lane;
-      Tracer trc(et == 0 ? p.trace : nullptr, 2);
-      int acc_i = 0, q = 0;
+      const int m = sub * 32 + lane;       // accumulator row
+      const uint32_t my_bias = bias_base + (uint32_t)team * 1024u;
+      const int bias_bar = team ? 8 : 1;   // named barrier of the team (ids 2..7: FULL / FREE)
+      Tracer trc(threadIdx.x == 64 ? p.trace : nullptr, 2);
+      int acc_i = 0, qbase = 0;
       for (int t = tile0; t < p.n_tiles; t += tstep) {
         const Tile x = decode_tile<kPair>(p, t, rank);
         const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
@@ -592,13 +597,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // passed its FULL arrive of the last sub-tile, which comes after its bias reads ... of ITS OWN rows only,
         // hence the 128-thread barrier below also orders the overwrite against slower warps)
         if (e.bias) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bias_bar) : "memory");
           for (int c = et; c < p.bn; c += 128) {
             const int col = x.col0 + c;
             const float bv = col < e.c_dst ? e.bias[col] : 0.f;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * c), "f"(bv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_bias + 4u * c), "f"(bv) : "memory");
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bias_bar) : "memory");
         }
         if (x.n_iters > 0) {
           mbar_wait(tmem_full_bar(as), aph);
@@ -608,8 +613,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * ACC_COLS);
         const int r_in = e.pair_sum ? (m >> 1) : m;      // my row inside pre / mask / output sub-tiles
         const bool writer = !e.pair_sum || (lane & 1) == 0;
+        // last sub-tile of this tile that belongs to my team (-1: none - possible only for one-sub-tile tiles)
+        const int last_s = (((qbase + n_sub - 1) & 1) == team) ? n_sub - 1 : n_sub - 2;
+        if (last_s < 0 && x.n_iters > 0) {   // nothing to read: hand the buffer back (after tmem_full, so the arrival lands in this tile's phase)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_tmem_empty(as);
+        }
 #pragma unroll 1
-        for (int s = 0; s < n_sub; ++s, ++q) {
+        for (int s = (qbase & 1) == team ? 0 : 1; s < n_sub; s += 2) {
+          const int q = qbase + s;
           const int buf = q & 1;
           float v[32];
           if (x.n_iters > 0) {
@@ -619,7 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          if (s == n_sub - 1 && x.n_iters > 0) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          if (s == last_s && x.n_iters > 0) {  // my team's part of the accumulator is read: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_tmem_empty(as);
@@ -629,7 +642,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; i += 4) {
               float4 bq;
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
-                           : "r"(bias_base + 4u * (s * SUB + i)) : "memory");
+                           : "r"(my_bias + 4u * (s * SUB + i)) : "memory");
               v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
             }
           }
@@ -693,6 +706,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("bar.arrive %0, 160;" ::"r"(bar_full(obuf)) : "memory");
           trc.ev(12, s);
         }
+        qbase += n_sub;
         if (x.n_iters > 0) ++acc_i;
       }
     }
@@ -812,7 +826,7 @@ static int sm_count() {
 static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
   if (groups == 1 && (cd_g % 16) != 0) return cd_g <= 16 ? 16 : (cd_g <= 128 ? ((cd_g + 15) / 16) * 16 : 128);
   static const int env_bn = getenv("STG_BN") ? atoi(getenv("STG_BN")) : 0;  // tuning overrides
-  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 64;
+  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 128;
   if (env_bn > 0 && cd_g % env_bn == 0) return env_bn;
   int best = 0;
   for (int bn = 256; bn >= 16; bn -= 16) {
@@ -826,7 +840,7 @@ static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
 
 // data-gradient column tiles are whole 64-channel boxes of the forward pack
 static int pick_bn_mn(int cd_g, int groups, int64_t row_tiles) {
-  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 64;
+  static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 128;
   if (cd_g % 64 != 0) return groups == 1 ? (cd_g <= 64 ? 64 : 128) : 0;
   int best = 0;
   for (int bn = 256; bn >= 64; bn -= 64) {
@@ -960,7 +974,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   bool pair = env_pair != 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
   p.pairs_per_res = (n_mt + 1) / 2;
   int b_bytes = (pair ? p.bn / 2 : p.bn) * KC * 2;
-  const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 1024 : 0;
+  const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 2048 : 0;
   const int avail = 212 * 1024 - epi_bytes;
   struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
   auto build = [&](int ng, TcP* out) {
@@ -1123,7 +1137,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const int n_pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 224 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 352 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[2];
     cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, true);
     if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmW, em, p));
@@ -1137,7 +1151,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 224 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 352 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);
   if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmW, em, p));
