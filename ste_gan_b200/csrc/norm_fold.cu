@@ -287,85 +287,192 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __re
 // wf[j][co][:] (coalesced; the transposition (ci, j) -> (j, ci) happens in shared memory).  Replaces the
 // scale + 32x32-tile pack pair, whose v reads were strided by k.
 constexpr int FOLD_ROW_MAX = 4096;
+constexpr int FOLD_RPB = 4;   // rows per block: one table search per block, the item is then walked forward
+// Both row kernels are pure HBM streams (v 4 B + pack 2 B per weight; dw + v + dv 12 B per weight).  The first versions
+// moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.  Now: 16-byte
+// accesses wherever the row is 16-byte aligned, all loads of a row issued before the first use, FOLD_RPB rows per block.
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 template <typename T>
-__global__ void __launch_bounds__(256) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items) {
-  __shared__ float row[FOLD_ROW_MAX];
+__device__ __forceinline__ void store8(T* dst, const float* w);
+template <>
+__device__ __forceinline__ void store8<float>(float* dst, const float* w) {
+  *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(w[4], w[5], w[6], w[7]);
+}
+template <>
+__device__ __forceinline__ void store8<bf16>(bf16* dst, const float* w) {
+  uint32_t q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
+    q[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
+  __shared__ __align__(16) float row[FOLD_ROW_MAX];
   __shared__ float red[32];
-  const int it = find_item(items, n_items, blockIdx.x, false);
-  const StgFoldItem d = items[it];
-  const int co = blockIdx.x - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
-  const float* vr = d.v + (int64_t)co * n;
-  float ss = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float x = vr[i];
-    if (i < FOLD_ROW_MAX) row[i] = x;
-    ss = fmaf(x, x, ss);
-  }
-  ss = block_sum(ss, red);   // (contains the barrier that publishes row[])
-  const float sc = d.g[co] / sqrtf(ss);
-  if (threadIdx.x == 0) d.scale[co] = sc;
-  T* wf = static_cast<T*>(d.wf);
-  if (d.flags & STG_PACK_UNFOLD) {           // wf[co][q], q = j*c_in + c  (groups == 1)
-    const int Kp = (k * cin_g + 7) / 8 * 8;
-    for (int q = threadIdx.x; q < Kp; q += 256) {
-      float w = 0.f;
-      if (q < k * cin_g) {
-        const int j = q / cin_g, c = q - j * cin_g, i = c * k + j;
-        w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc;
+  const int r_begin = blockIdx.x * FOLD_RPB, r_end = min(total_rows, r_begin + FOLD_RPB);
+  int it = find_item(items, n_items, r_begin, false);
+  StgFoldItem d = items[it];
+  for (int r = r_begin; r < r_end; ++r) {
+    while (r >= d.row0 + d.c_out) d = items[++it];
+    const int co = r - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+    const float* vr = d.v + (int64_t)co * n;
+    const bool staged = n <= FOLD_ROW_MAX;
+    float ss = 0.f;
+    __syncthreads();                                   // the previous row's readers are done with row[]
+    if ((n & 3) == 0 && al16(vr) && staged) {
+      const float4* v4 = reinterpret_cast<const float4*>(vr);
+      float4 x[4];                                     // n <= 4096: at most 4 float4 per thread, all in flight together
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = threadIdx.x + u * 256; if (i < n / 4) x[u] = v4[i]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * 256;
+        if (i < n / 4) {
+          reinterpret_cast<float4*>(row)[i] = x[u];
+          ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
+        }
       }
-      wf[(int64_t)co * Kp + q] = from_f<T>(w);
+    } else {
+      for (int i = threadIdx.x; i < n; i += 256) {
+        const float x = vr[i];
+        if (i < FOLD_ROW_MAX) row[i] = x;
+        ss = fmaf(x, x, ss);
+      }
     }
-    return;
-  }
-  const int pg = d.pg, c_in = cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
-  // this row's own group occupies columns [off, off + cin_g) of its pack group; the rest of the row is zero
-  const int off = ((co / cout_g) - (co / cout_gp) * (d.groups / pg)) * cin_g;
-  for (int j = 0; j < k; ++j) {
-    T* dst = wf + ((int64_t)j * d.c_out + co) * cin_gp;
-    for (int cip = threadIdx.x; cip < cin_gp; cip += 256) {
-      const int c = cip - off;
-      float w = 0.f;
-      if (c >= 0 && c < cin_g) { const int i = c * k + j; w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc; }
-      dst[cip] = from_f<T>(w);
+    ss = block_sum(ss, red);   // (contains the barrier that publishes row[])
+    const float sc = d.g[co] / sqrtf(ss);
+    if (threadIdx.x == 0) d.scale[co] = sc;
+    T* wf = static_cast<T*>(d.wf);
+    if (d.flags & STG_PACK_UNFOLD) {           // wf[co][q], q = j*c_in + c  (groups == 1)
+      const int Kp = (k * cin_g + 7) / 8 * 8;
+      for (int q = threadIdx.x; q < Kp; q += 256) {
+        float w = 0.f;
+        if (q < k * cin_g) {
+          const int j = q / cin_g, c = q - j * cin_g, i = c * k + j;
+          w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc;
+        }
+        wf[(int64_t)co * Kp + q] = from_f<T>(w);
+      }
+      continue;
+    }
+    const int pg = d.pg, c_in = cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
+    // this row's own group occupies columns [off, off + cin_g) of its pack group; the rest of the row is zero
+    const int off = ((co / cout_g) - (co / cout_gp) * (d.groups / pg)) * cin_g;
+    if ((cin_gp & 7) == 0 && staged && al16(wf)) {   // 8 consecutive input channels of one tap per thread: one 16 B (bf16) store
+      const int per_tap = cin_gp >> 3, total = k * per_tap;
+      for (int idx = threadIdx.x; idx < total; idx += 256) {
+        const int j = idx / per_tap, cip = (idx - j * per_tap) << 3;
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = cip + u - off;
+          w[u] = (c >= 0 && c < cin_g) ? row[c * k + j] * sc : 0.f;
+        }
+        store8<T>(wf + ((int64_t)j * d.c_out + co) * cin_gp + cip, w);
+      }
+    } else {
+      for (int j = 0; j < k; ++j) {
+        T* dst = wf + ((int64_t)j * d.c_out + co) * cin_gp;
+        for (int cip = threadIdx.x; cip < cin_gp; cip += 256) {
+          const int c = cip - off;
+          float w = 0.f;
+          if (c >= 0 && c < cin_g) { const int i = c * k + j; w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc; }
+          dst[cip] = from_f<T>(w);
+        }
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int accumulate) {
-  __shared__ float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
+__global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows,
+                                                           int accumulate) {
+  __shared__ __align__(16) float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
   __shared__ float red[32];
-  const int it = find_item(items, n_items, blockIdx.x, false);
-  const StgFoldItem d = items[it];
-  const int co = blockIdx.x - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
-  const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
-  const float* vr = d.v + (int64_t)co * n;
-  const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
-  const bool staged = n <= FOLD_ROW_MAX;
-  if (staged) {   // coalesced read of each tap's run of cin_g gradients, scattered (stride k, k odd) into shared memory
-    for (int j = 0; j < k; ++j)
-      for (int ci = threadIdx.x; ci < cin_g; ci += 256) sdw[ci * k + j] = dr[j * span + ci];
-    __syncthreads();
+  const int r_begin = blockIdx.x * FOLD_RPB, r_end = min(total_rows, r_begin + FOLD_RPB);
+  int it = find_item(items, n_items, r_begin, false);
+  StgFoldItem d = items[it];
+  for (int r = r_begin; r < r_end; ++r) {
+    while (r >= d.row0 + d.c_out) d = items[++it];
+    const int co = r - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+    const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
+    const float* vr = d.v + (int64_t)co * n;
+    const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
+    float* orow = d.dv + (int64_t)co * n;
+    const bool staged = n <= FOLD_ROW_MAX;
+    const bool vec = staged && (n & 3) == 0 && al16(vr) && al16(orow);
+    __syncthreads();                                  // the previous row's readers are done with sdw[]
+    float4 x[4];                                      // vec: the v row stays in registers for the second pass
+    if (vec) {
+      const float4* v4 = reinterpret_cast<const float4*>(vr);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = threadIdx.x + u * 256; if (i < n / 4) x[u] = v4[i]; }
+    }
+    if (staged) {   // coalesced read of each tap's run of cin_g gradients, scattered (stride k) into shared memory
+      if ((cin_g & 3) == 0 && (span & 3) == 0 && al16(dr)) {
+        const int per_tap = cin_g >> 2, total = k * per_tap;
+        for (int idx = threadIdx.x; idx < total; idx += 256) {
+          const int j = idx / per_tap, ci = (idx - j * per_tap) << 2;
+          const float4 g4 = *reinterpret_cast<const float4*>(dr + j * span + ci);
+          sdw[ci * k + j] = g4.x; sdw[(ci + 1) * k + j] = g4.y; sdw[(ci + 2) * k + j] = g4.z; sdw[(ci + 3) * k + j] = g4.w;
+        }
+      } else {
+        for (int j = 0; j < k; ++j)
+          for (int ci = threadIdx.x; ci < cin_g; ci += 256) sdw[ci * k + j] = dr[j * span + ci];
+      }
+      __syncthreads();
+    }
+    float ss = 0.f, dot = 0.f;
+    if (vec) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * 256;
+        if (i < n / 4) {
+          const float4 g4 = reinterpret_cast<const float4*>(sdw)[i];
+          ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
+          dot += x[u].x * g4.x + x[u].y * g4.y + x[u].z * g4.z + x[u].w * g4.w;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += 256) {
+        const float xv = vr[i];
+        float g;
+        if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
+        ss = fmaf(xv, xv, ss);
+        dot = fmaf(xv, g, dot);
+      }
+    }
+    ss = block_sum(ss, red);
+    dot = block_sum(dot, red);
+    const float norm = sqrtf(ss), gg = d.g[co];
+    const float a = gg / norm, bcoef = gg * dot / (norm * ss);
+    if (vec) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * 256;
+        if (i < n / 4) {
+          const float4 g4 = reinterpret_cast<const float4*>(sdw)[i];
+          float4 o = make_float4(a * g4.x - bcoef * x[u].x, a * g4.y - bcoef * x[u].y, a * g4.z - bcoef * x[u].z, a * g4.w - bcoef * x[u].w);
+          float4* op = reinterpret_cast<float4*>(orow) + i;
+          if (accumulate) { const float4 p = *op; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          *op = o;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += 256) {
+        float g;
+        if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
+        const float val = a * g - bcoef * vr[i];
+        orow[i] = accumulate ? (orow[i] + val) : val;
+      }
+    }
+    if (threadIdx.x == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
   }
-  float ss = 0.f, dot = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float x = vr[i];
-    float g;
-    if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
-    ss = fmaf(x, x, ss);
-    dot = fmaf(x, g, dot);
-  }
-  ss = block_sum(ss, red);
-  dot = block_sum(dot, red);
-  const float norm = sqrtf(ss), gg = d.g[co];
-  const float a = gg / norm, bcoef = gg * dot / (norm * ss);
-  float* orow = d.dv + (int64_t)co * n;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    float g;
-    if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
-    const float val = a * g - bcoef * vr[i];
-    orow[i] = accumulate ? (orow[i] + val) : val;
-  }
-  if (threadIdx.x == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
 }
 
 template <typename T>
@@ -478,8 +585,8 @@ extern "C" int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!items || n_items < 1 || total_rows < 1 || total_tiles < 0) return STG_EINVAL;
   if (total_tiles == 0) {  // row form: every item wants the forward pack only (wd == NULL)
-    if (dtype == STG_F32) wn_fold_rows_kernel<float><<<total_rows, 256, 0, s>>>(items, n_items);
-    else if (dtype == STG_BF16) wn_fold_rows_kernel<bf16><<<total_rows, 256, 0, s>>>(items, n_items);
+    if (dtype == STG_F32) wn_fold_rows_kernel<float><<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows);
+    else if (dtype == STG_BF16) wn_fold_rows_kernel<bf16><<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows);
     else return STG_EINVAL;
     STG_LAUNCH_CHECK();
     return STG_OK;
@@ -497,7 +604,7 @@ extern "C" int stg_weightnorm_fold_bwd_multi(const StgFoldItem* items, int n_ite
                                              stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!items || n_items < 1 || total_rows < 1) return STG_EINVAL;
-  wn_bwd_multi_kernel<<<total_rows, 256, 0, s>>>(items, n_items, accumulate);
+  wn_bwd_multi_kernel<<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
