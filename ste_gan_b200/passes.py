@@ -539,16 +539,37 @@ def discriminator_convs(model) -> List:
 def fold_discriminator(model, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True,
                        reuse: Optional[Dict[int, Folded]] = None,
                        persist: Optional[Dict[int, Folded]] = None,
-                       plan: Optional[FoldPlan] = None, refold: bool = True) -> Dict[int, Folded]:
+                       plan: Optional[FoldPlan] = None, refold: bool = True, sn_streams=None) -> Dict[int, Folded]:
     """Fold every discriminator conv.  Weight-norm folds depend on the weights only and may be
     reused between forwards (`reuse`); spectral-norm layers are ALWAYS re-folded because every
     training-mode forward of the reference runs one more power iteration (conv.py:94,101)."""
     if plan is not None:
-        # weight-norm convs: one multi-tensor launch (when the weights changed), spectral-norm convs one by one
+        # weight-norm convs: one multi-tensor launch (when the weights changed); spectral-norm convs one by one - each
+        # is a chain of ~7 small dependent kernels (power iteration, sigma, pack), so with `sn_streams` the layers'
+        # chains run side by side (and beside the multi-tensor launch) instead of back to back.  The same layer
+        # always goes to the same stream: its next power iteration is ordered behind this one.
+        sn = [c for c in discriminator_convs(model) if c.norm != "weight_norm"]
+        if sn_streams and sn:
+            cur = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            out = dict(plan.fold() if refold else plan.folds)
+            used = []
+            for i, c in enumerate(sn):
+                st = sn_streams[i % len(sn_streams)]
+                if st not in used:
+                    st.wait_event(ev)
+                    used.append(st)
+                with torch.cuda.stream(st):
+                    out[id(c)] = fold(c, dtype, training=training, want_dgrad=want_dgrad)
+            for st in used:
+                e2 = torch.cuda.Event()
+                e2.record(st)
+                cur.wait_event(e2)
+            return out
         out = dict(plan.fold() if refold else plan.folds)
-        for c in discriminator_convs(model):
-            if c.norm != "weight_norm":
-                out[id(c)] = fold(c, dtype, training=training, want_dgrad=want_dgrad)
+        for c in sn:
+            out[id(c)] = fold(c, dtype, training=training, want_dgrad=want_dgrad)
         return out
     out = {}
     for c in discriminator_convs(model):

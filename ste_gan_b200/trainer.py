@@ -94,10 +94,16 @@ class GanTrainer:
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # per pass: the heavy sub-discriminator
         self._wg = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # weight-gradient side streams
+        self._sn = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # spectral-norm fold chains, one per layer
+        self._aux = torch.cuda.Stream(device=dev)                                     # time-domain loss beside the D passes
         self.concurrent_d = True
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None
+
+    def _fold_d(self, refold: bool):
+        return passes.fold_discriminator(self.net_d, self.dtype, training=True, plan=self.d_plan, refold=refold,
+                                         sn_streams=self._sn if self.concurrent_d else None)
 
     def _fork(self) -> None:
         ev = torch.cuda.Event()
@@ -132,21 +138,33 @@ class GanTrainer:
         if not self.use_adv:
             self.x_pred, self._gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
             return
-        # folds first (the spectral-norm power iterations of the fake and the real forward happen in that order, as in
-        # train.py:190-191); then the real pass - which needs neither G nor x_pred - overlaps the generator forward
-        f1 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=not self._d_folded)
+        # The spectral-norm power iterations of the fake and the real forward happen in that order (train.py:190-191).
+        # Side stream: D folds (fake's, then real's) and the real pass, which needs neither G nor x_pred; current
+        # stream: G fold + generator forward, then - once the fake pass's folds are there - the fake pass.
+        refold_d = not self._d_folded
         self._d_folded = True
-        f2 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
-
-        def fake_side():
+        if self.concurrent_d:
+            cur = torch.cuda.current_stream()
+            self._fork()
+            with torch.cuda.stream(self._side):
+                f1 = self._fold_d(refold_d)
+                ev_f1 = torch.cuda.Event()
+                ev_f1.record(self._side)
+                f2 = self._fold_d(False)
+                res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(0))
             x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold(),
                                                     side=self._s2(1))
             self.x_pred, self._gctx = x_pred, gctx
-            return passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(1))
-
-        (res_r, ctx_r), (res_f, ctx_f) = self._two_passes(
-            lambda: passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(0)), fake_side)
-        x_pred = self.x_pred
+            cur.wait_event(ev_f1)
+            res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(1))
+            self._join()
+        else:
+            f1 = self._fold_d(refold_d)
+            f2 = self._fold_d(False)
+            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
+            self.x_pred, self._gctx = x_pred, gctx
+            res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1)
+            res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
         nd = len(res_f)
@@ -171,15 +189,36 @@ class GanTrainer:
         dt = self.dtype
         x_pred = self.x_pred
         dx_pred = torch.zeros_like(x_pred)
+        td_ev = None
+        if self.use_td and self.use_adv and self.concurrent_d:
+            # the time-domain loss needs only x_real / x_pred: it runs on its own stream beside the discriminator passes
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._aux.wait_event(ev)
+            with torch.cuda.stream(self._aux):
+                ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
+                td_ev = torch.cuda.Event()
+                td_ev.record(self._aux)
         if self.use_adv:
             if update_d:
                 self.D.adamw(self.lr, grad_scale=self.reducer.grad_scale)   # train.py:199
-            f3 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=update_d or not self._d_folded)
+            refold_d = update_d or not self._d_folded
             self._d_folded = True
-            f4 = passes.fold_discriminator(self.net_d, dt, training=True, plan=self.d_plan, refold=False)
-            (res_f, ctx_f), (res_r, _) = self._two_passes(
-                lambda: passes.discriminator_forward(self.net_d, x_pred, dt, f3, side=self._s2(0)),
-                lambda: passes.discriminator_forward(self.net_d, x_real, dt, f4, side=self._s2(1)))
+            if self.concurrent_d:
+                # current stream: folds of the fake pass, then (while the side stream already runs the fake pass) the
+                # real pass's power iteration and the real pass
+                f3 = self._fold_d(refold_d)
+                self._fork()
+                with torch.cuda.stream(self._side):
+                    res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3, side=self._s2(0))
+                f4 = self._fold_d(False)
+                res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4, side=self._s2(1))
+                self._join()
+            else:
+                f3 = self._fold_d(refold_d)
+                f4 = self._fold_d(False)
+                res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3)
+                res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4)
             self.d_folds = f4
             nd = len(res_f)
             dlog = ops.mse_const_multi([fm[-1] for fm in res_f], [1.0] * nd, self.slots, [1] * nd, 1.0, dt)   # train.py:210-211
@@ -193,8 +232,10 @@ class GanTrainer:
                 dfm = [[None] * (len(fm_f) - 1) for fm_f in res_f]
             dx_d = passes.discriminator_backward(self.net_d, ctx_f, dlog, dfm, want_input_grad=True, want_weight_grad=False,
                                                  side=self._s2(0))
+            if td_ev is not None:
+                torch.cuda.current_stream().wait_event(td_ev)
             ops.axpy_f32(dx_pred, dx_d, 1.0)
-        if self.use_td:
+        if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
         passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0))
         self._gctx = None
