@@ -242,10 +242,12 @@ class FoldPlan:
             return torch.zeros(dw_layout(f)[0], device=self.device, dtype=torch.float32)
         return self.arena[ent[0]:ent[0] + ent[1]]
 
-    def backward(self) -> None:
-        """dv, dg += fold-backward of everything accumulated in the arena since zero() (1 launch)."""
+    def backward(self, accumulate: bool = True) -> None:
+        """dv, dg (+)= fold-backward of everything accumulated in the arena since zero() (1 launch).  accumulate=False
+        overwrites: for a caller that knows this is the only contribution to these gradients since they were zeroed
+        (the fused train step) it saves re-reading every dv."""
         self._check_ptrs()
-        ops.weightnorm_fold_bwd_multi(self.table, self.n_items, self.total_rows, True)
+        ops.weightnorm_fold_bwd_multi(self.table, self.n_items, self.total_rows, accumulate)
 
 
 def unfold_input(f: Folded, src: Tensor, B: int, t_src: int, phases: int = 1) -> Tensor:
@@ -460,7 +462,7 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
 
 
 def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None,
-                       res_side=None) -> None:
+                       res_side=None, overwrite_grads: bool = False) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
     dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output.  With a FoldPlan the packed weight gradients go to
     its arena and the weight-norm backward of all 45 convs is one launch at the end."""
@@ -496,7 +498,7 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
             ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
     if plan is not None:
         plan.join_wgrads()
-        plan.backward()
+        plan.backward(accumulate=not overwrite_grads)
 
 
 # --------------------------------------------------------------------------------------

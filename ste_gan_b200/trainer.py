@@ -41,8 +41,11 @@ class FlatParams:
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatParams: move the module to a CUDA device first")
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        # every parameter starts on a 16-byte boundary (the 1-element bias / weight_g of the logits convs would otherwise
+        # misalign everything behind them and switch the fold kernels to 4-byte accesses); the gaps stay zero
+        al = lambda k: (k + 3) // 4 * 4
+        n = sum(al(p.numel()) for p in self.params)
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for p in self.params:
@@ -50,7 +53,7 @@ class FlatParams:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
+            off += al(k)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.step = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -183,7 +186,7 @@ class GanTrainer:
             lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True,
                                                   plan=self.d_plan, side=self._s2(1)))
         self.d_plan.join_wgrads()
-        self.d_plan.backward()
+        self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
 
     def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
         dt = self.dtype
@@ -237,7 +240,8 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0))
+        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
+                                  overwrite_grads=True)   # G.grad was zeroed in phase D; this is its only writer
         self._gctx = None
 
     def _phase_opt_g(self) -> None:
