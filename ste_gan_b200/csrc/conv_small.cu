@@ -41,41 +41,69 @@ struct C1P {
 };
 
 // One warp per input row: the k dot products of that row with the k taps, scattered (atomically) to the k output
-// rows it feeds (y is zeroed first; the centre tap adds the bias).  grid: (ceil(rows/32), B), 256 threads.
-template <int K>
+// rows it feeds (y is zeroed first; the centre tap adds the bias).  grid: (ceil(rows / 16), B), 256 threads = 8 warps x
+// 2 rows.  CI = C / 256 (0: any C): with CI known every 16-byte load of a row (and, once per warp, the lane's slice of
+// the taps, kept packed in registers) is issued before the first use - the first version walked 4 rows x C/256 chunks
+// with one load in flight per lane and staged fp32 taps in shared memory behind a block barrier (12-16 us per launch
+// for 13 MB that sit in L2).
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
+  float x[8], w[8];
+  unpack8(a, x); unpack8(b, w);
+  return x[0] * w[0] + x[1] * w[1] + x[2] * w[2] + x[3] * w[3] + x[4] * w[4] + x[5] * w[5] + x[6] * w[6] + x[7] * w[7];
+}
+template <int K, int CI>
 __global__ void __launch_bounds__(256) c1_fwd_kernel(const C1P p) {
-  extern __shared__ float wsm[];  // [K][C] fp32 taps
-  for (int i = threadIdx.x; i < K * p.C; i += 256) wsm[i] = to_f(p.w[i]);
-  __syncthreads();
+  constexpr int RW = 2;                       // rows per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const float bias0 = p.bias ? p.bias[0] : 0.f;
-  for (int rr = 0; rr < 4; ++rr) {             // 32 rows per block: the taps are staged once per 32 rows
-    const int r = blockIdx.x * 32 + warp * 4 + rr;
-    if (r >= p.rows) return;
-    const bf16* xr = p.x + ((int64_t)b * p.rows + r) * p.C;
-    float acc[K];
+  const int r0 = (blockIdx.x * 8 + warp) * RW;
+  if (r0 >= p.rows) return;
+  float acc[RW][K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) acc[j] = 0.f;
-    for (int c = lane * 8; c < p.C; c += 256) {
-      float xv[8];
-      unpack8(*reinterpret_cast<const uint4*>(xr + c), xv);
+  for (int rr = 0; rr < RW; ++rr)
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[j * p.C + c]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[j * p.C + c + 4]);
-        acc[j] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y + xv[6] * w1.z + xv[7] * w1.w;
-      }
+    for (int j = 0; j < K; ++j) acc[rr][j] = 0.f;
+  if constexpr (CI > 0) {
+    uint4 wq[K][CI], xq[RW][CI];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+      const bf16* xr = p.x + ((int64_t)b * p.rows + min(r0 + rr, p.rows - 1)) * p.C;
+#pragma unroll
+      for (int i = 0; i < CI; ++i) xq[rr][i] = *reinterpret_cast<const uint4*>(xr + i * 256 + lane * 8);
     }
 #pragma unroll
-    for (int j = 0; j < K; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < CI; ++i) wq[j][i] = __ldg(reinterpret_cast<const uint4*>(p.w + j * p.C + i * 256 + lane * 8));
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr)
+#pragma unroll
+      for (int i = 0; i < CI; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[rr][j] += dot8(xq[rr][i], wq[j][i]);
+  } else {
+    for (int rr = 0; rr < RW; ++rr) {
+      const bf16* xr = p.x + ((int64_t)b * p.rows + min(r0 + rr, p.rows - 1)) * p.C;
+      for (int c = lane * 8; c < p.C; c += 256) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xr + c);
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[rr][j] += dot8(xv, __ldg(reinterpret_cast<const uint4*>(p.w + j * p.C + c)));
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[rr][j] = warp_sum(acc[rr][j]);
+    const int r = r0 + rr;
+    if (lane == 0 && r < p.rows) {
       const int h = r / p.P;
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const int ho = h - (j - p.pad);          // output row whose tap j reads input row h
         // the centre tap reaches every output row exactly once: it carries the bias (y starts at 0)
-        if (ho >= 0 && ho < p.H) atomicAdd(p.y + (int64_t)b * p.rows + r - (j - p.pad) * p.P, acc[j] + (j == p.pad ? bias0 : 0.f));
+        if (ho >= 0 && ho < p.H) atomicAdd(p.y + (int64_t)b * p.rows + r - (j - p.pad) * p.P, acc[rr][j] + (j == p.pad ? bias0 : 0.f));
       }
     }
   }
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(256) c1_wgrad_kernel(const C1W p) {
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
   float bsum = 0.f;
   if (rl < lanes) {
-#pragma unroll 4
+#pragma unroll 8
     for (int r = r_begin + rl; r < r_end; r += lanes) {
       const int h = r / p.P;
       float xv[8];
@@ -174,8 +202,14 @@ __global__ void __launch_bounds__(256) c1_wgrad_kernel(const C1W p) {
       for (int l = 1; l < lanes; ++l)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] += part[(threadIdx.x + l * cg) * 8 + i];
+      float* dst = p.dw + j * p.C + c;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[j][0]), "f"(acc[j][1]), "f"(acc[j][2]), "f"(acc[j][3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(acc[j][4]), "f"(acc[j][5]), "f"(acc[j][6]), "f"(acc[j][7]) : "memory");
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(p.dw + j * p.C + c + i, acc[j][i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, acc[j][i]);
+      }
     }
   }
 }
@@ -201,8 +235,13 @@ static int launch_c1(const StgConv* d, cudaStream_t s) {
           d->bias, static_cast<float*>(d->y_raw)};
     if (d->pad < 0 || d->pad >= K) return STG_EUNSUPPORTED;   // the centre tap carries the bias
     STG_CUDA_CHECK(cudaMemsetAsync(p.y, 0, sizeof(float) * (size_t)d->n_samples * rows, s));
-    dim3 grid(ceil_div(rows, 32), d->n_samples);
-    c1_fwd_kernel<K><<<grid, 256, K * d->c_src * sizeof(float), s>>>(p);
+    dim3 grid(ceil_div(rows, 16), d->n_samples);
+    switch (d->c_src) {
+      case 256: c1_fwd_kernel<K, 1><<<grid, 256, 0, s>>>(p); break;
+      case 512: c1_fwd_kernel<K, 2><<<grid, 256, 0, s>>>(p); break;
+      case 1024: c1_fwd_kernel<K, 4><<<grid, 256, 0, s>>>(p); break;
+      default: c1_fwd_kernel<K, 0><<<grid, 256, 0, s>>>(p); break;
+    }
     STG_LAUNCH_CHECK();
     return STG_OK;
   }
@@ -234,10 +273,10 @@ static int launch_c1w(const StgWgrad* d, cudaStream_t s) {
   const int rows = d->t_out * d->phases;
   C1W p{rows, d->phases, d->t_out, d->c_in, d->k, d->pad, 0, static_cast<const bf16*>(d->x), static_cast<const bf16*>(d->dy),
         d->dw, d->dbias};
-  // ~96 blocks in total: every block ends with k*C atomics onto the same k*C addresses, so the block count is the
-  // contention per address (304 blocks made this kernel 28 us for 13 MB of input)
+  // every block ends with k*C reductions onto the same k*C addresses, so the block count is the contention per
+  // address (with scalar atomics 304 blocks made this kernel 28 us for 13 MB of input)
   const int lanes = 256 / (d->c_in / 8);
-  int blocks_per_sample = ceil_div(96, d->n_samples);
+  int blocks_per_sample = ceil_div(296, d->n_samples);   // (with 16-byte vector reductions; scalar atomics were limited to ~96 blocks)
   int rpb = ceil_div(rows, blocks_per_sample);
   if (rpb < 4 * lanes) rpb = 4 * lanes;
   p.rows_per_block = rpb;
