@@ -530,55 +530,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int my_tiles = (p.n_tiles - tile0 + tstep - 1) / tstep;
     const int q_total = my_tiles * n_sub;
     if (warp == 10) {
-      // ----- epilogue DMA warp -----
+      // ----- epilogue DMA warp: warp-uniform control flow, elected issue (see the producer warp) -----
       if (lane == 0) {
-        Tracer trc(p.trace, 3);
         for (int r = 0; r < p.n_res; ++r) { prefetch_tmap(&em.pre[r]); prefetch_tmap(&em.mask[r]); prefetch_tmap(&em.raw[r]); }
         prefetch_tmap(&em.post); prefetch_tmap(&em.act);
       }
       const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
       const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
+      const int rsh = e.pair_sum ? 1 : 0;
       // iterator over (tile, sub-tile) pairs for the operand loads, which run two sub-tiles ahead of the math
       int ld_t = tile0, ld_s = 0, ld_q = 0;
-      auto issue_loads = [&]() {  // lane 0 only
+      Tile lx = decode_tile<kPair>(p, ld_t < p.n_tiles ? ld_t : tile0, rank);
+      auto issue_loads = [&]() {
         if (e.n_in == 0 || ld_t >= p.n_tiles) return;
-        const Tile x = decode_tile<kPair>(p, ld_t, rank);
         const int buf = ld_q & 1;
-        const int col = x.col0 + ld_s * SUB;
-        const int r0 = x.h0 >> (e.pair_sum ? 1 : 0);                     // first h row of the tile in its residue class
-        mbar_expect_tx(in_bar(buf), in_bytes);
+        const int col = lx.col0 + ld_s * SUB;
+        const int r0 = lx.h0 >> rsh;                                     // first h row of the tile in its residue class
+        mbar_expect_tx_el(in_bar(buf), in_bytes);
         int i = 0;
-        if (e.has_pre) tma_load_4d(in_slot(buf, i++), &em.pre[x.res], in_bar(buf), col, 0, r0, x.b);
-        if (e.has_mask) tma_load_4d(in_slot(buf, i++), &em.mask[x.res], in_bar(buf), col, 0, r0, x.b);
-        if (e.has_post) tma_load_4d(in_slot(buf, i++), &em.post, in_bar(buf), col, 0, r0 >> e.post_shift, x.b);
+        if (e.has_pre) tma_load_4d_el(in_slot(buf, i++), &em.pre[lx.res], in_bar(buf), col, 0, r0, lx.b);
+        if (e.has_mask) tma_load_4d_el(in_slot(buf, i++), &em.mask[lx.res], in_bar(buf), col, 0, r0, lx.b);
+        if (e.has_post) tma_load_4d_el(in_slot(buf, i++), &em.post, in_bar(buf), col, 0, r0 >> e.post_shift, lx.b);
         ++ld_q;
-        if (++ld_s == n_sub) { ld_s = 0; ld_t += tstep; }
+        if (++ld_s == n_sub) {
+          ld_s = 0; ld_t += tstep;
+          if (ld_t < p.n_tiles) lx = decode_tile<kPair>(p, ld_t, rank);
+        }
       };
-      if (lane == 0) { issue_loads(); issue_loads(); }
+      issue_loads(); issue_loads();
       int q = 0;
       for (int t = tile0; t < p.n_tiles; t += tstep) {
         const Tile x = decode_tile<kPair>(p, t, rank);
-        const int r0_out = x.h0 >> (e.pair_sum ? 1 : 0);
+        const int r0_out = x.h0 >> rsh;
         for (int s = 0; s < n_sub; ++s, ++q) {
           const int obuf = q % 3;
           asm volatile("bar.sync %0, 160;" ::"r"(bar_full(obuf)) : "memory");   // output slots written, input slots consumed
-          if (lane == 0) {
-            const int col = x.col0 + s * SUB;
-            int o = 0;
-            if (e.has_raw) tma_store_4d(&em.raw[x.res], out_slot(obuf, o++), col, 0, r0_out, x.b);
-            if (e.has_act) {
-              tma_store_4d(&em.act, out_slot(obuf, o), col, 0, r0_out, x.b);
-              if (e.dup_rows) tma_store_4d(&em.act, out_slot(obuf, o), col, 1, r0_out, x.b);
-            }
-            bulk_commit();
-            issue_loads();                         // operands of sub-tile q+2 into the input slots just consumed
-            bulk_wait_read<1>();                   // stores of sub-tile q-1 have read their slots -> buffer (q+2)%3 is free
+          const int col = x.col0 + s * SUB;
+          int o = 0;
+          if (e.has_raw) tma_store_4d_el(&em.raw[x.res], out_slot(obuf, o++), col, 0, r0_out, x.b);
+          if (e.has_act) {
+            tma_store_4d_el(&em.act, out_slot(obuf, o), col, 0, r0_out, x.b);
+            if (e.dup_rows) tma_store_4d_el(&em.act, out_slot(obuf, o), col, 1, r0_out, x.b);
           }
+          bulk_commit_el();
+          issue_loads();                         // operands of sub-tile q+2 into the input slots just consumed
+          bulk_wait_read_el<1>();                // stores of sub-tile q-1 have read their slots -> buffer (q+2)%3 is free
           __syncwarp();
           if (q >= 1 && q + 2 < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free((q + 2) % 3)) : "memory");
         }
       }
-      if (lane == 0) bulk_wait_all();
+      bulk_wait_all_el();
     } else {
       // ----- math warps -----
       const int team = (warp - 2) >> 2;                 // 0 / 1: takes the sub-tiles with q & 1 == team

@@ -312,7 +312,7 @@ __device__ __forceinline__ void store8<bf16>(bf16* dst, const float* w) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
+__global__ void __launch_bounds__(256, 8) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
   __shared__ __align__(16) float row[FOLD_ROW_MAX];
   __shared__ float red[32];
   const int r_begin = blockIdx.x * FOLD_RPB, r_end = min(total_rows, r_begin + FOLD_RPB);
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) wn_fold_rows_kernel(const StgFoldItem* __
   }
 }
 
-__global__ void __launch_bounds__(256) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows,
+__global__ void __launch_bounds__(256, 8) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows,
                                                            int accumulate) {
   __shared__ __align__(16) float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
   __shared__ float red[32];

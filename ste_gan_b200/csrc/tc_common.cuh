@@ -167,6 +167,17 @@ __device__ __forceinline__ void umma_commit_el(uint32_t bar) {
   }
 }
 
+// elected TMA stores / bulk-group bookkeeping (bulk groups belong to the issuing THREAD: elect.sync with a full mask
+// picks the same lane every time, so stores, commit and wait of the epilogue DMA warp all land on one thread)
+__device__ __forceinline__ void tma_store_4d_el(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(STG_EL_BEGIN "@P_el cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t}"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_el() { asm volatile(STG_EL_BEGIN "@P_el cp.async.bulk.commit_group;\n\t}" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_el() { asm volatile(STG_EL_BEGIN "@P_el cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all_el() { asm volatile(STG_EL_BEGIN "@P_el cp.async.bulk.wait_group 0;\n\t}" ::: "memory"); }
+
 // ---- programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // start while its predecessor in the stream is still running: its prologue (barrier init, TMEM allocation, tensor-map
 // prefetch) overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor grid has COMPLETED and its memory
