@@ -266,7 +266,7 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int co
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool kStaged, bool kPair>
-__global__ void __launch_bounds__(kStaged ? 352 : 320, 1)
+__global__ void __launch_bounds__(kStaged ? 384 : 352, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ EpiMaps em, const TcP p) {
   constexpr int EPI_WARPS = 8;   // warps that read the accumulator (arrivals on tmem_empty)
@@ -324,14 +324,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (kPair) mbar_arrive_cluster(lead_tmem_empty_bar(a)); else mbar_arrive(tmem_empty_bar(a));
   };
 
-  if (warp == 0 && p.max_ntaps == 1) {
-    // ===== TMA producer, one tap per stage (the common case) =====
+  // Two producer warps: warp 0 loads the A (activation) boxes and posts the stage's expect_tx, the LAST warp of the CTA
+  // loads the W boxes of the same stage onto the same barrier (its complete_tx may land before the expect_tx - both
+  // belong to the same barrier phase, which cannot complete before warp 0's arrival).  One warp issuing both spent
+  // ~240 clk per stage on issue alone, more than the MMAs of a narrow (bn <= 128) stage.
+  constexpr int WPROD = kStaged ? 11 : 10;
+  if ((warp == 0 || warp == WPROD) && p.max_ntaps == 1) {
+    const bool do_a = warp == 0;
+    // ===== TMA producers, one tap per stage (the common case) =====
     // Warp-uniform control flow: every lane runs the loop, lane 0's instructions take effect.  The loop body is
     // kept to a wait, an expect_tx and the TMA issues - ring position and coordinates advance by increments (the
     // div/mod + table look-ups of the first version cost the issuing thread ~900 clk per stage, more than the
     // stage's MMAs).
     const bool lead = lane == 0;
-    Tracer trc(lead ? p.trace : nullptr, 0);
+    Tracer trc(lead && do_a ? p.trace : nullptr, 0);
     const uint32_t a_box_bytes = (uint32_t)(p.hb * p.pack * KC * 2);
     const uint32_t tx_bytes = (kPair ? 2u : 1u) * ((uint32_t)p.a_boxes * a_box_bytes + (uint32_t)b_bytes);
     const int row_step = p.hb * p.stride;
@@ -361,16 +367,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
           const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
           const uint32_t fb = kPair ? lead_full_bar(s) : full_bar(s);
-          // pair: both CTAs' bytes complete on the leader's barrier, which expects the sum
-          if (rank == 0) mbar_expect_tx_el(full_bar(s), tx_bytes);
           const int c0 = x.ch0 + chunk * KC;
+          if (do_a) {
+            // pair: both CTAs' bytes complete on the leader's barrier, which expects the sum
+            if (rank == 0) mbar_expect_tx_el(full_bar(s), tx_bytes);
 #pragma unroll 1
-          for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_4d_el<kPair>(a_dst + bx * a_box_bytes, &tmA, fb, c0, 0, row0 + bx * row_step, x.b);
+            for (int bx = 0; bx < p.a_boxes; ++bx)
+              tma_load_4d_el<kPair>(a_dst + bx * a_box_bytes, &tmA, fb, c0, 0, row0 + bx * row_step, x.b);
+          }
 #ifdef STG_PROF_LOOP
           const long long pc2 = clock64();
 #endif
-          if (p.b_mn == 0) {
+          if (do_a) {
+          } else if (p.b_mn == 0) {
             tma_load_3d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, chunk * KC, wc, tap);
           } else if (p.b_mn == 2) {  // forward pack seen as (64, co row, ci/64, tap): one box = the whole [bn/64][64][64] tile
             tma_load_4d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, 0, c0, wc, tap);
@@ -388,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
 #ifdef STG_PROF_LOOP
-    if (lead && p.trace && blockIdx.x == 0) for (int i = 0; i < 4; ++i) p.trace[1 + 3 * 5200 + i] = prof[i];
+    if (lead && do_a && p.trace && blockIdx.x == 0) for (int i = 0; i < 4; ++i) p.trace[1 + 3 * 5200 + i] = prof[i];
 #endif
   } else if (warp == 1 && p.max_ntaps == 1) {
     // ===== MMA issuer, one tap per stage (warp-uniform control flow; pair: the leader issues for both CTAs) =====
@@ -441,9 +450,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef STG_PROF_LOOP
     if (lead && p.trace && blockIdx.x == 0) for (int i = 0; i < 3; ++i) p.trace[1 + 3 * 5200 + 8 + i] = mprof[i];
 #endif
-  } else if (warp == 0) {
-    // ===== TMA producer, tap windows (warp-uniform control flow, lane 0's instructions take effect) =====
-    const bool lead = lane == 0;
+  } else if (warp == 0 || warp == WPROD) {
+    // ===== TMA producers, tap windows (warp 0: A window + expect_tx, last warp: the W tiles of the group's taps) =====
+    const bool do_a = warp == 0;
     int s = 0; uint32_t phs = 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const Tile x = decode_tile<kPair>(p, t, rank);
@@ -453,14 +462,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
        const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
        for (int chunk = 0; chunk < p.k_chunks; ++chunk) {
         mbar_wait(empty_bar(s), phs ^ 1);
-        mbar_expect_tx_el(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
         const uint32_t a_dst = smem_base + s * stage_bytes;
+        if (do_a) {
+          mbar_expect_tx_el(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
 #pragma unroll 1
-        for (int bx = 0; bx < p.a_boxes; ++bx)
-          tma_load_4d_el(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
-                         (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
+          for (int bx = 0; bx < p.a_boxes; ++bx)
+            tma_load_4d_el(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+                           (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
+        }
 #pragma unroll 1
-        for (int tl = 0; tl < nt; ++tl) {
+        for (int tl = 0; tl < (do_a ? 0 : nt); ++tl) {
           if (!p.b_mn) {
             tma_load_3d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
           } else if (p.b_mn == 2) {
@@ -1138,7 +1149,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const int n_pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 352 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[2];
     cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, true);
     if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmW, em, p));
@@ -1152,7 +1163,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 352 : 320); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);
   if (staged) STG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmW, em, p));
