@@ -173,6 +173,11 @@ int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, int total_r
                               stg_stream_t stream);
 int stg_weightnorm_fold_bwd_multi(const StgFoldItem* items, int n_items, int total_rows, int accumulate,
                                   stg_stream_t stream);
+/* The same for the table rows [row_base, row_base + n_rows) only (rows = output channels, numbered through the items in
+ * table order): the fold-backward of ONE gradient bucket, so that the data-parallel all-reduce of that bucket can start
+ * while the backward pass of the layers in front of it is still running. */
+int stg_weightnorm_fold_bwd_range(const StgFoldItem* items, int n_items, int row_base, int n_rows, int accumulate,
+                                  stg_stream_t stream);
 
 /* Number of groups the tcgen05 engine wants the packs of a (c_in, c_out, groups) convolution in (== groups
  * when no widening is needed or possible). */

@@ -65,6 +65,7 @@ _SIGS = {
     "stg_mse_const_multi": [_P, _I, _I, _I, _P, _F, _P],
     "stg_weightnorm_fold_multi": [_P, _I, _I, _I, _I, _P],
     "stg_weightnorm_fold_bwd_multi": [_P, _I, _I, _I, _P],
+    "stg_weightnorm_fold_bwd_range": [_P, _I, _I, _I, _I, _P],
     "stg_debug_set_trace": [_P],
     "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

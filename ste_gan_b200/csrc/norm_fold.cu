@@ -390,11 +390,11 @@ __global__ void __launch_bounds__(256, 8) wn_fold_rows_kernel(const StgFoldItem*
   }
 }
 
-__global__ void __launch_bounds__(256, 8) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows,
-                                                           int accumulate) {
+__global__ void __launch_bounds__(256, 8) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int row_base,
+                                                           int total_rows, int accumulate) {
   __shared__ __align__(16) float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
   __shared__ float red[32];
-  const int r_begin = blockIdx.x * FOLD_RPB, r_end = min(total_rows, r_begin + FOLD_RPB);
+  const int r_begin = row_base + blockIdx.x * FOLD_RPB, r_end = min(row_base + total_rows, r_begin + FOLD_RPB);   // rows [row_base, row_base + total_rows)
   int it = find_item(items, n_items, r_begin, false);
   StgFoldItem d = items[it];
   for (int r = r_begin; r < r_end; ++r) {
@@ -604,7 +604,16 @@ extern "C" int stg_weightnorm_fold_bwd_multi(const StgFoldItem* items, int n_ite
                                              stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!items || n_items < 1 || total_rows < 1) return STG_EINVAL;
-  wn_bwd_multi_kernel<<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows, accumulate);
+  wn_bwd_multi_kernel<<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, 0, total_rows, accumulate);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_weightnorm_fold_bwd_range(const StgFoldItem* items, int n_items, int row_base, int n_rows, int accumulate,
+                                             stg_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!items || n_items < 1 || row_base < 0 || n_rows < 1) return STG_EINVAL;
+  wn_bwd_multi_kernel<<<ceil_div(n_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, row_base, n_rows, accumulate);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

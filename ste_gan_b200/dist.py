@@ -80,6 +80,18 @@ class GradReducer:
         for h in handles:
             h.wait()
 
+    def all_reduce_async(self, flat_grad: torch.Tensor) -> list:
+        """Issue the bucketed all-reduce without waiting; pass the result to wait() before the gradient is consumed."""
+        if not self.enabled:
+            return []
+        return [dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                for lo, hi in self.buckets(flat_grad.numel())]
+
+    @staticmethod
+    def wait(handles: list) -> None:
+        for h in handles:
+            h.wait()
+
     def broadcast(self, flat: torch.Tensor, src: int = 0) -> None:
         if self.enabled:
             dist.broadcast(flat, src=src, group=self.group)

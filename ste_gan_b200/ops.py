@@ -238,6 +238,11 @@ def weightnorm_fold_bwd_multi(table: Tensor, n_items: int, total_rows: int, accu
           "stg_weightnorm_fold_bwd_multi")
 
 
+def weightnorm_fold_bwd_range(table: Tensor, n_items: int, row_base: int, n_rows: int, accumulate: bool = True) -> None:
+    check(_lib.load().stg_weightnorm_fold_bwd_range(_ptr(table), n_items, row_base, n_rows, int(accumulate), _stream()),
+          "stg_weightnorm_fold_bwd_range")
+
+
 def unfold(src: Tensor, *, n_samples: int, phases: int, t_src: int, t_dst: int, channels: int, k: int, dilation: int,
            stride: int, pad: int) -> Tensor:
     """im2col rows [B, t_dst*phases, roundup8(k*C)] of a channels-last (period-view) tensor, same dtype."""

@@ -218,6 +218,7 @@ class FoldPlan:
             else:
                 tile0 += m.kernel * f.pg * -(-(m.out_channels // f.pg) // 32) * -(-(m.in_channels // f.pg) // 32)
         self.n_items, self.total_rows, self.total_tiles = len(items), row0, (tile0 if self.need_wd else 0)
+        self.item_row0 = [it.row0 for it in items] + [row0]      # table row of each item's first output channel
         self.table = ops.fold_table(items, dev)
         self._ptrs = [(p.data_ptr(), p.grad.data_ptr()) for m in self.wn for p in (m.weight_v, m.weight_g)]
 
@@ -248,6 +249,14 @@ class FoldPlan:
         (the fused train step) it saves re-reading every dv."""
         self._check_ptrs()
         ops.weightnorm_fold_bwd_multi(self.table, self.n_items, self.total_rows, accumulate)
+
+
+    def backward_range(self, item_lo: int, item_hi: int, accumulate: bool = True) -> None:
+        """backward() for the weight-normed convs [item_lo, item_hi) of the plan only (one gradient bucket)."""
+        self._check_ptrs()
+        r0, r1 = self.item_row0[item_lo], self.item_row0[item_hi]
+        if r1 > r0:
+            ops.weightnorm_fold_bwd_range(self.table, self.n_items, r0, r1 - r0, accumulate)
 
 
 def unfold_input(f: Folded, src: Tensor, B: int, t_src: int, phases: int = 1) -> Tensor:
@@ -461,49 +470,78 @@ def generator_forward(model, speech_units: Tensor, session_ids: Optional[Tensor]
     return x_pred, ctx
 
 
+class GenBackward:
+    """Backward of generator_forward in resumable pieces, back to front: __init__ (tanh', last_conv), blocks(lo, hi)
+    (GBlocks hi-1 ... lo), finish() (gblocks.0, embeddings).  With a FoldPlan, bucket(item_lo, item_hi) completes one
+    gradient BUCKET: it waits for the bucket's weight-gradient kernels and runs the weight-norm backward of just those
+    convs, after which the bucket's slice of the flat gradient is final - the data-parallel all-reduce of that slice
+    can run while the layers in front of it are still in their backward pass."""
+
+    def __init__(self, model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None, res_side=None,
+                 overwrite_grads: bool = False):
+        self.model, self.ctx, self.plan, self.side, self.res_side = model, ctx, plan, side, res_side
+        self.accumulate = not overwrite_grads
+        B, dtype, folds = ctx.B, ctx.dtype, ctx.folds
+        if plan is not None:
+            plan.zero()
+            self.ws = plan
+            if side is not None:
+                plan.async_wgrads(side)             # `side`: extra stream for the weight-gradient kernels
+        else:
+            self.ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
+        self.gblocks = list(model.gblocks)[1:]
+        t = ctx.t_out
+        # tanh' from the output, then last_conv
+        dpre = ops.act_bwd(dx_pred.contiguous(), ctx.x_pred, ACT_TANH, dtype)
+        f = folds[id(model.last_conv[1])]
+        _wgrad(f, ctx.y_last_act, dpre, B, t, t, self.ws)
+        self.dy = _dgrad(f, dpre, B, t, t, mask=ctx.y_last_act, mask_mode=ACT_RELU)        # d(y8 raw)
+
+    def blocks(self, lo: int, hi: int) -> None:
+        for i in reversed(range(lo, hi)):
+            self.dy = gblock_bwd(self.gblocks[i], self.ctx.folds, self.ctx.blocks[i], self.dy, self.ctx.B, self.ws, side=self.res_side)
+
+    def finish(self) -> None:
+        model, ctx, dy, B = self.model, self.ctx, self.dy, self.ctx.B
+        # gblocks.0 and the embeddings
+        f0 = ctx.folds[id(model.gblocks[0])]
+        _wgrad(f0, ctx.x0, dy, B, ctx.T, ctx.T, self.ws)
+        if ctx.tables:
+            dx0 = _dgrad(f0, dy, B, ctx.T, ctx.T)
+            off = ctx.d_units
+            if len(ctx.tables) == 1:
+                ops.embed_concat_bwd(dx0, ctx.ids[0], off, _grad_of(ctx.tables[0]))
+            else:
+                d0, d1 = ctx.emb_dims
+                # [units | emb0 | emb1]: slice copies keep the kernel's contiguous-tail contract
+                ops.embed_concat_bwd(dx0[:, :, :off + d0].contiguous(), ctx.ids[0], off, _grad_of(ctx.tables[0]))
+                ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
+        self.dy = None
+
+    def bucket(self, item_lo: int, item_hi: int, last: bool = False) -> None:
+        """Convs [item_lo, item_hi) of generator_convs(model) are done: make their gradients final."""
+        plan = self.plan
+        if plan is None:
+            return
+        plan.join_wgrads()
+        plan.backward_range(item_lo, item_hi, accumulate=self.accumulate)
+        if not last and self.side is not None:
+            plan.async_wgrads(self.side)
+
+
 def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldPlan] = None, side=None,
                        res_side=None, overwrite_grads: bool = False) -> None:
     """Backward of generator_forward: accumulates into the .grad of every generator parameter.
     dx_pred: fp32 [B, 16T, C] gradient w.r.t. the tanh output.  With a FoldPlan the packed weight gradients go to
-    its arena and the weight-norm backward of all 45 convs is one launch at the end."""
-    B, dtype, folds = ctx.B, ctx.dtype, ctx.folds
-    if plan is not None:
-        plan.zero()
-        ws = plan
-        if side is not None:
-            plan.async_wgrads(side)             # `side`: extra stream for the 46 weight-gradient kernels
-    else:
-        ws = _Workspace([folds[id(c)] for c in generator_convs(model)], dx_pred.device)
-    blocks = list(model.gblocks)[1:]
-    t = ctx.t_out
-    # tanh' from the output, then last_conv
-    dpre = ops.act_bwd(dx_pred.contiguous(), ctx.x_pred, ACT_TANH, dtype)
-    f = folds[id(model.last_conv[1])]
-    _wgrad(f, ctx.y_last_act, dpre, B, t, t, ws)
-    dy = _dgrad(f, dpre, B, t, t, mask=ctx.y_last_act, mask_mode=ACT_RELU)        # d(y8 raw)
-    for i in reversed(range(len(blocks))):
-        dy = gblock_bwd(blocks[i], folds, ctx.blocks[i], dy, B, ws, side=res_side)
-    # gblocks.0 and the embeddings
-    f0 = folds[id(model.gblocks[0])]
-    _wgrad(f0, ctx.x0, dy, B, ctx.T, ctx.T, ws)
-    if ctx.tables:
-        dx0 = _dgrad(f0, dy, B, ctx.T, ctx.T)
-        off = ctx.d_units
-        if len(ctx.tables) == 1:
-            ops.embed_concat_bwd(dx0, ctx.ids[0], off, _grad_of(ctx.tables[0]))
-        else:
-            d0, d1 = ctx.emb_dims
-            # [units | emb0 | emb1]: slice copies keep the kernel's contiguous-tail contract
-            ops.embed_concat_bwd(dx0[:, :, :off + d0].contiguous(), ctx.ids[0], off, _grad_of(ctx.tables[0]))
-            ops.embed_concat_bwd(dx0, ctx.ids[1], off + d0, _grad_of(ctx.tables[1]))
+    its arena and the weight-norm backward of all convs is one launch at the end."""
+    gb = GenBackward(model, ctx, dx_pred, plan, side, res_side, overwrite_grads)
+    gb.blocks(0, len(gb.gblocks))
+    gb.finish()
     if plan is not None:
         plan.join_wgrads()
         plan.backward(accumulate=not overwrite_grads)
 
 
-# --------------------------------------------------------------------------------------
-# stream-level concurrency
-# --------------------------------------------------------------------------------------
 def fork_join(side: Optional["torch.cuda.Stream"], fn_side, fn_main):
     """Run fn_side on `side` and fn_main on the current stream, both ordered after everything enqueued so far;
     returns (fn_side(), fn_main()) once the current stream has been made to wait for `side`.  Works under CUDA

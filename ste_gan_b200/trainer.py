@@ -48,11 +48,14 @@ class FlatParams:
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
-        for p in self.params:
+        self.offsets: Dict[str, int] = {}        # parameter name -> offset into the flat buffers (registration order)
+        names = [nm for nm, _ in module.named_parameters()]
+        for nm, p in zip(names, self.params):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
+            self.offsets[nm] = off
             off += al(k)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
@@ -89,6 +92,8 @@ class GanTrainer:
         self.d_folds: Optional[Dict[int, passes.Folded]] = None
         self._d_persist: Dict[int, passes.Folded] = {}
         self._graphs = None
+        self._d_graphs = None
+        self._pending_g = None                  # handles of a deferred generator-gradient all-reduce (pipelined step_graph)
         self._static = None
         self.x_pred: Optional[Tensor] = None
         # the discriminator passes on x_pred and on x_real are independent: they run on two streams (forked from and
@@ -100,6 +105,20 @@ class GanTrainer:
         self._sn = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # spectral-norm fold chains, one per layer
         self._aux = torch.cuda.Stream(device=dev)                                     # time-domain loss beside the D passes
         self.concurrent_d = True
+        # Gradient buckets of the generator, back to front (= the order its backward completes them).  GBlocks
+        # [k2, n) + last_conv | [k1, k2) | [0, k1) + gblocks.0 + embeddings, cut where the parameter count from the
+        # front passes 1/3 and 2/3 (base model: GB3..GB8 | GB2 | GB1, ~8 M parameters each).  Each entry:
+        # (first GBlock, end GBlock, first conv, end conv of passes.generator_convs, flat-gradient slice).
+        nblk = len(list(net_g.gblocks)) - 1
+        first = [self.G.offsets[next(nm for nm in self.G.offsets if nm.startswith(f"gblocks.{i + 1}."))] for i in range(nblk)]
+        k1 = next((i for i in range(1, nblk) if first[i] * 3 >= self.G.numel), nblk)
+        k2 = next((i for i in range(k1, nblk) if first[i] * 3 >= 2 * self.G.numel), nblk)
+        k1, k2 = min(k1, nblk), min(max(k2, k1), nblk)
+        n_conv = 5 * nblk + 2
+        cut = lambda i: first[i] if i < nblk else self.G.offsets[next(nm for nm in self.G.offsets if nm.startswith("last_conv."))]
+        self.g_buckets = [(k2, nblk, 1 + 5 * k2, n_conv, (cut(k2) if k2 < nblk else cut(nblk), self.G.numel)),
+                          (k1, k2, 1 + 5 * k1, 1 + 5 * k2, (cut(k1), cut(k2) if k2 < nblk else cut(nblk))),
+                          (0, k1, 0, 1 + 5 * k1, (0, cut(k1)))]
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None
@@ -133,41 +152,40 @@ class GanTrainer:
         return ra, rb
 
     # ------------------------------------------------------------------ phases
-    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor) -> None:
-        dt = self.dtype
+    # Phase D is five pieces with three dependencies between them:
+    #     _d_folds -> _d_real --------------\
+    #        \ (f1)                         v
+    #   _g_forward -> _d_fake -----------> _d_update
+    # Eager steps (and the single-graph capture) run the top row on the side stream; the pipelined capture makes each
+    # piece its own CUDA graph so that the top row of step k+1 can start while step k's gradient all-reduce and
+    # generator optimiser are still running (step_graph).
+    def _d_folds(self) -> None:
+        """Discriminator folds of the fake pass (f1) and of the real pass (f2): the spectral-norm power iterations of
+        the two forwards happen in that order (train.py:190-191)."""
+        refold_d = not self._d_folded
+        self._d_folded = True
+        self._f1 = self._fold_d(refold_d)
+        self._ev_f1 = torch.cuda.Event()
+        self._ev_f1.record(torch.cuda.current_stream())
+        self._f2 = self._fold_d(False)
+
+    def _d_real(self, x_real: Tensor) -> None:
+        self._real = passes.discriminator_forward(self.net_d, x_real, self.dtype, self._f2, side=self._s2(0))
+
+    def _g_forward(self, su: Tensor, sess: Tensor, mode: Optional[Tensor]) -> None:
         self.slots.zero_()
         self.G.zero_grad(); self.D.zero_grad()
         self._gctx = None
-        if not self.use_adv:
-            self.x_pred, self._gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
-            return
-        # The spectral-norm power iterations of the fake and the real forward happen in that order (train.py:190-191).
-        # Side stream: D folds (fake's, then real's) and the real pass, which needs neither G nor x_pred; current
-        # stream: G fold + generator forward, then - once the fake pass's folds are there - the fake pass.
-        refold_d = not self._d_folded
-        self._d_folded = True
-        if self.concurrent_d:
-            cur = torch.cuda.current_stream()
-            self._fork()
-            with torch.cuda.stream(self._side):
-                f1 = self._fold_d(refold_d)
-                ev_f1 = torch.cuda.Event()
-                ev_f1.record(self._side)
-                f2 = self._fold_d(False)
-                res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2, side=self._s2(0))
-            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold(),
-                                                    side=self._s2(1))
-            self.x_pred, self._gctx = x_pred, gctx
-            cur.wait_event(ev_f1)
-            res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1, side=self._s2(1))
-            self._join()
-        else:
-            f1 = self._fold_d(refold_d)
-            f2 = self._fold_d(False)
-            x_pred, gctx = passes.generator_forward(self.net_g, su, sess, mode, dt, True, folds=self.g_plan.fold())
-            self.x_pred, self._gctx = x_pred, gctx
-            res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f1)
-            res_r, ctx_r = passes.discriminator_forward(self.net_d, x_real, dt, f2)
+        self.x_pred, self._gctx = passes.generator_forward(self.net_g, su, sess, mode, self.dtype, True, folds=self.g_plan.fold(),
+                                                           side=self._s2(1) if self.use_adv else None)
+
+    def _d_fake(self) -> None:
+        self._fake = passes.discriminator_forward(self.net_d, self.x_pred, self.dtype, self._f1, side=self._s2(1))
+
+    def _d_update(self) -> None:
+        dt = self.dtype
+        (res_f, ctx_f), (res_r, ctx_r) = self._fake, self._real
+        self._fake = self._real = None
         self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
         nd = len(res_f)
@@ -188,7 +206,31 @@ class GanTrainer:
         self.d_plan.join_wgrads()
         self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
 
-    def _phase_g(self, x_real: Tensor, update_d: bool = True) -> None:
+    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor) -> None:
+        if not self.use_adv:
+            self._g_forward(su, sess, mode)
+            return
+        if self.concurrent_d:
+            # side stream: D folds and the real pass, which needs neither G nor x_pred; current stream: G fold +
+            # generator forward, then - once the fake pass's folds are there - the fake pass
+            cur = torch.cuda.current_stream()
+            self._fork()
+            with torch.cuda.stream(self._side):
+                self._d_folds()
+                self._d_real(x_real)
+            self._g_forward(su, sess, mode)
+            cur.wait_event(self._ev_f1)
+            self._d_fake()
+            self._join()
+        else:
+            self._d_folds()
+            self._g_forward(su, sess, mode)
+            self._d_fake()
+            self._d_real(x_real)
+        self._d_update()
+
+    def _phase_g_head(self, x_real: Tensor, update_d: bool = True) -> None:
+        """Phase G up to and including the generator backward of the first (rearmost) gradient bucket."""
         dt = self.dtype
         x_pred = self.x_pred
         dx_pred = torch.zeros_like(x_pred)
@@ -240,9 +282,37 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        passes.generator_backward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
-                                  overwrite_grads=True)   # G.grad was zeroed in phase D; this is its only writer
-        self._gctx = None
+        # generator backward, bucket by bucket (G.grad was zeroed in phase D and this is its only writer: overwrite)
+        self._gb = passes.GenBackward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
+                                      overwrite_grads=True)
+        self._g_bucket(0)
+
+    def _g_bucket(self, i: int) -> None:
+        """Backward of the GBlocks of generator-gradient bucket i (after it, self.G.grad[slice i] is final)."""
+        lo, hi, c_lo, c_hi, _ = self.g_buckets[i]
+        gb = self._gb
+        gb.blocks(lo, hi)
+        if i == len(self.g_buckets) - 1:
+            gb.finish()
+        gb.bucket(c_lo, c_hi, last=i == len(self.g_buckets) - 1)
+        if i == len(self.g_buckets) - 1:
+            self._gb = self._gctx = None
+
+    def _phase_g(self, x_real: Tensor, update_d: bool = True, reduce: bool = False) -> list:
+        """Phase G; with reduce=True the all-reduce of each generator-gradient bucket is issued as soon as the bucket is
+        final (it then overlaps the backward of the buckets in front of it).  Returns the pending all-reduce handles."""
+        handles = []
+        self._phase_g_head(x_real, update_d)
+        for i in range(len(self.g_buckets)):
+            if i > 0:
+                self._g_bucket(i)
+            if reduce:
+                handles += self._reduce_g_bucket(i)
+        return handles
+
+    def _reduce_g_bucket(self, i: int) -> list:
+        lo, hi = self.g_buckets[i][4]
+        return self.reducer.all_reduce_async(self.G.grad[lo:hi]) if hi > lo else []
 
     def _phase_opt_g(self) -> None:
         self.G.adamw(self.lr, grad_scale=self.reducer.grad_scale)           # train.py:267
@@ -252,19 +322,29 @@ class GanTrainer:
              speaking_mode_ids: Optional[Tensor] = None) -> Tensor:
         """One train step on device tensors (eager launches).  Returns the loss-slot tensor (device, fp32[8]):
         see LOSS_NAMES; no host synchronisation happens here."""
+        self.flush()
         su = speech_units.contiguous().float()
         xr = x_real.contiguous().float()
         self._phase_d(su, session_ids, speaking_mode_ids, xr)
         self.reducer.all_reduce(self.D.grad)
-        self._phase_g(xr)
-        self.reducer.all_reduce(self.G.grad)
+        self.reducer.wait(self._phase_g(xr, reduce=True))
         self._phase_opt_g()
         return self.slots
 
-    def capture(self, batch: int, frames: int, unit_dim: int = 256, hop: int = 16, channels: int = 8) -> None:
-        """Capture the three phases as CUDA graphs over static input buffers (NCCL stays outside the
-        graphs).  Runs two eager warm-up steps on the current contents of the static buffers first."""
+    def capture(self, batch: int, frames: int, unit_dim: int = 256, hop: int = 16, channels: int = 8,
+                pipelined: Optional[bool] = None) -> None:
+        """Capture the step as CUDA graphs over static input buffers (NCCL stays outside the graphs).  Runs two eager
+        warm-up steps on the current contents of the static buffers first.
+
+        pipelined (default: whenever the discriminator passes run concurrently): phase D is captured as its five
+        pieces (see _d_folds) and step_graph() software-pipelines consecutive steps: the all-reduce of the generator
+        gradient and the generator's AdamW of step k run WHILE step k+1's discriminator folds and real pass - which
+        depend on neither - are already executing.  The generator parameters of the last step are final after flush()
+        (the eager step(), state_dict users and the inference engine call it)."""
         dev = self.device
+        if pipelined is None:
+            pipelined = self.concurrent_d and self.use_adv
+        self.flush()
         self._static = dict(
             su=torch.zeros(batch, frames, unit_dim, device=dev), sess=torch.zeros(batch, device=dev, dtype=torch.int64),
             x_real=torch.zeros(batch, frames * hop, channels, device=dev))
@@ -277,27 +357,86 @@ class GanTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1, pool=pool):
-            self._phase_d(s["su"], s["sess"], None, s["x_real"])
-        with torch.cuda.graph(g2, pool=pool):
-            self._phase_g(s["x_real"])
+        G = torch.cuda.CUDAGraph
+        if pipelined:
+            # the two rows of phase D replay CONCURRENTLY: they must not share a memory pool (blocks freed while one
+            # was captured would be handed to the other)
+            pool_a = torch.cuda.graph_pool_handle()
+            a1, a2, b1, b2, b3 = G(), G(), G(), G(), G()
+            with torch.cuda.graph(a1, pool=pool_a):
+                self._d_folds()
+            with torch.cuda.graph(a2, pool=pool_a):
+                self._d_real(s["x_real"])
+            with torch.cuda.graph(b1, pool=pool):
+                self._g_forward(s["su"], s["sess"], None)
+            with torch.cuda.graph(b2, pool=pool):
+                self._d_fake()
+            with torch.cuda.graph(b3, pool=pool):
+                self._d_update()
+            self._d_graphs = (a1, a2, b1, b2, b3)
+            self._pipe = torch.cuda.Stream(device=dev)
+            self._pipe_ev = [torch.cuda.Event() for _ in range(3)]
+            g1 = None
+        else:
+            self._d_graphs = None
+            g1 = G()
+            with torch.cuda.graph(g1, pool=pool):
+                self._phase_d(s["su"], s["sess"], None, s["x_real"])
+        # phase G: one graph per generator-gradient bucket (the bucket's all-reduce is issued between them)
+        g2 = [G() for _ in self.g_buckets]
+        with torch.cuda.graph(g2[0], pool=pool):
+            self._phase_g_head(s["x_real"])
+        for i in range(1, len(g2)):
+            with torch.cuda.graph(g2[i], pool=pool):
+                self._g_bucket(i)
+        g3 = G()
         with torch.cuda.graph(g3, pool=pool):
             self._phase_opt_g()
         self._graphs = (g1, g2, g3)
 
+    def flush(self) -> None:
+        """Complete a pipelined step: wait for the generator-gradient all-reduce and run the generator optimiser."""
+        if self._pending_g is not None:
+            self.reducer.wait(self._pending_g)
+            self._pending_g = None
+            self._graphs[2].replay()
+
     def step_graph(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor) -> Tensor:
-        """Replay the captured step; inputs may be pinned-host or device tensors (copied into the static buffers)."""
+        """Replay the captured step; inputs may be pinned-host or device tensors (copied into the static buffers).
+        With a pipelined capture the generator optimiser of this step is deferred into the next call (or flush())."""
         s = self._static
         s["su"].copy_(speech_units, non_blocking=True)
         s["sess"].copy_(session_ids, non_blocking=True)
         s["x_real"].copy_(x_real, non_blocking=True)
         g1, g2, g3 = self._graphs
-        g1.replay()
+        def phase_g() -> list:
+            handles = []
+            for i, gr in enumerate(g2):
+                gr.replay()
+                handles += self._reduce_g_bucket(i)     # overlaps the next bucket's backward
+            return handles
+        if self._d_graphs is None:
+            g1.replay()
+            self.reducer.all_reduce(self.D.grad)
+            self.reducer.wait(phase_g())
+            g3.replay()
+            return self.slots
+        a1, a2, b1, b2, b3 = self._d_graphs
+        ev0, ev_f, ev_r = self._pipe_ev
+        cur = torch.cuda.current_stream()
+        ev0.record(cur)                       # inputs copied, previous step's phase G done
+        self._pipe.wait_event(ev0)
+        with torch.cuda.stream(self._pipe):
+            a1.replay(); ev_f.record(self._pipe)
+            a2.replay(); ev_r.record(self._pipe)
+        self.flush()                          # previous step: all-reduce(G) + AdamW(G), beside a1 / a2
+        b1.replay()
+        cur.wait_event(ev_f)
+        b2.replay()
+        cur.wait_event(ev_r)
+        b3.replay()
         self.reducer.all_reduce(self.D.grad)
-        g2.replay()
-        self.reducer.all_reduce(self.G.grad)
-        g3.replay()
+        self._pending_g = phase_g()
         return self.slots
 
     def losses(self) -> Dict[str, float]:

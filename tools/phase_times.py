@@ -18,11 +18,25 @@ for conc in (True, False):
     for _ in range(5):
         tr.step_graph(*batch)
     torch.cuda.synchronize()
-    tot = [0.0, 0.0, 0.0]
+    tr.flush(); torch.cuda.synchronize()
     n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        tr.step_graph(*batch)
+    tr.flush(); e1.record(); torch.cuda.synchronize()
+    print(f"concurrent={conc}: pipelined step_graph {e0.elapsed_time(e1)/n:.3f} ms per step")
+    tr.capture(16, 100, pipelined=False)
+    for _ in range(3):
+        tr.step_graph(*batch)
+    torch.cuda.synchronize()
+    tot = [0.0, 0.0, 0.0]
     for _ in range(n):
         for i, gr in enumerate(tr._graphs):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            e0.record()
+            for g_ in (gr if isinstance(gr, list) else [gr]):    # phase G: one graph per gradient bucket
+                g_.replay()
+            e1.record(); torch.cuda.synchronize()
             tot[i] += e0.elapsed_time(e1)
     print(f"concurrent={conc}: phase D {tot[0]/n:.3f} ms, phase G {tot[1]/n:.3f} ms, G optimiser {tot[2]/n:.3f} ms, sum {sum(tot)/n:.3f} ms")
