@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __re
 // wf[j][co][:] (coalesced; the transposition (ci, j) -> (j, ci) happens in shared memory).  Replaces the
 // scale + 32x32-tile pack pair, whose v reads were strided by k.
 constexpr int FOLD_ROW_MAX = 4096;
-constexpr int FOLD_RPB = 4;   // rows per block: one table search per block, the item is then walked forward
+constexpr int FOLD_RPW = 4;               // rows per warp (fast path)
+constexpr int FOLD_RPB = 8 * FOLD_RPW;   // rows per block: one table search per warp / block, the item is then walked forward
 // Both row kernels are pure HBM streams (v 4 B + pack 2 B per weight; dw + v + dv 12 B per weight).  The first versions
 // moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.  Now: 16-byte
 // accesses wherever the row is 16-byte aligned, all loads of a row issued before the first use, FOLD_RPB rows per block.
@@ -311,167 +312,209 @@ __device__ __forceinline__ void store8<bf16>(bf16* dst, const float* w) {
   *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
 }
 
+// ---- warp-per-row fast path (plain convs: groups == pack groups == 1, k in {1, 3, 5}, c_in % 4 == 0, 16-byte aligned).
+// 4 input channels x k taps of the torch layout v[co][ci][j] are exactly k consecutive float4: a lane reads them, has the
+// (ci, j) -> (j, ci) transposition in REGISTERS and writes 4 consecutive channels per tap (8 B bf16 / 16 B fp32, the
+// warp's stores contiguous).  No shared memory, no block barrier: a warp streams its row twice (norm pass, then scale +
+// store pass - the second read hits L1/L2) with two channel groups per lane in flight.  ncu before: 1.7 TB/s,
+// sm__throughput 55 % (shared-memory transposition + block reductions).
+template <typename T> __device__ __forceinline__ void store4(T* dst, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+__device__ __forceinline__ bool fold_fast(const StgFoldItem& d) {
+  return d.flags == 0 && d.groups == 1 && d.pg == 1 && (d.k == 1 || d.k == 3 || d.k == 5) && (d.cin_g & 3) == 0 &&
+         al16(d.v) && al16(d.wf);
+}
+__device__ __forceinline__ bool fold_bwd_fast(const StgFoldItem& d) {
+  const int span = d.dw_span > 0 ? d.dw_span : d.cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * d.k;
+  return d.flags == 0 && d.groups == 1 && (d.k == 1 || d.k == 3 || d.k == 5) && (d.cin_g & 3) == 0 && (span & 3) == 0 &&
+         (ld & 3) == 0 && al16(d.v) && al16(d.dv) && al16(d.dw);
+}
+
+template <typename T, int K>
+__device__ __forceinline__ void fold_row_warp(const StgFoldItem& d, int co, int lane) {
+  const int cin = d.cin_g, ng = cin >> 2;
+  const float4* v4 = reinterpret_cast<const float4*>(d.v + (int64_t)co * cin * K);
+  float ss = 0.f;
+  for (int g = lane; g < ng; g += 64) {
+    float4 a[K], b[K];
+    const bool two = g + 32 < ng;
+#pragma unroll
+    for (int q = 0; q < K; ++q) a[q] = v4[g * K + q];
+#pragma unroll
+    for (int q = 0; q < K; ++q) b[q] = two ? v4[(g + 32) * K + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+      ss += a[q].x * a[q].x + a[q].y * a[q].y + a[q].z * a[q].z + a[q].w * a[q].w +
+            b[q].x * b[q].x + b[q].y * b[q].y + b[q].z * b[q].z + b[q].w * b[q].w;
+  }
+  ss = warp_sum(ss);
+  const float sc = d.g[co] / sqrtf(ss);
+  if (lane == 0) d.scale[co] = sc;
+  T* wf = static_cast<T*>(d.wf);
+  for (int g = lane; g < ng; g += 32) {
+    float f[4 * K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float4 x = v4[g * K + q];
+      f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)   // f[c * K + j] = v[co][4g + c][j]
+      store4<T>(wf + ((int64_t)j * d.c_out + co) * cin + 4 * g, f[j] * sc, f[K + j] * sc, f[2 * K + j] * sc, f[3 * K + j] * sc);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void fold_bwd_row_warp(const StgFoldItem& d, int co, int lane, int accumulate) {
+  const int cin = d.cin_g, ng = cin >> 2;
+  const int span = d.dw_span > 0 ? d.dw_span : cin, ld = d.dw_ld > 0 ? d.dw_ld : span * K;
+  const float4* v4 = reinterpret_cast<const float4*>(d.v + (int64_t)co * cin * K);
+  const float* dr = d.dw + (int64_t)co * ld;
+  float4* o4 = reinterpret_cast<float4*>(d.dv + (int64_t)co * cin * K);
+  float ss = 0.f, dot = 0.f;
+  for (int g = lane; g < ng; g += 32) {
+    float f[4 * K], w[K][4];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float4 x = v4[g * K + q];
+      f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float4 x = *reinterpret_cast<const float4*>(dr + j * span + 4 * g);
+      w[j][0] = x.x; w[j][1] = x.y; w[j][2] = x.z; w[j][3] = x.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < K; ++j) { ss = fmaf(f[c * K + j], f[c * K + j], ss); dot = fmaf(f[c * K + j], w[j][c], dot); }
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float norm = sqrtf(ss), gg = d.g[co];
+  const float a = gg / norm, bcoef = gg * dot / (norm * ss);
+  for (int g = lane; g < ng; g += 32) {
+    float f[4 * K], w[K][4], o[4 * K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float4 x = v4[g * K + q];
+      f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float4 x = *reinterpret_cast<const float4*>(dr + j * span + 4 * g);
+      w[j][0] = x.x; w[j][1] = x.y; w[j][2] = x.z; w[j][3] = x.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < K; ++j) o[c * K + j] = a * w[j][c] - bcoef * f[c * K + j];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      float4 r = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      if (accumulate) { const float4 p = o4[g * K + q]; r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+      o4[g * K + q] = r;
+    }
+  }
+  if (lane == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
+}
+
+// generic warp-per-row path (grouped convs with block-diagonal pack groups, im2col packs, odd layouts): these rows are
+// short (k37 grouped: 16-32 channels x 37 taps; first layers: 8 channels), so the strided re-reads of v stay in L1
 template <typename T>
-__global__ void __launch_bounds__(256, 8) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
-  __shared__ __align__(16) float row[FOLD_ROW_MAX];
-  __shared__ float red[32];
-  const int r_begin = blockIdx.x * FOLD_RPB, r_end = min(total_rows, r_begin + FOLD_RPB);
-  int it = find_item(items, n_items, r_begin, false);
-  StgFoldItem d = items[it];
-  for (int r = r_begin; r < r_end; ++r) {
-    while (r >= d.row0 + d.c_out) d = items[++it];
-    const int co = r - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
-    const float* vr = d.v + (int64_t)co * n;
-    const bool staged = n <= FOLD_ROW_MAX;
-    float ss = 0.f;
-    __syncthreads();                                   // the previous row's readers are done with row[]
-    if ((n & 3) == 0 && al16(vr) && staged) {
-      const float4* v4 = reinterpret_cast<const float4*>(vr);
-      float4 x[4];                                     // n <= 4096: at most 4 float4 per thread, all in flight together
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int i = threadIdx.x + u * 256; if (i < n / 4) x[u] = v4[i]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = threadIdx.x + u * 256;
-        if (i < n / 4) {
-          reinterpret_cast<float4*>(row)[i] = x[u];
-          ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
-        }
-      }
-    } else {
-      for (int i = threadIdx.x; i < n; i += 256) {
-        const float x = vr[i];
-        if (i < FOLD_ROW_MAX) row[i] = x;
-        ss = fmaf(x, x, ss);
-      }
+__device__ __forceinline__ void fold_row_warp_generic(const StgFoldItem& d, int co, int lane) {
+  const int n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+  const float* vr = d.v + (int64_t)co * n;
+  float ss = 0.f;
+  for (int i = lane; i < n; i += 32) { const float x = vr[i]; ss = fmaf(x, x, ss); }
+  ss = warp_sum(ss);
+  const float sc = d.g[co] / sqrtf(ss);
+  if (lane == 0) d.scale[co] = sc;
+  T* wf = static_cast<T*>(d.wf);
+  if (d.flags & STG_PACK_UNFOLD) {           // wf[co][q], q = j*c_in + c  (groups == 1)
+    const int Kp = (k * cin_g + 7) / 8 * 8;
+    for (int q = lane; q < Kp; q += 32) {
+      float w = 0.f;
+      if (q < k * cin_g) { const int j = q / cin_g, c = q - j * cin_g; w = vr[c * k + j] * sc; }
+      wf[(int64_t)co * Kp + q] = from_f<T>(w);
     }
-    ss = block_sum(ss, red);   // (contains the barrier that publishes row[])
-    const float sc = d.g[co] / sqrtf(ss);
-    if (threadIdx.x == 0) d.scale[co] = sc;
-    T* wf = static_cast<T*>(d.wf);
-    if (d.flags & STG_PACK_UNFOLD) {           // wf[co][q], q = j*c_in + c  (groups == 1)
-      const int Kp = (k * cin_g + 7) / 8 * 8;
-      for (int q = threadIdx.x; q < Kp; q += 256) {
-        float w = 0.f;
-        if (q < k * cin_g) {
-          const int j = q / cin_g, c = q - j * cin_g, i = c * k + j;
-          w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc;
-        }
-        wf[(int64_t)co * Kp + q] = from_f<T>(w);
-      }
-      continue;
-    }
-    const int pg = d.pg, c_in = cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
-    // this row's own group occupies columns [off, off + cin_g) of its pack group; the rest of the row is zero
-    const int off = ((co / cout_g) - (co / cout_gp) * (d.groups / pg)) * cin_g;
-    if ((cin_gp & 7) == 0 && staged && al16(wf)) {   // 8 consecutive input channels of one tap per thread: one 16 B (bf16) store
-      const int per_tap = cin_gp >> 3, total = k * per_tap;
-      for (int idx = threadIdx.x; idx < total; idx += 256) {
-        const int j = idx / per_tap, cip = (idx - j * per_tap) << 3;
-        float w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = cip + u - off;
-          w[u] = (c >= 0 && c < cin_g) ? row[c * k + j] * sc : 0.f;
-        }
-        store8<T>(wf + ((int64_t)j * d.c_out + co) * cin_gp + cip, w);
-      }
-    } else {
-      for (int j = 0; j < k; ++j) {
-        T* dst = wf + ((int64_t)j * d.c_out + co) * cin_gp;
-        for (int cip = threadIdx.x; cip < cin_gp; cip += 256) {
-          const int c = cip - off;
-          float w = 0.f;
-          if (c >= 0 && c < cin_g) { const int i = c * k + j; w = (i < FOLD_ROW_MAX ? row[i] : vr[i]) * sc; }
-          dst[cip] = from_f<T>(w);
-        }
-      }
+    return;
+  }
+  const int pg = d.pg, c_in = cin_g * d.groups, cin_gp = c_in / pg, cout_gp = d.c_out / pg, cout_g = d.c_out / d.groups;
+  // this row's own group occupies columns [off, off + cin_g) of its pack group; the rest of the row is zero
+  const int off = ((co / cout_g) - (co / cout_gp) * (d.groups / pg)) * cin_g;
+  for (int j = 0; j < k; ++j) {
+    T* dst = wf + ((int64_t)j * d.c_out + co) * cin_gp;
+    for (int cip = lane; cip < cin_gp; cip += 32) {
+      const int c = cip - off;
+      dst[cip] = from_f<T>((c >= 0 && c < cin_g) ? vr[c * k + j] * sc : 0.f);
     }
   }
 }
 
-__global__ void __launch_bounds__(256, 8) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int row_base,
-                                                           int total_rows, int accumulate) {
-  __shared__ __align__(16) float sdw[FOLD_ROW_MAX];   // the row's dw, transposed to v's (ci, j) order
-  __shared__ float red[32];
-  const int r_begin = row_base + blockIdx.x * FOLD_RPB, r_end = min(row_base + total_rows, r_begin + FOLD_RPB);   // rows [row_base, row_base + total_rows)
-  int it = find_item(items, n_items, r_begin, false);
+template <typename T>
+__global__ void __launch_bounds__(256, 4) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w_begin = blockIdx.x * FOLD_RPB + warp * FOLD_RPW, w_end = min(total_rows, w_begin + FOLD_RPW);
+  if (w_begin >= w_end) return;
+  int it = find_item(items, n_items, w_begin, false);
   StgFoldItem d = items[it];
-  for (int r = r_begin; r < r_end; ++r) {
+  for (int r = w_begin; r < w_end; ++r) {
     while (r >= d.row0 + d.c_out) d = items[++it];
-    const int co = r - d.row0, n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
-    const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
-    const float* vr = d.v + (int64_t)co * n;
-    const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
-    float* orow = d.dv + (int64_t)co * n;
-    const bool staged = n <= FOLD_ROW_MAX;
-    const bool vec = staged && (n & 3) == 0 && al16(vr) && al16(orow);
-    __syncthreads();                                  // the previous row's readers are done with sdw[]
-    float4 x[4];                                      // vec: the v row stays in registers for the second pass
-    if (vec) {
-      const float4* v4 = reinterpret_cast<const float4*>(vr);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int i = threadIdx.x + u * 256; if (i < n / 4) x[u] = v4[i]; }
-    }
-    if (staged) {   // coalesced read of each tap's run of cin_g gradients, scattered (stride k) into shared memory
-      if ((cin_g & 3) == 0 && (span & 3) == 0 && al16(dr)) {
-        const int per_tap = cin_g >> 2, total = k * per_tap;
-        for (int idx = threadIdx.x; idx < total; idx += 256) {
-          const int j = idx / per_tap, ci = (idx - j * per_tap) << 2;
-          const float4 g4 = *reinterpret_cast<const float4*>(dr + j * span + ci);
-          sdw[ci * k + j] = g4.x; sdw[(ci + 1) * k + j] = g4.y; sdw[(ci + 2) * k + j] = g4.z; sdw[(ci + 3) * k + j] = g4.w;
-        }
-      } else {
-        for (int j = 0; j < k; ++j)
-          for (int ci = threadIdx.x; ci < cin_g; ci += 256) sdw[ci * k + j] = dr[j * span + ci];
-      }
-      __syncthreads();
-    }
-    float ss = 0.f, dot = 0.f;
-    if (vec) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = threadIdx.x + u * 256;
-        if (i < n / 4) {
-          const float4 g4 = reinterpret_cast<const float4*>(sdw)[i];
-          ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
-          dot += x[u].x * g4.x + x[u].y * g4.y + x[u].z * g4.z + x[u].w * g4.w;
-        }
-      }
-    } else {
-      for (int i = threadIdx.x; i < n; i += 256) {
-        const float xv = vr[i];
-        float g;
-        if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
-        ss = fmaf(xv, xv, ss);
-        dot = fmaf(xv, g, dot);
-      }
-    }
-    ss = block_sum(ss, red);
-    dot = block_sum(dot, red);
-    const float norm = sqrtf(ss), gg = d.g[co];
-    const float a = gg / norm, bcoef = gg * dot / (norm * ss);
-    if (vec) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = threadIdx.x + u * 256;
-        if (i < n / 4) {
-          const float4 g4 = reinterpret_cast<const float4*>(sdw)[i];
-          float4 o = make_float4(a * g4.x - bcoef * x[u].x, a * g4.y - bcoef * x[u].y, a * g4.z - bcoef * x[u].z, a * g4.w - bcoef * x[u].w);
-          float4* op = reinterpret_cast<float4*>(orow) + i;
-          if (accumulate) { const float4 p = *op; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-          *op = o;
-        }
-      }
-    } else {
-      for (int i = threadIdx.x; i < n; i += 256) {
-        float g;
-        if (staged) g = sdw[i]; else { const int ci = i / k, j = i - ci * k; g = dr[j * span + ci]; }
-        const float val = a * g - bcoef * vr[i];
-        orow[i] = accumulate ? (orow[i] + val) : val;
-      }
-    }
-    if (threadIdx.x == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
+    const int co = r - d.row0;
+    if (!fold_fast(d)) fold_row_warp_generic<T>(d, co, lane);
+    else if (d.k == 3) fold_row_warp<T, 3>(d, co, lane);
+    else if (d.k == 1) fold_row_warp<T, 1>(d, co, lane);
+    else fold_row_warp<T, 5>(d, co, lane);
+  }
+}
+
+__device__ __forceinline__ void fold_bwd_row_warp_generic(const StgFoldItem& d, int co, int lane, int accumulate) {
+  const int n = d.cin_g * d.k, k = d.k, cin_g = d.cin_g;
+  const int span = d.dw_span > 0 ? d.dw_span : cin_g, ld = d.dw_ld > 0 ? d.dw_ld : span * k;
+  const float* vr = d.v + (int64_t)co * n;
+  const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
+  float* orow = d.dv + (int64_t)co * n;
+  float ss = 0.f, dot = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int ci = i / k, j = i - ci * k;
+    const float x = vr[i];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(x, dr[j * span + ci], dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float norm = sqrtf(ss), gg = d.g[co];
+  const float a = gg / norm, bcoef = gg * dot / (norm * ss);
+  for (int i = lane; i < n; i += 32) {
+    const int ci = i / k, j = i - ci * k;
+    const float val = a * dr[j * span + ci] - bcoef * vr[i];
+    orow[i] = accumulate ? (orow[i] + val) : val;
+  }
+  if (lane == 0) d.dg[co] = accumulate ? (d.dg[co] + dot / norm) : dot / norm;
+}
+
+__global__ void __launch_bounds__(256, 4) wn_bwd_multi_kernel(const StgFoldItem* __restrict__ items, int n_items, int row_base,
+                                                           int total_rows, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rows [row_base, row_base + total_rows)
+  const int w_begin = row_base + blockIdx.x * FOLD_RPB + warp * FOLD_RPW, w_end = min(row_base + total_rows, w_begin + FOLD_RPW);
+  if (w_begin >= w_end) return;
+  int it = find_item(items, n_items, w_begin, false);
+  StgFoldItem d = items[it];
+  for (int r = w_begin; r < w_end; ++r) {
+    while (r >= d.row0 + d.c_out) d = items[++it];
+    const int co = r - d.row0;
+    if (!fold_bwd_fast(d)) fold_bwd_row_warp_generic(d, co, lane, accumulate);
+    else if (d.k == 3) fold_bwd_row_warp<3>(d, co, lane, accumulate);
+    else if (d.k == 1) fold_bwd_row_warp<1>(d, co, lane, accumulate);
+    else fold_bwd_row_warp<5>(d, co, lane, accumulate);
   }
 }
 
