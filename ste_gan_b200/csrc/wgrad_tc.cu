@@ -287,7 +287,10 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
   p.chunks_per_sample = ceil_div(d->t_out, RK);
   p.total_chunks = d->n_samples * d->phases * p.chunks_per_sample;
   const int gx = p.x_tiles, gy = ceil_div(d->c_out, 128) * p.tap_groups;
-  int want = ceil_div(148, gx * gy);
+  // split-K factor: as many splits as still fit ONE wave (one CTA per SM: ~200 KB of shared memory each) - rounding up
+  // (180 CTAs for 36 tiles) put a second, nearly empty wave behind the first
+  static const int n_sm = [] { int d = 0, n = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+  int want = n_sm / (gx * gy);
   if (want < 1) want = 1;
   if (want > p.total_chunks) want = p.total_chunks;
   p.chunks_per_split = ceil_div(p.total_chunks, want);
