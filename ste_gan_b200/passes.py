@@ -637,21 +637,26 @@ def _heavy_split(subs: Sequence) -> Tuple[List[int], List[int]]:
     return heavy, [i for i in range(len(subs)) if i not in heavy]
 
 
-def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded], side=None):
+def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded], side=None,
+                          subset: Optional[Sequence[int]] = None):
     """DiscriminatorSmall.forward / Discriminator.forward (discriminator.py:144-155,180-191).
     x: fp32 [B,T,C].  Returns (results, ctx): results[d] = channels-last feature maps
     [B, H*p, C_j] in `dtype` with the fp32 logits last.  `side`: optional extra CUDA stream; the sub-discriminators
-    are independent, so the full-rate scale discriminator runs there while the others run on the current stream."""
+    are independent, so the full-rate scale discriminator runs there while the others run on the current stream.
+    `subset`: run only these sub-discriminators (indices into disc_subnets); the other entries stay None."""
     x = x.contiguous().float()
     B, T, Cc = x.shape
     ctx = DiscCtx(B=B, T=T, C=Cc, dtype=dtype, folds=folds)
     subs = disc_subnets(model)
     # multi-scale inputs: fp32, AvgPool1d(4,2,1) between (and after) the scales (discriminator.py:153)
+    wanted = set(range(len(subs)) if subset is None else subset)
+    last_scale = max([i for i in wanted if subs[i][0] == "S"], default=-1)
     scale_in, xs = {}, x
     for i, (kind, d) in enumerate(subs):
         if kind == "S":
             scale_in[i] = xs
-            xs = ops.avgpool4(xs)
+            if subset is None or i < last_scale:      # (the reference also pools once more after the last scale)
+                xs = ops.avgpool4(xs)
     results: List = [None] * len(subs)
     sub_ctx: List = [None] * len(subs)
 
@@ -683,13 +688,32 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
             results[i], sub_ctx[i] = fmaps, sub
 
     heavy, rest = _heavy_split(subs)
-    if side is not None and heavy:
+    heavy, rest = [i for i in heavy if i in wanted], [i for i in rest if i in wanted]
+    if side is not None and heavy and rest:
         fork_join(side, lambda: run(heavy), lambda: run(rest))
     else:
-        run(list(range(len(subs))))
+        run(heavy + rest)
     ctx.subs = sub_ctx
     ctx.keep = (scale_in, xs)
     return results, ctx
+
+
+def split_disc_batch(results: List, ctx: DiscCtx, idx: Sequence[int], n_first: int):
+    """A forward over the concatenation [first n_first samples | rest] for the sub-discriminators `idx` ->
+    (feature maps of the first part, of the second part, per-sub contexts of the first part for a backward through
+    it).  Everything returned is a contiguous leading / trailing slice of the batched tensors (no copies)."""
+    res_a: List = [None] * len(results)
+    res_b: List = [None] * len(results)
+    sub_a: List = [None] * len(results)
+    for i in idx:
+        res_a[i] = [fm[:n_first] for fm in results[i]]
+        res_b[i] = [fm[n_first:] for fm in results[i]]
+        sub = dict(ctx.subs[i])
+        sub["inputs"] = [t[:n_first] for t in sub["inputs"]]
+        if "x_scale" in sub:
+            sub["x_scale"] = sub["x_scale"][:n_first]
+        sub_a[i] = sub
+    return res_a, res_b, sub_a
 
 
 def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tensor]],

@@ -250,15 +250,36 @@ class GanTrainer:
             refold_d = update_d or not self._d_folded
             self._d_folded = True
             if self.concurrent_d:
-                # current stream: folds of the fake pass, then (while the side stream already runs the fake pass) the
-                # real pass's power iteration and the real pass
+                # The fake and the real pass use the same weights - except in the spectral-norm sub-discriminator (the
+                # full-rate scale stack), whose sigma advances between the two forwards.  So: that sub-discriminator
+                # runs once per pass (fake on the side stream as soon as its folds are there, real after the second
+                # power iteration), and ALL THE OTHERS run ONCE on the concatenated batch [x_pred | x_real]: half the
+                # launches and twice the rows per launch for layers that had too few tiles to fill the chip.
+                subs = passes.disc_subnets(self.net_d)
+                heavy, rest = passes._heavy_split(subs)
+                p_idx = [i for i in rest if subs[i][0] == "P"]
+                s_idx = [i for i in rest if subs[i][0] == "S"]
+                Bq = x_pred.shape[0]
                 f3 = self._fold_d(refold_d)
+                x_cat = torch.cat([x_pred, x_real], 0)
+                fwd = lambda x, f, idx: passes.discriminator_forward(self.net_d, x, dt, f, subset=idx) if idx else (None, None)
                 self._fork()
-                with torch.cuda.stream(self._side):
-                    res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3, side=self._s2(0))
-                f4 = self._fold_d(False)
-                res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4, side=self._s2(1))
+                with torch.cuda.stream(self._side):       # side: fake pass of the spectral-norm stack | its side: S stacks, batched
+                    (rs, cs), (rh_f, ch_f) = passes.fork_join(self._s2(0), lambda: fwd(x_cat, f3, s_idx), lambda: fwd(x_pred, f3, heavy))
+                f4 = self._fold_d(False)                  # current: second power iteration, then real pass of that stack | P stacks, batched
+                (rh_r, _), (rp, cp) = passes.fork_join(self._s2(1), lambda: fwd(x_real, f4, heavy), lambda: fwd(x_cat, f3, p_idx))
                 self._join()
+                res_f, res_r, sub_f = [None] * len(subs), [None] * len(subs), [None] * len(subs)
+                for r_b, c_b, idx in ((rp, cp, p_idx), (rs, cs, s_idx)):
+                    if idx:
+                        a, b, sa = passes.split_disc_batch(r_b, c_b, idx, Bq)
+                        for i in idx:
+                            res_f[i], res_r[i], sub_f[i] = a[i], b[i], sa[i]
+                for i in heavy:
+                    res_f[i], res_r[i], sub_f[i] = rh_f[i], rh_r[i], ch_f.subs[i]
+                assert all(r is not None for r in res_f)
+                ctx_f = passes.DiscCtx(B=Bq, T=x_pred.shape[1], C=x_pred.shape[2], dtype=dt, folds=f3, subs=sub_f)
+                ctx_f.keep = (ch_f, cp, cs, x_cat)
             else:
                 f3 = self._fold_d(refold_d)
                 f4 = self._fold_d(False)
