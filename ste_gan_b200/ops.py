@@ -395,9 +395,9 @@ def l1_mean_multi(pairs, out_slot: Tensor, grad_scale: float, want_grad: bool = 
     return das if want_grad else None
 
 
-def mse_const_multi(xs, targets, slots: Tensor, slot_idx, grad_scale: float, dx_dtype: torch.dtype):
+def mse_const_multi(xs, targets, slots: Tensor, slot_idx, grad_scale: float, dx_dtype: torch.dtype, outs=None):
     """LSGAN terms over a list of logits tensors in one launch: slots[slot_idx[i]] += mean((x_i - target_i)^2);
-    returns [dx_i] in `dx_dtype`."""
+    returns [dx_i] in `dx_dtype` (written into outs[i] where given: contiguous, same element count)."""
     n = len(xs)
     if n > _lib.MAX_LOSS_ITEMS:
         raise _lib.StgError("mse_const_multi: too many tensors")
@@ -405,7 +405,11 @@ def mse_const_multi(xs, targets, slots: Tensor, slot_idx, grad_scale: float, dx_
     dxs = []
     for i, x in enumerate(xs):
         _need(x, x.numel(), xs[0].dtype, "x")
-        dx = torch.empty(x.shape, device=x.device, dtype=dx_dtype)
+        if outs is not None and outs[i] is not None:
+            dx = outs[i]
+            _need(dx, x.numel(), dx_dtype, "out")
+        else:
+            dx = torch.empty(x.shape, device=x.device, dtype=dx_dtype)
         dxs.append(dx)
         items[i] = _lib.StgMseItem(_ptr(x), _ptr(dx), x.numel(), float(targets[i]), int(slot_idx[i]))
     check(_lib.load().stg_mse_const_multi(items, n, code_of(xs[0].dtype), code_of(dx_dtype), _ptr(slots), float(grad_scale),

@@ -725,7 +725,7 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
     Returns d/dx fp32 [B,T,C] when want_input_grad.  `side`: optional extra stream for the full-rate scale
     discriminator (see discriminator_forward)."""
     B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
-    dev = ctx.subs[0]["inputs"][0].device
+    dev = next(sub for sub in ctx.subs if sub is not None)["inputs"][0].device
     if plan is not None and want_weight_grad:
         ws = plan                                 # caller zeroes the arena and runs plan.backward() after its passes
     else:
@@ -739,6 +739,8 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
     def run(idx: List[int]) -> None:
         for di in idx:
             sub = ctx.subs[di]
+            if sub is None:                         # a forward with `subset`: this sub-discriminator ran elsewhere
+                continue
             d, phases, inputs, ts = sub["mod"], sub["phases"], sub["inputs"], sub["ts"]
             convs = list(d.layers) + [d.output]
             g = dlogits[di]
@@ -764,15 +766,15 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
                 else:
                     scale_grad[di] = dxin
 
-    heavy, rest = _heavy_split([(sub["kind"], None) for sub in ctx.subs])
-    if side is not None and heavy:
+    heavy, rest = _heavy_split([(sub["kind"] if sub is not None else "-", None) for sub in ctx.subs])
+    if side is not None and heavy and any(ctx.subs[i] is not None for i in rest):
         fork_join(side, lambda: run(heavy), lambda: run(rest))
     else:
         run(list(range(n_sub)))
     if want_input_grad:
         # x_s(i+1) = avgpool(x_s(i)): fold the chain from the coarsest scale back to the input
         carry = None
-        for di in reversed([i for i, sub in enumerate(ctx.subs) if sub["kind"] == "S"]):
+        for di in reversed([i for i, sub in enumerate(ctx.subs) if sub is not None and sub["kind"] == "S"]):
             t_in, cur = ctx.subs[di]["t_in0"], scale_grad[di]
             if carry is not None:
                 if cur is None:

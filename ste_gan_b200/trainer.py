@@ -169,8 +169,22 @@ class GanTrainer:
         self._ev_f1.record(torch.cuda.current_stream())
         self._f2 = self._fold_d(False)
 
+    # The fake and the real pass share their weights except in the spectral-norm sub-discriminator (the full-rate scale
+    # stack: its sigma advances between the two forwards).  With `concurrent_d` that stack runs once per pass and all
+    # the others run ONCE, forward and backward, on the concatenated batch [x_pred | x_real]: half the launches, twice
+    # the rows per launch (their layers have too few tiles to fill the chip), one weight-gradient contraction over both.
+    def _split_subs(self):
+        subs = passes.disc_subnets(self.net_d)
+        heavy, rest = passes._heavy_split(subs)
+        return subs, heavy, [i for i in rest if subs[i][0] == "P"], [i for i in rest if subs[i][0] == "S"]
+
     def _d_real(self, x_real: Tensor) -> None:
-        self._real = passes.discriminator_forward(self.net_d, x_real, self.dtype, self._f2, side=self._s2(0))
+        self._x_real = x_real
+        if self.concurrent_d:      # only the spectral-norm stack: the rest waits for x_pred and runs batched (_d_fake)
+            _, heavy, _, _ = self._split_subs()
+            self._real = passes.discriminator_forward(self.net_d, x_real, self.dtype, self._f2, subset=heavy) if heavy else (None, None)
+        else:
+            self._real = passes.discriminator_forward(self.net_d, x_real, self.dtype, self._f2)
 
     def _g_forward(self, su: Tensor, sess: Tensor, mode: Optional[Tensor]) -> None:
         self.slots.zero_()
@@ -180,29 +194,72 @@ class GanTrainer:
                                                            side=self._s2(1) if self.use_adv else None)
 
     def _d_fake(self) -> None:
-        self._fake = passes.discriminator_forward(self.net_d, self.x_pred, self.dtype, self._f1, side=self._s2(1))
+        dt = self.dtype
+        if not self.concurrent_d:
+            self._fake = passes.discriminator_forward(self.net_d, self.x_pred, dt, self._f1)
+            return
+        _, heavy, p_idx, s_idx = self._split_subs()
+        fwd = lambda x, idx: passes.discriminator_forward(self.net_d, x, dt, self._f1, subset=idx) if idx else (None, None)
+        x_cat = torch.cat([self.x_pred, self._x_real], 0)
+        # current: fake pass of the spectral-norm stack | side2[1]: S stacks batched | side2[0]: P stacks batched
+        ((rs, cs), (rp, cp)), (rh, ch) = passes.fork_join(
+            self._s2(1), lambda: passes.fork_join(self._s2(0), lambda: fwd(x_cat, p_idx), lambda: fwd(x_cat, s_idx))[::-1],
+            lambda: fwd(self.x_pred, heavy))
+        self._fake = (rh, ch)
+        self._batched = (rp, cp, rs, cs, x_cat)
 
     def _d_update(self) -> None:
         dt = self.dtype
-        (res_f, ctx_f), (res_r, ctx_r) = self._fake, self._real
-        self._fake = self._real = None
-        self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
+        if not self.concurrent_d:
+            (res_f, ctx_f), (res_r, ctx_r) = self._fake, self._real
+            self._fake = self._real = None
+            self._last_d_fmaps = (res_f, res_r, ctx_f)      # kept for the parity tests (references only)
+            nd = len(res_f)
+            dl = ops.mse_const_multi([fm[-1] for fm in res_f] + [fm[-1] for fm in res_r], [0.0] * nd + [1.0] * nd, self.slots,
+                                     [0] * (2 * nd), 1.0, dt)
+            self.d_plan.zero()
+            passes.discriminator_backward(self.net_d, ctx_f, dl[:nd], None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
+            passes.discriminator_backward(self.net_d, ctx_r, dl[nd:], None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
+            self.d_plan.backward(accumulate=False)
+            return
+        subs, heavy, p_idx, s_idx = self._split_subs()
+        (rh_f, ch_f), (rh_r, ch_r) = self._fake, self._real
+        rp, cp, rs, cs, x_cat = self._batched
+        self._fake = self._real = self._batched = None
+        Bq, nd = self.x_pred.shape[0], len(subs)
+        # per-pass views of every feature map (parity tests; the loss below needs the logits of each pass)
+        res_f, res_r = [None] * nd, [None] * nd
+        for r_b, c_b, idx in ((rp, cp, p_idx), (rs, cs, s_idx)):
+            if idx:
+                a, b, _ = passes.split_disc_batch(r_b, c_b, idx, Bq)
+                for i in idx:
+                    res_f[i], res_r[i] = a[i], b[i]
+        for i in heavy:
+            res_f[i], res_r[i] = rh_f[i], rh_r[i]
+        self._last_d_fmaps = (res_f, res_r, ch_f)
         # loss_D = sum_i mse(fake_i, 0) + mse(real_i, 1) and its gradients, one launch      train.py:192-196
-        nd = len(res_f)
+        # (batched stacks: the two gradients land in the two halves of one [2B, rows, 1] tensor)
+        dcat = {i: torch.empty((2 * Bq,) + tuple(res_f[i][-1].shape[1:]), device=self.device, dtype=dt) for i in p_idx + s_idx}
+        outs = [dcat[i][:Bq] if i in dcat else None for i in range(nd)] + [dcat[i][Bq:] if i in dcat else None for i in range(nd)]
         dl = ops.mse_const_multi([fm[-1] for fm in res_f] + [fm[-1] for fm in res_r], [0.0] * nd + [1.0] * nd, self.slots,
-                                 [0] * (2 * nd), 1.0, dt)
+                                 [0] * (2 * nd), 1.0, dt, outs=outs)
         dl_f, dl_r = dl[:nd], dl[nd:]
-        # both passes accumulate their packed weight gradients in the plan's arena; the weight-norm backward is
+        dl_b = [dcat.get(i) for i in range(nd)]
+        # every pass / stack accumulates its packed weight gradients in the plan's arena; the weight-norm backward is
         # linear in them, so it runs once (spectral-norm layers un-fold per pass: their sigma differs)
         self.d_plan.zero()
-        if self.concurrent_d:    # every backward branch (2 passes x {scale-0, rest}) sends its wgrads to its own side stream
-            cur = torch.cuda.current_stream()
-            self.d_plan.async_wgrads({st.cuda_stream: w for st, w in zip((cur, self._side, self._side2[0], self._side2[1]), self._wg)})
-        self._two_passes(
-            lambda: passes.discriminator_backward(self.net_d, ctx_f, dl_f, None, want_input_grad=False, want_weight_grad=True,
-                                                  plan=self.d_plan, side=self._s2(0)),
-            lambda: passes.discriminator_backward(self.net_d, ctx_r, dl_r, None, want_input_grad=False, want_weight_grad=True,
-                                                  plan=self.d_plan, side=self._s2(1)))
+        cur = torch.cuda.current_stream()
+        # four backward branches, each with its own weight-gradient side stream
+        self.d_plan.async_wgrads({st.cuda_stream: w for st, w in zip((cur, self._side, self._side2[0], self._side2[1]), self._wg)})
+        bwd = lambda ctx, dlog: passes.discriminator_backward(self.net_d, ctx, dlog, None, want_input_grad=False,
+                                                              want_weight_grad=True, plan=self.d_plan) if ctx is not None else None
+        only = lambda dlog, idx: [dlog[i] if i in idx else None for i in range(nd)]
+        self._fork()
+        with torch.cuda.stream(self._side):       # side: spectral-norm stack, fake | its side: spectral-norm stack, real
+            passes.fork_join(self._s2(0), lambda: bwd(ch_r, only(dl_r, heavy)), lambda: bwd(ch_f, only(dl_f, heavy)))
+        # current: P stacks, batched | its side: S stacks, batched
+        passes.fork_join(self._s2(1), lambda: bwd(cs, only(dl_b, s_idx)), lambda: bwd(cp, only(dl_b, p_idx)))
+        self._join()
         self.d_plan.join_wgrads()
         self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
 
