@@ -590,7 +590,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (q >= 1 && q + 2 < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free((q + 2) % 3)) : "memory");
         }
       }
-      bulk_wait_all_el();
+      bulk_wait_read_el<0>();   // the stores have READ their shared-memory slots; their global writes complete by the end of the grid
     } else {
       // ----- math warps -----
       const int team = (warp - 2) >> 2;                 // 0 / 1: takes the sub-tiles with q & 1 == team

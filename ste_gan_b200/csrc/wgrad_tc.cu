@@ -207,7 +207,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       tmem_ld16(t_lane + (uint32_t)(p.n_taps * p.bnw), v);
       if (co0 + row < p.c_out) atomicAdd(p.dbias + co0 + row, v[0]);
     }
-    if (threadIdx.x == 64) bulk_wait_all();
+    if (threadIdx.x == 64) bulk_wait_read<0>();   // reductions have read their staging tiles; they complete by the end of the grid
   }
   tc_fence_before();
   __syncthreads();
