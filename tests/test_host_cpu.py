@@ -91,7 +91,15 @@ def _dp_worker(rank, world, port, out):
     red.all_reduce(g)
     flat = torch.arange(8.0) * (r + 1)
     red.broadcast(flat, src=0)
-    ok = red.enabled and bool((g == 3.0).all()) and red.grad_scale == 0.5 and bool((flat == torch.arange(8.0)).all())
+    # the bucket-by-bucket exchange of the generator gradient: slices reduced asynchronously, back to front, waited on
+    # together (trainer._reduce_g_bucket / flush)
+    g2 = torch.full((900,), float(r + 1))
+    handles = []
+    for lo_, hi_ in ((600, 900), (300, 600), (0, 300)):
+        handles += red.all_reduce_async(g2[lo_:hi_])
+    red.wait(handles)
+    ok = red.enabled and bool((g == 3.0).all()) and red.grad_scale == 0.5 and bool((flat == torch.arange(8.0)).all()) \
+        and bool((g2 == 3.0).all()) and len(handles) >= 3
     lo, hi = shard_range(r, w, 32)
     out[rank] = (ok, lo, hi)
     dist.destroy_process_group()
