@@ -77,6 +77,12 @@ struct TcP {
   // residue class are numbered mt = b * tiles_m + tm and the CTA of cluster rank r takes mt = 2 * pair + r.  An odd count
   // leaves the last pair's rank-1 CTA with b == n_samples: its loads are zero-filled and its stores clipped by the TMA unit.
   int n_samples, pairs_per_res;
+  // Row classes (staged, stride-1, single-phase kernels): T rows per sample rarely fill whole 128-row tiles (T = 100 /
+  // 200 / 400: 78 %).  The rows of a sample are cut into 128-row tiles plus a binary tail (64 / 32 / 16 / 8 rows), and a
+  // tail tile gathers the SAME seg-row slice of 128 / seg consecutive samples with one (C, seg rows, samples) TMA box -
+  // loads, epilogue operands and stores alike.  Class c: cls_seg rows per sample starting at row cls_h0, cls_tps tiles
+  // per sample (full tiles) or 0 (tail: one tile per 128 / seg samples); row tiles [cls_mt0[c], cls_mt0[c+1]).
+  int n_cls, cls_mt0[5], cls_seg[4], cls_h0[4], cls_tps[4];
   // Tap groups ("A windows"): the taps of one group read row-shifted views of ONE TMA-loaded window of
   // nh + max_shift h rows (UMMA descriptors take any row offset into a 128B-swizzled tile - the swizzle is a
   // function of the shared-memory address, tools/rowshift_probe.py), so a k-tap conv loads its activations
@@ -93,9 +99,10 @@ struct TcP {
 constexpr int MAX_STAGED_RES = 4;   // residue classes the staged epilogue has tensor maps for
 // Epilogue tensors as 4-D maps (C, phase, h, B) - per residue class of a strided data-gradient: class r holds the
 // rows h = h'*s + r, i.e. base + r rows, h stride s rows, extent ceil((T - r)/s) - and y_act as (C, dup, h, B).
-struct EpiMaps {
-  CUtensorMap pre[MAX_STAGED_RES], mask[MAX_STAGED_RES], raw[MAX_STAGED_RES], post, act;
+struct EpiMaps {   // index: residue class (strided data-gradients) or row class (see TcP::n_cls) - never both
+  CUtensorMap pre[MAX_STAGED_RES], mask[MAX_STAGED_RES], raw[MAX_STAGED_RES], post[MAX_STAGED_RES], act[MAX_STAGED_RES];
 };
+struct TmA4 { CUtensorMap m[4]; };   // activation map per row class
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* o) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -168,7 +175,7 @@ struct Tracer {
 
 // ---------------------------------------------------------------------------------------------- tiles
 struct Tile {
-  int b, res, h0, col0, ch0, wcol0, g0, n_iters;
+  int b, res, h0, col0, ch0, wcol0, g0, n_iters, cls;
 };
 template <bool kPair>
 __device__ __forceinline__ Tile decode_tile(const TcP& p, int t, int rank) {
@@ -181,10 +188,25 @@ __device__ __forceinline__ Tile decode_tile(const TcP& p, int t, int rank) {
     const int pm = u % p.pairs_per_res; x.res = u / p.pairs_per_res;
     const int mt = 2 * pm + rank;
     x.b = mt / p.tiles_m; tm = mt - x.b * p.tiles_m;
+  } else if (p.n_cls > 1) {
+    int c = 0;
+    while (c + 1 < p.n_cls && u >= p.cls_mt0[c + 1]) ++c;
+    const int idx = u - p.cls_mt0[c];
+    x.cls = c; x.res = 0;
+    if (p.cls_tps[c] > 0) { x.b = idx / p.cls_tps[c]; tm = idx - x.b * p.cls_tps[c]; }
+    else { x.b = idx * (TM / p.cls_seg[c]); tm = 0; }
+    x.h0 = p.cls_h0[c] + tm * TM;
+    x.col0 = tn * p.bn;
+    x.ch0 = (x.col0 / p.cd_g) * p.cs_g;
+    x.wcol0 = x.col0 % p.cd_g;
+    x.g0 = p.res_gfirst[0];
+    x.n_iters = (p.res_gfirst[1] - x.g0) * p.k_chunks;
+    return x;
   } else {
     tm = u % p.tiles_m; u /= p.tiles_m;
     x.res = u % p.n_res; x.b = u / p.n_res;
   }
+  x.cls = 0;
   x.h0 = tm * p.nh;
   x.col0 = tn * p.bn;
   x.ch0 = (x.col0 / p.cd_g) * p.cs_g;  // first source channel of this column tile's group
@@ -267,7 +289,7 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int co
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kStaged ? 384 : 352, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ EpiMaps em, const TcP p) {
   constexpr int EPI_WARPS = 8;   // warps that read the accumulator (arrivals on tmem_empty)
   extern __shared__ uint8_t smem_raw[];
@@ -297,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   pdl_trigger();   // the next kernel of the stream may start its prologue now (it still waits for this grid to complete)
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
+    for (int c = 0; c < p.n_cls; ++c) prefetch_tmap(&tmA4.m[c]);
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
@@ -373,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rank == 0) mbar_expect_tx_el(full_bar(s), tx_bytes);
 #pragma unroll 1
             for (int bx = 0; bx < p.a_boxes; ++bx)
-              tma_load_4d_el<kPair>(a_dst + bx * a_box_bytes, &tmA, fb, c0, 0, row0 + bx * row_step, x.b);
+              tma_load_4d_el<kPair>(a_dst + bx * a_box_bytes, &tmA4.m[x.cls], fb, c0, 0, row0 + bx * row_step, x.b);
           }
 #ifdef STG_PROF_LOOP
           const long long pc2 = clock64();
@@ -467,7 +489,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx_el(full_bar(s), (uint32_t)(p.a_boxes * p.hb * p.pack * KC * 2 + nt * b_bytes));
 #pragma unroll 1
           for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_4d_el(a_dst + bx * p.hb * p.pack * KC * 2, &tmA, full_bar(s), x.ch0 + chunk * KC, 0,
+            tma_load_4d_el(a_dst + bx * p.hb * p.pack * KC * 2, &tmA4.m[0], full_bar(s), x.ch0 + chunk * KC, 0,
                            (x.h0 + bx * p.hb) * p.stride + p.tt.g_off[g], x.b);
         }
 #pragma unroll 1
@@ -543,8 +565,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 10) {
       // ----- epilogue DMA warp: warp-uniform control flow, elected issue (see the producer warp) -----
       if (lane == 0) {
-        for (int r = 0; r < p.n_res; ++r) { prefetch_tmap(&em.pre[r]); prefetch_tmap(&em.mask[r]); prefetch_tmap(&em.raw[r]); }
-        prefetch_tmap(&em.post); prefetch_tmap(&em.act);
+        for (int r = 0; r < max(p.n_res, p.n_cls); ++r) {
+          prefetch_tmap(&em.pre[r]); prefetch_tmap(&em.mask[r]); prefetch_tmap(&em.raw[r]);
+          if (r < p.n_cls) { prefetch_tmap(&em.post[r]); prefetch_tmap(&em.act[r]); }
+        }
       }
       const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
       const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
@@ -559,9 +583,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r0 = lx.h0 >> rsh;                                     // first h row of the tile in its residue class
         mbar_expect_tx_el(in_bar(buf), in_bytes);
         int i = 0;
-        if (e.has_pre) tma_load_4d_el(in_slot(buf, i++), &em.pre[lx.res], in_bar(buf), col, 0, r0, lx.b);
-        if (e.has_mask) tma_load_4d_el(in_slot(buf, i++), &em.mask[lx.res], in_bar(buf), col, 0, r0, lx.b);
-        if (e.has_post) tma_load_4d_el(in_slot(buf, i++), &em.post, in_bar(buf), col, 0, r0 >> e.post_shift, lx.b);
+        const int mv = lx.res + lx.cls;                                  // map variant: residue class or row class
+        if (e.has_pre) tma_load_4d_el(in_slot(buf, i++), &em.pre[mv], in_bar(buf), col, 0, r0, lx.b);
+        if (e.has_mask) tma_load_4d_el(in_slot(buf, i++), &em.mask[mv], in_bar(buf), col, 0, r0, lx.b);
+        if (e.has_post) tma_load_4d_el(in_slot(buf, i++), &em.post[lx.cls], in_bar(buf), col, 0, r0 >> e.post_shift, lx.b);
         ++ld_q;
         if (++ld_s == n_sub) {
           ld_s = 0; ld_t += tstep;
@@ -578,10 +603,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("bar.sync %0, 160;" ::"r"(bar_full(obuf)) : "memory");   // output slots written, input slots consumed
           const int col = x.col0 + s * SUB;
           int o = 0;
-          if (e.has_raw) tma_store_4d_el(&em.raw[x.res], out_slot(obuf, o++), col, 0, r0_out, x.b);
+          if (e.has_raw) tma_store_4d_el(&em.raw[x.res + x.cls], out_slot(obuf, o++), col, 0, r0_out, x.b);
           if (e.has_act) {
-            tma_store_4d_el(&em.act, out_slot(obuf, o), col, 0, r0_out, x.b);
-            if (e.dup_rows) tma_store_4d_el(&em.act, out_slot(obuf, o), col, 1, r0_out, x.b);
+            tma_store_4d_el(&em.act[x.cls], out_slot(obuf, o), col, 0, r0_out, x.b);
+            if (e.dup_rows) tma_store_4d_el(&em.act[x.cls], out_slot(obuf, o), col, 1, r0_out, x.b);
           }
           bulk_commit_el();
           issue_loads();                         // operands of sub-tile q+2 into the input slots just consumed
@@ -835,11 +860,37 @@ static int sm_count() {
 
 // Column-tile width: the widest tile that still leaves about one tile per SM (small layers would otherwise run
 // on a fraction of the chip); a column tile never straddles groups.
-static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
+// Cost model for the column-tile width (STG_BN_MODEL=0: the ">= min tiles" rule below).  One CTA per SM walks
+// ceil(tiles / SMs) tiles; a tile's main loop costs n_stages x (max(2 bn, 200) + 60) clk (the MMAs of a 64-deep stage against the
+// producers' issue floor), epilogues hide behind the next tile's main loop except the last one (bn / 32 sub-tiles of
+// ~200 clk with two teams).  Picks the divisor of cd_g with the smallest makespan; ties go to the wider tile.
+static int pick_bn_model(int cd_g, int groups, int64_t row_tiles, int n_stages, int step) {
+  int best = 0;
+  double best_t = 0;
+  for (int bn = 256; bn >= step; bn -= step) {
+    if (cd_g % bn) continue;
+    const int64_t tiles = row_tiles * (cd_g / bn) * groups;
+    const double waves = (double)((tiles + sm_count() - 1) / sm_count());
+    const double stage = (2.0 * bn > 200.0 ? 2.0 * bn : 200.0) + 60.0;   // + barrier round trip / commit latency per stage
+    const double t = waves * n_stages * stage + (bn / 32.0) * 200.0;
+    if (best == 0 || t < best_t * 0.999) { best = bn; best_t = t; }
+  }
+  return best;
+}
+static bool bn_model_on() {
+  static const bool on = !(getenv("STG_BN_MODEL") && atoi(getenv("STG_BN_MODEL")) == 0);
+  return on;
+}
+
+static int pick_bn(int cd_g, int groups, int64_t row_tiles, int n_stages) {
   if (groups == 1 && (cd_g % 16) != 0) return cd_g <= 16 ? 16 : (cd_g <= 128 ? ((cd_g + 15) / 16) * 16 : 128);
   static const int env_bn = getenv("STG_BN") ? atoi(getenv("STG_BN")) : 0;  // tuning overrides
   static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 128;
   if (env_bn > 0 && cd_g % env_bn == 0) return env_bn;
+  if (bn_model_on()) {
+    const int b = pick_bn_model(cd_g, groups, row_tiles, n_stages, 32);   // multiples of 32: staged-epilogue sub-tiles
+    if (b > 0) return b;
+  }
   int best = 0;
   for (int bn = 256; bn >= 16; bn -= 16) {
     if (cd_g % bn) continue;
@@ -851,9 +902,13 @@ static int pick_bn(int cd_g, int groups, int64_t row_tiles) {
 }
 
 // data-gradient column tiles are whole 64-channel boxes of the forward pack
-static int pick_bn_mn(int cd_g, int groups, int64_t row_tiles) {
+static int pick_bn_mn(int cd_g, int groups, int64_t row_tiles, int n_stages) {
   static const int min_tiles = getenv("STG_MIN_TILES") ? atoi(getenv("STG_MIN_TILES")) : 128;
   if (cd_g % 64 != 0) return groups == 1 ? (cd_g <= 64 ? 64 : 128) : 0;
+  if (bn_model_on()) {
+    const int b = pick_bn_model(cd_g, groups, row_tiles, n_stages, 64);
+    if (b > 0) return b;
+  }
   int best = 0;
   for (int bn = 256; bn >= 64; bn -= 64) {
     if (cd_g % bn) continue;
@@ -907,17 +962,17 @@ int tc_pack_groups(int c_in, int c_out, int groups) {
 // tensor map of an epilogue operand / output for residue class `res` of `n_res`: [B][T][P][C] seen as
 // (C, P, h', B) with h = h'*n_res + res; box = (32, pack, box_h, 1).  `dup`: y_act as [B][T][2][C] -> (C, 2, h, B).
 static int epi_map(CUtensorMap* m, const void* base, int C, int P, int T, int B, int res, int n_res, int pack, int box_h,
-                   bool dup) {
+                   bool dup, int box_b = 1) {
   if (dup) {
     const uint64_t dims[4] = {(uint64_t)C, 2, (uint64_t)T, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)T * C * 4};
-    const uint32_t box[4] = {SUB, 1, (uint32_t)box_h, 1};
+    const uint32_t box[4] = {SUB, 1, (uint32_t)box_h, (uint32_t)box_b};
     return make_tmap_bf16(m, base, 4, dims, strides, box, nullptr, 64);
   }
   const int h_ext = (T - res + n_res - 1) / n_res;
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)P, (uint64_t)h_ext, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)n_res * P * C * 2, (uint64_t)T * P * C * 2};
-  const uint32_t box[4] = {SUB, (uint32_t)pack, (uint32_t)box_h, 1};
+  const uint32_t box[4] = {SUB, (uint32_t)pack, (uint32_t)box_h, (uint32_t)box_b};
   const bf16* b0 = static_cast<const bf16*>(base) + (int64_t)res * P * C;
   return make_tmap_bf16(m, b0, 4, dims, strides, box, nullptr, 64);
 }
@@ -935,8 +990,10 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   tile_geometry(d, &p.pack, &p.nh, &p.n_res, &p.tiles_m);
   p.mrows = p.nh * p.pack;
   p.b_mn = d->transposed ? 1 : 0;
-  p.bn = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m)
-                : pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m);
+  // stages of one tile: taps (of one residue class) x 64-channel chunks
+  const int n_stages_est = ceil_div(d->k, p.n_res) * p.k_chunks;
+  p.bn = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est)
+                : pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est);
   if (p.bn <= 0) return STG_EUNSUPPORTED;
   p.tmem_cols = 512;  // two accumulator buffers ACC_COLS apart
   // ---- taps per residue class, as (source offset, weight index)
@@ -971,6 +1028,33 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
                       p.n_res <= MAX_STAGED_RES && (p.n_res == 1 || (!d->add_post && !d->y_act)) && (p.bn % SUB) == 0 &&
                       (!d->post_shift || (rows_per_phase % 2) == 0);
 
+  // ---- row classes (see TcP::n_cls): 128-row tiles + a binary tail whose tiles gather several samples
+  struct RowCls { int seg, h0, tps; };
+  RowCls rc[4];
+  int n_rc = 0;
+  int64_t cls_tiles = 0;
+  static const int env_cls = getenv("STG_ROWCLS") ? atoi(getenv("STG_ROWCLS")) : 1;
+  if (env_cls && staged && d->phases == 1 && p.n_res == 1 && d->stride == 1) {
+    const int full = d->t_dst / TM;
+    int r = d->t_dst % TM, h = full * TM;
+    if (full > 0) rc[n_rc++] = RowCls{TM, 0, full};
+    while (r > 0) {
+      int seg = 8;
+      while (seg * 2 <= r) seg *= 2;                                  // largest power of two <= r (at least 8)
+      if (n_rc == 3 || r < 8) { seg = 8; while (seg < r) seg *= 2; }  // last slot: one class covers what is left
+      rc[n_rc++] = seg >= TM ? RowCls{TM, h, 1} : RowCls{seg, h, 0};
+      h += seg; r -= seg < r ? seg : r;
+    }
+    for (int c = 0; c < n_rc; ++c)
+      cls_tiles += rc[c].tps > 0 ? (int64_t)d->n_samples * rc[c].tps : ceil_div(d->n_samples, TM / rc[c].seg);
+    const int64_t classic = (int64_t)d->n_samples * p.tiles_m;
+    if (n_rc < 2 || cls_tiles >= classic) n_rc = 0;
+    if (n_rc) {   // the column tile is chosen for the new tile count
+      const int bn2 = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, cls_tiles, n_stages_est) : pick_bn(p.cd_g, d->groups, cls_tiles, n_stages_est);
+      if (bn2 > 0 && (bn2 % SUB) == 0) p.bn = bn2; else n_rc = 0;
+    }
+  }
+
   // ---- tap groups (A windows) and pipeline depth.  Taps of a group must lie on one row lattice of the strided
   // A box (same offset mod stride) and close enough for the window to fit its boxes; candidates: <= ng taps per
   // group, pick the ng with the least shared-memory ingest per tile among those that leave >= 3 (else 2) stages.
@@ -983,7 +1067,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   static const int env_pair = getenv("STG_PAIR") ? atoi(getenv("STG_PAIR")) : 0;
   p.n_samples = d->n_samples;
   const int n_mt = d->n_samples * p.tiles_m;
-  bool pair = env_pair != 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
+  bool pair = env_pair != 0 && n_rc == 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
   p.pairs_per_res = (n_mt + 1) / 2;
   int b_bytes = (pair ? p.bn / 2 : p.bn) * KC * 2;
   const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 2048 : 0;
@@ -1071,6 +1155,13 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     }
     if (!best.ok) return STG_EUNSUPPORTED;
   }
+  if (n_rc && best.ng != 1) n_rc = 0;   // tap windows load (128 + shift)-row boxes of one sample: classic tiles
+  p.n_cls = n_rc ? n_rc : 1;
+  p.cls_mt0[0] = 0;
+  for (int c = 0; c < p.n_cls; ++c) {
+    p.cls_seg[c] = n_rc ? rc[c].seg : TM; p.cls_h0[c] = n_rc ? rc[c].h0 : 0; p.cls_tps[c] = n_rc ? rc[c].tps : p.tiles_m;
+    p.cls_mt0[c + 1] = p.cls_mt0[c] + (n_rc ? (rc[c].tps > 0 ? d->n_samples * rc[c].tps : ceil_div(d->n_samples, TM / rc[c].seg)) : 0);
+  }
   build(best.ng, &p);
   p.hb = best.hb; p.a_boxes = best.a_boxes; p.a_bytes = best.a_bytes; p.max_ntaps = best.ng; p.stages = best.stages;
   const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
@@ -1082,16 +1173,21 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
             d->t_dst, d->transposed, p.bn, (int)staged, p.max_ntaps, p.stages, p.hb, p.a_boxes, p.a_bytes, p.res_gfirst[p.n_res],
             p.tiles_m, p.n_res, smem);
 
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmW;
+  TmA4 tmA;
   EpiMaps em;
   memset(&em, 0, sizeof(em));
-  {
+  memset(&tmA, 0, sizeof(tmA));
+  for (int c = 0; c < p.n_cls; ++c) {
     const uint64_t C = d->c_src, P = d->phases, T = d->t_src, B = d->n_samples;
     const uint64_t dims[4] = {C, P, T, B};
     const uint64_t strides[3] = {C * 2, P * C * 2, T * P * C * 2};
-    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.pack, (uint32_t)(p.hb * p.stride), 1};
+    // row class c: seg rows of TM / seg consecutive samples (classic tiles: hb rows of one sample)
+    const uint32_t box_h = n_rc ? (uint32_t)rc[c].seg : (uint32_t)(p.hb * p.stride);
+    const uint32_t box_b = n_rc && rc[c].tps == 0 ? (uint32_t)(TM / rc[c].seg) : 1u;
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.pack, box_h, box_b};
     const uint32_t es[4] = {1, 1, (uint32_t)p.stride, 1};
-    int r = make_tmap_bf16(&tmA, d->src, 4, dims, strides, box, es);
+    int r = make_tmap_bf16(&tmA.m[c], d->src, 4, dims, strides, box, es);
     if (r) return r;
   }
   if (!p.b_mn) {
@@ -1123,13 +1219,23 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const int box_h = d->pair_sum ? 64 : p.nh;          // h rows of one box (x pack phases = rows of the sub-tile)
     const int t_rows = rows_per_phase;                  // output rows per phase (after pair_sum)
     int r = 0;
-    for (int res = 0; res < p.n_res; ++res) {
+    for (int res = 0; res < (n_rc ? 0 : p.n_res); ++res) {
       if (e.has_pre) r |= epi_map(&em.pre[res], d->add_pre, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
       if (e.has_mask) r |= epi_map(&em.mask[res], d->mask, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
       if (e.has_raw) r |= epi_map(&em.raw[res], d->y_raw, d->c_dst, d->phases, t_rows, d->n_samples, res, p.n_res, p.pack, box_h, false);
     }
-    if (e.has_post) r |= epi_map(&em.post, d->add_post, d->c_dst, d->phases, t_rows >> d->post_shift, d->n_samples, 0, 1, p.pack, box_h >> d->post_shift, false);
-    if (e.has_act) r |= epi_map(&em.act, d->y_act, d->c_dst, d->phases, t_rows, d->n_samples, 0, 1, p.pack, box_h, d->dup_rows != 0);
+    if (!n_rc) {
+      if (e.has_post) r |= epi_map(&em.post[0], d->add_post, d->c_dst, d->phases, t_rows >> d->post_shift, d->n_samples, 0, 1, p.pack, box_h >> d->post_shift, false);
+      if (e.has_act) r |= epi_map(&em.act[0], d->y_act, d->c_dst, d->phases, t_rows, d->n_samples, 0, 1, p.pack, box_h, d->dup_rows != 0);
+    }
+    for (int c = 0; c < n_rc; ++c) {   // row classes: boxes of (seg [/ 2] rows) x (TM / seg samples)
+      const int bh = d->pair_sum ? rc[c].seg / 2 : rc[c].seg, bb = rc[c].tps == 0 ? TM / rc[c].seg : 1;
+      if (e.has_pre) r |= epi_map(&em.pre[c], d->add_pre, d->c_dst, 1, t_rows, d->n_samples, 0, 1, 1, bh, false, bb);
+      if (e.has_mask) r |= epi_map(&em.mask[c], d->mask, d->c_dst, 1, t_rows, d->n_samples, 0, 1, 1, bh, false, bb);
+      if (e.has_raw) r |= epi_map(&em.raw[c], d->y_raw, d->c_dst, 1, t_rows, d->n_samples, 0, 1, 1, bh, false, bb);
+      if (e.has_post) r |= epi_map(&em.post[c], d->add_post, d->c_dst, 1, t_rows >> d->post_shift, d->n_samples, 0, 1, 1, bh >> d->post_shift, false, bb);
+      if (e.has_act) r |= epi_map(&em.act[c], d->y_act, d->c_dst, 1, t_rows, d->n_samples, 0, 1, 1, bh, d->dup_rows != 0, bb);
+    }
     if (r) return STG_ECUDA;
   }
   static bool attr_set = false;
@@ -1157,7 +1263,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     STG_LAUNCH_CHECK();
     return STG_OK;
   }
-  const int64_t n_tiles = (int64_t)d->n_samples * p.n_res * p.tiles_m * p.tiles_n;
+  const int64_t n_tiles = n_rc ? (int64_t)p.cls_mt0[p.n_cls] * p.tiles_n : (int64_t)d->n_samples * p.n_res * p.tiles_m * p.tiles_n;
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();

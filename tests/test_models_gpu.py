@@ -340,7 +340,10 @@ def test_cuda_graph_step_matches_eager():
     # the pipelined replay defers the last generator optimiser step: flush(), then the parameters agree as well
     assert t2._d_graphs is not None and t2._pending_g is not None
     t2.flush()
-    assert O.rel_l2(t2.G.flat, t1.G.flat) < 1e-3 and O.rel_l2(t2.D.flat, t1.D.flat) < 1e-3
+    # Tolerance: the weight-gradient reductions (TMA reduce-add, atomics) are order-nondeterministic, and AdamW's first
+    # steps turn noise-level gradients into +-lr updates, so two runs of the SAME schedule differ by ~1e-3 here; a lost
+    # optimiser step would be ~7e-3 (lr / |w|).
+    assert O.rel_l2(t2.G.flat, t1.G.flat) < 3e-3 and O.rel_l2(t2.D.flat, t1.D.flat) < 3e-3
 
 
 def test_cuda_graph_step_unpipelined_matches_pipelined():
@@ -359,7 +362,7 @@ def test_cuda_graph_step_unpipelined_matches_pipelined():
     a, b = t1.losses(), t2.losses()
     for k in a:
         assert abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
-    assert O.rel_l2(t2.G.flat, t1.G.flat) < 1e-3 and O.rel_l2(t2.D.flat, t1.D.flat) < 1e-3
+    assert O.rel_l2(t2.G.flat, t1.G.flat) < 3e-3 and O.rel_l2(t2.D.flat, t1.D.flat) < 3e-3      # (see above)
 
 
 def test_no_cpu_fallback():
