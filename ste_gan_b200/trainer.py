@@ -137,20 +137,6 @@ class GanTrainer:
         ev.record(self._side)
         torch.cuda.current_stream().wait_event(ev)
 
-    def _two_passes(self, fn_a, fn_b):
-        """Run fn_a on the side stream and fn_b on the current stream; returns (fn_a(), fn_b()) after the join.
-        Every tensor the two functions create stays referenced until the caller's phase ends, and the side stream
-        always re-synchronises with the current one at the next fork, so the caching allocator's per-stream pools
-        cannot hand a block to the other stream while it is still in use."""
-        if not self.concurrent_d:
-            return fn_a(), fn_b()
-        self._fork()
-        with torch.cuda.stream(self._side):
-            ra = fn_a()
-        rb = fn_b()
-        self._join()
-        return ra, rb
-
     # ------------------------------------------------------------------ phases
     # Phase D is five pieces with three dependencies between them:
     #     _d_folds -> _d_real --------------\
