@@ -265,6 +265,9 @@ const char* stg_last_cuda_error(void);
 int stg_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long stg_launch_count(void);
+/* Upper bound on the SMs the persistent tcgen05 kernels occupy from now on (0 = all).  The data-parallel trainer lowers
+ * it while it captures the graphs that run beside a gradient all-reduce, so that the communicator's CTAs find free SMs. */
+void stg_set_sm_limit(int n_sms);
 /* 1 if the tcgen05 engine can take this contraction (shape/alignment rules in DESIGN.md), else 0. */
 int stg_conv_tc_supported(const StgConv* d);
 int stg_wgrad_tc_supported(const StgWgrad* d);

@@ -86,7 +86,7 @@ _SIGS = {
     "stg_l1_mean": [_P, _P, _I, _L, _P, _F, _P, _P],
     "stg_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _F, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["stg_strerror", "stg_last_cuda_error", "stg_version", "stg_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["stg_strerror", "stg_last_cuda_error", "stg_version", "stg_launch_count", "stg_set_sm_limit"])
 
 _lib = None
 
@@ -117,6 +117,8 @@ def load(build_if_missing: bool = True):
     lib.stg_last_cuda_error.restype = C.c_char_p
     lib.stg_version.argtypes = []
     lib.stg_version.restype = C.c_int
+    lib.stg_set_sm_limit.argtypes = [C.c_int]
+    lib.stg_set_sm_limit.restype = None
     lib.stg_launch_count.argtypes = []
     lib.stg_launch_count.restype = C.c_ulonglong
     _lib = lib

@@ -20,6 +20,7 @@ void set_cuda_error(cudaError_t e, const char* where);
   } while (0)
 
 extern unsigned long long g_launch_count;  // kernels launched by this library (process-wide)
+extern int g_sm_limit;                     // SMs the persistent tcgen05 kernels may occupy (0 = all), stg_set_sm_limit
 #define STG_LAUNCH_CHECK()                 \
   do {                                     \
     ++::stg::g_launch_count;               \

@@ -855,11 +855,9 @@ static int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
       n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;   // stg_set_sm_limit: leave SMs to a concurrent communicator
 }
 
-// Column-tile width: the widest tile that still leaves about one tile per SM (small layers would otherwise run
-// on a fraction of the chip); a column tile never straddles groups.
 // Cost model for the column-tile width (STG_BN_MODEL=0: the ">= min tiles" rule below).  One CTA per SM walks
 // ceil(tiles / SMs) tiles; a tile's main loop costs n_stages x (max(2 bn, 200) + 60) clk (the MMAs of a 64-deep stage against the
 // producers' issue floor), epilogues hide behind the next tile's main loop except the last one (bn / 32 sub-tiles of

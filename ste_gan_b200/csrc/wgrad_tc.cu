@@ -290,7 +290,8 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
   // split-K factor: as many splits as still fit ONE wave (one CTA per SM: ~200 KB of shared memory each) - rounding up
   // (180 CTAs for 36 tiles) put a second, nearly empty wave behind the first
   static const int n_sm = [] { int d = 0, n = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
-  int want = n_sm / (gx * gy);
+  const int sms = (g_sm_limit > 0 && g_sm_limit < n_sm) ? g_sm_limit : n_sm;
+  int want = sms / (gx * gy);
   if (want < 1) want = 1;
   if (want > p.total_chunks) want = p.total_chunks;
   p.chunks_per_split = ceil_div(p.total_chunks, want);

@@ -422,15 +422,32 @@ class GanTrainer:
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
         G = torch.cuda.CUDAGraph
+        # graphs that replay beside a gradient all-reduce leave a few SMs to the communicator (STG_NCCL_SMS, default 0 =
+        # off: the persistent conv kernels otherwise hold every SM and the NCCL CTAs only get in between launches)
+        import contextlib, os
+        from . import _lib
+        reserve = int(os.environ.get("STG_NCCL_SMS", "0")) if self.reducer.enabled else 0
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+
+        @contextlib.contextmanager
+        def beside_allreduce():
+            if reserve > 0:
+                _lib.load().stg_set_sm_limit(n_sm - reserve)
+            try:
+                yield
+            finally:
+                if reserve > 0:
+                    _lib.load().stg_set_sm_limit(0)
         if pipelined:
             # the two rows of phase D replay CONCURRENTLY: they must not share a memory pool (blocks freed while one
             # was captured would be handed to the other)
             pool_a = torch.cuda.graph_pool_handle()
             a1, a2, b1, b2, b3 = G(), G(), G(), G(), G()
-            with torch.cuda.graph(a1, pool=pool_a):
-                self._d_folds()
-            with torch.cuda.graph(a2, pool=pool_a):
-                self._d_real(s["x_real"])
+            with beside_allreduce():      # (the deferred last bucket of the previous step)
+                with torch.cuda.graph(a1, pool=pool_a):
+                    self._d_folds()
+                with torch.cuda.graph(a2, pool=pool_a):
+                    self._d_real(s["x_real"])
             with torch.cuda.graph(b1, pool=pool):
                 self._g_forward(s["su"], s["sess"], None)
             with torch.cuda.graph(b2, pool=pool):
@@ -451,7 +468,7 @@ class GanTrainer:
         with torch.cuda.graph(g2[0], pool=pool):
             self._phase_g_head(s["x_real"])
         for i in range(1, len(g2)):
-            with torch.cuda.graph(g2[i], pool=pool):
+            with beside_allreduce(), torch.cuda.graph(g2[i], pool=pool):
                 self._g_bucket(i)
         g3 = G()
         with torch.cuda.graph(g3, pool=pool):
