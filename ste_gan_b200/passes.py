@@ -542,6 +542,23 @@ def generator_backward(model, ctx: GenCtx, dx_pred: Tensor, plan: Optional[FoldP
         plan.backward(accumulate=not overwrite_grads)
 
 
+def fork_many(streams: Sequence["torch.cuda.Stream"], fns: Sequence) -> None:
+    """Run fns[0] on the current stream and fns[1 + i] on streams[i], all ordered after everything enqueued so far; the
+    current stream then waits for every side stream (same contract as fork_join, results through closures)."""
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    for st, fn in zip(streams, fns[1:]):
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            fn()
+    fns[0]()
+    for st in streams[:len(fns) - 1]:
+        e2 = torch.cuda.Event()
+        e2.record(st)
+        cur.wait_event(e2)
+
+
 def fork_join(side: Optional["torch.cuda.Stream"], fn_side, fn_main):
     """Run fn_side on `side` and fn_main on the current stream, both ordered after everything enqueued so far;
     returns (fn_side(), fn_main()) once the current stream has been made to wait for `side`.  Works under CUDA
@@ -638,12 +655,14 @@ def _heavy_split(subs: Sequence) -> Tuple[List[int], List[int]]:
 
 
 def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int, Folded], side=None,
-                          subset: Optional[Sequence[int]] = None):
+                          subset: Optional[Sequence[int]] = None, spread: Optional[Sequence] = None):
     """DiscriminatorSmall.forward / Discriminator.forward (discriminator.py:144-155,180-191).
     x: fp32 [B,T,C].  Returns (results, ctx): results[d] = channels-last feature maps
     [B, H*p, C_j] in `dtype` with the fp32 logits last.  `side`: optional extra CUDA stream; the sub-discriminators
     are independent, so the full-rate scale discriminator runs there while the others run on the current stream.
-    `subset`: run only these sub-discriminators (indices into disc_subnets); the other entries stay None."""
+    `subset`: run only these sub-discriminators (indices into disc_subnets); the other entries stay None.
+    `spread`: extra CUDA streams; the (independent) sub-discriminators are dealt round-robin to the current stream and
+    these - each stack is a chain of ~6 small dependent launches, five of them back to back was the longest branch."""
     x = x.contiguous().float()
     B, T, Cc = x.shape
     ctx = DiscCtx(B=B, T=T, C=Cc, dtype=dtype, folds=folds)
@@ -689,7 +708,11 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
 
     heavy, rest = _heavy_split(subs)
     heavy, rest = [i for i in heavy if i in wanted], [i for i in rest if i in wanted]
-    if side is not None and heavy and rest:
+    if spread:
+        todo = heavy + rest
+        lanes = [todo[j::len(spread) + 1] for j in range(len(spread) + 1)]
+        fork_many(list(spread), [(lambda idx=idx: run(idx)) for idx in lanes if idx])
+    elif side is not None and heavy and rest:
         fork_join(side, lambda: run(heavy), lambda: run(rest))
     else:
         run(heavy + rest)
@@ -718,7 +741,8 @@ def split_disc_batch(results: List, ctx: DiscCtx, idx: Sequence[int], n_first: i
 
 def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tensor]],
                            dfmaps: Optional[Sequence[Sequence[Optional[Tensor]]]] = None, want_input_grad: bool = False,
-                           want_weight_grad: bool = True, plan: Optional[FoldPlan] = None, side=None) -> Optional[Tensor]:
+                           want_weight_grad: bool = True, plan: Optional[FoldPlan] = None, side=None,
+                           spread: Optional[Sequence] = None) -> Optional[Tensor]:
     """Backward through one discriminator forward.
     dlogits[d]: gradient w.r.t. the logits of sub-discriminator d (`dtype`, same shape) or None;
     dfmaps[d][j]: gradient w.r.t. feature map j (`dtype`) or None.
@@ -767,7 +791,11 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
                     scale_grad[di] = dxin
 
     heavy, rest = _heavy_split([(sub["kind"] if sub is not None else "-", None) for sub in ctx.subs])
-    if side is not None and heavy and any(ctx.subs[i] is not None for i in rest):
+    if spread and not want_input_grad and plan is not None:   # (the input gradient is accumulated by one branch only)
+        todo = [i for i in range(n_sub) if ctx.subs[i] is not None]
+        lanes = [todo[j::len(spread) + 1] for j in range(len(spread) + 1)]
+        fork_many(list(spread), [(lambda idx=idx: run(idx)) for idx in lanes if idx])
+    elif side is not None and heavy and any(ctx.subs[i] is not None for i in rest):
         fork_join(side, lambda: run(heavy), lambda: run(rest))
     else:
         run(list(range(n_sub)))
