@@ -54,7 +54,7 @@ __global__ void reflect_pad_bwd_kernel(const T* __restrict__ dout, int T_, int C
     float g = to_f(dout[((int64_t)b * Tp + t) * C + c]);
     const int m = 2 * (T_ - 1) - t;
     if (m >= T_ && m < Tp) g += to_f(dout[((int64_t)b * Tp + m) * C + c]);
-    dx[i] += g;
+    atomicAdd(dx + i, g);   // the period stacks' backward branches run on different streams and all add into dx
   }
 }
 

@@ -791,10 +791,17 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
                     scale_grad[di] = dxin
 
     heavy, rest = _heavy_split([(sub["kind"] if sub is not None else "-", None) for sub in ctx.subs])
-    if spread and not want_input_grad and plan is not None:   # (the input gradient is accumulated by one branch only)
-        todo = [i for i in range(n_sub) if ctx.subs[i] is not None]
-        lanes = [todo[j::len(spread) + 1] for j in range(len(spread) + 1)]
-        fork_many(list(spread), [(lambda idx=idx: run(idx)) for idx in lanes if idx])
+    if spread and (plan is not None or not want_weight_grad):   # (a _Workspace bump allocator is not safe across branches)
+        # the stacks are independent (reflect_pad_right_bwd adds into dx atomically): the full-rate scale stack on
+        # `side` when given, the others dealt round-robin over the current stream and `spread`
+        h_here = [i for i in heavy if ctx.subs[i] is not None] if side is not None else []
+        todo = [i for i in range(n_sub) if ctx.subs[i] is not None and i not in h_here]
+        lanes = [l for l in (todo[j::len(spread) + 1] for j in range(len(spread) + 1)) if l]
+        fns = [(lambda idx=idx: run(idx)) for idx in lanes] or [lambda: None]
+        streams = list(spread)[:len(fns) - 1]
+        if h_here:
+            fns.append(lambda: run(h_here)); streams.append(side)
+        fork_many(streams, fns)
     elif side is not None and heavy and any(ctx.subs[i] is not None for i in rest):
         fork_join(side, lambda: run(heavy), lambda: run(rest))
     else:

@@ -344,7 +344,7 @@ class GanTrainer:
             else:
                 dfm = [[None] * (len(fm_f) - 1) for fm_f in res_f]
             dx_d = passes.discriminator_backward(self.net_d, ctx_f, dlog, dfm, want_input_grad=True, want_weight_grad=False,
-                                                 side=self._s2(0))
+                                                 side=self._s2(0), spread=self._ps if self.concurrent_d else None)
             if td_ev is not None:
                 torch.cuda.current_stream().wait_event(td_ev)
             ops.axpy_f32(dx_pred, dx_d, 1.0)
