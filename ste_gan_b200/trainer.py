@@ -101,8 +101,9 @@ class GanTrainer:
         # sub-148-tile kernels of the small discriminator layers leave idle
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # per pass: the heavy sub-discriminator
-        self._wg = [torch.cuda.Stream(device=dev) for _ in range(6)]                  # weight-gradient side streams
+        self._wg = [torch.cuda.Stream(device=dev) for _ in range(7)]                  # weight-gradient side streams
         self._ps = [torch.cuda.Stream(device=dev) for _ in range(2)]                  # period stacks dealt over these + their branch's stream
+        self._ss = [torch.cuda.Stream(device=dev)]                                    # the same for the batched scale stacks
         self._sn = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # spectral-norm fold chains, one per layer
         self._aux = torch.cuda.Stream(device=dev)                                     # time-domain loss beside the D passes
         self.concurrent_d = True
@@ -187,7 +188,7 @@ class GanTrainer:
             return
         _, heavy, p_idx, s_idx = self._split_subs()
         fwd = lambda x, idx: passes.discriminator_forward(self.net_d, x, dt, self._f1, subset=idx,
-                                                          spread=self._ps if idx is p_idx else None) if idx else (None, None)
+                                                          spread=self._ps if idx is p_idx else (self._ss if idx is s_idx else None)) if idx else (None, None)
         x_cat = torch.cat([self.x_pred, self._x_real], 0)
         # current: fake pass of the spectral-norm stack | side2[1]: S stacks batched | side2[0]: P stacks batched
         ((rs, cs), (rp, cp)), (rh, ch) = passes.fork_join(
@@ -238,10 +239,10 @@ class GanTrainer:
         self.d_plan.zero()
         cur = torch.cuda.current_stream()
         # four backward branches, each with its own weight-gradient side stream
-        self.d_plan.async_wgrads({st.cuda_stream: w for st, w in zip((cur, self._side, self._side2[0], self._side2[1], *self._ps), self._wg)})
+        self.d_plan.async_wgrads({st.cuda_stream: w for st, w in zip((cur, self._side, self._side2[0], self._side2[1], *self._ps, *self._ss), self._wg)})
         bwd = lambda ctx, dlog: passes.discriminator_backward(self.net_d, ctx, dlog, None, want_input_grad=False,
                                                               want_weight_grad=True, plan=self.d_plan,
-                                                              spread=self._ps if ctx is cp else None) if ctx is not None else None
+                                                              spread=self._ps if ctx is cp else (self._ss if ctx is cs else None)) if ctx is not None else None
         only = lambda dlog, idx: [dlog[i] if i in idx else None for i in range(nd)]
         self._fork()
         with torch.cuda.stream(self._side):       # side: spectral-norm stack, fake | its side: spectral-norm stack, real
@@ -309,7 +310,7 @@ class GanTrainer:
                 f3 = self._fold_d(refold_d)
                 x_cat = torch.cat([x_pred, x_real], 0)
                 fwd = lambda x, f, idx: passes.discriminator_forward(self.net_d, x, dt, f, subset=idx,
-                                                                     spread=self._ps if idx is p_idx else None) if idx else (None, None)
+                                                                     spread=self._ps if idx is p_idx else (self._ss if idx is s_idx else None)) if idx else (None, None)
                 self._fork()
                 with torch.cuda.stream(self._side):       # side: fake pass of the spectral-norm stack | its side: S stacks, batched
                     (rs, cs), (rh_f, ch_f) = passes.fork_join(self._s2(0), lambda: fwd(x_cat, f3, s_idx), lambda: fwd(x_pred, f3, heavy))
