@@ -293,6 +293,7 @@ constexpr int FOLD_RPB = 8 * FOLD_RPW;   // rows per block: one table search per
 // moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.  Now: 16-byte
 // accesses wherever the row is 16-byte aligned, all loads of a row issued before the first use, FOLD_RPB rows per block.
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool al16_host(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
 __device__ __forceinline__ void store8(T* dst, const float* w);
@@ -481,10 +482,14 @@ __device__ __forceinline__ void fold_bwd_row_warp_generic(const StgFoldItem& d, 
   const float* vr = d.v + (int64_t)co * n;
   const float* dr = d.dw + (int64_t)co * ld + span_goff(co, cin_g, d.c_out / d.groups, span);
   float* orow = d.dv + (int64_t)co * n;
+  // First pass: lanes walk the GRADIENT in its own order (tap-major: dr[j * span + ci], consecutive ci) so that its first
+  // touch is coalesced; the matching v elements (ci * k + j) are k floats apart - a row is at most a few KB and stays in
+  // L1.  (Walking v's order made every warp load of the k = 37 grouped rows touch 32 different lines of dw.)
   float ss = 0.f, dot = 0.f;
-  for (int i = lane; i < n; i += 32) {
-    const int ci = i / k, j = i - ci * k;
-    const float x = vr[i];
+  const int total = k * cin_g;
+  for (int i = lane; i < total; i += 32) {
+    const int j = i / cin_g, ci = i - j * cin_g;
+    const float x = vr[ci * k + j];
     ss = fmaf(x, x, ss);
     dot = fmaf(x, dr[j * span + ci], dot);
   }
@@ -492,7 +497,7 @@ __device__ __forceinline__ void fold_bwd_row_warp_generic(const StgFoldItem& d, 
   dot = warp_sum(dot);
   const float norm = sqrtf(ss), gg = d.g[co];
   const float a = gg / norm, bcoef = gg * dot / (norm * ss);
-  for (int i = lane; i < n; i += 32) {
+  for (int i = lane; i < n; i += 32) {   // second pass in v / dv order (coalesced stores); the row's dw lines are in L1 now
     const int ci = i / k, j = i - ci * k;
     const float val = a * dr[j * span + ci] - bcoef * vr[i];
     orow[i] = accumulate ? (orow[i] + val) : val;
@@ -518,6 +523,29 @@ __global__ void __launch_bounds__(256, 4) wn_bwd_multi_kernel(const StgFoldItem*
   }
 }
 
+// Forward pack of a plain conv (groups == 1, k in {1, 3, 5}, c_in % 4 == 0) with a given per-row scale: the register
+// transposition of fold_row_warp without the norm pass.  Used for the spectral-norm layers (scale = 1 / sigma), whose
+// largest (512 -> 1024, k 5: 10.5 MB) took 23 us per power iteration in the generic strided pack.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ v, const float* __restrict__ scale, int c_out,
+                                                        int cin, T* __restrict__ wf) {
+  const int co = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (co >= c_out) return;
+  const float sc = scale[co];
+  const float4* v4 = reinterpret_cast<const float4*>(v + (int64_t)co * cin * K);
+  for (int g = lane; g < (cin >> 2); g += 32) {
+    float f[4 * K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float4 x = v4[g * K + q];
+      f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      store4<T>(wf + ((int64_t)j * c_out + co) * cin + 4 * g, f[j] * sc, f[K + j] * sc, f[2 * K + j] * sc, f[3 * K + j] * sc);
+  }
+}
+
 template <typename T>
 int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, int pg, int flags, T* wf,
                  T* wd, cudaStream_t s) {
@@ -531,7 +559,13 @@ int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k
   if (pg <= 0) pg = groups;
   if (groups % pg) return STG_EINVAL;
   const int c_in = cin_g * groups, cin_gp = c_in / pg, cout_gp = c_out / pg;
-  if (wf) {
+  if (wf && groups == 1 && (k == 1 || k == 3 || k == 5) && (cin_g & 3) == 0 && al16_host(v) && al16_host(wf)) {
+    const int nb = ceil_div(c_out, 8);
+    if (k == 1) pack_rows_kernel<T, 1><<<nb, 256, 0, s>>>(v, scale, c_out, cin_g, wf);
+    else if (k == 3) pack_rows_kernel<T, 3><<<nb, 256, 0, s>>>(v, scale, c_out, cin_g, wf);
+    else pack_rows_kernel<T, 5><<<nb, 256, 0, s>>>(v, scale, c_out, cin_g, wf);
+    STG_LAUNCH_CHECK();
+  } else if (wf) {
     dim3 g1(ceil_div(cin_gp * k, 256), c_out);
     pack_fwd_kernel<T><<<g1, 256, 0, s>>>(v, scale, c_out, cin_g, k, groups, pg, wf);
     STG_LAUNCH_CHECK();
