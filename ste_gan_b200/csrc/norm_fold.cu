@@ -287,7 +287,11 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __re
 // wf[j][co][:] (coalesced; the transposition (ci, j) -> (j, ci) happens in shared memory).  Replaces the
 // scale + 32x32-tile pack pair, whose v reads were strided by k.
 constexpr int FOLD_ROW_MAX = 4096;
-constexpr int FOLD_RPW = 4;               // rows per warp (fast path)
+#ifndef STG_FOLD_RPW
+#define STG_FOLD_RPW 1
+#endif
+constexpr int FOLD_RPW = STG_FOLD_RPW;     // rows per warp: 1 = one table search per row, but 4x the warps in flight (4 rows per warp
+                                           // left the discriminator's 7.8 K rows with 13 warps per SM, each a serial chain of rows)
 constexpr int FOLD_RPB = 8 * FOLD_RPW;   // rows per block: one table search per warp / block, the item is then walked forward
 // Both row kernels are pure HBM streams (v 4 B + pack 2 B per weight; dw + v + dv 12 B per weight).  The first versions
 // moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.  Now: 16-byte
