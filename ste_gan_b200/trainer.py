@@ -75,7 +75,7 @@ class FlatParams:
 class GanTrainer:
     def __init__(self, net_g, net_d, precision: str = "bf16", lr: float = 2e-4, w_td: float = W_TD_DEFAULT,
                  w_fm: float = W_FM_DEFAULT, loss_adversarial: bool = True, loss_multi_td: bool = True,
-                 loss_feat_match: bool = True, group=None):
+                 loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None):
         self.net_g, self.net_d = net_g, net_d
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.lr, self.w_td, self.w_fm = lr, w_td, w_fm
@@ -121,6 +121,9 @@ class GanTrainer:
         self.g_buckets = [(k2, nblk, 1 + 5 * k2, n_conv, (cut(k2) if k2 < nblk else cut(nblk), self.G.numel)),
                           (k1, k2, 1 + 5 * k1, 1 + 5 * k2, (cut(k1), cut(k2) if k2 < nblk else cut(nblk))),
                           (0, k1, 0, 1 + 5 * k1, (0, cut(k1)))]
+        # without a data-parallel group there is nothing to overlap: one bucket (one fold-backward launch, one graph)
+        if (grad_buckets if grad_buckets is not None else (3 if self.reducer.enabled else 1)) == 1:
+            self.g_buckets = [(0, nblk, 0, n_conv, (0, self.G.numel))]
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None

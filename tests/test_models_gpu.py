@@ -351,8 +351,9 @@ def test_cuda_graph_step_unpipelined_matches_pipelined():
     from ste_gan_b200.trainer import GanTrainer
     su, sess, x_real = (t.cuda() for t in O.synthetic_batch(2, 100, seed=7))
     g1, d1 = _fresh_nets(); g2, d2 = _fresh_nets()
-    t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="bf16")
-    t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="bf16")
+    t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="bf16")                    # one gradient bucket (no data-parallel group)
+    t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="bf16", grad_buckets=3)    # the three-bucket generator backward
+    assert len(t1.g_buckets) == 1 and len(t2.g_buckets) == 3
     t1.capture(2, 100, pipelined=False)
     t2.capture(2, 100, pipelined=True)
     for _ in range(3):
