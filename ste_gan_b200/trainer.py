@@ -415,7 +415,8 @@ class GanTrainer:
         (the eager step(), state_dict users and the inference engine call it)."""
         dev = self.device
         if pipelined is None:
-            pipelined = self.concurrent_d and self.use_adv
+            import os
+            pipelined = self.concurrent_d and self.use_adv and os.environ.get("STG_PIPELINE", "1") != "0"
         self.flush()
         self._static = dict(
             su=torch.zeros(batch, frames, unit_dim, device=dev), sess=torch.zeros(batch, device=dev, dtype=torch.int64),
