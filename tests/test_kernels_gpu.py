@@ -441,3 +441,18 @@ def test_adamw_matches_torch():
         ops.adamw(p, g.cuda(), m, v, step, 2e-4)
     assert int(step.item()) == 5
     assert rel_l2(p.cpu(), pr.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("env", [{"STG_PAIR": "1"}, {"STG_ROWCLS": "0", "STG_BN_MODEL": "0", "STG_PDL": "0"}],
+                         ids=["cta_pairs", "classic_tiles_no_pdl"])
+def test_tcgen05_engine_variants_in_a_child_process(env):
+    """The engine variants are chosen by environment variables that the library reads once per process: CTA pairs
+    (cta_group::2, opt-in) and the classic tiling (no row classes, ">= min tiles" column width, no programmatic
+    dependent launch).  Re-run the tcgen05 convolution parity cases in a child process for each."""
+    import os, subprocess, sys
+    child_env = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "tcgen05_fwd or tcgen05_dgrad or fused_epilogue"],
+                       env=child_env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
