@@ -194,6 +194,13 @@ int stg_unfold(const void* src, int dtype, int B, int phases, int t_src, int t_d
 int stg_unfold_bwd(const void* dout, int dtype, int B, int phases, int t_src, int t_dst, int C, int k, int dilation,
                    int stride, int pad, float* dsrc, stg_stream_t stream);
 
+/* First layer of a period stack, fused (models/discriminator.py:26,36,77,86): reflect-pad right to a multiple of `period`,
+ * [B,C,T/p,p] view, Conv2d(C -> c_out, (k,1), stride (stride,1), padding (pad,0)), bias, LeakyReLU(slope), from the fp32
+ * input x [B][T][C] to the bf16 channels-last map y [B][H_out*period][c_out].  wf: the STG_PACK_UNFOLD forward pack
+ * [c_out][roundup8(k*C)] in bf16.  Same values as stg_unfold + stg_conv on the tensor engine (bf16 operands, fp32 sums). */
+int stg_period_first_layer(const float* x, const void* wf, const float* bias, int B, int T, int C, int period, int c_out,
+                           int k, int stride, int pad, float slope, void* y, stg_stream_t stream);
+
 /* models/generator.py:143-146,154: x0[b][t] = concat(units[b][t][0:d_units], emb[ids[b]][0:d_emb]) in `dtype`. */
 int stg_embed_concat(const float* units, const float* emb, const int64_t* ids, int B, int T, int d_units, int d_emb,
                      int dtype, void* x0, stg_stream_t stream);

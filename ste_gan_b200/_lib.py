@@ -70,6 +70,7 @@ _SIGS = {
     "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "stg_period_first_layer": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, _P, _P],
     "stg_embed_concat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "stg_embed_concat_bwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "stg_reflect_pad_right": [_P, _I, _I, _I, _I, _I, _P, _P],

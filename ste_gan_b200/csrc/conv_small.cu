@@ -214,6 +214,56 @@ __global__ void __launch_bounds__(256) c1_wgrad_kernel(const C1W p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First layer of a period stack, fused: reflect-pad right (discriminator.py:36,86) + period view + Conv2d(C -> c_out,
+// (k,1), stride (s,1), padding (pad,0)) + bias + LeakyReLU, from the fp32 discriminator input straight to the bf16
+// channels-last feature map.  K = k*C is 24-40: as im2col rows + a one-stage tensor-core GEMM this was three launches
+// (pad, unfold, conv: 4 + 6 + 14 us) for ~3 MB of output; here one thread produces 8 output channels of one output row.
+// Inputs and weights are rounded to bf16 exactly as that path did (fp32 accumulation).
+struct PFirst {
+  int B, T, C, P, H, Ho, c_out, k, stride, pad, Kp;
+  float slope;
+  const float* x;      // [B][T][C] fp32
+  const bf16* w;       // unfold pack [c_out][Kp], q = j*C + c
+  const float* bias;   // [c_out]
+  bf16* y;             // [B][Ho*P][c_out]
+};
+__global__ void __launch_bounds__(256) period_first_kernel(const PFirst p) {
+  extern __shared__ float wsm[];                 // [c_out][k*C + 1] (+1: the 4 channel groups of a row hit 4 banks) | bias
+  const int kc = p.k * p.C, ld = kc + 1;
+  float* bsm = wsm + p.c_out * ld;
+  for (int i = threadIdx.x; i < p.c_out * kc; i += 256) { const int co = i / kc, q = i - co * kc; wsm[co * ld + q] = to_f(p.w[co * p.Kp + q]); }
+  for (int i = threadIdx.x; i < p.c_out; i += 256) bsm[i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
+  const int cg = p.c_out >> 3, rows = p.Ho * p.P;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (int64_t)p.B * rows * cg) return;
+  const int g = (int)(idx % cg);
+  const int64_t rr = idx / cg;
+  const int row = (int)(rr % rows), b = (int)(rr / rows);
+  const int ho = row / p.P, ph = row - ho * p.P;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = bsm[g * 8 + o];
+  for (int j = 0; j < p.k; ++j) {
+    const int hi = ho * p.stride + j - p.pad;
+    if (hi < 0 || hi >= p.H) continue;
+    int t = hi * p.P + ph;
+    if (t >= p.T) t = 2 * (p.T - 1) - t;          // reflected tail
+    const float* xr = p.x + ((int64_t)b * p.T + t) * p.C;
+    for (int c = 0; c < p.C; ++c) {
+      const float xv = __bfloat162float(__float2bfloat16_rn(xr[c]));
+      const float* wr = wsm + (g * 8) * ld + j * p.C + c;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(xv, wr[o * ld], acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = fmaxf(acc[o], p.slope * acc[o]);
+  *reinterpret_cast<uint4*>(p.y + ((int64_t)b * rows + row) * p.c_out + g * 8) = pack8(acc);
+}
+
 }  // namespace
 
 bool conv_c1_supported(const StgConv* d) {
@@ -297,3 +347,24 @@ int wgrad_c1(const StgWgrad* d, cudaStream_t s) {
 }
 
 }  // namespace stg
+
+extern "C" int stg_period_first_layer(const float* x, const void* wf, const float* bias, int B, int T, int C, int period,
+                                      int c_out, int k, int stride, int pad, float slope, void* y, stg_stream_t stream) {
+  using namespace stg;
+  if (!x || !wf || !y || B < 1 || T < 2 || C < 1 || period < 1 || k < 1 || stride < 1 || pad < 0) return STG_EINVAL;
+  if ((c_out & 7) != 0 || c_out > 256 || k * C > 256) return STG_EUNSUPPORTED;
+  PFirst p;
+  p.B = B; p.T = T; p.C = C; p.P = period; p.c_out = c_out; p.k = k; p.stride = stride; p.pad = pad; p.slope = slope;
+  const int t_pad = T + (period - T % period);      // reflect pad is always >= 1 (discriminator.py:36,86)
+  if (t_pad - T >= T) return STG_EUNSUPPORTED;
+  p.H = t_pad / period;
+  p.Ho = (p.H + 2 * pad - (k - 1) - 1) / stride + 1;
+  p.Kp = (k * C + 7) / 8 * 8;
+  p.x = x; p.w = static_cast<const bf16*>(wf); p.bias = bias; p.y = static_cast<bf16*>(y);
+  const int64_t total = (int64_t)B * p.Ho * period * (c_out / 8);
+  const size_t smem = sizeof(float) * ((size_t)c_out * (k * C + 1) + c_out);
+  period_first_kernel<<<(unsigned)((total + 255) / 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+

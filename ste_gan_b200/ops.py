@@ -7,7 +7,7 @@ fault, not an exception).  No CPU fallback exists: tensors must live on a CUDA d
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -260,6 +260,20 @@ def unfold_bwd(dout: Tensor, dsrc: Tensor, *, n_samples: int, phases: int, t_src
     _need(dsrc, n_samples * phases * t_src * channels, torch.float32, "dsrc")
     check(_lib.load().stg_unfold_bwd(_ptr(dout), code_of(dout.dtype), n_samples, phases, t_src, t_dst, channels, k,
                                      dilation, stride, pad, _ptr(dsrc), _stream()), "stg_unfold_bwd")
+
+
+def period_first_layer(x: Tensor, wf: Tensor, bias: Optional[Tensor], *, period: int, c_out: int, k: int, stride: int, pad: int,
+                       slope: float = 0.1) -> Tuple[Tensor, int]:
+    """Fused first layer of a period stack: fp32 x [B,T,C] -> (bf16 [B, H_out*period, c_out], H_out)."""
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    t_pad = T + (period - T % period)
+    h_out = (t_pad // period + 2 * pad - (k - 1) - 1) // stride + 1
+    _need(wf, c_out * round_up8(k * Cc), torch.bfloat16, "wf")
+    y = torch.empty((B, h_out * period, c_out), device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().stg_period_first_layer(_ptr(x), _ptr(wf), _ptr(bias), B, T, Cc, period, c_out, k, stride, pad, float(slope),
+                                             _ptr(y), _stream()), "stg_period_first_layer")
+    return y, h_out
 
 
 def embed_concat(units: Tensor, emb: Optional[Tensor], ids: Optional[Tensor], dtype: torch.dtype) -> Tensor:

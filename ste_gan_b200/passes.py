@@ -682,21 +682,35 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
     def run(idx: List[int]) -> None:
         for i in idx:
             kind, d = subs[i]
+            fused0 = False
             if kind == "P":
                 p = d.period
                 t_pad = T + (p - T % p)          # reflect pad is always >= 1 (discriminator.py:36,86)
-                src = ops.reflect_pad_right(x, t_pad, dtype)
                 phases, t = p, t_pad // p
+                l0, f0_ = d.layers[0], folds[id(d.layers[0])]
+                # bf16: pad + period view + first conv + LeakyReLU in ONE launch from the fp32 input (K = k*C <= 40);
+                # the im2col rows that the first layer's weight gradient wants are rebuilt in the backward pass
+                fused0 = (f0_.unfold and dtype == torch.bfloat16 and l0.groups == 1 and l0.dilation == 1 and
+                          l0.out_channels % 8 == 0 and t_pad - T < T)
+                src = None if fused0 else ops.reflect_pad_right(x, t_pad, dtype)
             else:
                 src = ops.cast(scale_in[i], dtype)
                 phases, t = 1, scale_in[i].shape[1]
             f0 = folds[id(d.layers[0])]
-            if f0.unfold:                         # im2col rows replace the raw input (kept for the first layer's wgrad)
+            if f0.unfold and not fused0:          # im2col rows replace the raw input (kept for the first layer's wgrad)
                 src = unfold_input(f0, src, B, t, phases)
             sub = dict(kind=kind, phases=phases, inputs=[src], ts=[t], t_in0=scale_in[i].shape[1] if kind == "S" else T, mod=d)
             fmaps = []
             h = src
-            for layer in d.layers:
+            layers = list(d.layers)
+            if fused0:
+                l0 = layers[0]
+                h, t = ops.period_first_layer(x, f0.wf, l0.bias.data, period=phases, c_out=l0.out_channels, k=l0.kernel,
+                                              stride=l0.stride, pad=l0.pad, slope=0.1)
+                fmaps.append(h); sub["inputs"].append(h); sub["ts"].append(t)
+                sub["x0"] = x                     # inputs[0] (None) is rebuilt from this by first_layer_input()
+                layers = layers[1:]
+            for layer in layers:
                 _, h, t = _fwd(folds[id(layer)], h, B, t, phases=phases, act=ACT_LEAKY, want_act=True)
                 fmaps.append(h); sub["inputs"].append(h); sub["ts"].append(t)
             logits, _, t = _fwd(folds[id(d.output)], h, B, t, phases=phases, want_raw=True, out_f32=True)
@@ -721,6 +735,14 @@ def discriminator_forward(model, x: Tensor, dtype: torch.dtype, folds: Dict[int,
     return results, ctx
 
 
+def first_layer_input(sub: dict, f: Folded, B: int, dtype: torch.dtype) -> Tensor:
+    """The im2col rows of a period stack's first layer when the forward ran it fused (inputs[0] is None): reflect pad +
+    unfold of the saved fp32 input - in the backward pass, off the forward's critical path."""
+    x, p, t = sub["x0"], sub["phases"], sub["ts"][0]
+    src = ops.reflect_pad_right(x, t * p, dtype)
+    return unfold_input(f, src, B, t, p)
+
+
 def split_disc_batch(results: List, ctx: DiscCtx, idx: Sequence[int], n_first: int):
     """A forward over the concatenation [first n_first samples | rest] for the sub-discriminators `idx` ->
     (feature maps of the first part, of the second part, per-sub contexts of the first part for a backward through
@@ -732,7 +754,9 @@ def split_disc_batch(results: List, ctx: DiscCtx, idx: Sequence[int], n_first: i
         res_a[i] = [fm[:n_first] for fm in results[i]]
         res_b[i] = [fm[n_first:] for fm in results[i]]
         sub = dict(ctx.subs[i])
-        sub["inputs"] = [t[:n_first] for t in sub["inputs"]]
+        sub["inputs"] = [t[:n_first] if t is not None else None for t in sub["inputs"]]
+        if "x0" in sub:
+            sub["x0"] = sub["x0"][:n_first]
         if "x_scale" in sub:
             sub["x_scale"] = sub["x_scale"][:n_first]
         sub_a[i] = sub
@@ -749,7 +773,7 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
     Returns d/dx fp32 [B,T,C] when want_input_grad.  `side`: optional extra stream for the full-rate scale
     discriminator (see discriminator_forward)."""
     B, T, Cc, dtype, folds = ctx.B, ctx.T, ctx.C, ctx.dtype, ctx.folds
-    dev = next(sub for sub in ctx.subs if sub is not None)["inputs"][0].device
+    dev = next(sub for sub in ctx.subs if sub is not None)["inputs"][1].device
     if plan is not None and want_weight_grad:
         ws = plan                                 # caller zeroes the arena and runs plan.backward() after its passes
     else:
@@ -777,7 +801,8 @@ def discriminator_backward(model, ctx: DiscCtx, dlogits: Sequence[Optional[Tenso
             for j in reversed(range(len(convs))):
                 f = folds[id(convs[j])]
                 if want_weight_grad:
-                    _wgrad(f, inputs[j], g, B, ts[j], ts[j + 1], ws, phases=phases)
+                    xin = inputs[j] if inputs[j] is not None else first_layer_input(sub, f, B, dtype)
+                    _wgrad(f, xin, g, B, ts[j], ts[j + 1], ws, phases=phases)
                 if j == 0:
                     if want_input_grad:
                         dxin = _dgrad(f, g, B, ts[1], ts[0], phases=phases, out_f32=True)

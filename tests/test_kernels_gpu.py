@@ -456,3 +456,28 @@ def test_tcgen05_engine_variants_in_a_child_process(env):
                        env=child_env, capture_output=True, text=True, timeout=900,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+@pytest.mark.parametrize("geom", [(2, 1600, 2, 3, 1, 2), (3, 1601, 11, 3, 1, 2), (2, 640, 5, 5, 3, 2)], ids=["p2", "p11_odd", "p5_k5s3"])
+def test_period_first_layer_fused(geom):
+    """stg_period_first_layer (reflect pad + period view + conv + bias + LeakyReLU in one launch) against an fp64
+    F.pad(reflect) + Conv2d on bf16-rounded operands."""
+    from ste_gan_b200 import ops
+    B, T, p, k, s, pad = geom
+    C, co = 8, 32
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, C, generator=gen)
+    w = torch.randn(co, C, k, generator=gen) / (C * k) ** 0.5
+    bias = torch.randn(co, generator=gen)
+    Kp = (k * C + 7) // 8 * 8
+    wf = torch.zeros(co, Kp)
+    wf[:, :k * C] = w.permute(0, 2, 1).reshape(co, k * C)           # q = j*C + c
+    y, h_out = ops.period_first_layer(x.cuda(), wf.cuda().bfloat16(), bias.cuda(), period=p, c_out=co, k=k, stride=s, pad=pad)
+    xb, wb = x.bfloat16().double(), w.bfloat16().double()
+    t_pad = T + (p - T % p)
+    xp = F.pad(xb.transpose(1, 2), (0, t_pad - T), mode="reflect")   # [B,C,t_pad]
+    x4 = xp.view(B, C, t_pad // p, p)
+    ref = F.leaky_relu(F.conv2d(x4, wb.unsqueeze(-1), bias.double(), stride=(s, 1), padding=(pad, 0)), 0.1)   # [B,co,Ho,p]
+    assert ref.shape[2] == h_out
+    ref = ref.permute(0, 2, 3, 1).reshape(B, h_out * p, co)
+    assert rel_l2(y.float().cpu(), ref) < 5e-3      # bf16 output rounding
