@@ -42,7 +42,6 @@ using namespace tc;
 
 constexpr int TM = 128;        // rows per CTA tile
 constexpr int KC = 64;         // channels per K chunk (128 B of bf16)
-constexpr int A_BYTES = TM * KC * 2;
 constexpr int MAX_STAGES = 8;
 constexpr int ACC_COLS = 256;  // TMEM column distance between the two accumulator buffers
 constexpr int SUB = 32;        // staged epilogue: columns per sub-tile (64-byte rows, SWIZZLE_64B)
@@ -144,7 +143,6 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& q) {
 }
 // Branch-free activation forms keep the unrolled epilogue small enough for the instruction cache (a per-element
 // switch with tanhf inlined 32x made the epilogue body ~50 KB and instruction-fetch bound).
-__device__ __forceinline__ float slope_of(int act) { return act == STG_ACT_RELU ? 0.f : (act == STG_ACT_LEAKY ? 0.1f : 1.f); }
 __device__ __forceinline__ float fast_tanh(float x) {
   const float t = __expf(-2.f * fabsf(x));
   return copysignf(__fdividef(1.f - t, 1.f + t), x);
@@ -512,7 +510,6 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
     }
   } else if (warp == 1) {
     // ===== MMA issuer, tap windows (warp-uniform control flow) =====
-    const bool lead = lane == 0;
     const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
     int s = 0, acc_i = 0; uint32_t phs = 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
@@ -1251,8 +1248,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     p.n_tiles = (int)n_tiles;
     const int max_pairs = sm_count() / 2;
     const int n_pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[2];
     cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, true);
@@ -1265,8 +1261,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);

@@ -282,11 +282,9 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const StgFoldItem* __re
   }
 }
 
-// Row form of the fold (forward pack only - the tcgen05 data-gradient reads it too): one block per output channel
-// stages the v row in shared memory (one coalesced read), reduces ||v||, and writes scale plus the k rows
-// wf[j][co][:] (coalesced; the transposition (ci, j) -> (j, ci) happens in shared memory).  Replaces the
-// scale + 32x32-tile pack pair, whose v reads were strided by k.
-constexpr int FOLD_ROW_MAX = 4096;
+// Row form of the fold (forward pack only - the tcgen05 data-gradient reads it too) and of its backward: one WARP per
+// output channel (weight row), see fold_row_warp below.  Replaced the scale + 32x32-tile pack pair, whose v reads were
+// strided by k, and a block-per-row version that transposed (ci, j) -> (j, ci) through shared memory.
 #ifndef STG_FOLD_RPW
 #define STG_FOLD_RPW 1
 #endif
@@ -294,28 +292,9 @@ constexpr int FOLD_RPW = STG_FOLD_RPW;     // rows per warp: 1 = one table searc
                                            // left the discriminator's 7.8 K rows with 13 warps per SM, each a serial chain of rows)
 constexpr int FOLD_RPB = 8 * FOLD_RPW;   // rows per block: one table search per warp / block, the item is then walked forward
 // Both row kernels are pure HBM streams (v 4 B + pack 2 B per weight; dw + v + dv 12 B per weight).  The first versions
-// moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.  Now: 16-byte
-// accesses wherever the row is 16-byte aligned, all loads of a row issued before the first use, FOLD_RPB rows per block.
+// moved 4 bytes per thread per instruction with one block per row: ~1 KB in flight per block, 1.2-1.4 TB/s.
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool al16_host(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-template <typename T>
-__device__ __forceinline__ void store8(T* dst, const float* w);
-template <>
-__device__ __forceinline__ void store8<float>(float* dst, const float* w) {
-  *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(w[4], w[5], w[6], w[7]);
-}
-template <>
-__device__ __forceinline__ void store8<bf16>(bf16* dst, const float* w) {
-  uint32_t q[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
-    q[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
-}
 
 // ---- warp-per-row fast path (plain convs: groups == pack groups == 1, k in {1, 3, 5}, c_in % 4 == 0, 16-byte aligned).
 // 4 input channels x k taps of the torch layout v[co][ci][j] are exactly k consecutive float4: a lane reads them, has the

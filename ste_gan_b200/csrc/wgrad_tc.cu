@@ -334,8 +334,7 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(gx, gy, nsplit);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   cfg.attrs = at; cfg.numAttrs = tc_launch_attrs(at, false);
