@@ -72,6 +72,24 @@ class FlatParams:
         ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay, grad_scale)
 
 
+def generator_grad_buckets(offsets: Dict[str, int], numel: int, nblk: int) -> list:
+    """Gradient buckets of the generator, back to front (= the order its backward completes them): GBlocks [k2, n) +
+    last_conv | [k1, k2) | [0, k1) + gblocks.0 + embeddings, cut at the GBlock boundaries nearest to 1/3 and 2/3 of the
+    parameters (base model: GB3..GB8 | GB2 | GB1, ~8 M parameters each).  `offsets`: parameter name -> offset into the flat
+    buffer (registration order).  Each entry: (first GBlock, end GBlock, first conv, end conv of
+    passes.generator_convs, flat-gradient slice)."""
+    first = [offsets[next(nm for nm in offsets if nm.startswith(f"gblocks.{i + 1}."))] for i in range(nblk)]
+    last = offsets[next(nm for nm in offsets if nm.startswith("last_conv."))]
+    near = lambda frac, lo: min(range(lo, nblk), key=lambda i: abs(first[i] - frac * numel), default=nblk)
+    k1 = near(1.0 / 3.0, 1)            # the GBlock boundary nearest to 1/3 ...
+    k2 = near(2.0 / 3.0, k1)           # ... and to 2/3 of the parameters
+    n_conv = 5 * nblk + 2
+    cut = lambda i: first[i] if i < nblk else last
+    return [(k2, nblk, 1 + 5 * k2, n_conv, (cut(k2), numel)),
+            (k1, k2, 1 + 5 * k1, 1 + 5 * k2, (cut(k1), cut(k2))),
+            (0, k1, 0, 1 + 5 * k1, (0, cut(k1)))]
+
+
 class GanTrainer:
     def __init__(self, net_g, net_d, precision: str = "bf16", lr: float = 2e-4, w_td: float = W_TD_DEFAULT,
                  w_fm: float = W_FM_DEFAULT, loss_adversarial: bool = True, loss_multi_td: bool = True,
@@ -111,19 +129,11 @@ class GanTrainer:
         # [k2, n) + last_conv | [k1, k2) | [0, k1) + gblocks.0 + embeddings, cut where the parameter count from the
         # front passes 1/3 and 2/3 (base model: GB3..GB8 | GB2 | GB1, ~8 M parameters each).  Each entry:
         # (first GBlock, end GBlock, first conv, end conv of passes.generator_convs, flat-gradient slice).
-        nblk = len(list(net_g.gblocks)) - 1
-        first = [self.G.offsets[next(nm for nm in self.G.offsets if nm.startswith(f"gblocks.{i + 1}."))] for i in range(nblk)]
-        k1 = next((i for i in range(1, nblk) if first[i] * 3 >= self.G.numel), nblk)
-        k2 = next((i for i in range(k1, nblk) if first[i] * 3 >= 2 * self.G.numel), nblk)
-        k1, k2 = min(k1, nblk), min(max(k2, k1), nblk)
-        n_conv = 5 * nblk + 2
-        cut = lambda i: first[i] if i < nblk else self.G.offsets[next(nm for nm in self.G.offsets if nm.startswith("last_conv."))]
-        self.g_buckets = [(k2, nblk, 1 + 5 * k2, n_conv, (cut(k2) if k2 < nblk else cut(nblk), self.G.numel)),
-                          (k1, k2, 1 + 5 * k1, 1 + 5 * k2, (cut(k1), cut(k2) if k2 < nblk else cut(nblk))),
-                          (0, k1, 0, 1 + 5 * k1, (0, cut(k1)))]
+        self.g_buckets = generator_grad_buckets(self.G.offsets, self.G.numel, len(list(net_g.gblocks)) - 1)
         # without a data-parallel group there is nothing to overlap: one bucket (one fold-backward launch, one graph)
         if (grad_buckets if grad_buckets is not None else (3 if self.reducer.enabled else 1)) == 1:
-            self.g_buckets = [(0, nblk, 0, n_conv, (0, self.G.numel))]
+            nblk = len(list(net_g.gblocks)) - 1
+            self.g_buckets = [(0, nblk, 0, 5 * nblk + 2, (0, self.G.numel))]
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None

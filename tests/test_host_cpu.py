@@ -122,3 +122,28 @@ def test_precision_context():
     assert ste_gan_b200.get_precision() == "fp32"
     with pytest.raises(ValueError):
         ste_gan_b200.set_precision("fp8")
+
+
+def test_generator_gradient_buckets():
+    """The three data-parallel gradient buckets of the base generator: contiguous, back to front, ~1/3 of the
+    parameters each, cut at GBlock boundaries (trainer.generator_grad_buckets; flat offsets 16-byte aligned as in
+    FlatParams)."""
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    from ste_gan_b200.trainer import generator_grad_buckets
+    torch.manual_seed(0)
+    g = EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8)
+    offsets, off = {}, 0
+    for nm, p in g.named_parameters():
+        offsets[nm] = off
+        off += (p.numel() + 3) // 4 * 4
+    nblk = len(list(g.gblocks)) - 1
+    b = generator_grad_buckets(offsets, off, nblk)
+    assert len(b) == 3 and nblk == 8
+    # GBlocks: [2, 8) | [1, 2) | [0, 1)   convs of passes.generator_convs: gblocks.0 = 0, GBlock i = 1 + 5 i .. , last_conv = 41
+    assert [(x[0], x[1]) for x in b] == [(2, 8), (1, 2), (0, 1)]
+    assert [(x[2], x[3]) for x in b] == [(11, 42), (6, 11), (0, 6)]
+    # flat slices: back to front, contiguous, covering everything, roughly balanced
+    assert b[0][4][1] == off and b[2][4][0] == 0 and b[0][4][0] == b[1][4][1] and b[1][4][0] == b[2][4][1]
+    assert b[0][4][0] == offsets["gblocks.3.conv1.2.bias"] or b[0][4][0] == min(v for k, v in offsets.items() if k.startswith("gblocks.3."))
+    sizes = [x[4][1] - x[4][0] for x in b]
+    assert all(0.25 * off < s < 0.42 * off for s in sizes), sizes
