@@ -287,6 +287,10 @@ int stg_debug_set_trace(void* buf);
 /* debug hardware probe (csrc/debug_probe.cu): one 128x64x64 MMA whose A operand starts `shift` rows into a TMA-loaded
  * [rows_a][64] bf16 tile, descriptor base-offset field = base_off; out = float [128][64]. */
 int stg_debug_rowshift(const void* x, const void* w, int rows_a, int shift, int base_off, float* out, stg_stream_t stream);
+/* Host-only diagnostic: row classes of the tcgen05 convolution for t_dst output rows per sample (128-row tiles + binary
+ * tail tiles that gather one row slice of several samples).  out[3c..3c+2] = rows per sample, first row, tiles per sample
+ * (0: one tile per 128/rows samples); returns the number of classes (<= 4).  No GPU needed. */
+int stg_debug_row_classes(int t_dst, int* out);
 
 #ifdef __cplusplus
 }

@@ -913,6 +913,31 @@ static int pick_bn_mn(int cd_g, int groups, int64_t row_tiles, int n_stages) {
   return best;
 }
 
+// Row classes of a sample of t_dst rows (TcP::n_cls): whole 128-row tiles, then a binary tail (64 / 32 / 16 / 8 rows) whose
+// tiles gather the same row slice of 128 / seg samples; at most 4 classes - the last one covers whatever is left.
+// seg: rows per sample, h0: first row, tps: tiles per sample (0: one tile per 128 / seg samples).
+struct RowCls { int seg, h0, tps; };
+static int row_classes(int t_dst, RowCls* rc) {
+  int n = 0;
+  const int full = t_dst / TM;
+  int r = t_dst % TM, h = full * TM;
+  if (full > 0) rc[n++] = RowCls{TM, 0, full};
+  while (r > 0) {
+    int seg = 8;
+    while (seg * 2 <= r) seg *= 2;                               // largest power of two <= r (at least 8)
+    if (n == 3 || r < 8) { seg = 8; while (seg < r) seg *= 2; }  // last slot: one class covers what is left
+    rc[n++] = seg >= TM ? RowCls{TM, h, 1} : RowCls{seg, h, 0};
+    h += seg; r -= seg < r ? seg : r;
+  }
+  return n;
+}
+int debug_row_classes(int t_dst, int* out) {   // out[3 * c + {0, 1, 2}] = seg, h0, tps
+  RowCls rc[4];
+  const int n = row_classes(t_dst, rc);
+  for (int c = 0; c < n; ++c) { out[3 * c] = rc[c].seg; out[3 * c + 1] = rc[c].h0; out[3 * c + 2] = rc[c].tps; }
+  return n;
+}
+
 static void tile_geometry(const StgConv* d, int* pack, int* nh, int* n_res, int* tiles_m) {
   *pack = d->phases;
   *nh = TM / d->phases;
@@ -1024,22 +1049,12 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
                       (!d->post_shift || (rows_per_phase % 2) == 0);
 
   // ---- row classes (see TcP::n_cls): 128-row tiles + a binary tail whose tiles gather several samples
-  struct RowCls { int seg, h0, tps; };
   RowCls rc[4];
   int n_rc = 0;
   int64_t cls_tiles = 0;
   static const int env_cls = getenv("STG_ROWCLS") ? atoi(getenv("STG_ROWCLS")) : 1;
   if (env_cls && staged && d->phases == 1 && p.n_res == 1 && d->stride == 1) {
-    const int full = d->t_dst / TM;
-    int r = d->t_dst % TM, h = full * TM;
-    if (full > 0) rc[n_rc++] = RowCls{TM, 0, full};
-    while (r > 0) {
-      int seg = 8;
-      while (seg * 2 <= r) seg *= 2;                                  // largest power of two <= r (at least 8)
-      if (n_rc == 3 || r < 8) { seg = 8; while (seg < r) seg *= 2; }  // last slot: one class covers what is left
-      rc[n_rc++] = seg >= TM ? RowCls{TM, h, 1} : RowCls{seg, h, 0};
-      h += seg; r -= seg < r ? seg : r;
-    }
+    n_rc = row_classes(d->t_dst, rc);
     for (int c = 0; c < n_rc; ++c)
       cls_tiles += rc[c].tps > 0 ? (int64_t)d->n_samples * rc[c].tps : ceil_div(d->n_samples, TM / rc[c].seg);
     const int64_t classic = (int64_t)d->n_samples * p.tiles_m;

@@ -60,3 +60,10 @@ extern "C" int stg_debug_rowshift(const void* x, const void* w, int rows_a, int 
   STG_LAUNCH_CHECK();
   return STG_OK;
 }
+
+// Host-only: the row classes the tcgen05 convolution uses for a sample of t_dst rows (conv_tc.cu: row_classes).
+namespace stg { int debug_row_classes(int t_dst, int* out); }
+extern "C" int stg_debug_row_classes(int t_dst, int* out) {
+  if (t_dst < 1 || !out) return STG_EINVAL;
+  return stg::debug_row_classes(t_dst, out);
+}

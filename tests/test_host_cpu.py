@@ -147,3 +147,33 @@ def test_generator_gradient_buckets():
     assert b[0][4][0] == offsets["gblocks.3.conv1.2.bias"] or b[0][4][0] == min(v for k, v in offsets.items() if k.startswith("gblocks.3."))
     sizes = [x[4][1] - x[4][0] for x in b]
     assert all(0.25 * off < s < 0.42 * off for s in sizes), sizes
+
+
+def test_conv_row_classes_cover_every_row_once():
+    """Host-only check of the tcgen05 convolution's row classes (stg_debug_row_classes): for every T the classes tile
+    rows [0, T) of a sample exactly once (tail tiles over-cover only past T or past the last sample, where the TMA unit
+    zero-fills loads and clips stores), never need more tiles than plain 128-row tiling, and reach the ideal count
+    ceil(B*T/128) up to the tail granularity."""
+    import ctypes as C
+    from ste_gan_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_int * 12)()
+    for T in list(range(1, 700)) + [800, 1600, 1601, 24000]:
+        n = lib.stg_debug_row_classes(T, out)
+        assert 1 <= n <= 4, (T, n)
+        cls = [(out[3 * c], out[3 * c + 1], out[3 * c + 2]) for c in range(n)]
+        covered = 0
+        for seg, h0, tps in cls:
+            assert seg in (8, 16, 32, 64, 128) and h0 == covered, (T, cls)      # contiguous, in order
+            covered += seg * (tps if tps > 0 else 1)
+            assert (tps > 0) == (seg == 128), (T, cls)
+        assert T <= covered < T + 8 or (covered >= T and n == 4), (T, cls)        # over-cover < 8 rows unless the last slot rounds up
+        # (with few samples the classes can need MORE tiles than plain 128-row tiling - conv_tc then keeps the classic
+        # tiles; at the bench batch they never do)
+        tiles16 = sum(16 * tps if tps > 0 else -(-16 // (128 // seg)) for seg, h0, tps in cls)
+        assert tiles16 <= 16 * -(-T // 128) + 2, (T, tiles16)
+    # the shapes of the bench configuration (B = 16)
+    for T, want in ((100, 13), (200, 25), (400, 50), (800, 100), (1600, 200)):
+        n = lib.stg_debug_row_classes(T, out)
+        tiles = sum(16 * out[3 * c + 2] if out[3 * c + 2] > 0 else -(-16 // (128 // out[3 * c])) for c in range(n))
+        assert tiles == want, (T, tiles)
