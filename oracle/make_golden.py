@@ -17,6 +17,9 @@ Fixtures (all fp32, seed 0):
                       forwards, so the spectral-norm power iteration is pinned).
   train_step_b1.pt    BASELINE.json configs[0]: G + small D fwd/bwd, B=1, T=100:
                       losses, G output, per-parameter gradient norms and samples.
+  emg_encoder_tiny.pt (no CUDA path yet) a model_size=32, 2-layer EMG encoder in eval
+                      mode: state_dict, two inputs (25 and 111 frames), both outputs, the speech-unit and
+                      phoneme losses and the gradient of their sum w.r.t. the EMG input.
 """
 import os
 import sys
@@ -169,5 +172,50 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def emg_encoder_fixture():
+    """the frozen EMG encoder (eval mode) and the two losses taken through it, from the reference
+    modules (ste_gan/models/emg_encoder.py, ste_gan/losses/emg_encoder_loss.py).  torch 2.11's nn.TransformerEncoder
+    .forward rejects the reference's custom layer (it reads self_attn.batch_first; the reference pins torch 2.0.1), so
+    the encoder's own layers are applied one after the other - exactly what 2.0.1 does for a mask-free stack."""
+    from ste_gan.models.emg_encoder import EMGEncoderTransformer
+    torch.manual_seed(0)
+    enc = EMGEncoderTransformer(8, 256, 48, model_size=32, num_extra_res_blocks=3, num_transformer_layers=2).eval()
+    for mod in enc.modules():           # non-trivial BatchNorm statistics (a trained checkpoint has them)
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5); mod.bias.data.normal_(0, 0.2)
+    with torch.no_grad():               # weights on the fp16 grid: the fixture stores them as halves (0.9 MB instead of 2.4)
+        for t in list(enc.parameters()) + [b for b in enc.buffers() if b.is_floating_point()]:
+            t.copy_(t.half().float())
+
+    def fwd(x):
+        h = enc.conv_blocks(x.transpose(1, 2)).transpose(1, 2)
+        h = enc.w_raw_in(h).transpose(0, 1)
+        for layer in enc.transformer.layers:
+            h = layer(h)
+        h = h.transpose(0, 1)
+        return enc.w_out(h), enc.w_aux(h)
+
+    cases = []
+    for i, shape in enumerate(((2, 400, 8), (1, 1776, 8))):       # 25 frames; 111 frames (> 100: out-of-range positions)
+        g = torch.Generator().manual_seed(20 + i)
+        x = torch.tanh(torch.randn(*shape, generator=g)).requires_grad_(True)
+        units, phon = fwd(x)
+        tgt = torch.randn(units.shape, generator=g)
+        ph = torch.randint(0, 48, phon.shape[:2], generator=g)
+        unit_loss = F.pairwise_distance(tgt.reshape(-1, 256), units.reshape(-1, 256)).mean()     # emg_encoder_loss.py:63-67
+        ce = F.cross_entropy(phon.transpose(1, 2), ph)                                           # :80-83
+        (dx,) = torch.autograd.grad(unit_loss + ce, x)
+        cases.append(dict(x=x.detach(), unit_target=tgt, phoneme_target=ph, units=units.detach(), phonemes=phon.detach(),
+                          unit_loss=unit_loss.detach(), phoneme_loss=ce.detach(), dx=dx))
+    torch.save(dict(state_dict={k: (v.half() if v.is_floating_point() else v.clone()) for k, v in enc.state_dict().items()}, cases=cases),
+               os.path.join(OUT, "emg_encoder_tiny.pt"))
+    print("emg_encoder_tiny.pt", sum(v.numel() for v in enc.state_dict().values()), "weights")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "emg_encoder":     # only the fixture of the section-8f row
+        emg_encoder_fixture()
+    else:
+        main()
+        emg_encoder_fixture()

@@ -103,3 +103,22 @@ def test_oracle_vs_live_reference():
         ref = d(xs)
         got = O.discriminator_forward(sdd, xs, small=True, training=False)
     assert max(O.rel_l2(a, b) for fa, fb in zip(got, ref) for a, b in zip(fa, fb)) < 1e-5
+
+
+def test_emg_encoder_oracle_matches_reference_fixture():
+    """SURVEY.md 8f rank 1 (no CUDA path yet - this pins the oracle for it): the frozen EMG encoder's forward, the
+    speech-unit / phoneme losses taken through it and the gradient of their sum w.r.t. the EMG input, against the
+    reference modules' outputs (25 frames, and 111 frames > the 100-frame relative-position range)."""
+    from oracle import emg_encoder_oracle as E
+    fx = torch.load(os.path.join(GOLD, "emg_encoder_tiny.pt"))
+    sd = {k: v.double() for k, v in fx["state_dict"].items()}      # stored as halves (the reference ran on exactly these values)
+    for case in fx["cases"]:
+        x = case["x"].double().requires_grad_(True)
+        units, phon = E.emg_encoder_forward(sd, x)
+        assert list(units.shape) == list(case["units"].shape) and list(phon.shape) == list(case["phonemes"].shape)
+        assert O.rel_l2(units, case["units"]) < 1e-5 and O.rel_l2(phon, case["phonemes"]) < 1e-5
+        ul, ce = E.encoder_losses(units, phon, case["unit_target"].double(), case["phoneme_target"])
+        assert abs(float(ul) - float(case["unit_loss"])) < 1e-5 * float(case["unit_loss"])
+        assert abs(float(ce) - float(case["phoneme_loss"])) < 1e-5 * float(case["phoneme_loss"])
+        (dx,) = torch.autograd.grad(ul + ce, x)
+        assert O.rel_l2(dx, case["dx"]) < 1e-4
