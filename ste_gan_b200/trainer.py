@@ -539,6 +539,18 @@ class GanTrainer:
         self._pending_g = phase_g()
         return self.slots
 
+    def save_checkpoint(self, directory, steps: int, epoch: int, final: bool = False) -> None:
+        """The reference's netG-/netD-/checkpoint-{steps:08d}.pt triple (train.py:421-436), optimiser state in
+        torch.optim.AdamW format - see checkpoint.py."""
+        from . import checkpoint
+        checkpoint.save_checkpoint(self, directory, steps, epoch, final)
+
+    def load_latest_checkpoint(self, directory):
+        """Resume from the newest triple in `directory` (utils/common.py:23-61), written by either loop.
+        Returns (start_epoch, steps)."""
+        from . import checkpoint
+        return checkpoint.load_latest_checkpoint(self, directory)
+
     def losses(self) -> Dict[str, float]:
         """Host read of the loss slots (synchronises)."""
         v = self.slots.tolist()

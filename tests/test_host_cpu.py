@@ -177,3 +177,63 @@ def test_conv_row_classes_cover_every_row_once():
         n = lib.stg_debug_row_classes(T, out)
         tiles = sum(16 * out[3 * c + 2] if out[3 * c + 2] > 0 else -(-16 // (128 // out[3 * c])) for c in range(n))
         assert tiles == want, (T, tiles)
+
+
+def test_checkpoint_interchange_with_torch_adamw(tmp_path):
+    """SURVEY.md 8f rank 3 (host side, CPU): the fused trainer's flat AdamW moments <-> the state_dict of the reference's
+    torch.optim.AdamW (ste_gan/utils/common.py:23-61, train.py:421-436) - both directions, file naming and the choice of
+    the latest checkpoint, the `_orig_mod.` key fix."""
+    from ste_gan_b200 import checkpoint as ck
+    from ste_gan_b200.models.discriminator import DiscriminatorSmall
+    torch.manual_seed(0)
+    net = DiscriminatorSmall(8)                       # has 1-element parameters: exercises the 16-byte aligned layout
+    params = list(net.parameters())
+    opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.8, 0.99))
+    for it in range(3):
+        for p in params:
+            p.grad = torch.randn_like(p) * 0.01
+        opt.step()
+    ref_sd = opt.state_dict()
+    shapes = [(nm, p.shape) for nm, p in net.named_parameters()]
+    offsets, off = {}, 0
+    for nm, p in net.named_parameters():              # FlatParams' layout
+        offsets[nm] = off
+        off += (p.numel() + 3) // 4 * 4
+    m, v = torch.full((off,), 7.0), torch.full((off,), 7.0)
+    step = ck.adamw_state_to_flat(ref_sd, shapes, offsets, m, v)
+    assert step == 3
+    for i, (nm, shp) in enumerate(shapes):
+        n = int(torch.Size(shp).numel())
+        assert torch.equal(m[offsets[nm]:offsets[nm] + n].view(shp), ref_sd["state"][i]["exp_avg"])
+        assert torch.equal(v[offsets[nm]:offsets[nm] + n].view(shp), ref_sd["state"][i]["exp_avg_sq"])
+    assert float(m.sum()) == pytest.approx(float(sum(s["exp_avg"].double().sum() for s in ref_sd["state"].values())), rel=1e-5)  # gaps are zero
+    back = ck.flat_to_adamw_state(shapes, offsets, m, v, step, dict(lr=2e-4))
+    opt2 = torch.optim.AdamW(params, lr=1.0)          # a fresh reference optimiser accepts the converted state ...
+    opt2.load_state_dict(back)
+    sd2 = opt2.state_dict()
+    assert sd2["param_groups"][0]["lr"] == 2e-4 and sd2["param_groups"][0]["betas"] == (0.8, 0.99)
+    for i in range(len(shapes)):
+        assert float(sd2["state"][i]["step"]) == 3.0
+        assert torch.equal(sd2["state"][i]["exp_avg"], ref_sd["state"][i]["exp_avg"])
+        assert torch.equal(sd2["state"][i]["exp_avg_sq"], ref_sd["state"][i]["exp_avg_sq"])
+    # ... and continues exactly like the original one
+    w0 = [p.detach().clone() for p in params]
+    grads = [torch.randn_like(p) * 0.01 for p in params]
+    for p, g_ in zip(params, grads):
+        p.grad = g_.clone()
+    opt.step()
+    w_ref = [p.detach().clone() for p in params]
+    with torch.no_grad():
+        for p, w in zip(params, w0):
+            p.copy_(w)
+    opt2.step()
+    assert all(torch.equal(a, b.detach()) for a, b in zip(w_ref, params))
+    # file naming / latest selection / key fix
+    for n in (100, 2500, 30):
+        torch.save({}, tmp_path / f"checkpoint-{n:08d}.pt")
+    torch.save({}, tmp_path / "checkpoint-final.pt")
+    assert ck.latest_step(tmp_path) == "00002500" and ck.latest_step(tmp_path / "nope") is None
+    fixed = ck.fix_state_dict({"_orig_mod.gblocks.0.bias": 1, "last_conv.1.bias": 2})
+    assert list(fixed) == ["gblocks.0.bias", "last_conv.1.bias"]
+    with pytest.raises(ValueError):
+        ck.adamw_state_to_flat(ref_sd, shapes[:-1], offsets, m, v)

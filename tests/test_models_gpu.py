@@ -372,3 +372,33 @@ def test_no_cpu_fallback():
     su, sess, _ = O.synthetic_batch(1, 8)
     with pytest.raises(RuntimeError):
         g(su, sess, torch.zeros(1, dtype=torch.long))
+
+
+def test_checkpoint_round_trip_through_reference_format(tmp_path):
+    """save_checkpoint writes the reference's netG- / netD- / checkpoint-{steps:08d}.pt triple (train.py:421-436) with the
+    optimiser state as torch.optim.AdamW state_dicts; a fresh trainer resumes from it (utils/common.py:23-61) with
+    identical parameters, moments and step counters, and the next step gives the same losses."""
+    from ste_gan_b200.trainer import GanTrainer
+    batch = [t.cuda() for t in O.synthetic_batch(2, 64, seed=21)]
+    g1, d1 = _fresh_nets(); g2, d2 = _fresh_nets()
+    t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="fp32")
+    for _ in range(2):
+        t1.step(*batch)
+    t1.save_checkpoint(tmp_path, steps=2, epoch=1)
+    assert sorted(f.name for f in tmp_path.iterdir()) == ["checkpoint-00000002.pt", "netD-00000002.pt", "netG-00000002.pt"]
+    ck = torch.load(tmp_path / "checkpoint-00000002.pt")
+    assert set(ck) == {"epoch", "steps", "optG", "optD"} and float(ck["optG"]["state"][0]["step"]) == 2.0
+    # the reference's own optimiser class loads it
+    ref_opt = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(p.shape)) for p in g1.parameters()], lr=1.0)
+    ref_opt.load_state_dict(ck["optG"])
+    t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="fp32")
+    t2.step(*[torch.zeros_like(b) for b in batch])            # (state that the load must overwrite)
+    assert t2.load_latest_checkpoint(tmp_path) == (1, 2)
+    for a, b in ((t1.G, t2.G), (t1.D, t2.D)):
+        assert torch.equal(a.flat, b.flat) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and int(a.step) == int(b.step)
+    for k, v in d1.state_dict().items():                      # buffers too (spectral-norm u / v)
+        assert torch.equal(v, d2.state_dict()[k]), k
+    t1.step(*batch); t2.step(*batch)
+    a, b = t1.losses(), t2.losses()
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
