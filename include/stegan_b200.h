@@ -262,9 +262,12 @@ int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int d
                         stg_stream_t stream);
 
 /* torch.optim.AdamW (ste_gan/constants.py:57; train.py:80-81,199,267) over one flat fp32 buffer.
- * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable. */
-int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream);
+ * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable.
+ * lr_dev (device float[1], or NULL to use the host value `lr`): the learning rate is read on the device at execution
+ * time, so the reference's per-epoch ExponentialLR(.999) (train.py:98-104,470-472) changes it between replays of a
+ * captured graph. */
+int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+              float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream);
 
 /* diagnostics */
 const char* stg_strerror(int code);

@@ -74,6 +74,37 @@ def _normed_weight(sd: StateDict, prefix: str, training: bool) -> Tensor:
 
 
 # --------------------------------------------------------------------------
+# activations with an injected sign pattern (parity tests only)
+# --------------------------------------------------------------------------
+class _ActWithMask(torch.autograd.Function):
+    """relu / leaky_relu whose BACKWARD takes the slope pattern from `mask` (True: slope 1) instead of from
+    the sign of its own input.  ReLU / LeakyReLU have a discontinuous derivative: a pre-activation that is
+    zero to within rounding takes the other slope in a lower-precision implementation and changes every
+    gradient upstream of it by a finite amount.  Feeding the implementation-under-test's OWN sign pattern
+    into the oracle's backward makes both differentiate the same piecewise-linear branch, so the remaining
+    gradient difference is arithmetic only and every tensor can be held to the stated tolerance."""
+
+    @staticmethod
+    def forward(ctx, x, mask, slope):
+        ctx.save_for_backward(mask)
+        ctx.slope = slope
+        return torch.where(x > 0, x, x * slope)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * torch.where(mask, torch.ones((), dtype=g.dtype), torch.full((), ctx.slope, dtype=g.dtype)), None, None
+
+
+def _act(x: Tensor, slope: float, mask: Optional[Tensor]) -> Tensor:
+    """relu (slope 0) / leaky_relu(slope); with `mask` (bool, same shape) the backward uses its pattern."""
+    if mask is None:
+        return F.relu(x) if slope == 0.0 else F.leaky_relu(x, slope)
+    assert mask.shape == x.shape, (mask.shape, x.shape)
+    return _ActWithMask.apply(x, mask, slope)
+
+
+# --------------------------------------------------------------------------
 # generator (models/generator.py:78-162, layers/conv.py:29-84)
 # --------------------------------------------------------------------------
 def _wnconv1d(sd: StateDict, prefix: str, x: Tensor, dilation: int = 1, padding: int = 0) -> Tensor:
@@ -81,20 +112,23 @@ def _wnconv1d(sd: StateDict, prefix: str, x: Tensor, dilation: int = 1, padding:
     return F.conv1d(x, w, sd[prefix + "bias"], dilation=dilation, padding=padding)
 
 
-def gblock_forward(sd: StateDict, prefix: str, x: Tensor, upsample: int) -> Tensor:
+def gblock_forward(sd: StateDict, prefix: str, x: Tensor, upsample: int,
+                   masks: Optional[Sequence[Tensor]] = None) -> Tensor:
     """GBlock.forward (layers/conv.py:82-84).  Sequential indices shift by one
-    when an nn.Upsample is present (layers/conv.py:38-56)."""
+    when an nn.Upsample is present (layers/conv.py:38-56).
+    masks (parity tests): sign patterns of the block's four ReLU inputs, see _ActWithMask."""
     o = 1 if upsample > 1 else 0
     up = (lambda t: F.interpolate(t, scale_factor=float(upsample), mode="nearest")) if upsample > 1 else (lambda t: t)
+    m = masks if masks is not None else [None] * 4
     # conv1 = ReLU -> [Up] -> WNConv(k3,d1,p1) -> ReLU -> WNConv(k3,d3,p3)   (conv.py:38-53)
-    h = _wnconv1d(sd, f"{prefix}conv1.{1 + o}.", up(F.relu(x)), dilation=1, padding=1)
-    h = _wnconv1d(sd, f"{prefix}conv1.{3 + o}.", F.relu(h), dilation=3, padding=3)
+    h = _wnconv1d(sd, f"{prefix}conv1.{1 + o}.", up(_act(x, 0.0, m[0])), dilation=1, padding=1)
+    h = _wnconv1d(sd, f"{prefix}conv1.{3 + o}.", _act(h, 0.0, m[1]), dilation=3, padding=3)
     # res1 = [Up] -> WNConv(k1) on the un-ReLU'd input                         (conv.py:55-56)
     r = _wnconv1d(sd, f"{prefix}res1.{o}.", up(x))
     h = h + r                                                                 # conv.py:83
     # conv2 = ReLU -> WNConv(k3,d9,p9) -> ReLU -> WNConv(k3,d27,p27)           (conv.py:61-75)
-    c = _wnconv1d(sd, f"{prefix}conv2.1.", F.relu(h), dilation=9, padding=9)
-    c = _wnconv1d(sd, f"{prefix}conv2.3.", F.relu(c), dilation=27, padding=27)
+    c = _wnconv1d(sd, f"{prefix}conv2.1.", _act(h, 0.0, m[2]), dilation=9, padding=9)
+    c = _wnconv1d(sd, f"{prefix}conv2.3.", _act(c, 0.0, m[3]), dilation=27, padding=27)
     return h + c                                                              # conv.py:84
 
 
@@ -106,9 +140,11 @@ def generator_upsamples(speech_feature_type: str = "SPEECH_UNITS") -> List[int]:
 
 def generator_forward(sd: StateDict, speech_units: Tensor, session_ids: Tensor,
                       speaking_mode_ids: Optional[Tensor] = None,
-                      speech_feature_type: str = "SPEECH_UNITS") -> Tensor:
+                      speech_feature_type: str = "SPEECH_UNITS",
+                      masks: Optional[Sequence] = None) -> Tensor:
     """EMGGeneratorGanTTS.forward (models/generator.py:140-162):
-    [B,T,D] units (+ session / speaking-mode embeddings) -> [B,16T,8] in (-1,1)."""
+    [B,T,D] units (+ session / speaking-mode embeddings) -> [B,16T,8] in (-1,1).
+    masks (parity tests): [4 masks per GBlock] * 8 + [mask of last_conv's ReLU], [B,C,T] bool."""
     x = speech_units
     T = x.shape[1]
     if "session_embeddings.weight" in sd:                                     # generator.py:143-146
@@ -120,8 +156,8 @@ def generator_forward(sd: StateDict, speech_units: Tensor, session_ids: Tensor,
     x = x.transpose(1, 2)                                                     # generator.py:154
     x = _wnconv1d(sd, "gblocks.0.", x)                                        # generator.py:119
     for i, up in enumerate(generator_upsamples(speech_feature_type)):         # generator.py:121-130
-        x = gblock_forward(sd, f"gblocks.{i + 1}.", x, up)
-    x = _wnconv1d(sd, "last_conv.1.", F.relu(x), padding=1)                   # generator.py:133-137
+        x = gblock_forward(sd, f"gblocks.{i + 1}.", x, up, masks[i] if masks is not None else None)
+    x = _wnconv1d(sd, "last_conv.1.", _act(x, 0.0, masks[-1] if masks is not None else None), padding=1)   # generator.py:133-137
     return torch.tanh(x.transpose(1, 2))                                      # generator.py:157-160
 
 
@@ -139,7 +175,8 @@ FULL_S_LAYERS = lambda c: [(c, 128, 15, 1, 7, 1), (128, 128, 41, 2, 20, 4), (128
                            (1024, 1024, 41, 1, 20, 16), (1024, 1024, 5, 1, 2, 1)]
 
 
-def disc_p_forward(sd: StateDict, prefix: str, x: Tensor, period: int, small: bool, training: bool) -> List[Tensor]:
+def disc_p_forward(sd: StateDict, prefix: str, x: Tensor, period: int, small: bool, training: bool,
+                   masks: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
     """DiscriminatorSmallerP.forward / DiscriminatorP.forward (discriminator.py:84-93 / :34-43).
     x is [B,C,T].  Reflect pad on the right by period - T % period (always >= 1)."""
     layers = (SMALL_P_LAYERS if small else FULL_P_LAYERS)(x.shape[1])
@@ -148,20 +185,23 @@ def disc_p_forward(sd: StateDict, prefix: str, x: Tensor, period: int, small: bo
     fmaps = []
     for j, (_, _, k, s, p, _) in enumerate(layers):
         w = _normed_weight(sd, f"{prefix}layers.{j}.", training)
-        x = F.leaky_relu(F.conv2d(x, w, sd[f"{prefix}layers.{j}.bias"], stride=(s, 1), padding=(p, 0)), 0.1)
+        x = _act(F.conv2d(x, w, sd[f"{prefix}layers.{j}.bias"], stride=(s, 1), padding=(p, 0)), 0.1,
+                 masks[j] if masks is not None else None)
         fmaps.append(x)
     w = _normed_weight(sd, f"{prefix}output.", training)
     fmaps.append(F.conv2d(x, w, sd[f"{prefix}output.bias"], padding=(1, 0)))
     return fmaps
 
 
-def disc_s_forward(sd: StateDict, prefix: str, x: Tensor, small: bool, training: bool) -> List[Tensor]:
+def disc_s_forward(sd: StateDict, prefix: str, x: Tensor, small: bool, training: bool,
+                   masks: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
     """DiscriminatorSmallerS.forward / DiscriminatorS.forward (discriminator.py:61-67 / :113-119)."""
     layers = (SMALL_S_LAYERS if small else FULL_S_LAYERS)(x.shape[1])
     fmaps = []
     for j, (_, _, k, s, p, g) in enumerate(layers):
         w = _normed_weight(sd, f"{prefix}layers.{j}.", training)
-        x = F.leaky_relu(F.conv1d(x, w, sd[f"{prefix}layers.{j}.bias"], stride=s, padding=p, groups=g), 0.1)
+        x = _act(F.conv1d(x, w, sd[f"{prefix}layers.{j}.bias"], stride=s, padding=p, groups=g), 0.1,
+                 masks[j] if masks is not None else None)
         fmaps.append(x)
     w = _normed_weight(sd, f"{prefix}output.", training)
     fmaps.append(F.conv1d(x, w, sd[f"{prefix}output.bias"], padding=1))
@@ -169,15 +209,18 @@ def disc_s_forward(sd: StateDict, prefix: str, x: Tensor, small: bool, training:
 
 
 def discriminator_forward(sd: StateDict, x: Tensor, small: bool = True, training: bool = True,
-                          num_multi_pool: int = 5, num_multi_scale: int = 3) -> List[List[Tensor]]:
+                          num_multi_pool: int = 5, num_multi_scale: int = 3,
+                          masks: Optional[Sequence[Sequence[Tensor]]] = None) -> List[List[Tensor]]:
     """DiscriminatorSmall.forward / Discriminator.forward (discriminator.py:144-155 / :180-191).
-    x is [B,T,C]; returns 8 lists of feature maps with the logits last."""
+    x is [B,T,C]; returns 8 lists of feature maps with the logits last.
+    masks (parity tests): per sub-discriminator, the sign pattern of every LeakyReLU output (reference layout)."""
     x = x.transpose(1, 2)
     results = []
+    mk = lambda i: masks[i] if masks is not None else None
     for i in range(num_multi_pool):
-        results.append(disc_p_forward(sd, f"multi_pooled_disc.{i}.", x, PRIME_RATIOS[i], small, training))
+        results.append(disc_p_forward(sd, f"multi_pooled_disc.{i}.", x, PRIME_RATIOS[i], small, training, mk(i)))
     for i in range(num_multi_scale):
-        results.append(disc_s_forward(sd, f"multi_scale_disc.{i}.", x, small, training))
+        results.append(disc_s_forward(sd, f"multi_scale_disc.{i}.", x, small, training, mk(num_multi_pool + i)))
         x = F.avg_pool1d(x, kernel_size=4, stride=2, padding=1)              # discriminator.py:140,153
     return results
 
@@ -269,19 +312,23 @@ def is_buffer_key(sd: StateDict, k: str) -> bool:
 
 def losses_and_grads(sd_g: StateDict, sd_d: StateDict, speech_units: Tensor, session_ids: Tensor,
                      x_real: Tensor, small: bool = True, speech_feature_type: str = "SPEECH_UNITS",
-                     d_lr_step=None) -> Dict[str, object]:
+                     d_lr_step=None, masks: Optional[Dict[str, object]] = None,
+                     speaking_mode_ids: Optional[Tensor] = None) -> Dict[str, object]:
     """One iteration of train.py:165-268 up to (and excluding) the optimizer
     arithmetic, returning every consumed quantity.  `d_lr_step(sd_d, grads)` -
     if given - is applied between the D and G phases (train.py:199) so that
     the G phase sees the updated discriminator, as in the reference.
-    Spectral-norm buffers in `sd_d` advance 4 times (4 training forwards)."""
+    Spectral-norm buffers in `sd_d` advance 4 times (4 training forwards).
+    masks (parity tests, see _ActWithMask): optional sign patterns under the keys "g" (generator_forward),
+    "d_fake_det", "d_real", "d_fake" (discriminator_forward of that pass)."""
+    masks = masks or {}
     g = {k: (v.detach().clone().requires_grad_(True)) for k, v in sd_g.items()}
     d = {k: (v if is_buffer_key(sd_d, k) else v.detach().clone().requires_grad_(True)) for k, v in sd_d.items()}
     out: Dict[str, object] = {}
-    x_pred = generator_forward(g, speech_units, session_ids, None, speech_feature_type)     # train.py:182
+    x_pred = generator_forward(g, speech_units, session_ids, speaking_mode_ids, speech_feature_type, masks.get("g"))   # train.py:182
     out["x_pred"] = x_pred.detach()
-    d_fake_det = discriminator_forward(d, x_pred.detach(), small)                           # :190
-    d_real = discriminator_forward(d, x_real, small)                                        # :191
+    d_fake_det = discriminator_forward(d, x_pred.detach(), small, masks=masks.get("d_fake_det"))   # :190
+    d_real = discriminator_forward(d, x_real, small, masks=masks.get("d_real"))              # :191
     loss_d = lsgan_d_loss(d_fake_det, d_real)                                               # :192-196
     dparams = [k for k in d if not is_buffer_key(sd_d, k)]
     dgrads = torch.autograd.grad(loss_d, [d[k] for k in dparams])                           # :198
@@ -292,7 +339,7 @@ def losses_and_grads(sd_g: StateDict, sd_d: StateDict, speech_units: Tensor, ses
     if d_lr_step is not None:                                                               # :199
         with torch.no_grad():
             d_lr_step(d, out["grad_d"])
-    d_fake = discriminator_forward(d, x_pred, small)                                        # :206
+    d_fake = discriminator_forward(d, x_pred, small, masks=masks.get("d_fake"))              # :206
     d_real2 = discriminator_forward(d, x_real, small)                                       # :207
     loss_adv = lsgan_g_loss(d_fake)                                                         # :209-211
     td, td_parts = multi_td_loss(x_real, x_pred)                                            # :215

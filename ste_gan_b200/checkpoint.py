@@ -100,7 +100,9 @@ def save_checkpoint(trainer, directory, steps: int, epoch: int, final: bool = Fa
     cpu = lambda sd: OrderedDict((k, t.detach().cpu().clone()) for k, t in sd.items())
     torch.save(cpu(trainer.net_g.state_dict()), d / f"netG-{tag}.pt")
     torch.save(cpu(trainer.net_d.state_dict()), d / f"netD-{tag}.pt")
-    hyper = dict(lr=trainer.lr)
+    # `initial_lr` is what torch.optim.lr_scheduler writes into every param group; the reference re-creates
+    # ExponentialLR(..., last_epoch=start_epoch) right after loading (train.py:98-104), which REQUIRES the key
+    hyper = dict(lr=trainer.lr, initial_lr=trainer.base_lr)
     opt = lambda net, fp: flat_to_adamw_state(_shapes(net), fp.offsets, fp.m, fp.v, int(fp.step.item()), hyper)
     torch.save(dict(epoch=epoch, steps=steps, optG=opt(trainer.net_g, trainer.G), optD=opt(trainer.net_d, trainer.D)),
                d / f"checkpoint-{tag}.pt")
@@ -126,5 +128,9 @@ def load_latest_checkpoint(trainer, directory) -> Tuple[int, int]:
         lr = ck[key]["param_groups"][0].get("lr")
         if lr is not None:
             trainer.lr = float(lr)                      # (ExponentialLR has been applied to it, train.py:98-104)
-    trainer._d_folded = False                           # the discriminator's packed operands are stale (G re-folds every step)
+        if ck[key]["param_groups"][0].get("initial_lr") is not None:
+            trainer.base_lr = float(ck[key]["param_groups"][0]["initial_lr"])
+    # the discriminator's packed operands are stale, and a captured phase-D graph does not re-pack them (it reuses the
+    # packs of the previous step's phase G): re-pack eagerly, now (G re-packs at the start of every step)
+    trainer.refold()
     return int(ck["epoch"]), int(ck["steps"])

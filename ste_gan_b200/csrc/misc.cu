@@ -120,8 +120,10 @@ __global__ void axpy_kernel(float* __restrict__ y, const T* __restrict__ x, floa
 __global__ void step_inc_kernel(int64_t* step) { *step += 1; }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                    float* __restrict__ v, int64_t n, float lr_host,
+                                                    const float* __restrict__ lr_dev, float b1, float b2, float eps,
                                                     float wd, const int64_t* __restrict__ step, float gscale) {
+  const float lr = lr_dev ? *lr_dev : lr_host;   // device-resident learning rate: a schedule changes it without re-capturing graphs
   const float t = (float)(*step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -281,12 +283,12 @@ extern "C" int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, i
   return STG_OK;
 }
 
-extern "C" int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                         float eps, float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream) {
+extern "C" int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
+                         float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream) {
   if (!p || !g || !m || !v || !step_count) return STG_EINVAL;
   step_inc_kernel<<<1, 1, 0, S_>>>(step_count);
   STG_LAUNCH_CHECK();
-  adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_count, grad_scale);
+  adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step_count, grad_scale);
   STG_LAUNCH_CHECK();
   return STG_OK;
 }

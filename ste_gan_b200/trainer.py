@@ -65,7 +65,7 @@ class FlatParams:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2,
+    def adamw(self, lr, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2,
               grad_scale: float = 1.0) -> None:
         """torch.optim.AdamW(lr=2e-4, betas=(.8,.99)) - ste_gan/constants.py:57.  grad_scale = 1/world
         turns the all-reduced gradient SUM into the data-parallel mean inside the kernel."""
@@ -96,7 +96,7 @@ class GanTrainer:
                  loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None):
         self.net_g, self.net_d = net_g, net_d
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.lr, self.w_td, self.w_fm = lr, w_td, w_fm
+        self.w_td, self.w_fm = w_td, w_fm
         self.use_adv, self.use_td, self.use_fm = loss_adversarial, loss_multi_td, loss_feat_match
         self.G, self.D = FlatParams(net_g), FlatParams(net_d)
         # packed operands, gradient arenas and multi-tensor fold tables at fixed addresses (after the re-homing above)
@@ -106,6 +106,12 @@ class GanTrainer:
         self.reducer = GradReducer(group)
         dev = self.G.flat.device
         self.device = dev
+        # The learning rate lives on the DEVICE (next to FlatParams.step): the AdamW kernels read it when they run, so
+        # the reference's per-epoch ExponentialLR(.999) (train.py:98-104,470-472) and the lr restored from a checkpoint
+        # take effect in captured CUDA graphs as well.  `trainer.lr = x` updates both copies.
+        self.base_lr = float(lr)                  # ExponentialLR's `initial_lr` (checkpoint interchange)
+        self._lr = float(lr)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.slots = torch.zeros(8, device=dev, dtype=torch.float32)
         self.d_folds: Optional[Dict[int, passes.Folded]] = None
         self._d_persist: Dict[int, passes.Folded] = {}
@@ -134,6 +140,21 @@ class GanTrainer:
         if (grad_buckets if grad_buckets is not None else (3 if self.reducer.enabled else 1)) == 1:
             nblk = len(list(net_g.gblocks)) - 1
             self.g_buckets = [(0, nblk, 0, 5 * nblk + 2, (0, self.G.numel))]
+
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.flush()                              # a deferred generator AdamW of the previous step keeps ITS learning rate
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)               # stream-ordered; graphs replayed after this read the new value
+
+    def scheduler_step(self, gamma: float = 0.999) -> float:
+        """One ExponentialLR step (train.py:98-104: gamma .999, stepped once per epoch at train.py:470-472)."""
+        self.lr = self._lr * gamma
+        return self._lr
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None
@@ -306,7 +327,7 @@ class GanTrainer:
                 td_ev.record(self._aux)
         if self.use_adv:
             if update_d:
-                self.D.adamw(self.lr, grad_scale=self.reducer.grad_scale)   # train.py:199
+                self.D.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale)   # train.py:199
             refold_d = update_d or not self._d_folded
             self._d_folded = True
             if self.concurrent_d:
@@ -347,6 +368,7 @@ class GanTrainer:
                 res_f, ctx_f = passes.discriminator_forward(self.net_d, x_pred, dt, f3)
                 res_r, _ = passes.discriminator_forward(self.net_d, x_real, dt, f4)
             self.d_folds = f4
+            self._last_g_fmaps = (res_f, res_r)             # kept for the parity tests (references only)
             nd = len(res_f)
             dlog = ops.mse_const_multi([fm[-1] for fm in res_f], [1.0] * nd, self.slots, [1] * nd, 1.0, dt)   # train.py:210-211
             if self.use_fm:                                                 # train.py:259-262, one launch for all 27 maps
@@ -365,6 +387,7 @@ class GanTrainer:
         if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
         # generator backward, bucket by bucket (G.grad was zeroed in phase D and this is its only writer: overwrite)
+        self._last_gctx = self._gctx                       # kept for the parity tests (references only)
         self._gb = passes.GenBackward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
                                       overwrite_grads=True)
         self._g_bucket(0)
@@ -397,7 +420,7 @@ class GanTrainer:
         return self.reducer.all_reduce_async(self.G.grad[lo:hi]) if hi > lo else []
 
     def _phase_opt_g(self) -> None:
-        self.G.adamw(self.lr, grad_scale=self.reducer.grad_scale)           # train.py:267
+        self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale)       # train.py:267
 
     # ------------------------------------------------------------------ public API
     def step(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,
@@ -415,8 +438,11 @@ class GanTrainer:
 
     def capture(self, batch: int, frames: int, unit_dim: int = 256, hop: int = 16, channels: int = 8,
                 pipelined: Optional[bool] = None) -> None:
-        """Capture the step as CUDA graphs over static input buffers (NCCL stays outside the graphs).  Runs two eager
-        warm-up steps on the current contents of the static buffers first.
+        """Capture the step as CUDA graphs over static input buffers (NCCL stays outside the graphs).  Two eager
+        warm-up steps run first (allocator / lazy-initialisation warm-up, on all-zero inputs); the trainer's state -
+        parameters, AdamW moments and step counters, spectral-norm u / v, loss slots - is snapshotted before and
+        restored after them, so capture() leaves the training state exactly as it found it (resume-then-capture is
+        safe, and `steps` in the next checkpoint still counts real steps only).
 
         pipelined (default: whenever the discriminator passes run concurrently): phase D is captured as its five
         pieces (see _d_folds) and step_graph() software-pipelines consecutive steps: the all-reduce of the generator
@@ -430,14 +456,18 @@ class GanTrainer:
         self.flush()
         self._static = dict(
             su=torch.zeros(batch, frames, unit_dim, device=dev), sess=torch.zeros(batch, device=dev, dtype=torch.int64),
-            x_real=torch.zeros(batch, frames * hop, channels, device=dev))
+            x_real=torch.zeros(batch, frames * hop, channels, device=dev),
+            mode=torch.zeros(batch, device=dev, dtype=torch.int64) if self.net_g.use_speaking_mode_embedding else None)
         s = self._static
+        snap = self._snapshot_state()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.step(s["su"], s["sess"], s["x_real"])
+                self.step(s["su"], s["sess"], s["x_real"], s["mode"])
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore_state(snap)
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
         G = torch.cuda.CUDAGraph
@@ -468,7 +498,7 @@ class GanTrainer:
                 with torch.cuda.graph(a2, pool=pool_a):
                     self._d_real(s["x_real"])
             with torch.cuda.graph(b1, pool=pool):
-                self._g_forward(s["su"], s["sess"], None)
+                self._g_forward(s["su"], s["sess"], s["mode"])
             with torch.cuda.graph(b2, pool=pool):
                 self._d_fake()
             with torch.cuda.graph(b3, pool=pool):
@@ -481,7 +511,7 @@ class GanTrainer:
             self._d_graphs = None
             g1 = G()
             with torch.cuda.graph(g1, pool=pool):
-                self._phase_d(s["su"], s["sess"], None, s["x_real"])
+                self._phase_d(s["su"], s["sess"], s["mode"], s["x_real"])
         # phase G: one graph per generator-gradient bucket (the bucket's all-reduce is issued between them)
         g2 = [G() for _ in self.g_buckets]
         with torch.cuda.graph(g2[0], pool=pool):
@@ -494,6 +524,30 @@ class GanTrainer:
             self._phase_opt_g()
         self._graphs = (g1, g2, g3)
 
+    def _sn_buffers(self) -> list:
+        return [b for c in passes.discriminator_convs(self.net_d) if c.norm != "weight_norm" for b in (c.weight_u, c.weight_v)]
+
+    def _snapshot_state(self) -> dict:
+        return dict(flat=[(fp, fp.flat.clone(), fp.m.clone(), fp.v.clone(), fp.step.clone()) for fp in (self.G, self.D)],
+                    sn=[(b, b.clone()) for b in self._sn_buffers()], slots=self.slots.clone())
+
+    def _restore_state(self, snap: dict) -> None:
+        for fp, flat, m, v, step in snap["flat"]:
+            fp.flat.copy_(flat); fp.m.copy_(m); fp.v.copy_(v); fp.step.copy_(step)
+            fp.grad.zero_()
+        for b, val in snap["sn"]:
+            b.copy_(val)
+        self.slots.copy_(snap["slots"])
+        self.refold()
+
+    def refold(self) -> None:
+        """Re-pack the weight-normed discriminator convs from the current weights, eagerly.  Inside the captured step the
+        discriminator packs are refreshed right after ITS optimiser step (phase G) and phase D of the next step reuses
+        them, so anything that changes the weights from outside - a checkpoint load, the state restore of capture() -
+        must re-pack here.  (The generator re-packs at the start of every step.)"""
+        self.d_plan.fold()
+        self._d_folded = True
+
     def flush(self) -> None:
         """Complete a pipelined step: wait for the generator-gradient all-reduce and run the generator optimiser."""
         if self._pending_g is not None:
@@ -501,13 +555,18 @@ class GanTrainer:
             self._pending_g = None
             self._graphs[2].replay()
 
-    def step_graph(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor) -> Tensor:
+    def step_graph(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,
+                   speaking_mode_ids: Optional[Tensor] = None) -> Tensor:
         """Replay the captured step; inputs may be pinned-host or device tensors (copied into the static buffers).
         With a pipelined capture the generator optimiser of this step is deferred into the next call (or flush())."""
         s = self._static
         s["su"].copy_(speech_units, non_blocking=True)
         s["sess"].copy_(session_ids, non_blocking=True)
         s["x_real"].copy_(x_real, non_blocking=True)
+        if s["mode"] is not None:
+            if speaking_mode_ids is None:
+                raise ValueError("step_graph: this generator uses speaking-mode embeddings - pass speaking_mode_ids")
+            s["mode"].copy_(speaking_mode_ids, non_blocking=True)
         g1, g2, g3 = self._graphs
         def phase_g() -> list:
             handles = []

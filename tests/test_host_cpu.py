@@ -207,9 +207,14 @@ def test_checkpoint_interchange_with_torch_adamw(tmp_path):
         assert torch.equal(m[offsets[nm]:offsets[nm] + n].view(shp), ref_sd["state"][i]["exp_avg"])
         assert torch.equal(v[offsets[nm]:offsets[nm] + n].view(shp), ref_sd["state"][i]["exp_avg_sq"])
     assert float(m.sum()) == pytest.approx(float(sum(s["exp_avg"].double().sum() for s in ref_sd["state"].values())), rel=1e-5)  # gaps are zero
-    back = ck.flat_to_adamw_state(shapes, offsets, m, v, step, dict(lr=2e-4))
+    back = ck.flat_to_adamw_state(shapes, offsets, m, v, step, dict(lr=2e-4 * 0.999 ** 2, initial_lr=2e-4))
     opt2 = torch.optim.AdamW(params, lr=1.0)          # a fresh reference optimiser accepts the converted state ...
     opt2.load_state_dict(back)
+    # ... and the reference's resume path can re-create its scheduler on it (train.py:98-104:
+    # ExponentialLR(opt, gamma=.999, last_epoch=start_epoch) raises KeyError without `initial_lr` in the param groups)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt2, gamma=0.999, last_epoch=2)
+    assert sched.base_lrs == [2e-4] and opt2.param_groups[0]["lr"] == pytest.approx(2e-4 * 0.999 ** 2)
+    opt2.param_groups[0]["lr"] = 2e-4
     sd2 = opt2.state_dict()
     assert sd2["param_groups"][0]["lr"] == 2e-4 and sd2["param_groups"][0]["betas"] == (0.8, 0.99)
     for i in range(len(shapes)):

@@ -152,65 +152,101 @@ def _flat_rel_l2(mine: dict, ref: dict) -> float:
 
 # LeakyReLU / ReLU have a discontinuous derivative: a pre-activation that is zero to within the arithmetic's
 # rounding gets the other slope ("sign flip") and changes the gradient of everything upstream of it by a
-# finite amount.  tools/sn_probe.py + tools/grad_probe.py measured: ONE flipped element out of 4.1e5 in
-# multi_scale_disc.0 (fp32 vs the fp64 oracle) moves that stack's first-layer weight gradient by 1.7e-3
-# although every feature map agrees to 2e-6; in bf16 ~0.25 % of the elements flip, which shows up as 5-8 %
-# on d(loss)/d(feature map) and - because the synthetic x_real is WHITE noise, so nothing averages out - as
-# 3-7 % on the 8 first-layer weight tensors of the real pass.  The criterion of BASELINE.json (gradients
-# within 1e-4 / 2e-2) is therefore applied to the gradient of each network as a whole and to every tensor
-# that has no flipped element upstream; tensors behind a flip get the bound below ("Parity").
-FLIP_BOUND = {"fp32": 5e-3, "bf16": 1e-1}
+# finite amount (tools/sn_probe.py, tools/grad_probe.py: ONE flipped element out of 4.1e5 moves a first-layer
+# weight gradient by 1.7e-3 in fp32; in bf16 ~0.25 % of the elements flip).  Round 1 loosened the bound for
+# tensors behind a flip; now the ORACLE is made flip-aware instead: its backward takes the sign pattern of every
+# ReLU / LeakyReLU from the CUDA path's own saved activations (oracle._ActWithMask), so both differentiate the
+# same piecewise-linear branch and EVERY gradient tensor is held to the north_star tolerance (1e-4 / 2e-2).
+def disc_masks(fmaps, d):
+    """sign patterns of a CUDA discriminator pass (channels-last feature maps) in the reference layout"""
+    from ste_gan_b200 import passes
+    out = []
+    for (kind, sub), fm in zip(passes.disc_subnets(d), fmaps):
+        out.append([passes.to_reference_layout(a.float().cpu(), kind, getattr(sub, "period", 1)) > 0 for a in fm[:-1]])
+    return out
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_train_step_losses_and_grads_vs_oracle(prec):
-    """One fused train step (B=2, T=100) against the oracle: G output, every loss term, the gradient w.r.t.
-    every parameter of G (through D, TD and FM) and of D."""
+def gen_masks(gctx):
+    """sign patterns of the generator's ReLU inputs from the saved (post-ReLU) activations of its forward"""
+    cl = lambda t: t.float().cpu().transpose(1, 2) > 0
+    out = []
+    for s in gctx.blocks:
+        xa = s["x_act"][:, ::2] if s["up"] > 1 else s["x_act"]       # rows are duplicated where the block upsamples
+        out.append([cl(xa), cl(s["a1"]), cl(s["h_act"]), cl(s["a3"])])
+    out.append(cl(gctx.y_last_act))
+    return out
+
+
+def run_step_vs_oracle(g, d, batch, prec, small=True, speaking_mode_ids=None, speech_feature_type="SPEECH_UNITS"):
+    """One fused train step against the flip-aware oracle: G output, every feature map of the three discriminator
+    passes that carry gradients, every loss term, and the gradient of EVERY parameter tensor of G and D."""
     from ste_gan_b200 import passes
     from ste_gan_b200.trainer import GanTrainer
-    g, d = _fresh_nets()
     sd_g, sd_d = cpu_sd(g), cpu_sd(d)
-    su, sess, x_real = O.synthetic_batch(2, 100, seed=3)
+    su, sess, x_real = batch
+    tol = TOL[prec]
+    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
+    mode = speaking_mode_ids.cuda() if speaking_mode_ids is not None else None
+    tr._phase_d(su.cuda(), sess.cuda(), mode, x_real.cuda())
+    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
+    fm_fake_det, fm_real = tr._last_d_fmaps[:2]
+    tr._phase_g(x_real.cuda(), update_d=False)
+    fm_fake = tr._last_g_fmaps[0]
+    masks = dict(g=gen_masks(tr._last_gctx), d_fake_det=disc_masks(fm_fake_det, d), d_real=disc_masks(fm_real, d),
+                 d_fake=disc_masks(fm_fake, d))
     # the oracle is evaluated in float64: both the reference (fp32) and this library approximate the same function
     f64 = lambda sd: {k: v.double() for k, v in sd.items()}
-    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=True)
-    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
-    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
-    tol = TOL[prec]
+    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=small, masks=masks,
+                             speaking_mode_ids=speaking_mode_ids, speech_feature_type=speech_feature_type)
     assert O.rel_l2(tr.x_pred, ref["x_pred"]) < tol
-    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
-    # feature maps of both D-phase passes + sign flips per sub-discriminator
     subs = passes.disc_subnets(d)
-    flipped = set()
-    for mine, theirs in zip(tr._last_d_fmaps[:2], (ref["d_fake_det"], ref["d_real"])):
+    n_flip = 0
+    for mine, theirs in ((fm_fake_det, ref["d_fake_det"]), (fm_real, ref["d_real"]), (fm_fake, ref["d_fake"])):
         for di, (fm_m, fm_o) in enumerate(zip(mine, theirs)):
             kind, sub = subs[di]
             for j, (a, b) in enumerate(zip(fm_m, fm_o)):
                 a = passes.to_reference_layout(a.float().cpu(), kind, getattr(sub, "period", 1))
                 assert O.rel_l2(a, b) < tol, (di, j)
-                if j + 1 < len(fm_m) and int(((a > 0) != (b > 0)).sum()) > 0:
-                    flipped.add(di)
-    tr._phase_g(x_real.cuda(), update_d=False)
+                if j + 1 < len(fm_m):
+                    n_flip += int(((a > 0) != (b > 0)).sum())
     L = tr.losses()
-    for mine, theirs in (("loss_d", "loss_d"), ("loss_adv", "loss_adv"), ("loss_fm", "loss_fm"), ("loss_td", "loss_td"),
-                         ("loss_g", "loss_g")):
-        assert abs(L[mine] - float(ref[theirs])) <= tol * max(1.0, abs(float(ref[theirs]))), (mine, L[mine], float(ref[theirs]))
+    for k in ("loss_d", "loss_adv", "loss_fm", "loss_td", "loss_g"):
+        assert abs(L[k] - float(ref[k])) <= tol * max(1.0, abs(float(ref[k]))), (k, L[k], float(ref[k]))
     gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
     flat_d, flat_g = _flat_rel_l2(gd, ref["grad_d"]), _flat_rel_l2(gg, ref["grad_g"])
     bad = {k: O.rel_l2(gd[k], ref["grad_d"][k]) for k in gd}
     bad_g = {k: O.rel_l2(gg[k], ref["grad_g"][k]) for k in gg}
-    print(f"[{prec}] grad_d flat {flat_d:.3e} worst {max(bad.values()):.3e} ({max(bad, key=bad.get)}); "
+    print(f"[{prec} B={su.shape[0]}] grad_d flat {flat_d:.3e} worst {max(bad.values()):.3e} ({max(bad, key=bad.get)}); "
           f"grad_g flat {flat_g:.3e} worst {max(bad_g.values()):.3e} ({max(bad_g, key=bad_g.get)}); "
-          f"sub-discriminators with flipped activations: {sorted(flipped)}")
+          f"discriminator activations whose sign differs from the unmasked oracle forward: {n_flip}")
     assert flat_d < tol and flat_g < tol
-    prefixes = [f"multi_pooled_disc.{i}." for i in range(len(d.multi_pooled_disc))] + \
-               [f"multi_scale_disc.{i}." for i in range(len(d.multi_scale_disc))]
-    for k, e in bad.items():
-        di = next(i for i, p in enumerate(prefixes) if k.startswith(p))
-        assert e < (FLIP_BOUND[prec] if di in flipped else tol), (k, e, di in flipped)
-    # G: in fp32 no generator ReLU flips at this seed; in bf16 the bound applies to the worst tensor
-    for k, e in bad_g.items():
+    for k, e in {**bad, **bad_g}.items():
         assert e < tol, (k, e)
+    return tr, ref
+
+
+@pytest.mark.parametrize("batch", [2, 16], ids=["B2", "B16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_train_step_losses_and_grads_vs_oracle(prec, batch):
+    """One fused train step at T=100 - B=2 and the BENCHMARKED configuration B=16 (BASELINE.json configs[1]; the
+    batched [fake | real] discriminator stacks then run 32 samples) - against the flip-aware oracle, every tensor held
+    to 1e-4 (fp32) / 2e-2 (bf16)."""
+    g, d = _fresh_nets()
+    run_step_vs_oracle(g, d, O.synthetic_batch(batch, 100, seed=3), prec)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_speaking_mode_embedding_train_step(prec):
+    """use_speaking_mode_embedding=True (generator.py:104-107,148-151): 256 + 64 + 64 = 384 input channels, two
+    embedding tables, both with gradients."""
+    from ste_gan_b200.models.discriminator import DiscriminatorSmall
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, use_speaking_mode_embedding=True, channels=256))
+    d = seeded(lambda: DiscriminatorSmall(8))
+    su, sess, x_real = O.synthetic_batch(3, 40, seed=12)
+    mode = torch.tensor([2, 0, 1])
+    tr, ref = run_step_vs_oracle(g, d, (su, sess, x_real), prec, speaking_mode_ids=mode)
+    assert "speaking_mode_embeddings.weight" in ref["grad_g"]
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -224,25 +260,10 @@ def test_mfcc_generator_variant(prec):
     from ste_gan_b200.trainer import GanTrainer
     g = seeded(lambda: EMGGeneratorGanTTS("MFCCS", 25, 17, 8, channels=256))
     d = seeded(lambda: DiscriminatorSmall(8))
-    sd_g, sd_d = cpu_sd(g), cpu_sd(d)
     su, sess, x_real = O.synthetic_batch(2, 100, seed=6, unit_dim=25, hop=8)
     assert x_real.shape[1] == 800
-    f64 = lambda sd: {k: v.double() for k, v in sd.items()}
-    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=True, speech_feature_type="MFCCS")
-    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
-    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
-    tol = TOL[prec]
+    tr, _ = run_step_vs_oracle(g, d, (su, sess, x_real), prec, speech_feature_type="MFCCS")
     assert tr.x_pred.shape == (2, 800, 8)
-    assert O.rel_l2(tr.x_pred, ref["x_pred"]) < tol
-    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
-    tr._phase_g(x_real.cuda(), update_d=False)
-    L = tr.losses()
-    for k in ("loss_d", "loss_adv", "loss_fm", "loss_td", "loss_g"):
-        assert abs(L[k] - float(ref[k])) <= tol * max(1.0, abs(float(ref[k]))), (k, L[k], float(ref[k]))
-    gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
-    assert _flat_rel_l2(gd, ref["grad_d"]) < tol and _flat_rel_l2(gg, ref["grad_g"]) < tol
-    for k in ("gblocks.0.weight_v", "gblocks.0.weight_g", "gblocks.0.bias", "session_embeddings.weight"):
-        assert O.rel_l2(gg[k], ref["grad_g"][k]) < tol, k
 
 
 def test_full_discriminator_train_step_bf16():
@@ -252,19 +273,7 @@ def test_full_discriminator_train_step_bf16():
     from ste_gan_b200.models.generator import EMGGeneratorGanTTS
     g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, channels=128))
     _, d = _fresh_nets(small=False)
-    sd_g, sd_d = cpu_sd(g), cpu_sd(d)
-    su, sess, x_real = O.synthetic_batch(2, 64, seed=8)
-    f64 = lambda sd: {k: v.double() for k, v in sd.items()}
-    ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=False)
-    tr = GanTrainer(g.cuda(), d.cuda(), precision="bf16")
-    tr._phase_d(su.cuda(), sess.cuda(), None, x_real.cuda())
-    gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
-    tr._phase_g(x_real.cuda(), update_d=False)
-    L = tr.losses()
-    for k in ("loss_d", "loss_adv", "loss_fm", "loss_td", "loss_g"):
-        assert abs(L[k] - float(ref[k])) <= 2e-2 * max(1.0, abs(float(ref[k]))), (k, L[k], float(ref[k]))
-    gg = {n: p.grad.detach().cpu() for n, p in g.named_parameters()}
-    assert _flat_rel_l2(gd, ref["grad_d"]) < 2e-2 and _flat_rel_l2(gg, ref["grad_g"]) < 2e-2
+    run_step_vs_oracle(g, d, O.synthetic_batch(2, 64, seed=8), "bf16", small=False)
 
 
 def test_autograd_dropin_matches_fused_step():
@@ -326,11 +335,7 @@ def test_cuda_graph_step_matches_eager():
     g1, d1 = _fresh_nets(); g2, d2 = _fresh_nets()
     t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="bf16")
     t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="bf16")
-    t2.capture(2, 100)
-    # capture() ran warm-up steps on zero inputs: bring t1 to the same state
-    z = (torch.zeros_like(su), torch.zeros_like(sess), torch.zeros_like(x_real))
-    for _ in range(2):
-        t1.step(z[0], z[1], z[2])
+    t2.capture(2, 100)               # (its warm-up steps leave no trace in the training state: see the test below)
     for _ in range(2):
         t1.step(su, sess, x_real)
         t2.step_graph(su, sess, x_real)
@@ -364,6 +369,104 @@ def test_cuda_graph_step_unpipelined_matches_pipelined():
     for k in a:
         assert abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
     assert O.rel_l2(t2.G.flat, t1.G.flat) < 3e-3 and O.rel_l2(t2.D.flat, t1.D.flat) < 3e-3      # (see above)
+
+
+def _state_of(tr):
+    return [t.clone() for fp in (tr.G, tr.D) for t in (fp.flat, fp.m, fp.v, fp.step)] + [b.clone() for b in tr._sn_buffers()]
+
+
+def test_capture_preserves_training_state():
+    """capture() warms up with two real steps on zero inputs; parameters, AdamW moments, step counters and the
+    spectral-norm u / v must come out of it bit-identical (resume-then-capture is safe)."""
+    from ste_gan_b200.trainer import GanTrainer
+    batch = [t.cuda() for t in O.synthetic_batch(2, 64, seed=31)]
+    g, d = _fresh_nets()
+    tr = GanTrainer(g.cuda(), d.cuda(), precision="bf16")
+    tr.step(*batch)
+    before = _state_of(tr)
+    tr.capture(2, 64)
+    torch.cuda.synchronize()
+    for a, b in zip(before, _state_of(tr)):
+        assert torch.equal(a, b)
+    assert int(tr.G.step) == 1 and int(tr.D.step) == 1
+
+
+def test_learning_rate_is_read_on_the_device_under_graphs():
+    """`trainer.lr = x` after capture() reaches the AdamW kernels inside the replayed graphs (ExponentialLR per epoch,
+    train.py:470-472; lr restored by load_latest_checkpoint).  lr = 0 with weight decay off the table (decay = 1 - lr*wd)
+    must freeze both networks exactly; restoring it must move them again."""
+    from ste_gan_b200.trainer import GanTrainer
+    batch = [t.cuda() for t in O.synthetic_batch(2, 64, seed=32)]
+    g, d = _fresh_nets()
+    tr = GanTrainer(g.cuda(), d.cuda(), precision="bf16")
+    tr.capture(2, 64)
+    tr.step_graph(*batch); tr.flush()
+    tr.lr = 0.0
+    g0, d0 = tr.G.flat.clone(), tr.D.flat.clone()
+    tr.step_graph(*batch); tr.flush()
+    assert torch.equal(tr.G.flat, g0) and torch.equal(tr.D.flat, d0)
+    assert tr.scheduler_step(0.5) == 0.0
+    tr.lr = 2e-4
+    assert abs(tr.scheduler_step(0.999) - 2e-4 * 0.999) < 1e-12 and abs(float(tr.lr_dev) - 2e-4 * 0.999) < 1e-10
+    tr.step_graph(*batch); tr.flush()
+    assert not torch.equal(tr.G.flat, g0) and not torch.equal(tr.D.flat, d0)
+
+
+def test_adamw_graph_replay_follows_exponential_lr():
+    """The fused AdamW kernel with a device-resident lr, captured ONCE and replayed over two 'epochs' of three steps,
+    against torch.optim.AdamW + ExponentialLR(gamma) (train.py:80-81,98-104,470-472; constants.py:57)."""
+    from ste_gan_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    n, gamma = 4096, 0.9
+    p0 = torch.randn(n, generator=gen)
+    grads = [torch.randn(n, generator=gen) for _ in range(6)]
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=2e-4, betas=(0.8, 0.99))
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma)
+    p, g = p0.clone().cuda(), torch.zeros(n).cuda()
+    m, v = torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    step = torch.zeros(1, dtype=torch.int64).cuda()
+    lr = torch.full((1,), 2e-4).cuda()
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.adamw(p, g, m, v, step, lr)           # warm-up launch, undone below
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    p.copy_(p0); m.zero_(); v.zero_(); step.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.adamw(p, g, m, v, step, lr)
+    for epoch in range(2):
+        for i in range(3):
+            g.copy_(grads[3 * epoch + i]); graph.replay()
+            ref_p.grad = grads[3 * epoch + i].clone(); opt.step()
+        sched.step()
+        lr.fill_(sched.get_last_lr()[0])
+    assert int(step) == 6 and O.rel_l2(p, ref_p) < 1e-6
+
+
+def test_checkpoint_resume_into_captured_graphs(tmp_path):
+    """capture -> load_latest_checkpoint -> step_graph runs on the LOADED weights (the discriminator packs are re-packed
+    eagerly by the load: a captured phase-D graph would otherwise reuse the packs of the pre-load weights)."""
+    from ste_gan_b200.trainer import GanTrainer
+    batch = [t.cuda() for t in O.synthetic_batch(2, 64, seed=33)]
+    g1, d1 = _fresh_nets(); g2, d2 = _fresh_nets(); g3, d3 = _fresh_nets()
+    t1 = GanTrainer(g1.cuda(), d1.cuda(), precision="bf16")
+    for _ in range(3):
+        t1.step(*batch)
+    t1.lr = 1.5e-4
+    t1.save_checkpoint(tmp_path, steps=3, epoch=1)
+    t2 = GanTrainer(g2.cuda(), d2.cuda(), precision="bf16")      # graphs captured BEFORE the load
+    t2.capture(2, 64)
+    assert t2.load_latest_checkpoint(tmp_path) == (1, 3) and t2.lr == 1.5e-4
+    t3 = GanTrainer(g3.cuda(), d3.cuda(), precision="bf16")      # eager reference from the same checkpoint
+    t3.load_latest_checkpoint(tmp_path)
+    t2.step_graph(*batch); t2.flush()
+    t3.step(*batch)
+    a, b = t2.losses(), t3.losses()
+    for k in a:
+        assert abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    assert O.rel_l2(t2.G.flat, t3.G.flat) < 3e-3 and O.rel_l2(t2.D.flat, t3.D.flat) < 3e-3
+    assert int(t2.G.step) == 4 and int(t2.D.step) == 4
 
 
 def test_no_cpu_fallback():
@@ -402,3 +505,74 @@ def test_checkpoint_round_trip_through_reference_format(tmp_path):
     a, b = t1.losses(), t2.losses()
     for k in a:
         assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("batch", [1, 4], ids=["B1", "B4"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_generate_30s_utterance_vs_oracle(nets, prec, batch):
+    """BASELINE.json configs[3], the BENCHMARKED inference shape: 1500 unit frames -> 24000 x 8 EMG samples (row classes,
+    tile counts and the column-tile choice all change with T), batch 1 and the batch-4 throughput mode; the module
+    path (`generate`) and - in bf16 - the serving engine's CUDA-graph replay that bench.py times."""
+    import ste_gan_b200
+    from ste_gan_b200.inference import UtteranceGenerator
+    g = nets[0].cuda()
+    su, sess, _ = O.synthetic_batch(batch, 1500, seed=30 + batch)
+    with torch.no_grad():
+        ref = O.generator_forward(cpu_sd(g), su, sess)
+    assert ref.shape == (batch, 24000, 8)
+    with ste_gan_b200.precision(prec):
+        y = g.generate(su.cuda(), sess.cuda(), torch.zeros(batch, dtype=torch.long).cuda())
+    assert y.shape == ref.shape and O.rel_l2(y, ref) < TOL[prec]
+    worst = max(O.rel_l2(y[b], ref[b]) for b in range(batch))          # per utterance, not only in aggregate
+    assert worst < TOL[prec], worst
+    ug = UtteranceGenerator(g, prec)
+    for _ in range(2):                                                   # capture, then a replay
+        y2 = ug.generate_graph(su.pin_memory(), sess.pin_memory())
+    assert O.rel_l2(y2, ref) < TOL[prec]
+
+
+def test_generate_from_data_dict(nets):
+    """EMGGenerator.generate_from_data_dict (generator.py:52-75): a dataset item (2-D units, scalar ids) -> [16T, C] on the
+    CPU; a batched item keeps its batch dimension."""
+    import ste_gan_b200
+    from ste_gan_b200.constants import DataType
+    g = nets[0].cuda()
+    su, sess, _ = O.synthetic_batch(1, 37, seed=41)
+    item = {DataType.SPEECH_UNITS: su[0], DataType.SESSION_INDEX: sess[0], DataType.SPEAKING_MODE_INDEX: torch.tensor(0)}
+    with torch.no_grad():
+        ref = O.generator_forward(cpu_sd(g), su, sess)
+    with ste_gan_b200.precision("fp32"):
+        y = g.generate_from_data_dict(item, torch.device("cuda"))
+    assert y.device.type == "cpu" and y.shape == (37 * 16, 8)
+    assert O.rel_l2(y, ref[0]) < 1e-4
+    batched = {DataType.SPEECH_UNITS: su, DataType.SESSION_INDEX: sess, DataType.SPEAKING_MODE_INDEX: torch.zeros(1, dtype=torch.long)}
+    with ste_gan_b200.precision("fp32"):
+        yb = g.generate_from_data_dict(batched, torch.device("cuda"))
+    assert yb.shape == (37 * 16, 8) and O.rel_l2(yb, ref[0]) < 1e-4     # squeeze(0) of a batch of one (generator.py:75)
+
+
+@pytest.mark.parametrize("window,pad", [(9, True), (5, True), (9, False)])
+def test_average_filter_module(window, pad):
+    """AverageFilter (layers/average_filter.py:10-28): reflect pad window//2 + AvgPool1d(window, stride 1)."""
+    import torch.nn.functional as F
+    from ste_gan_b200.layers.average_filter import AverageFilter
+    x = torch.randn(3, 8, 203, generator=torch.Generator().manual_seed(5))
+    af = AverageFilter(8, window, pad_signal=pad)
+    y = af(x.cuda())
+    ref = O.average_filter(x, window) if pad else F.avg_pool1d(x, kernel_size=window, stride=1)
+    assert y.shape == ref.shape and O.rel_l2(y, ref) < 1e-6
+    with pytest.raises(RuntimeError):
+        af(x)                                                            # no CPU path
+
+
+def test_data_parallel_matches_single_process():
+    """N ranks through the bucketed, pipelined graph step == one process on the global batch (tools/dp_check.py under
+    torchrun, 2 GPUs, fp32).  Skipped on single-GPU boxes; the log of the last multi-GPU run is kept under profiles/."""
+    import subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tools", "dp_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "dp_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
