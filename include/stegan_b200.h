@@ -220,6 +220,9 @@ int stg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
 /* out = dy * act'(y), the derivative expressed through the activation OUTPUT y (tanh of models/generator.py:160);
  * dy, y float32, out in `dtype`. */
 int stg_act_bwd(const float* dy, const float* y, int mode, int64_t n, int dtype, void* out, stg_stream_t stream);
+/* out[r (dup: 2r and 2r+1)] = relu(src[r]) over rows of C elements: the ReLU -> nn.Upsample(2) prologue of a GBlock used
+ * on its own (layers/conv.py:38-40); inside the models the previous convolution's epilogue produces it. */
+int stg_relu_rows(const void* src, int dtype, int64_t rows, int C, int dup, void* out, stg_stream_t stream);
 /* out[r] = in[2r] + in[2r+1] over rows of C elements (backward of nearest-upsample x2). */
 int stg_pair_sum_rows(const void* in, int64_t rows_out, int C, int dtype, void* out, stg_stream_t stream);
 int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, int64_t n, stg_stream_t stream); /* y += alpha*x */
@@ -233,6 +236,23 @@ int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, int64_t n, s
  */
 int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses, const float* grad_scale,
                 float* dx_gen, float* scratch, stg_stream_t stream);
+/* The same loss for ANY list of (win, shift) resolutions (n_res <= 8), with or without the reflect-padded windowing
+ * (TimeDomainFeatureLoss.apply_padding_windowing) and any odd average-filter window - the constructor arguments of
+ * losses/time_domain_loss.py:20-33.  The upstream gradients come from the host array grad_scale[n_res] or, when
+ * grad_scale_dev != NULL, from a DEVICE array read at execution time (no host synchronisation inside autograd). */
+int stg_td_loss_ex(const float* x_real, const float* x_gen, int B, int T, int C, int n_res, const int* wins,
+                   const int* shifts, int pad_windows, int avg_window, float* losses, const float* grad_scale,
+                   const float* grad_scale_dev, float* dx_gen, float* scratch, stg_stream_t stream);
+/* TimeDomainFeatureLoss.calculate_time_domain_features (time_domain_loss.py:57-68): x [B][T][C] -> feats [B][F][C][4] =
+ * [mean(low), sum(low^2), sum(hi^2), mean(hi)] per frame, low = avg(avg(x)), hi = |x - low|.  scratch: float[2*B*T*C]. */
+int stg_td_features(const float* x, int B, int T, int C, int win, int shift, int pad_windows, int avg_window,
+                    float* feats, float* scratch, stg_stream_t stream);
+/* frame_means / frame_power (time_domain_loss.py:43-49): mean and sum of squares per frame, [B][F][C] each (either may
+ * be NULL); window_signal (time_domain_loss.py:35-41): the frames themselves, out [B][F][C][win]. */
+int stg_frame_stats(const float* x, int B, int T, int C, int win, int shift, int pad_windows, float* mean, float* power,
+                    stg_stream_t stream);
+int stg_window_signal(const float* x, int B, int T, int C, int win, int shift, int pad_windows, float* out,
+                      stg_stream_t stream);
 /* AverageFilter (layers/average_filter.py:10-28) on `rows` independent series of length T (float32):
  * reflect pad window/2 (if pad) then mean over `window`, stride 1. */
 int stg_average_filter(const float* x, int64_t rows, int T, int window, int pad, float* out, stg_stream_t stream);

@@ -237,25 +237,28 @@ def average_filter(x: Tensor, window: int = 9) -> Tensor:
     return F.avg_pool1d(F.pad(x, (p, p), mode="reflect"), kernel_size=window, stride=1)
 
 
-def td_features(x: Tensor, win: int, shift: int) -> Tensor:
-    """calculate_time_domain_features (time_domain_loss.py:57-68). x is [B,T,C] -> [B,F,C,4]."""
-    low = average_filter(average_filter(x.transpose(1, 2))).transpose(1, 2)   # :51-55
-    hi = (x - low).abs()                                                      # :59-60
-
-    def frames(s: Tensor) -> Tensor:                                          # window_signal :35-41
-        # F.pad(x, (0,0,p,p), 'reflect') on a 3-D tensor pads the time axis (dim 1)
+def window_signal(s: Tensor, win: int, shift: int, pad: bool = True) -> Tensor:
+    """TimeDomainFeatureLoss.window_signal (time_domain_loss.py:35-41): [B,T,C] -> [B,F,C,win].
+    F.pad(x, (0,0,p,p), 'reflect') on a 3-D tensor pads the time axis (dim 1)."""
+    if pad:
         p = win // 2
         idx = torch.arange(-p, s.shape[1] + p).abs()
         idx = torch.where(idx >= s.shape[1], 2 * (s.shape[1] - 1) - idx, idx)
-        return s[:, idx, :].unfold(1, win, shift)
+        s = s[:, idx, :]
+    return s.unfold(1, win, shift)
 
-    fl, fh = frames(low), frames(hi)
+
+def td_features(x: Tensor, win: int, shift: int, pad: bool = True, avg_window: int = 9) -> Tensor:
+    """calculate_time_domain_features (time_domain_loss.py:57-68). x is [B,T,C] -> [B,F,C,4]."""
+    low = average_filter(average_filter(x.transpose(1, 2), avg_window), avg_window).transpose(1, 2)   # :51-55
+    hi = (x - low).abs()                                                      # :59-60
+    fl, fh = window_signal(low, win, shift, pad), window_signal(hi, win, shift, pad)
     return torch.stack([fl.mean(-1), (fl ** 2).sum(-1), (fh ** 2).sum(-1), fh.mean(-1)], dim=-1)  # :62-67
 
 
-def td_loss(x_real: Tensor, x_gen: Tensor, win: int, shift: int) -> Tensor:
+def td_loss(x_real: Tensor, x_gen: Tensor, win: int, shift: int, pad: bool = True, avg_window: int = 9) -> Tensor:
     """TimeDomainFeatureLoss.time_domain_loss (time_domain_loss.py:70-73)."""
-    return F.l1_loss(td_features(x_gen, win, shift), td_features(x_real, win, shift).detach())
+    return F.l1_loss(td_features(x_gen, win, shift, pad, avg_window), td_features(x_real, win, shift, pad, avg_window).detach())
 
 
 def multi_td_loss(x_real: Tensor, x_gen: Tensor) -> Tuple[Tensor, List[Tensor]]:

@@ -81,8 +81,13 @@ _SIGS = {
     "stg_cast": [_P, _I, _P, _I, _L, _P],
     "stg_act_bwd": [_P, _P, _I, _L, _I, _P, _P],
     "stg_pair_sum_rows": [_P, _L, _I, _I, _P, _P],
+    "stg_relu_rows": [_P, _I, _L, _I, _I, _P, _P],
     "stg_axpy_f32": [_P, _P, _I, _F, _L, _P],
     "stg_td_loss": [_P, _P, _I, _I, _I, _P, C.POINTER(C.c_float), _P, _P, _P],
+    "stg_td_loss_ex": [_P, _P, _I, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I, _I, _P, C.POINTER(C.c_float), _P, _P, _P, _P],
+    "stg_td_features": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "stg_frame_stats": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "stg_window_signal": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_average_filter": [_P, _L, _I, _I, _I, _P, _P],
     "stg_mse_const": [_P, _I, _L, _F, _P, _F, _P, _I, _P],
     "stg_l1_mean": [_P, _P, _I, _L, _P, _F, _P, _P],

@@ -98,26 +98,41 @@ class DiscriminatorFn(torch.autograd.Function):
         return (None, dx) + tuple(col.grads)
 
 
-class MultiTdLossFn(torch.autograd.Function):
-    """(loss_20_8, loss_51_13, loss_80_16) = TD(x_real, x_gen) - losses/time_domain_loss.py:96-103."""
+_TD_RES = ((20, 8), (51, 13), (80, 16))        # time_domain_loss.py:88-93
+
+
+class TdLossFn(torch.autograd.Function):
+    """losses[n_res] = TD(x_real, x_gen) for a list of (win, shift) resolutions - losses/time_domain_loss.py:70-73,96-103.
+    The backward hands the upstream gradients to the kernels as a DEVICE array: no host synchronisation."""
 
     @staticmethod
-    def forward(ctx, x_real, x_gen):
-        _require_cuda(x_gen, "MultiTimeDomainFeatureLoss")
+    def forward(ctx, x_real, x_gen, resolutions, pad_windows, avg_window):
+        _require_cuda(x_gen, "TimeDomainFeatureLoss")
         xr, xg = x_real.detach().contiguous().float(), x_gen.detach().contiguous().float()
-        losses = torch.zeros(3, device=xg.device, dtype=torch.float32)
-        ops.td_loss(xr, xg, losses)
+        losses = torch.zeros(len(resolutions), device=xg.device, dtype=torch.float32)
+        ops.td_loss_ex(xr, xg, resolutions, losses, pad_windows=pad_windows, avg_window=avg_window)
         ctx.save_for_backward(xr, xg)
+        ctx.cfg = (tuple(resolutions), pad_windows, avg_window)
         return losses
 
     @staticmethod
     def backward(ctx, g):
         xr, xg = ctx.saved_tensors
-        # the three partial losses share one backward; their upstream gradients are applied per resolution
+        res, pad_windows, avg_window = ctx.cfg
+        # the partial losses share one backward; their upstream gradients are applied per resolution, on the device
         dx = torch.zeros_like(xg)
-        scratch = torch.zeros(3, device=xg.device, dtype=torch.float32)
-        ops.td_loss(xr, xg, scratch, grad_scale=g.float().tolist(), dx_gen=dx)   # host read of 3 upstream scalars
-        return None, dx
+        scratch = torch.zeros(len(res), device=xg.device, dtype=torch.float32)
+        ops.td_loss_ex(xr, xg, res, scratch, pad_windows=pad_windows, avg_window=avg_window,
+                       grad_scale=g.detach().contiguous().float(), dx_gen=dx)
+        return None, dx, None, None, None
+
+
+class MultiTdLossFn:
+    """(loss_20_8, loss_51_13, loss_80_16) = TD(x_real, x_gen) - losses/time_domain_loss.py:96-103."""
+
+    @staticmethod
+    def apply(x_real, x_gen):
+        return TdLossFn.apply(x_real, x_gen, _TD_RES, True, 9)
 
 
 class SingleConvFn(torch.autograd.Function):
@@ -170,13 +185,12 @@ class GBlockFn(torch.autograd.Function):
         dtype = act_dtype()
         B, C, T = x.shape
         x_raw = x.transpose(1, 2).contiguous().to(dtype)
-        # layout plumbing for the stand-alone layer API only; inside the models relu / upsample are
-        # produced by the previous convolution's epilogue
-        x_act = torch.relu(x_raw)
-        if blk.upsample > 1:
-            x_act = x_act.repeat_interleave(blk.upsample, dim=1)
+        # stand-alone layer API only; inside the models relu / upsample are produced by the previous convolution's epilogue
+        if blk.upsample not in (1, 2):
+            raise ValueError("GBlock upsample must be 1 or 2 on this path")
+        x_act = ops.relu_rows(x_raw, blk.upsample > 1)
         folds = {id(c): passes.fold(c, dtype) for c in blk.convs().values()}
-        y, _, s = passes.gblock_fwd(blk, folds, x_raw, x_act.contiguous(), B, T, want_raw=True, want_act=False,
+        y, _, s = passes.gblock_fwd(blk, folds, x_raw, x_act, B, T, want_raw=True, want_act=False,
                                     dup_next=False)
         ctx.blk, ctx.folds, ctx.saved, ctx.B, ctx.in_dtype = blk, folds, s, B, x.dtype
         return y.to(x.dtype).transpose(1, 2)

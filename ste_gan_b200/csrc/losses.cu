@@ -12,36 +12,39 @@ __device__ __forceinline__ int reflect(int t, int T_) {
 }
 __device__ __forceinline__ float sgn(float d) { return (float)((d > 0.f) - (d < 0.f)); }
 
-// low = avg9(avg9(x)) with reflect padding at each stage; hi = |x - low|     (time_domain_loss.py:51-60)
-__global__ void td_filter_kernel(const float* __restrict__ x, int T_, int C, int64_t total, float* __restrict__ low,
+// low = avg(avg(x)) (window 2*half+1, 9 in the reference) with reflect padding at each stage; hi = |x - low|
+// (time_domain_loss.py:51-60)
+__global__ void td_filter_kernel(const float* __restrict__ x, int T_, int C, int64_t total, int half, float* __restrict__ low,
                                  float* __restrict__ hi) {
+  const float iw = 1.f / (float)(2 * half + 1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int64_t bt = i / C;
     const int t = (int)(bt % T_);
     const float* xs = x + (bt - t) * C + c;  // sample base, channel c; element t at xs[t*C]
     float s2 = 0.f;
-    for (int a = -4; a <= 4; ++a) {
+    for (int a = -half; a <= half; ++a) {
       const int u = reflect(t + a, T_);
       float s1 = 0.f;
-#pragma unroll
-      for (int q = -4; q <= 4; ++q) s1 += xs[(int64_t)reflect(u + q, T_) * C];
-      s2 += s1 * (1.f / 9.f);
+      for (int q = -half; q <= half; ++q) s1 += xs[(int64_t)reflect(u + q, T_) * C];
+      s2 += s1 * iw;
     }
-    const float lw = s2 * (1.f / 9.f);
+    const float lw = s2 * iw;
     low[i] = lw;
     hi[i] = fabsf(xs[(int64_t)t * C] - lw);
   }
 }
 
-struct TdRes { int win, shift, frames; };
+struct TdRes { int win, shift, frames, start0; };   // start0: first sample of frame 0 (-win/2 with padded windowing, else 0)
 
 // one thread per (b, f, c): 4 features of real and generated, L1, optional scatter of d/dlow, d/dhi
 __global__ void __launch_bounds__(256) td_feature_kernel(const float* __restrict__ low_r, const float* __restrict__ hi_r,
                                                          const float* __restrict__ low_g, const float* __restrict__ hi_g,
                                                          int B, int T_, int C, TdRes r, float* __restrict__ loss_slot,
-                                                         float gscale, float* __restrict__ dlow, float* __restrict__ dhi) {
+                                                         float gscale_host, const float* __restrict__ gscale_dev,
+                                                         float* __restrict__ dlow, float* __restrict__ dhi) {
   __shared__ float red[32];
+  const float gscale = gscale_dev ? *gscale_dev : gscale_host;   // upstream gradient of this resolution's loss
   const int64_t total = (int64_t)B * r.frames * C;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float inv_n = 1.f / (float)(total * 4);
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(256) td_feature_kernel(const float* __restrict
     const int64_t bf = i / C;
     const int f = (int)(bf % r.frames), b = (int)(bf / r.frames);
     const int64_t base = (int64_t)b * T_ * C + c;
-    const int start = f * r.shift - r.win / 2;
+    const int start = f * r.shift + r.start0;
     float ml_r = 0, pl_r = 0, ph_r = 0, mh_r = 0, ml_g = 0, pl_g = 0, ph_g = 0, mh_g = 0;
     for (int j = 0; j < r.win; ++j) {
       const int64_t o = base + (int64_t)reflect(start + j, T_) * C;
@@ -85,16 +88,15 @@ __global__ void td_bwd_split_kernel(const float* __restrict__ x, const float* __
     dx[i] += d;
   }
 }
-// transpose of the reflect-padded 9-tap mean: out[reflect(t+a)] += z[t]/9
-__global__ void td_avg9_t_kernel(const float* __restrict__ z, int T_, int C, int64_t total, float* __restrict__ out) {
+// transpose of the reflect-padded (2*half+1)-tap mean: out[reflect(t+a)] += z[t]/window
+__global__ void td_avg9_t_kernel(const float* __restrict__ z, int T_, int C, int64_t total, int half, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int64_t bt = i / C;
     const int t = (int)(bt % T_);
     const int64_t base = (bt - t) * C + c;
-    const float v = z[i] * (1.f / 9.f);
-#pragma unroll
-    for (int a = -4; a <= 4; ++a) atomicAdd(out + base + (int64_t)reflect(t + a, T_) * C, v);
+    const float v = z[i] / (float)(2 * half + 1);
+    for (int a = -half; a <= half; ++a) atomicAdd(out + base + (int64_t)reflect(t + a, T_) * C, v);
   }
 }
 
@@ -217,6 +219,37 @@ __global__ void average_filter_kernel(const float* __restrict__ x, int64_t rows,
   }
 }
 
+// framed mean and power of one signal: one thread per (b, f, c)   (time_domain_loss.py:35-49)
+__global__ void frame_stats_kernel(const float* __restrict__ x, int B, int T_, int C, TdRes r, float* __restrict__ mean,
+                                   float* __restrict__ power, int out_stride, int mean_off, int power_off) {
+  const int64_t total = (int64_t)B * r.frames * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bf = i / C;
+    const int f = (int)(bf % r.frames), b = (int)(bf / r.frames);
+    const int64_t base = (int64_t)b * T_ * C + c;
+    const int start = f * r.shift + r.start0;
+    float m = 0.f, p = 0.f;
+    for (int j = 0; j < r.win; ++j) {
+      const float a = x[base + (int64_t)reflect(start + j, T_) * C];
+      m += a; p = fmaf(a, a, p);
+    }
+    if (mean) mean[i * out_stride + mean_off] = m / (float)r.win;
+    if (power) power[i * out_stride + power_off] = p;
+  }
+}
+// Tensor.unfold(1, win, shift) of the (reflect-padded) signal: out[b][f][c][j]   (time_domain_loss.py:35-41)
+__global__ void window_signal_kernel(const float* __restrict__ x, int B, int T_, int C, TdRes r, float* __restrict__ out) {
+  const int64_t total = (int64_t)B * r.frames * C * r.win;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % r.win);
+    int64_t q = i / r.win;
+    const int c = (int)(q % C); q /= C;
+    const int f = (int)(q % r.frames), b = (int)(q / r.frames);
+    out[i] = x[((int64_t)b * T_ + reflect(f * r.shift + r.start0 + j, T_)) * C + c];
+  }
+}
+
 inline int grid_for(int64_t n, int per_thread = 1) {
   int64_t b = ceil_div64(n, 256 * (int64_t)per_thread);
   const int64_t cap = 148 * 8;
@@ -229,37 +262,91 @@ inline int grid_for(int64_t n, int per_thread = 1) {
 using namespace stg;
 #define S_ static_cast<cudaStream_t>(stream)
 
-extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses,
-                           const float* grad_scale, float* dx_gen, float* scratch, stg_stream_t stream) {
-  if (!x_real || !x_gen || !losses || !scratch || T < 48 || (dx_gen && !grad_scale)) return STG_EINVAL;
+static bool td_res(int T, int win, int shift, int pad_windows, TdRes* r) {
+  if (win < 1 || shift < 1) return false;
+  const int padded = pad_windows ? T + 2 * (win / 2) : T;
+  if (padded < win || (pad_windows && win / 2 >= T)) return false;   // reflect padding needs pad < T
+  r->win = win; r->shift = shift; r->start0 = pad_windows ? -(win / 2) : 0;
+  r->frames = (padded - win) / shift + 1;
+  return true;
+}
+
+extern "C" int stg_td_loss_ex(const float* x_real, const float* x_gen, int B, int T, int C, int n_res, const int* wins,
+                              const int* shifts, int pad_windows, int avg_window, float* losses,
+                              const float* grad_scale, const float* grad_scale_dev, float* dx_gen, float* scratch,
+                              stg_stream_t stream) {
+  if (!x_real || !x_gen || !losses || !scratch || !wins || !shifts || n_res < 1 || n_res > 8) return STG_EINVAL;
+  if (avg_window < 1 || (avg_window & 1) == 0 || avg_window / 2 >= T) return STG_EINVAL;
+  if (dx_gen && !grad_scale && !grad_scale_dev) return STG_EINVAL;
+  TdRes rs[8];
+  for (int i = 0; i < n_res; ++i) if (!td_res(T, wins[i], shifts[i], pad_windows, &rs[i])) return STG_EINVAL;
+  const int half = avg_window / 2;
   const int64_t n = (int64_t)B * T * C;
   float *low_r = scratch, *hi_r = scratch + n, *low_g = scratch + 2 * n, *hi_g = scratch + 3 * n;
   float *dlow = scratch + 4 * n, *dhi = scratch + 5 * n;
-  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_real, T, C, n, low_r, hi_r);
+  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_real, T, C, n, half, low_r, hi_r);
   STG_LAUNCH_CHECK();
-  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_gen, T, C, n, low_g, hi_g);
+  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x_gen, T, C, n, half, low_g, hi_g);
   STG_LAUNCH_CHECK();
-  STG_CUDA_CHECK(cudaMemsetAsync(losses, 0, 3 * sizeof(float), S_));
+  STG_CUDA_CHECK(cudaMemsetAsync(losses, 0, n_res * sizeof(float), S_));
   if (dx_gen) STG_CUDA_CHECK(cudaMemsetAsync(dlow, 0, 2 * n * sizeof(float), S_));
-  const int wins[3] = {20, 51, 80}, shifts[3] = {8, 13, 16};  // time_domain_loss.py:88-93
-  for (int i = 0; i < 3; ++i) {
-    TdRes r;
-    r.win = wins[i]; r.shift = shifts[i];
-    r.frames = (T + 2 * (r.win / 2) - r.win) / r.shift + 1;
-    const int64_t total = (int64_t)B * r.frames * C;
-    td_feature_kernel<<<(int)ceil_div64(total, 256), 256, 0, S_>>>(low_r, hi_r, low_g, hi_g, B, T, C, r, losses + i,
-                                                                   dx_gen ? grad_scale[i] : 0.f, dx_gen ? dlow : nullptr, dhi);
+  for (int i = 0; i < n_res; ++i) {
+    const int64_t total = (int64_t)B * rs[i].frames * C;
+    td_feature_kernel<<<(int)ceil_div64(total, 256), 256, 0, S_>>>(
+        low_r, hi_r, low_g, hi_g, B, T, C, rs[i], losses + i, (dx_gen && grad_scale) ? grad_scale[i] : 0.f,
+        (dx_gen && grad_scale_dev) ? grad_scale_dev + i : nullptr, dx_gen ? dlow : nullptr, dhi);
     STG_LAUNCH_CHECK();
   }
   if (dx_gen) {
     td_bwd_split_kernel<<<grid_for(n), 256, 0, S_>>>(x_gen, low_g, dlow, dhi, n, dx_gen);
     STG_LAUNCH_CHECK();
     STG_CUDA_CHECK(cudaMemsetAsync(dhi, 0, n * sizeof(float), S_));
-    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dlow, T, C, n, dhi);  // dhi <- A^T z
+    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dlow, T, C, n, half, dhi);  // dhi <- A^T z
     STG_LAUNCH_CHECK();
-    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dhi, T, C, n, dx_gen);  // dx += A^T A^T z
+    td_avg9_t_kernel<<<grid_for(n), 256, 0, S_>>>(dhi, T, C, n, half, dx_gen);  // dx += A^T A^T z
     STG_LAUNCH_CHECK();
   }
+  return STG_OK;
+}
+
+extern "C" int stg_td_loss(const float* x_real, const float* x_gen, int B, int T, int C, float* losses,
+                           const float* grad_scale, float* dx_gen, float* scratch, stg_stream_t stream) {
+  const int wins[3] = {20, 51, 80}, shifts[3] = {8, 13, 16};  // time_domain_loss.py:88-93
+  return stg_td_loss_ex(x_real, x_gen, B, T, C, 3, wins, shifts, 1, 9, losses, grad_scale, nullptr, dx_gen, scratch, stream);
+}
+
+extern "C" int stg_td_features(const float* x, int B, int T, int C, int win, int shift, int pad_windows, int avg_window,
+                               float* feats, float* scratch, stg_stream_t stream) {
+  TdRes r;
+  if (!x || !feats || !scratch || !td_res(T, win, shift, pad_windows, &r)) return STG_EINVAL;
+  if (avg_window < 1 || (avg_window & 1) == 0 || avg_window / 2 >= T) return STG_EINVAL;
+  const int64_t n = (int64_t)B * T * C, total = (int64_t)B * r.frames * C;
+  float *low = scratch, *hi = scratch + n;
+  td_filter_kernel<<<grid_for(n), 256, 0, S_>>>(x, T, C, n, avg_window / 2, low, hi);
+  STG_LAUNCH_CHECK();
+  // stacked on the last axis: [mean(low), power(low), power(hi), mean(hi)]   (time_domain_loss.py:62-67)
+  frame_stats_kernel<<<grid_for(total), 256, 0, S_>>>(low, B, T, C, r, feats, feats, 4, 0, 1);
+  STG_LAUNCH_CHECK();
+  frame_stats_kernel<<<grid_for(total), 256, 0, S_>>>(hi, B, T, C, r, feats, feats, 4, 3, 2);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_frame_stats(const float* x, int B, int T, int C, int win, int shift, int pad_windows, float* mean,
+                               float* power, stg_stream_t stream) {
+  TdRes r;
+  if (!x || (!mean && !power) || !td_res(T, win, shift, pad_windows, &r)) return STG_EINVAL;
+  frame_stats_kernel<<<grid_for((int64_t)B * r.frames * C), 256, 0, S_>>>(x, B, T, C, r, mean, power, 1, 0, 0);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_window_signal(const float* x, int B, int T, int C, int win, int shift, int pad_windows, float* out,
+                                 stg_stream_t stream) {
+  TdRes r;
+  if (!x || !out || !td_res(T, win, shift, pad_windows, &r)) return STG_EINVAL;
+  window_signal_kernel<<<grid_for((int64_t)B * r.frames * C * win), 256, 0, S_>>>(x, B, T, C, r, out);
+  STG_LAUNCH_CHECK();
   return STG_OK;
 }
 

@@ -94,6 +94,19 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int6
     dst[i] = from_f<D>(to_f(src[i]));
 }
 
+// out rows (dup: rows 2r and 2r+1) = relu(src row r): the ReLU -> nn.Upsample(2) prologue of a stand-alone GBlock
+template <typename T>
+__global__ void relu_rows_kernel(const T* __restrict__ src, int64_t rows, int C, int dup, T* __restrict__ out) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const T v = from_f<T>(fmaxf(to_f(src[i]), 0.f));
+    if (dup) { out[(2 * r) * C + c] = v; out[(2 * r + 1) * C + c] = v; }
+    else out[i] = v;
+  }
+}
+
 template <typename T>
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int mode, int64_t n,
                                T* __restrict__ out) {
@@ -253,6 +266,15 @@ extern "C" int stg_cast(const void* src, int sd, void* dst, int dd, int64_t n, s
   else if (sd == STG_BF16 && dd == STG_F32) cast_kernel<bf16, float><<<g, 256, 0, S_>>>((const bf16*)src, (float*)dst, n);
   else if (sd == STG_F32 && dd == STG_F32) cast_kernel<float, float><<<g, 256, 0, S_>>>((const float*)src, (float*)dst, n);
   else if (sd == STG_BF16 && dd == STG_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, S_>>>((const bf16*)src, (bf16*)dst, n);
+  else return STG_EINVAL;
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
+extern "C" int stg_relu_rows(const void* src, int dtype, int64_t rows, int C, int dup, void* out, stg_stream_t stream) {
+  if (!src || !out || rows < 1 || C < 1) return STG_EINVAL;
+  if (dtype == STG_F32) relu_rows_kernel<float><<<grid_for(rows * C), 256, 0, S_>>>((const float*)src, rows, C, dup, (float*)out);
+  else if (dtype == STG_BF16) relu_rows_kernel<bf16><<<grid_for(rows * C), 256, 0, S_>>>((const bf16*)src, rows, C, dup, (bf16*)out);
   else return STG_EINVAL;
   STG_LAUNCH_CHECK();
   return STG_OK;

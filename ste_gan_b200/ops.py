@@ -351,6 +351,15 @@ def average_filter(x: Tensor, window: int, pad: bool) -> Tensor:
     return out
 
 
+def relu_rows(x: Tensor, dup: bool) -> Tensor:
+    """[B, T, C] -> relu(x) with every row written twice when `dup` ([B, 2T, C])."""
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, None, "x")
+    out = torch.empty((B, T * (2 if dup else 1), Cc), device=x.device, dtype=x.dtype)
+    check(_lib.load().stg_relu_rows(_ptr(x), code_of(x.dtype), B * T, Cc, int(dup), _ptr(out), _stream()), "stg_relu_rows")
+    return out
+
+
 def pair_sum_rows(x: Tensor, rows_out: int, Cc: int) -> Tensor:
     _need(x, 2 * rows_out * Cc, None, "x")
     out = torch.empty((rows_out, Cc), device=x.device, dtype=x.dtype)
@@ -373,6 +382,63 @@ def td_loss(x_real: Tensor, x_gen: Tensor, losses: Tensor, grad_scale=None, dx_g
     gs = (C.c_float * 3)(*([0.0] * 3 if grad_scale is None else [float(g) for g in grad_scale]))
     check(_lib.load().stg_td_loss(_ptr(x_real), _ptr(x_gen), B, T, Cc, _ptr(losses), gs, _ptr(dx_gen),
                                   _ptr(scratch), _stream()), "stg_td_loss")
+
+
+def n_frames(T: int, win: int, shift: int, pad: bool) -> int:
+    return ((T + 2 * (win // 2) if pad else T) - win) // shift + 1
+
+
+def td_loss_ex(x_real: Tensor, x_gen: Tensor, resolutions, losses: Tensor, *, pad_windows: bool = True, avg_window: int = 9,
+               grad_scale=None, dx_gen: Optional[Tensor] = None) -> None:
+    """stg_td_loss for any [(win, shift)] list.  grad_scale: None (no backward), a list of host floats, or a DEVICE
+    fp32[n_res] tensor (read when the kernels run - no host synchronisation)."""
+    B, T, Cc = x_gen.shape
+    n, nr = B * T * Cc, len(resolutions)
+    _need(x_real, n, torch.float32, "x_real"); _need(x_gen, n, torch.float32, "x_gen")
+    _need(losses, nr, torch.float32, "losses"); _need(dx_gen, n, torch.float32, "dx_gen")
+    scratch = torch.empty((6 * n + 8,), device=x_gen.device, dtype=torch.float32)
+    wins = (C.c_int * nr)(*[int(w) for w, _ in resolutions]); shifts = (C.c_int * nr)(*[int(s_) for _, s_ in resolutions])
+    gs_host, gs_dev = None, None
+    if isinstance(grad_scale, torch.Tensor):
+        _need(grad_scale, nr, torch.float32, "grad_scale")
+        gs_dev = grad_scale
+    elif grad_scale is not None:
+        gs_host = (C.c_float * nr)(*[float(g) for g in grad_scale])
+    check(_lib.load().stg_td_loss_ex(_ptr(x_real), _ptr(x_gen), B, T, Cc, nr, wins, shifts, int(pad_windows), int(avg_window),
+                                     _ptr(losses), gs_host, _ptr(gs_dev), _ptr(dx_gen), _ptr(scratch), _stream()), "stg_td_loss_ex")
+
+
+def td_features(x: Tensor, win: int, shift: int, pad_windows: bool = True, avg_window: int = 9) -> Tensor:
+    """[B,T,C] fp32 -> [B,F,C,4] time-domain features (time_domain_loss.py:57-68)."""
+    x = x.contiguous().float()
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    out = torch.empty((B, n_frames(T, win, shift, pad_windows), Cc, 4), device=x.device, dtype=torch.float32)
+    scratch = torch.empty((2 * B * T * Cc,), device=x.device, dtype=torch.float32)
+    check(_lib.load().stg_td_features(_ptr(x), B, T, Cc, win, shift, int(pad_windows), avg_window, _ptr(out), _ptr(scratch),
+                                      _stream()), "stg_td_features")
+    return out
+
+
+def frame_stats(x: Tensor, win: int, shift: int, pad_windows: bool, want_mean: bool, want_power: bool):
+    x = x.contiguous().float()
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    F_ = n_frames(T, win, shift, pad_windows)
+    mean = torch.empty((B, F_, Cc), device=x.device, dtype=torch.float32) if want_mean else None
+    power = torch.empty((B, F_, Cc), device=x.device, dtype=torch.float32) if want_power else None
+    check(_lib.load().stg_frame_stats(_ptr(x), B, T, Cc, win, shift, int(pad_windows), _ptr(mean), _ptr(power), _stream()),
+          "stg_frame_stats")
+    return mean, power
+
+
+def window_signal(x: Tensor, win: int, shift: int, pad_windows: bool) -> Tensor:
+    x = x.contiguous().float()
+    B, T, Cc = x.shape
+    _need(x, B * T * Cc, torch.float32, "x")
+    out = torch.empty((B, n_frames(T, win, shift, pad_windows), Cc, win), device=x.device, dtype=torch.float32)
+    check(_lib.load().stg_window_signal(_ptr(x), B, T, Cc, win, shift, int(pad_windows), _ptr(out), _stream()), "stg_window_signal")
+    return out
 
 
 def mse_const(x: Tensor, target: float, out_slot: Optional[Tensor], grad_scale: float = 0.0, dx: Optional[Tensor] = None) -> None:
