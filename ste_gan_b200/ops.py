@@ -18,6 +18,8 @@ from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, BF16, ENGINE_AUTO, E
 Tensor = torch.Tensor
 _engine_override: Optional[int] = None  # tests force an engine through this
 profile = None  # bench.py sets this to a list: every conv / wgrad launch is then bracketed by CUDA events
+flop_log = None  # bench.py sets this to a list: every conv / wgrad launch appends its ALGORITHMIC flops / bytes (no events:
+                 # safe under CUDA-graph capture, where it records exactly the launches the timed graphs replay)
 
 
 def set_engine(engine: Optional[int]) -> None:
@@ -59,9 +61,11 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
          pair_sum: bool = False, post_shift: int = 0, mask: Optional[Tensor] = None, mask_mode: int = ACT_NONE,
          act: int = ACT_NONE, dup_rows: bool = False, bias: Optional[Tensor] = None, add_pre: Optional[Tensor] = None,
          add_post: Optional[Tensor] = None, y_raw: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
-         engine: int = ENGINE_AUTO, w_fwd_pack: bool = False) -> None:
+         engine: int = ENGINE_AUTO, w_fwd_pack: bool = False, acct_groups: Optional[int] = None) -> None:
     """One StgConv launch (see include/stegan_b200.h for the exact contraction + epilogue).
-    w_fwd_pack (transposed only): `w` is the forward pack wf - what the tcgen05 engine wants for data-gradients."""
+    w_fwd_pack (transposed only): `w` is the forward pack wf - what the tcgen05 engine wants for data-gradients.
+    acct_groups: the MODULE's group count when `groups` is a (merged) pack-group count - only used to account the
+    algorithmic FLOPs of the launch (block-diagonal packs run redundant MMAs that are not work)."""
     dt = src.dtype
     nv = n_samples * phases
     t_out = t_dst // 2 if pair_sum else t_dst
@@ -83,21 +87,27 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
                 w_fwd_pack=int(w_fwd_pack), src=_ptr(src), w=_ptr(w), bias=_ptr(bias), add_pre=_ptr(add_pre), mask=_ptr(mask),
                 add_post=_ptr(add_post), y_raw=_ptr(y_raw), y_act=_ptr(y_act))
     lib = _lib.load()
-    if profile is None:
+    if profile is None and flop_log is None:
         check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
         return
     route = {1: "simt", 2: "tcgen05", 3: "matvec"}[lib.stg_conv_route(C.byref(d))]
+    ag = acct_groups if acct_groups is not None else groups
+    flops = 2.0 * nv * t_src * c_src * k * (c_dst // ag) if transposed else 2.0 * nv * t_dst * c_dst * k * (c_src // ag)
+    esz = 2 if dt == torch.bfloat16 else 4
+    nbytes = esz * (nv * t_src * c_src + k * c_dst * (c_src // ag)) + sum(
+        t.numel() * t.element_size() for t in (add_pre, mask, add_post, y_raw, y_act) if t is not None)
+    rec = dict(kind=("dgrad" if transposed else "fwd"), engine=route, flops=flops, bytes=nbytes,
+               shape=(n_samples, phases, t_src, t_dst, c_src, c_dst, k, dilation, stride, ag))
+    if flop_log is not None:
+        flop_log.append(rec)
+    if profile is None:
+        check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
     e1.record()
-    flops = 2.0 * nv * t_src * c_src * k * (c_dst // groups) if transposed else 2.0 * nv * t_dst * c_dst * k * (c_src // groups)
-    esz = 2 if dt == torch.bfloat16 else 4
-    nbytes = esz * (nv * t_src * c_src + k * c_dst * (c_src // groups)) + sum(
-        t.numel() * t.element_size() for t in (add_pre, mask, add_post, y_raw, y_act) if t is not None)
-    profile.append(dict(kind=("dgrad" if transposed else "fwd"), engine=route, flops=flops,
-                        bytes=nbytes, events=(e0, e1),
-                        shape=(n_samples, phases, t_src, t_dst, c_src, c_dst, k, dilation, stride, groups)))
+    profile.append(dict(rec, events=(e0, e1)))
 
 
 def conv_tc_supported(**kw) -> bool:
@@ -130,19 +140,24 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
                  n_samples=n_samples, phases=phases, t_in=t_in, t_out=t_out, c_in=c_in, c_out=c_out, groups=groups,
                  k=k, dilation=dilation, stride=stride, pad=pad, x=_ptr(x), dy=_ptr(dy), dw=_ptr(dw), dbias=_ptr(dbias))
     lib = _lib.load()
-    if profile is None:
+    if profile is None and flop_log is None:
         check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
         return
     route = {1: "simt", 2: "tcgen05", 3: "matvec"}[lib.stg_wgrad_route(C.byref(d))]
+    esz = 2 if x.dtype == torch.bfloat16 else 4
+    rec = dict(kind="wgrad", engine=route, flops=2.0 * nv * t_out * c_out * k * (c_in // groups),
+               bytes=esz * nv * (t_in * c_in + t_out * c_out) + 4 * c_out * k * (c_in // groups),
+               shape=(n_samples, phases, t_in, t_out, c_in, c_out, k, dilation, stride, groups))
+    if flop_log is not None:
+        flop_log.append(rec)
+    if profile is None:
+        check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
     e1.record()
-    esz = 2 if x.dtype == torch.bfloat16 else 4
-    profile.append(dict(kind="wgrad", engine=route,
-                        flops=2.0 * nv * t_out * c_out * k * (c_in // groups),
-                        bytes=esz * nv * (t_in * c_in + t_out * c_out) + 4 * c_out * k * (c_in // groups),
-                        events=(e0, e1), shape=(n_samples, phases, t_in, t_out, c_in, c_out, k, dilation, stride, groups)))
+    profile.append(dict(rec, events=(e0, e1)))
 
 
 def tc_pack_groups(c_in: int, c_out: int, groups: int) -> int:

@@ -281,7 +281,7 @@ def _fwd(f: Folded, src: Tensor, B: int, t_src: int, *, phases: int = 1, act: in
     else:
         ops.conv(src, f.wf, n_samples=B, phases=phases, t_src=t_src, t_dst=t_dst, c_src=m.in_channels, c_dst=m.out_channels,
                  groups=f.pg, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, bias=m.bias.data, act=act,
-                 dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act)
+                 dup_rows=dup, add_post=add_post, post_shift=post_shift, y_raw=y_raw, y_act=y_act, acct_groups=m.groups)
     return y_raw, y_act, t_dst
 
 
@@ -307,7 +307,7 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
     ops.conv(dy, f.wf if fwd_pack else f.wd, n_samples=B, phases=phases, t_src=t_dy, t_dst=t_x, c_src=m.out_channels,
              c_dst=m.in_channels, groups=f.pg, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, transposed=True,
              pair_sum=pair_sum, mask=mask, mask_mode=mask_mode, add_pre=add_pre, add_post=add_post, y_raw=dx,
-             w_fwd_pack=fwd_pack)
+             w_fwd_pack=fwd_pack, acct_groups=m.groups)
     return dx
 
 

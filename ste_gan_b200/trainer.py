@@ -208,10 +208,13 @@ class GanTrainer:
         else:
             self._real = passes.discriminator_forward(self.net_d, x_real, self.dtype, self._f2)
 
-    def _g_forward(self, su: Tensor, sess: Tensor, mode: Optional[Tensor]) -> None:
+    def _g_forward(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_pred: Optional[Tensor] = None) -> None:
         self.slots.zero_()
         self.G.zero_grad(); self.D.zero_grad()
         self._gctx = None
+        if x_pred is not None:            # discriminator-only workload (disc_losses_step): the fake batch is an input
+            self.x_pred = x_pred
+            return
         self.x_pred, self._gctx = passes.generator_forward(self.net_g, su, sess, mode, self.dtype, True, folds=self.g_plan.fold(),
                                                            side=self._s2(1) if self.use_adv else None)
 
@@ -287,9 +290,9 @@ class GanTrainer:
         self.d_plan.join_wgrads()
         self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
 
-    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor) -> None:
+    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor, x_pred: Optional[Tensor] = None) -> None:
         if not self.use_adv:
-            self._g_forward(su, sess, mode)
+            self._g_forward(su, sess, mode, x_pred)
             return
         if self.concurrent_d:
             # side stream: D folds and the real pass, which needs neither G nor x_pred; current stream: G fold +
@@ -299,19 +302,29 @@ class GanTrainer:
             with torch.cuda.stream(self._side):
                 self._d_folds()
                 self._d_real(x_real)
-            self._g_forward(su, sess, mode)
+            self._g_forward(su, sess, mode, x_pred)
             cur.wait_event(self._ev_f1)
             self._d_fake()
             self._join()
         else:
             self._d_folds()
-            self._g_forward(su, sess, mode)
+            self._g_forward(su, sess, mode, x_pred)
             self._d_fake()
             self._d_real(x_real)
         self._d_update()
 
     def _phase_g_head(self, x_real: Tensor, update_d: bool = True) -> None:
         """Phase G up to and including the generator backward of the first (rearmost) gradient bucket."""
+        dx_pred = self._g_losses(x_real, update_d)
+        # generator backward, bucket by bucket (G.grad was zeroed in phase D and this is its only writer: overwrite)
+        self._last_gctx = self._gctx                       # kept for the parity tests (references only)
+        self._gb = passes.GenBackward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
+                                      overwrite_grads=True)
+        self._g_bucket(0)
+
+    def _g_losses(self, x_real: Tensor, update_d: bool = True) -> Tensor:
+        """Phase G in front of the generator: D optimiser step, the two discriminator passes with the updated weights,
+        adv + 15 TD + 7 FM (train.py:206-217,257-263) and their gradient w.r.t. x_pred (returned, fp32 [B,T,C])."""
         dt = self.dtype
         x_pred = self.x_pred
         dx_pred = torch.zeros_like(x_pred)
@@ -386,11 +399,7 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
-        # generator backward, bucket by bucket (G.grad was zeroed in phase D and this is its only writer: overwrite)
-        self._last_gctx = self._gctx                       # kept for the parity tests (references only)
-        self._gb = passes.GenBackward(self.net_g, self._gctx, dx_pred, plan=self.g_plan, side=self._s2(1), res_side=self._s2(0),
-                                      overwrite_grads=True)
-        self._g_bucket(0)
+        return dx_pred
 
     def _g_bucket(self, i: int) -> None:
         """Backward of the GBlocks of generator-gradient bucket i (after it, self.G.grad[slice i] is final)."""
@@ -435,6 +444,15 @@ class GanTrainer:
         self.reducer.wait(self._phase_g(xr, reduce=True))
         self._phase_opt_g()
         return self.slots
+
+    def disc_losses_step(self, x_pred: Tensor, x_real: Tensor) -> Tensor:
+        """BASELINE.json configs[4]: the discriminator stacks + multi-TD + feature-matching + LSGAN losses of one train
+        step in isolation, forward and backward - everything of train.py:189-264 except the generator: phase D on the
+        given fake batch (two passes, loss_D, weight gradients, D AdamW), then phase G's two passes with the updated
+        weights, the three losses and their gradient w.r.t. x_pred, which is returned (fp32 [B,T,C]).  Eager launches;
+        capturable into one CUDA graph (no collective: single-process workload)."""
+        self._phase_d(None, None, None, x_real, x_pred=x_pred)
+        return self._g_losses(x_real, update_d=True)
 
     def capture(self, batch: int, frames: int, unit_dim: int = 256, hop: int = 16, channels: int = 8,
                 pipelined: Optional[bool] = None) -> None:

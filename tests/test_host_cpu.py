@@ -242,3 +242,13 @@ def test_checkpoint_interchange_with_torch_adamw(tmp_path):
     assert list(fixed) == ["gblocks.0.bias", "last_conv.1.bias"]
     with pytest.raises(ValueError):
         ck.adamw_state_to_flat(ref_sd, shapes[:-1], offsets, m, v)
+
+
+def test_synthetic_batch_matches_oracle_generator():
+    """bench.py's GPU arm draws its inputs from ste_gan_b200.synthetic (it must not import oracle/); the tests draw theirs
+    from the oracle: the two generators are the same sequence."""
+    from oracle import ste_gan_oracle as O
+    from ste_gan_b200.synthetic import synthetic_batch
+    for kw in (dict(batch=3, frames=7, seed=5), dict(batch=2, frames=4, seed=9, unit_dim=25, hop=8)):
+        for a, b in zip(synthetic_batch(**kw), O.synthetic_batch(**kw)):
+            assert torch.equal(a, b)
