@@ -140,6 +140,9 @@ class RefTrainer:
         self.scaler.update()
         return x_pred.grad
 
+    def load_generator_state(self, sd):
+        self.netG.load_state_dict({k: v.detach().to(self.device) for k, v in sd.items()})
+
     @torch.inference_mode()
     def generate(self, su, sess):
         dev = self.device
@@ -184,6 +187,9 @@ class PortTrainer:
             loss_g = O.lsgan_g_loss(d_fake) + W_TD * O.multi_td_loss(x_real, x_pred)[0] + W_FM * O.feature_matching_loss(d_fake, d_real)
         loss_g.backward()
         return x_pred.grad
+
+    def load_generator_state(self, sd):
+        self.ot.g = {k: v.detach().clone().to(self.device) for k, v in sd.items()}
 
     @torch.inference_mode()
     def generate(self, su, sess):

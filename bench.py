@@ -28,6 +28,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -198,7 +199,8 @@ def cupti_by_kernel(fn, n_rep: int):
         nm = e["name"]
         key = next((k for k in KERNEL_KEYS if k in nm), None)
         if key is None:
-            key = "other:" + nm.split("(")[0].split("<")[0].split("::")[-1][:40]
+            ids = [w for w in re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*[<(]", nm) if w not in ("void", "anonymous")]
+            key = "other:" + (ids[0] if ids else nm)[:48]
         a = out.setdefault(key, [0, 0.0])
         a[0] += 1; a[1] += float(e["dur"])
     span = (max(e["ts"] + e["dur"] for e in ks) - min(e["ts"] for e in ks)) / n_rep
@@ -358,6 +360,7 @@ def run_ours(args):
                             "tensor_frac": round(G_FWD_GFLOP_PER_FRAME * INFER_FRAMES * IB / ms_inf_b / peaks["tflops"], 4)},
                  "cpu_baseline": None}
     if cpu_arm is not None:      # the reference's generate() on the host cores: 1 warm-up + 2 timed 30 s utterances
+        cpu_arm.tr.load_generator_state({k: v.cpu() for k, v in g.state_dict().items()})   # the weights the GPU engine serves
         cpu_arm.tr.generate(su_i, sess_i)
         t0 = time.perf_counter()
         for _ in range(2):
@@ -462,7 +465,9 @@ def run_ours(args):
                         "timeline_span_us_per_step": round(span, 1) if isinstance(span, float) else None,
                         "step_tflops": round(STEP_GFLOP_PER_SAMPLE * BATCH_PER_GPU / ms_step, 2),
                         "step_frac": round(STEP_GFLOP_PER_SAMPLE * BATCH_PER_GPU / ms_step / peaks["tflops"], 4),
-                        "by_kernel": by_kernel, "hbm": hbm}
+                        "by_kernel": by_kernel, "hbm": hbm,
+                        "timeline_top": [{"kernel": k, "launches_per_step": round(v[0], 1), "busy_us_per_step": round(v[1], 1)}
+                                         for k, v in sorted((timeline or {}).items(), key=lambda kv: -kv[1][1])[:16]]}
         return roofline
 
     roofline = roofline_block()

@@ -153,7 +153,9 @@ int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const flo
  *   row0  = running sum of c_out (one block per output channel), total_rows = its end value
  *   tile0 = running sum of pack tiles: k * pack_groups * ceil(c_out/pg/32) * ceil(c_in/pg/32), or for
  *           STG_PACK_UNFOLD ceil(c_out/32) * ceil(roundup8(k*c_in)/32); total_tiles = its end value
- * total_tiles = 0 selects the row form, valid when every item has wd == NULL (forward pack only).
+ * total_tiles <= 0 selects the row form (a warp per output-channel row, forward packs only); -total_tiles is then the
+ * number of transposition blocks that build the K-major data-gradient packs wd of the grouped convs from their forward
+ * packs: an item with wd != NULL has k * pg blocks, tile0 = running block count (items without wd: no blocks).
  * stg_weightnorm_fold_multi fills wf / wd / scale of every item; stg_weightnorm_fold_bwd_multi turns every
  * item's dw (layout dw_ld / dw_span, see stg_wgrad_layout) into dv / dg.
  */
@@ -310,6 +312,10 @@ int stg_debug_set_trace(void* buf);
 /* debug hardware probe (csrc/debug_probe.cu): one 128x64x64 MMA whose A operand starts `shift` rows into a TMA-loaded
  * [rows_a][64] bf16 tile, descriptor base-offset field = base_off; out = float [128][64]. */
 int stg_debug_rowshift(const void* x, const void* w, int rows_a, int shift, int base_off, float* out, stg_stream_t stream);
+/* debug hardware probe (csrc/debug_probe.cu): the per-group MMAs of a grouped convolution - A [128][64] bf16 with 64/cin_g
+ * groups side by side on K, W compact [(64/cin_g)*cout_g][cin_g] loaded with a 32- / 64- / 128-byte swizzle, one N = cout_g
+ * MMA chain per group into its own accumulator columns; out = float [128][(64/cin_g)*cout_g]. */
+int stg_debug_group_mma(const void* x, const void* w, int cin_g, int cout_g, float* out, stg_stream_t stream);
 /* Host-only diagnostic: row classes of the tcgen05 convolution for t_dst output rows per sample (128-row tiles + binary
  * tail tiles that gather one row slice of several samples).  out[3c..3c+2] = rows per sample, first row, tiles per sample
  * (0: one tile per 128/rows samples); returns the number of classes (<= 4).  No GPU needed. */

@@ -69,6 +69,7 @@ _SIGS = {
     "stg_debug_set_trace": [_P],
     "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_debug_row_classes": [_I, _P],
+    "stg_debug_group_mma": [_P, _P, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_period_first_layer": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, _P, _P],

@@ -89,6 +89,13 @@ struct TcP {
   int hb, a_bytes, max_ntaps;  // h rows per A box, bytes reserved for the window (1024-aligned), taps per stage slot
   int b_mn;                    // data-gradient: W tiles are [64 co rows][64 ci] boxes of the FORWARD pack (MN-major B operand);
                                // 2 = all bn/64 boxes of a tile come from ONE 4-D TMA box (c_dst/g % 64 == 0)
+  // Compact groups (grouped convs whose groups have 16 / 32 / 64 source channels; K-major W only).  A 64-channel K chunk of
+  // the activations holds cu_fpc = 64 / cu_k whole groups ("units") side by side; the W tile of a stage is the COMPACT
+  // [cu_fpc * cu_n rows][cu_k] block of the pack (rows of 32 / 64 / 128 bytes, loaded with the matching swizzle), and
+  // every unit gets its own MMA chain - N = cu_n, A descriptor advanced to the unit's channels inside the swizzle atom,
+  // accumulator columns (chunk * cu_fpc + q) * cu_n.  Nothing is multiplied by the zeros of a block-diagonal weight
+  // tile any more and the W bytes per stage shrink by 64 / cu_k (hardware check: tools/group_mma_probe.py).
+  int cu_k, cu_n, cu_fpc;      // cu_k == 0: off
   int res_gfirst[MAX_RES + 1]; // groups of residue r: [res_gfirst[r], res_gfirst[r+1])
   TapTables tt;
   long long* trace;            // debug timeline (stg_debug_set_trace) or nullptr
@@ -293,7 +300,8 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_bytes = (kPair ? p.bn / 2 : p.bn) * KC * 2;   // B tile bytes staged by THIS CTA (a pair splits the columns)
+  // B tile bytes staged by THIS CTA per tap (a pair splits the columns; compact groups: only the rows of the chunk's units)
+  const int b_bytes = p.cu_k ? p.cu_fpc * p.cu_n * p.cu_k * 2 : (kPair ? p.bn / 2 : p.bn) * KC * 2;
   const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
   const TcEpi& e = p.e;
   // pair kernels: cluster rank (0 = leader: issues the MMAs, owns the full / tmem_empty barriers), pair tile walk
@@ -399,6 +407,8 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           const long long pc2 = clock64();
 #endif
           if (do_a) {
+          } else if (p.cu_k) {       // compact groups: [cu_fpc * cu_n rows][cu_k] block of the units of this chunk
+            tma_load_3d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, 0, x.col0 + chunk * p.cu_fpc * p.cu_n, tap);
           } else if (p.b_mn == 0) {
             tma_load_3d_el<kPair>(a_dst + p.a_bytes, &tmW, fb, chunk * KC, wc, tap);
           } else if (p.b_mn == 2) {  // forward pack seen as (64, co row, ci/64, tap): one box = the whole [bn/64][64][64] tile
@@ -423,6 +433,11 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
     // ===== MMA issuer, one tap per stage (warp-uniform control flow; pair: the leader issues for both CTAs) =====
     const bool lead = lane == 0;
     const uint32_t idesc = idesc_bf16_f32(kPair ? 2 * TM : TM, p.bn, 0, p.b_mn ? 1 : 0);
+    const uint32_t idesc_u = idesc_bf16_f32(TM, p.cu_k ? p.cu_n : p.bn, 0, 0);   // compact groups: N = one unit's columns
+    // ... K steps per unit = 1 << cu_ks, B descriptor without its start address, start-address step between units
+    const int cu_ks = p.cu_k == 16 ? 0 : (p.cu_k == 32 ? 1 : 2), cu_km = (1 << cu_ks) - 1;
+    const uint64_t cu_bhi = smem_desc_kmajor_narrow(0, p.cu_k ? p.cu_k * 2 : 128);
+    const int cu_bq = (p.cu_n * p.cu_k * 2) >> 4;
     Tracer trc(lead ? p.trace : nullptr, 1);
     // descriptors of stage 0; a stage further on adds stage_bytes >> 4 to the 14-bit start-address field (no carry:
     // every operand address is below 256 KB)
@@ -442,6 +457,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
       tc_fence_after();
       trc.ev(2, t);
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
+      int cu_chunk = 0;
       for (int it = 0; it < x.n_iters; ++it) {
 #ifdef STG_PROF_LOOP
         const long long mc0 = clock64();
@@ -453,9 +469,24 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
         const long long mc1 = clock64();
 #endif
         const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * dstep), bd = bdesc0 + (uint64_t)((uint32_t)s * dstep);
+        if (p.cu_k) {
+          // compact groups: one MMA chain per unit of this chunk (see TcP::cu_k); `it` walks (tap group, chunk) with the
+          // chunk fastest, so a unit's columns are first written while it < k_chunks.  A chunk is always 4 K steps:
+          // step i belongs to unit q = i >> cu_ks, K step i & (kpu - 1) of that unit.
+          const uint32_t dcol = d_tmem + (uint32_t)(cu_chunk * p.cu_fpc * p.cu_n);
+          if (++cu_chunk == p.k_chunks) cu_chunk = 0;
+          const uint64_t bu = cu_bhi | (uint64_t)(((smem_base + (uint32_t)(s * stage_bytes) + (uint32_t)p.a_bytes) >> 4) & 0x3FFFu);
+          const uint32_t acc0 = it >= p.k_chunks ? 1u : 0u;
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks)
-          umma_bf16_el<kPair>(d_tmem, ad + 2 * ks, bd + bstep * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          for (int i = 0; i < KC / 16; ++i) {
+            const int q = i >> cu_ks, ks = i & cu_km;
+            umma_bf16_el<kPair>(dcol + (uint32_t)(q * p.cu_n), ad + 2 * i, bu + (uint64_t)(q * cu_bq + 2 * ks), idesc_u, (acc0 | (uint32_t)(ks > 0)));
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            umma_bf16_el<kPair>(d_tmem, ad + 2 * ks, bd + bstep * ks, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
         umma_commit_el<kPair>(empty_bar(s));
         if (it == x.n_iters - 1) umma_commit_el<kPair>(tmem_full_bar(as));
         if (++s == p.stages) { s = 0; phs ^= 1u; }
@@ -492,7 +523,10 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
         }
 #pragma unroll 1
         for (int tl = 0; tl < (do_a ? 0 : nt); ++tl) {
-          if (!p.b_mn) {
+          if (p.cu_k) {
+            tma_load_3d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), 0, x.col0 + chunk * p.cu_fpc * p.cu_n,
+                           p.tt.tap_w[t0 + tl]);
+          } else if (!p.b_mn) {
             tma_load_3d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), chunk * KC, x.col0, p.tt.tap_w[t0 + tl]);
           } else if (p.b_mn == 2) {
             tma_load_4d_el(a_dst + p.a_bytes + tl * b_bytes, &tmW, full_bar(s), 0, x.ch0 + chunk * KC, x.wcol0 / 64,
@@ -511,6 +545,10 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
   } else if (warp == 1) {
     // ===== MMA issuer, tap windows (warp-uniform control flow) =====
     const uint32_t idesc = idesc_bf16_f32(TM, p.bn, 0, p.b_mn ? 1 : 0);
+    const uint32_t idesc_u = idesc_bf16_f32(TM, p.cu_k ? p.cu_n : p.bn, 0, 0);
+    const int cu_ks = p.cu_k == 16 ? 0 : (p.cu_k == 32 ? 1 : 2), cu_km = (1 << cu_ks) - 1;
+    const uint64_t cu_bhi = smem_desc_kmajor_narrow(0, p.cu_k ? p.cu_k * 2 : 128);
+    const int cu_bq = (p.cu_n * p.cu_k * 2) >> 4;
     int s = 0, acc_i = 0; uint32_t phs = 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const Tile x = decode_tile<kPair>(p, t, rank);
@@ -530,6 +568,17 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           // tap = the same window, `tap_shift` h rows (x pack phase rows of 128 B) further down
           const uint64_t adesc = smem_desc_kmajor_sw128(a_addr + (uint32_t)(p.tt.tap_shift[t0 + tl] * p.pack * KC * 2));
           const uint32_t b_addr = a_addr + p.a_bytes + tl * b_bytes;
+          if (p.cu_k) {   // compact groups: one MMA chain per unit of this chunk (see TcP::cu_k and the one-tap issuer)
+            const uint32_t dcol = d_tmem + (uint32_t)(chunk * p.cu_fpc * p.cu_n);
+            const uint64_t bu = cu_bhi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+            const uint32_t acc0 = (it >= p.k_chunks || tl > 0) ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < KC / 16; ++i) {
+              const int q = i >> cu_ks, ks = i & cu_km;
+              umma_bf16_el(dcol + (uint32_t)(q * p.cu_n), adesc + 2 * i, bu + (uint64_t)(q * cu_bq + 2 * ks), idesc_u, (acc0 | (uint32_t)(ks > 0)));
+            }
+            continue;
+          }
           const uint64_t bdesc = p.b_mn ? smem_desc_mnmajor_sw128(b_addr, 8192, 1024) : smem_desc_kmajor_sw128(b_addr);
           const uint64_t bstep = p.b_mn ? 128 : 2;
 #pragma unroll
@@ -834,7 +883,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -945,18 +995,37 @@ static void tile_geometry(const StgConv* d, int* pack, int* nh, int* n_res, int*
   *tiles_m = ceil_div(ceil_div(d->t_dst, *n_res), *nh);
 }
 
+// Compact groups (TcP::cu_k): groups of ku in {16, 32, 64} source channels and nu % 16 == 0 destination channels.  A CTA
+// tile covers f groups, the smallest divisor of `groups` that makes whole 64-channel K chunks on the source side and whole
+// 64-column blocks on the destination side (the geometry the block-diagonal packs had); 0 = not possible.
+static int compact_merge(int ku, int nu, int groups) {
+  if ((ku != 16 && ku != 32 && ku != 64) || (nu % 16) != 0) return 0;
+  for (int f = 1; f <= groups; ++f) {
+    if (groups % f) continue;
+    if ((ku * f) % KC == 0 && (nu * f) % KC == 0) return nu * f <= 256 ? f : 0;
+  }
+  return 0;
+}
+
 bool conv_tc_supported(const StgConv* d) {
   if (d->dtype != STG_BF16) return false;
   if (d->k > STG_MAX_TAPS || d->k < 1) return false;
   if ((d->c_src % 8) != 0) return false;                 // 16-byte global strides for TMA
   if (d->phases > 64) return false;
   if (d->groups > 1) {
-    if ((d->c_src / d->groups) % KC) return false;       // whole K chunks per group (see stg_tc_pack_groups)
     if (((d->c_dst / d->groups) % 16) != 0) return false;
+    if ((d->c_src / d->groups) % KC) {                   // narrow groups: compact-group path (K-major W only)
+      if (d->transposed && d->w_fwd_pack) return false;
+      if (compact_merge(d->c_src / d->groups, d->c_dst / d->groups, d->groups) == 0) return false;
+    } else if (d->transposed && !d->w_fwd_pack && d->c_src / d->groups != KC) {
+      return false;                                      // K-major data-gradient packs of wide groups: not needed, not built
+    }
   }
-  if (d->transposed && !d->w_fwd_pack) return false;     // the data-gradient reads the forward pack (MN-major B operand)
+  // data-gradients read the forward pack as an MN-major B operand (w_fwd_pack) or - grouped convs - a K-major
+  // data-gradient pack wd [k][c_in][c_out/g] through the same code path as a forward convolution
+  if (d->transposed && !d->w_fwd_pack && d->groups == 1) return false;
   if (d->transposed && ((d->c_dst / d->groups) % 8) != 0) return false;
-  if (d->transposed && d->groups > 1 && ((d->c_dst / d->groups) % 64) != 0) return false;
+  if (d->transposed && d->w_fwd_pack && d->groups > 1 && ((d->c_dst / d->groups) % 64) != 0) return false;
   if (d->transposed && d->stride > MAX_RES) return false;
   if (d->transposed && d->stride > 1 && d->pair_sum) return false;
   if (!d->transposed && d->stride > 4) return false;
@@ -971,7 +1040,16 @@ bool conv_tc_supported(const StgConv* d) {
 int tc_pack_groups(int c_in, int c_out, int groups) {
   if (groups <= 1) return 1;
   const int cin_g = c_in / groups, cout_g = c_out / groups;
-  // smallest merge factor f | groups with (cin_g * f) % 64 == 0 and (cout_g * f) % 64 == 0 (dgrad K chunks)
+  // Units of the compact-group path: the smallest merge m | groups whose merged group has 16 / 32 / 64 (or a multiple of 64)
+  // channels on BOTH sides - the forward conv contracts over the input side, the data-gradient over the output side, and
+  // an MMA K step is 16 channels.  The packs are block-diagonal only inside a unit (m > 1: groups of 8 channels).
+  auto side_ok = [](int c) { return c == 16 || c == 32 || (c % KC) == 0; };
+  static const int env_legacy = getenv("STG_GROUP_MERGE") ? atoi(getenv("STG_GROUP_MERGE")) : 0;   // 1: round-1 block-diagonal packs
+  for (int m = 1; m <= groups && !env_legacy; ++m) {
+    if (groups % m) continue;
+    if (side_ok(cin_g * m) && side_ok(cout_g * m)) return groups / m;
+  }
+  // fallback: merge to whole 64-channel K chunks on both sides (redundant MMAs on the zeros)
   for (int f = 1; f <= groups; ++f) {
     if (groups % f) continue;
     if ((cin_g * f) % KC == 0 && (cout_g * f) % KC == 0) return groups / f;
@@ -1006,14 +1084,23 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   p.trace = g_trace;
   p.phases = d->phases; p.t_dst = d->t_dst; p.stride = d->transposed ? 1 : d->stride;
   p.cs_g = d->c_src / d->groups; p.cd_g = d->c_dst / d->groups;
+  int tile_groups = d->groups;     // groups as the tile walk sees them
+  p.cu_k = p.cu_n = p.cu_fpc = 0;
+  if (d->groups > 1 && (p.cs_g % KC) != 0) {   // compact groups: a tile covers f units (see TcP::cu_k)
+    const int f = compact_merge(p.cs_g, p.cd_g, d->groups);
+    if (f == 0) return STG_EUNSUPPORTED;
+    p.cu_k = p.cs_g; p.cu_n = p.cd_g; p.cu_fpc = KC / p.cs_g;
+    p.cs_g *= f; p.cd_g *= f; tile_groups = d->groups / f;
+  }
   p.k_chunks = ceil_div(p.cs_g, KC);
   tile_geometry(d, &p.pack, &p.nh, &p.n_res, &p.tiles_m);
   p.mrows = p.nh * p.pack;
-  p.b_mn = d->transposed ? 1 : 0;
+  p.b_mn = (d->transposed && d->w_fwd_pack) ? 1 : 0;
   // stages of one tile: taps (of one residue class) x 64-channel chunks
   const int n_stages_est = ceil_div(d->k, p.n_res) * p.k_chunks;
-  p.bn = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est)
-                : pick_bn(p.cd_g, d->groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est);
+  p.bn = p.cu_k ? p.cd_g   // compact groups: a column tile is the whole merged group
+       : p.b_mn ? pick_bn_mn(p.cd_g, tile_groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est)
+                : pick_bn(p.cd_g, tile_groups, (int64_t)d->n_samples * p.n_res * p.tiles_m, n_stages_est);
   if (p.bn <= 0) return STG_EUNSUPPORTED;
   p.tmem_cols = 512;  // two accumulator buffers ACC_COLS apart
   // ---- taps per residue class, as (source offset, weight index)
@@ -1060,7 +1147,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     const int64_t classic = (int64_t)d->n_samples * p.tiles_m;
     if (n_rc < 2 || cls_tiles >= classic) n_rc = 0;
     if (n_rc) {   // the column tile is chosen for the new tile count
-      const int bn2 = p.b_mn ? pick_bn_mn(p.cd_g, d->groups, cls_tiles, n_stages_est) : pick_bn(p.cd_g, d->groups, cls_tiles, n_stages_est);
+      const int bn2 = p.cu_k ? p.cd_g : p.b_mn ? pick_bn_mn(p.cd_g, tile_groups, cls_tiles, n_stages_est) : pick_bn(p.cd_g, tile_groups, cls_tiles, n_stages_est);
       if (bn2 > 0 && (bn2 % SUB) == 0) p.bn = bn2; else n_rc = 0;
     }
   }
@@ -1077,9 +1164,9 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   static const int env_pair = getenv("STG_PAIR") ? atoi(getenv("STG_PAIR")) : 0;
   p.n_samples = d->n_samples;
   const int n_mt = d->n_samples * p.tiles_m;
-  bool pair = env_pair != 0 && n_rc == 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
+  bool pair = env_pair != 0 && p.cu_k == 0 && n_rc == 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
   p.pairs_per_res = (n_mt + 1) / 2;
-  int b_bytes = (pair ? p.bn / 2 : p.bn) * KC * 2;
+  int b_bytes = p.cu_k ? p.cu_fpc * p.cu_n * p.cu_k * 2 : (pair ? p.bn / 2 : p.bn) * KC * 2;
   const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 2048 : 0;
   const int avail = 212 * 1024 - epi_bytes;
   struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
@@ -1200,7 +1287,15 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     int r = make_tmap_bf16(&tmA.m[c], d->src, 4, dims, strides, box, es);
     if (r) return r;
   }
-  if (!p.b_mn) {
+  if (p.cu_k) {
+    // compact pack [k][c_dst][cu_k]: rows of 32 / 64 / 128 bytes, box = the rows of one chunk's units, matching swizzle
+    const uint64_t C = p.cu_k, N = d->c_dst, K = d->k;
+    const uint64_t dims[3] = {C, N, K};
+    const uint64_t strides[2] = {C * 2, N * C * 2};
+    const uint32_t box[3] = {(uint32_t)p.cu_k, (uint32_t)(p.cu_fpc * p.cu_n), 1};
+    int r = make_tmap_bf16(&tmW, d->w, 3, dims, strides, box, nullptr, p.cu_k * 2);
+    if (r) return r;
+  } else if (!p.b_mn) {
     const uint64_t C = p.cs_g, N = d->c_dst, K = d->k;
     const uint64_t dims[3] = {C, N, K};
     const uint64_t strides[2] = {C * 2, N * C * 2};

@@ -42,10 +42,68 @@ rowshift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_before(); __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
+// Second probe: the per-group MMAs of a grouped convolution.  A = [128][64] bf16 (SWIZZLE_128B, 64 / cin_g groups side by
+// side on K), W = compact [n_g * cout_g][cin_g] bf16 loaded with the swizzle that matches its row length (32 / 64 / 128 B).
+// Group q: D[:, q*cout_g .. +cout_g] = A[:, q*cin_g .. +cin_g] * W[q*cout_g .. +cout_g][:]^T as cin_g/16 MMAs of N = cout_g
+// whose A descriptor starts q*cin_g*2 bytes into the swizzle atom, whose B descriptor starts q*cout_g rows into the narrow tile
+// and whose accumulator starts q*cout_g TMEM columns in.
+__global__ void __launch_bounds__(128, 1)
+group_mma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int cin_g, int cout_g,
+                       float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_addr = base, w_addr = base + 16384, bar = base + 16384 + 32768, done = bar + 8, slot = bar + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_g = 64 / cin_g, row_bytes = cin_g * 2, n_cols = n_g * cout_g;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  uint32_t tmem; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)(128 * 128 + n_cols * row_bytes));
+    tma_load_3d(a_addr, &tmA, bar, 0, 0, 0);
+    tma_load_3d(w_addr, &tmW, bar, 0, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t idesc = idesc_bf16_f32(128, cout_g, 0, 0);
+    const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
+    for (int q = 0; q < n_g; ++q) {
+      const uint64_t bdesc = smem_desc_kmajor_narrow(w_addr + (uint32_t)(q * cout_g * row_bytes), row_bytes);
+      for (int ks = 0; ks < cin_g / 16; ++ks)
+        umma_bf16(tmem + (uint32_t)(q * cout_g), adesc + 2 * (q * (cin_g / 16) + ks), bdesc + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  for (int c = 0; c < n_cols; c += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+    for (int i = 0; i < 16; ++i) out[(warp * 32 + lane) * n_cols + c + i] = v[i];
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
 }  // namespace
 }  // namespace stg
 
 using namespace stg;
+/* x: bf16 [128][64], w: bf16 [(64/cin_g)*cout_g][cin_g], out: float [128][(64/cin_g)*cout_g]; cin_g in {16,32,64}, cout_g % 16 == 0 */
+extern "C" int stg_debug_group_mma(const void* x, const void* w, int cin_g, int cout_g, float* out, stg_stream_t stream) {
+  if ((cin_g != 16 && cin_g != 32 && cin_g != 64) || cout_g % 16 || cout_g < 16 || (64 / cin_g) * cout_g > 256) return STG_EINVAL;
+  const int n_cols = (64 / cin_g) * cout_g;
+  CUtensorMap tmA, tmW;
+  { const uint64_t dims[3] = {64, 128, 1}; const uint64_t st[2] = {128, 128 * 128};
+    const uint32_t box[3] = {64, 128, 1}; int r = make_tmap_bf16(&tmA, x, 3, dims, st, box, nullptr); if (r) return r; }
+  { const uint64_t dims[3] = {(uint64_t)cin_g, (uint64_t)n_cols, 1}; const uint64_t st[2] = {(uint64_t)cin_g * 2, (uint64_t)n_cols * cin_g * 2};
+    const uint32_t box[3] = {(uint32_t)cin_g, (uint32_t)n_cols, 1};
+    int r = make_tmap_bf16(&tmW, w, 3, dims, st, box, nullptr, cin_g * 2); if (r) return r; }
+  STG_CUDA_CHECK(cudaFuncSetAttribute(group_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  group_mma_probe_kernel<<<1, 128, 56 * 1024, static_cast<cudaStream_t>(stream)>>>(tmA, tmW, cin_g, cout_g, out);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
+
 /* x: bf16 [rows_a][64] (rows_a <= 256), w: bf16 [64][64], out: float [128][64] */
 extern "C" int stg_debug_rowshift(const void* x, const void* w, int rows_a, int shift, int base_off, float* out,
                                   stg_stream_t stream) {

@@ -442,6 +442,28 @@ __device__ __forceinline__ void fold_row_warp_generic(const StgFoldItem& d, int 
   }
 }
 
+// Data-gradient packs of the grouped convs from their FORWARD packs (row form of the multi-tensor fold): one block per
+// (item, tap, pack group) transposes the contiguous [cout_gp x cin_gp] slab wf[j][u*cout_gp ..][:] into the contiguous
+// [cin_gp x cout_gp] slab wd[j][u*cin_gp ..][:] through shared memory - both sides fully coalesced (a per-row scatter
+// of 2-byte elements cost 40 us per discriminator fold).  Items without wd have no blocks (tile0 = running block count).
+template <typename T>
+__global__ void __launch_bounds__(256) wd_from_wf_kernel(const StgFoldItem* __restrict__ items, int n_items) {
+  __shared__ T slab[8192];
+  const int it = find_item(items, n_items, blockIdx.x, true);
+  const StgFoldItem d = items[it];
+  const int local = blockIdx.x - d.tile0, j = local / d.pg, u = local - j * d.pg;
+  const int c_in = d.cin_g * d.groups, cin_gp = c_in / d.pg, cout_gp = d.c_out / d.pg, n = cin_gp * cout_gp;
+  const T* src = static_cast<const T*>(d.wf) + ((int64_t)j * d.c_out + (int64_t)u * cout_gp) * cin_gp;
+  T* dst = static_cast<T*>(d.wd) + ((int64_t)j * c_in + (int64_t)u * cin_gp) * cout_gp;
+  if (n <= 8192) {
+    for (int i = threadIdx.x; i < n; i += 256) slab[i] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) { const int c = i / cout_gp, r = i - c * cout_gp; dst[i] = slab[r * cin_gp + c]; }
+  } else {   // (wide block-diagonal fallback packs: plain strided reads)
+    for (int i = threadIdx.x; i < n; i += 256) { const int c = i / cout_gp, r = i - c * cout_gp; dst[i] = src[(int64_t)r * cin_gp + c]; }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 4) wn_fold_rows_kernel(const StgFoldItem* __restrict__ items, int n_items, int total_rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -643,12 +665,17 @@ extern "C" int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span
 extern "C" int stg_weightnorm_fold_multi(const StgFoldItem* items, int n_items, int total_rows, int total_tiles, int dtype,
                                          stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!items || n_items < 1 || total_rows < 1 || total_tiles < 0) return STG_EINVAL;
-  if (total_tiles == 0) {  // row form: every item wants the forward pack only (wd == NULL)
+  if (!items || n_items < 1 || total_rows < 1) return STG_EINVAL;
+  if (total_tiles <= 0) {  // row form: forward packs; -total_tiles = transposition blocks of the grouped convs' wd packs
     if (dtype == STG_F32) wn_fold_rows_kernel<float><<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows);
     else if (dtype == STG_BF16) wn_fold_rows_kernel<bf16><<<ceil_div(total_rows, FOLD_RPB), 256, 0, s>>>(items, n_items, total_rows);
     else return STG_EINVAL;
     STG_LAUNCH_CHECK();
+    if (total_tiles < 0) {
+      if (dtype == STG_F32) return STG_EINVAL;           // (fp32 packs come from the tile form)
+      wd_from_wf_kernel<bf16><<<-total_tiles, 256, 0, s>>>(items, n_items);
+      STG_LAUNCH_CHECK();
+    }
     return STG_OK;
   }
   wn_scale_multi_kernel<<<total_rows, 256, 0, s>>>(items, n_items);

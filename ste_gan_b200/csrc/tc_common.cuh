@@ -323,6 +323,17 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
+// K-major operand tile whose rows are only 32 or 64 bytes long (16 / 32 bf16: the per-group K extent of a grouped
+// convolution), TMA-loaded with the matching 32- / 64-byte swizzle; 8-row groups are 8 * row_bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_kmajor_narrow(uint32_t smem_addr, int row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 32 ? 6 : (row_bytes == 64 ? 4 : 2)) << 61;   // SWIZZLE_32B / _64B / _128B
+  return d;
+}
 // MN-major operand tile: [k rows][64 mn elements] per 128 B row, 128-byte swizzle.
 // lbo = byte distance between 64-element MN groups, sbo = byte distance between 8-row K groups.
 __device__ __forceinline__ uint64_t smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {

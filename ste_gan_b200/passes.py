@@ -70,7 +70,9 @@ def fold(mod, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True
     buffers across calls (fixed addresses, so CUDA graphs that read them stay valid)."""
     pg, unf = pack_mode(mod, dtype)
     kp = ops.round_up8(mod.kernel * mod.in_channels) if unf else 0
-    want_dgrad = want_dgrad and dtype != torch.bfloat16    # bf16 data-gradients read the forward pack
+    # bf16 data-gradients read the forward pack - except grouped convs, whose tensor-engine data-gradient wants the
+    # K-major pack wd [k][c_in][c_out/pg] (compact groups, conv_tc.cu)
+    want_dgrad = want_dgrad and (dtype != torch.bfloat16 or mod.groups > 1)
     if mod.norm == "weight_norm":
         prev = persist.get(id(mod)) if persist is not None else None
         out = (prev.wf, prev.wd, prev.scale) if prev is not None and prev.dtype == dtype and prev.wd is not None else None
@@ -167,7 +169,8 @@ class FoldPlan:
     def __init__(self, convs: Sequence, dtype: torch.dtype):
         from . import _lib
         self.dtype = dtype
-        self.need_wd = dtype != torch.bfloat16     # bf16: data-gradients read the forward pack (tcgen05, MN-major operand)
+        self.need_wd = dtype != torch.bfloat16     # bf16: data-gradients read the forward pack (tcgen05, MN-major operand) ...
+        need_wd = lambda m: self.need_wd or m.groups > 1   # ... except grouped convs (K-major wd, compact groups)
         self.wn = [c for c in convs if c.norm == "weight_norm"]
         dev = self.wn[0].bias.device
         self.device = dev
@@ -181,14 +184,14 @@ class FoldPlan:
             nf = sf[0] * sf[1] * (sf[2] if len(sf) > 2 else 1)
             nf_al = (nf + 63) // 64 * 64                       # 128-byte aligned packs (TMA base addresses)
             metas.append((m, pg, unf, sf, sd, nf, nf_al))
-            n_pack += (2 if self.need_wd else 1) * nf_al; n_scale += (m.out_channels + 3) // 4 * 4
+            n_pack += (2 if need_wd(m) else 1) * nf_al; n_scale += (m.out_channels + 3) // 4 * 4
         self._packs = torch.zeros(n_pack, device=dev, dtype=dtype)
         self._scales = torch.zeros(n_scale, device=dev, dtype=torch.float32)
         po = so = 0
         for (m, pg, unf, sf, sd, nf, nf_al) in metas:
             wf = self._packs[po:po + nf].view(sf); po += nf_al
             wd = None
-            if self.need_wd:
+            if need_wd(m):
                 wd = self._packs[po:po + nf].view(sd); po += nf_al
             scale = self._scales[so:so + m.out_channels]; so += (m.out_channels + 3) // 4 * 4
             kp = ops.round_up8(m.kernel * m.in_channels) if unf else 0
@@ -213,11 +216,13 @@ class FoldPlan:
                 c_out=m.out_channels, cin_g=cin_g, k=m.kernel, groups=m.groups, pg=f.pg,
                 flags=_lib.PACK_UNFOLD if f.unfold else 0, dw_ld=ld, dw_span=span, row0=row0, tile0=tile0))
             row0 += m.out_channels
-            if f.unfold:
+            if not self.need_wd:          # row form: tile0 counts the wd transposition blocks of the grouped convs
+                tile0 += m.kernel * f.pg if f.wd is not None else 0
+            elif f.unfold:
                 tile0 += -(-m.out_channels // 32) * -(-f.kp // 32)
             else:
                 tile0 += m.kernel * f.pg * -(-(m.out_channels // f.pg) // 32) * -(-(m.in_channels // f.pg) // 32)
-        self.n_items, self.total_rows, self.total_tiles = len(items), row0, (tile0 if self.need_wd else 0)
+        self.n_items, self.total_rows, self.total_tiles = len(items), row0, (tile0 if self.need_wd else -tile0)
         self.item_row0 = [it.row0 for it in items] + [row0]      # table row of each item's first output channel
         self.table = ops.fold_table(items, dev)
         self._ptrs = [(p.data_ptr(), p.grad.data_ptr()) for m in self.wn for p in (m.weight_v, m.weight_g)]
@@ -302,8 +307,9 @@ def _dgrad(f: Folded, dy: Tensor, B: int, t_dy: int, t_x: int, *, phases: int = 
         return dx if out_f32 else ops.cast(dx, f.dtype)
     rows = t_x // 2 if pair_sum else t_x
     dx = torch.empty((B, rows * phases, m.in_channels), device=dy.device, dtype=torch.float32 if out_f32 else f.dtype)
-    # bf16 (tensor engine / logits matvec): data-gradients read the FORWARD pack; fp32 (CUDA-core engine): the wd pack
-    fwd_pack = f.dtype == torch.bfloat16
+    # bf16 (tensor engine / logits matvec): data-gradients read the FORWARD pack - grouped convs the K-major wd pack;
+    # fp32 (CUDA-core engine): the wd pack
+    fwd_pack = f.dtype == torch.bfloat16 and not (m.groups > 1 and f.wd is not None)
     ops.conv(dy, f.wf if fwd_pack else f.wd, n_samples=B, phases=phases, t_src=t_dy, t_dst=t_x, c_src=m.out_channels,
              c_dst=m.in_channels, groups=f.pg, k=m.kernel, dilation=m.dilation, stride=m.stride, pad=m.pad, transposed=True,
              pair_sum=pair_sum, mask=mask, mask_mode=mask_mode, add_pre=add_pre, add_post=add_post, y_raw=dx,

@@ -53,7 +53,8 @@ def make_case(case, seed=0):
 
 
 def _pack_groups(ops, case, engine):
-    """tcgen05 engine: narrow groups are merged into block-diagonal ones of >= 64 channels."""
+    """tcgen05 engine: the pack groups are the UNITS of the compact-group path (groups of fewer than 16 channels are merged
+    into block-diagonal units; everything else keeps the module's own groups)."""
     name, B, p, T, ci, co, k, d, s, pad, g = case
     return ops.tc_pack_groups(ci, co, g) if engine == ops.ENGINE_TCGEN05 else g
 
@@ -77,7 +78,8 @@ def run_dgrad(ops, case, dtype, engine, dy, w, To):
     name, B, p, T, ci, co, k, d, s, pad, g = case
     dev = "cuda"
     pg = _pack_groups(ops, case, engine)
-    fwd_pack = engine == ops.ENGINE_TCGEN05      # the tensor engine reads the forward pack as an MN-major operand
+    # the tensor engine reads the forward pack as an MN-major operand - grouped convs the K-major data-gradient pack
+    fwd_pack = engine == ops.ENGINE_TCGEN05 and g == 1
     we = expand_groups(w, g, pg)
     wd = (pack_fwd(we) if fwd_pack else pack_dgrad(we, pg)).to(dev, dtype)
     g = pg
@@ -151,11 +153,12 @@ def test_simt_bf16(case):
 
 def _tc_conv_desc(ops, case, transposed):
     name, B, p, T, ci, co, k, d, s, pad, g = case
+    grouped = g > 1
     g = ops.tc_pack_groups(ci, co, g)
     To = t_out_of(T, k, d, s, pad)
     if transposed:
         return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci, groups=g, k=k,
-                    dilation=d, stride=s, pad=pad, transposed=1, w_fwd_pack=1, src=1, w=1, y_raw=1)
+                    dilation=d, stride=s, pad=pad, transposed=1, w_fwd_pack=0 if grouped else 1, src=1, w=1, y_raw=1)
     return dict(dtype=1, engine=2, n_samples=B, phases=p, t_src=T, t_dst=To, c_src=ci, c_dst=co, groups=g, k=k,
                 dilation=d, stride=s, pad=pad, transposed=0, src=1, w=1, y_raw=1)
 
@@ -298,14 +301,16 @@ def test_weightnorm_fold_fwd_bwd(shape):
 @pytest.mark.parametrize("shape", [(256, 32, 37, 4), (512, 16, 37, 16), (256, 8, 41, 16), (1024, 64, 41, 16)],
                          ids=["g4", "g16", "g16_c8", "g16_c64"])
 def test_fold_pack_groups(shape):
-    """Narrow groups merged into block-diagonal packs of >= 64 channels (what the tcgen05 engine reads)."""
+    """Pack groups of the tensor engine = the units of the compact-group path: groups keep their own 16 / 32 / 64-channel
+    packs, groups of 8 channels are merged pairwise into block-diagonal units; forward and K-major data-gradient packs."""
     from ste_gan_b200 import ops
     co, cg, k, groups = shape
     gen = torch.Generator().manual_seed(co + k)
     v = torch.randn(co, cg, k, generator=gen); g = torch.rand(co, 1, 1, generator=gen) + 0.5
     w = v * (g / v.norm(2, dim=(1, 2), keepdim=True))
     pg = ops.tc_pack_groups(cg * groups, co, groups)
-    assert groups % pg == 0 and (cg * groups // pg) % 64 == 0 and (co // pg) % 64 == 0
+    unit_in, unit_out = cg * groups // pg, co // pg
+    assert groups % pg == 0 and unit_in == max(cg, 16) and (unit_out in (16, 32) or unit_out % 64 == 0)
     wf, wd, _ = ops.weightnorm_fold(v.cuda(), g.cuda(), groups, torch.bfloat16, pack_groups=pg)
     we = expand_groups(w, groups, pg)
     for mine, ref in ((wf, pack_fwd(we)), (wd, pack_dgrad(we, pg))):

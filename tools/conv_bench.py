@@ -19,6 +19,11 @@ SHAPES = [
     ("s_k5_T400", 1, 400, 512, 1024, 5, 1, 1, 2, 1),
     ("s_k37g4_T1600", 1, 1600, 128, 256, 37, 1, 2, 18, 4),
     ("s_k37g16_T800", 1, 800, 256, 512, 37, 1, 2, 18, 16),
+    ("f_k41g4_T1600", 1, 1600, 128, 128, 41, 1, 2, 20, 4),
+    ("f_k41g16c8_T800", 1, 800, 128, 256, 41, 1, 2, 20, 16),
+    ("f_k41g16s4_T400", 1, 400, 256, 512, 41, 1, 4, 20, 16),
+    ("f_k41g16s4_T100", 1, 100, 512, 1024, 41, 1, 4, 20, 16),
+    ("f_k41g16_T25", 1, 25, 1024, 1024, 41, 1, 1, 20, 16),
     ("s_out_T400", 1, 400, 1024, 1, 3, 1, 1, 1, 1),
     ("p11_l3", 11, 50, 256, 512, 3, 1, 3, 2, 1),
     ("p2_l3", 2, 269, 256, 512, 3, 1, 3, 2, 1),
@@ -72,9 +77,10 @@ def main():
                                                   k=k, dilation=d, stride=s, pad=pad, bias=bias, act=ops.ACT_RELU,
                                                   add_post=res if co >= 8 else None, y_raw=y, y_act=ya)))
         if which in ("dgrad", "all") and co >= 8:
-            runs.append(("dgrad", lambda: ops.conv(dy, wf, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci,
+            # grouped convs: K-major data-gradient pack (compact groups); the others read the forward pack (MN-major)
+            runs.append(("dgrad", lambda: ops.conv(dy, wd if g > 1 else wf, n_samples=B, phases=p, t_src=To, t_dst=T, c_src=co, c_dst=ci,
                                                     groups=pg, k=k, dilation=d, stride=s, pad=pad, transposed=True, mask=x,
-                                                    mask_mode=ops.ACT_RELU, y_raw=dx, w_fwd_pack=True)))
+                                                    mask_mode=ops.ACT_RELU, y_raw=dx, w_fwd_pack=g == 1)))
         if which in ("wgrad", "all") and co >= 32:
             runs.append(("wgrad", lambda: ops.wgrad(x, dy, dw, db, n_samples=B, phases=p, t_in=T, t_out=To, c_in=ci, c_out=co,
                                                     groups=g, k=k, dilation=d, stride=s, pad=pad)))
