@@ -287,9 +287,13 @@ int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int d
  * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable.
  * lr_dev (device float[1], or NULL to use the host value `lr`): the learning rate is read on the device at execution
  * time, so the reference's per-epoch ExponentialLR(.999) (train.py:98-104,470-472) changes it between replays of a
- * captured graph. */
+ * captured graph.
+ * enable (device int32[1], or NULL = always): when *enable == 0 the whole update - step counter included - is skipped;
+ * after an executed update the flag is cleared.  This lets ONE captured graph hold "apply the previous step's generator
+ * gradient, if there is one" at its head (where it overlaps work that does not depend on the generator). */
 int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
-              float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream);
+              float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, int32_t* enable,
+              stg_stream_t stream);
 
 /* diagnostics */
 const char* stg_strerror(int code);

@@ -130,12 +130,19 @@ __global__ void axpy_kernel(float* __restrict__ y, const T* __restrict__ x, floa
     y[i] = fmaf(alpha, to_f(x[i]), y[i]);
 }
 
-__global__ void step_inc_kernel(int64_t* step) { *step += 1; }
+__global__ void step_inc_kernel(int64_t* step, const int32_t* __restrict__ enable) {
+  if (enable == nullptr || *enable != 0) *step += 1;
+}
+__global__ void flag_clear_kernel(int32_t* flag) { *flag = 0; }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr_host,
                                                     const float* __restrict__ lr_dev, float b1, float b2, float eps,
-                                                    float wd, const int64_t* __restrict__ step, float gscale) {
+                                                    float wd, const int64_t* __restrict__ step, float gscale,
+                                                    const int32_t* __restrict__ enable) {
+  // `enable` (device flag, or NULL = always): a CUDA graph that holds this update replays it unconditionally; the flag
+  // turns the replay into a no-op when there is no pending gradient (first replay, or after an explicit flush)
+  if (enable != nullptr && *enable == 0) return;
   const float lr = lr_dev ? *lr_dev : lr_host;   // device-resident learning rate: a schedule changes it without re-capturing graphs
   const float t = (float)(*step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
@@ -306,12 +313,17 @@ extern "C" int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, i
 }
 
 extern "C" int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
-                         float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, stg_stream_t stream) {
+                         float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, int32_t* enable,
+                         stg_stream_t stream) {
   if (!p || !g || !m || !v || !step_count) return STG_EINVAL;
-  step_inc_kernel<<<1, 1, 0, S_>>>(step_count);
+  step_inc_kernel<<<1, 1, 0, S_>>>(step_count, enable);
   STG_LAUNCH_CHECK();
-  adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step_count, grad_scale);
+  adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step_count, grad_scale, enable);
   STG_LAUNCH_CHECK();
+  if (enable) {                    // consumed: the next replay is a no-op until somebody sets the flag again
+    flag_clear_kernel<<<1, 1, 0, S_>>>(enable);
+    STG_LAUNCH_CHECK();
+  }
   return STG_OK;
 }
 

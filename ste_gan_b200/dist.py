@@ -59,6 +59,20 @@ class GradReducer:
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.bucket = max(1, int(bucket_mb * (1 << 20) // 4))
+        # Our own NCCL communicator (ste_gan_b200/nccl.py): all-reduces on explicit streams, capturable inside the CUDA
+        # graphs of the train step.  GPU + NCCL backend only; the gloo tests exercise the torch.distributed path.
+        self.comm = None
+        if self.enabled and torch.cuda.is_available() and dist.get_backend(group) == "nccl" and \
+                os.environ.get("STG_OWN_NCCL", "1") != "0":
+            from .nccl import NcclComm
+            self.comm = NcclComm(group)
+
+    def all_reduce_on(self, flat_slice: torch.Tensor, stream: "torch.cuda.Stream") -> None:
+        """SUM all-reduce of a slice of a flat gradient, enqueued on `stream` through the own communicator (works
+        eagerly and under CUDA-graph capture; ordering against other streams is the caller's business)."""
+        if self.comm is None:
+            raise RuntimeError("GradReducer.all_reduce_on needs the own NCCL communicator (CUDA + nccl backend)")
+        self.comm.all_reduce(flat_slice, stream)
 
     @property
     def grad_scale(self) -> float:

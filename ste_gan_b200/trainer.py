@@ -66,10 +66,10 @@ class FlatParams:
         self.grad.zero_()
 
     def adamw(self, lr, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2,
-              grad_scale: float = 1.0) -> None:
+              grad_scale: float = 1.0, enable: Optional[Tensor] = None) -> None:
         """torch.optim.AdamW(lr=2e-4, betas=(.8,.99)) - ste_gan/constants.py:57.  grad_scale = 1/world
         turns the all-reduced gradient SUM into the data-parallel mean inside the kernel."""
-        ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay, grad_scale)
+        ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, enable)
 
 
 def generator_grad_buckets(offsets: Dict[str, int], numel: int, nblk: int) -> list:
@@ -104,6 +104,9 @@ class GanTrainer:
         self.d_plan = passes.FoldPlan(passes.discriminator_convs(net_d), self.dtype)
         self._d_folded = False                  # d_plan packs match the current D weights
         self.reducer = GradReducer(group)
+        # data parallel with the own NCCL communicator: the all-reduces are stream-ordered launches issued INSIDE the phases
+        # (and therefore inside the captured graphs); without it (STG_OWN_NCCL=0) torch.distributed calls between the graphs
+        self._inline = self.reducer.comm is not None
         dev = self.G.flat.device
         self.device = dev
         # The learning rate lives on the DEVICE (next to FlatParams.step): the AdamW kernels read it when they run, so
@@ -130,6 +133,11 @@ class GanTrainer:
         self._ss = [torch.cuda.Stream(device=dev)]                                    # the same for the batched scale stacks
         self._sn = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # spectral-norm fold chains, one per layer
         self._aux = torch.cuda.Stream(device=dev)                                     # time-domain loss beside the D passes
+        self._comm = torch.cuda.Stream(device=dev)                                    # gradient all-reduces (own NCCL communicator)
+        self._pend = torch.zeros(1, device=dev, dtype=torch.int32)                    # device flag: a generator AdamW is pending (fused graph)
+        self._fused = None                                                            # (step graph, flush graph) of the fused capture
+        self._pending_host = False
+        self._d_reduce_ev = None
         self.concurrent_d = True
         # Gradient buckets of the generator, back to front (= the order its backward completes them).  GBlocks
         # [k2, n) + last_conv | [k1, k2) | [0, k1) + gblocks.0 + embeddings, cut where the parameter count from the
@@ -162,6 +170,26 @@ class GanTrainer:
     def _fold_d(self, refold: bool):
         return passes.fold_discriminator(self.net_d, self.dtype, training=True, plan=self.d_plan, refold=refold,
                                          sn_streams=self._sn if self.concurrent_d else None)
+
+    def _reduce(self, flat_slice: Tensor):
+        """Data parallel: all-reduce (sum) a slice of a flat gradient on the communication stream, ordered after
+        everything enqueued on the current stream so far; returns the event to wait for before the slice is consumed
+        (None without a data-parallel group).  Stream-ordered only - no host wait - so it is the same under capture."""
+        if not self.reducer.enabled or flat_slice.numel() == 0:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._comm.wait_event(ev)
+        self.reducer.all_reduce_on(flat_slice, self._comm)
+        done = torch.cuda.Event()
+        done.record(self._comm)
+        return done
+
+    @staticmethod
+    def _wait_events(evs) -> None:
+        for e in evs:
+            if e is not None:
+                torch.cuda.current_stream().wait_event(e)
 
     def _fork(self) -> None:
         ev = torch.cuda.Event()
@@ -247,6 +275,7 @@ class GanTrainer:
             passes.discriminator_backward(self.net_d, ctx_f, dl[:nd], None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
             passes.discriminator_backward(self.net_d, ctx_r, dl[nd:], None, want_input_grad=False, want_weight_grad=True, plan=self.d_plan)
             self.d_plan.backward(accumulate=False)
+            self._reduce_d()
             return
         subs, heavy, p_idx, s_idx = self._split_subs()
         (rh_f, ch_f), (rh_r, ch_r) = self._fake, self._real
@@ -289,9 +318,22 @@ class GanTrainer:
         self._join()
         self.d_plan.join_wgrads()
         self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
+        self._reduce_d()
 
-    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor, x_pred: Optional[Tensor] = None) -> None:
+    def _reduce_d(self) -> None:
+        """Data parallel: the discriminator gradient is exchanged in one piece right behind its backward pass - everything
+        that follows (D AdamW, the passes of phase G) depends on it.  (own communicator: in-stream, also under capture)"""
+        if self._inline:
+            self._wait_events([self._reduce(self.D.grad)])
+
+    def _phase_d(self, su: Tensor, sess: Tensor, mode: Optional[Tensor], x_real: Tensor, x_pred: Optional[Tensor] = None,
+                 head=None) -> None:
+        """`head` (fused graph): runs on the current stream right before the generator fold + forward - the pending
+        generator update of the previous step - while the discriminator folds and the real pass of the spectral-norm
+        stack, which do not depend on the generator, already run on the side stream."""
+        head = head or (lambda: None)
         if not self.use_adv:
+            head()
             self._g_forward(su, sess, mode, x_pred)
             return
         if self.concurrent_d:
@@ -302,12 +344,14 @@ class GanTrainer:
             with torch.cuda.stream(self._side):
                 self._d_folds()
                 self._d_real(x_real)
+            head()
             self._g_forward(su, sess, mode, x_pred)
             cur.wait_event(self._ev_f1)
             self._d_fake()
             self._join()
         else:
             self._d_folds()
+            head()
             self._g_forward(su, sess, mode, x_pred)
             self._d_fake()
             self._d_real(x_real)
@@ -412,24 +456,49 @@ class GanTrainer:
         if i == len(self.g_buckets) - 1:
             self._gb = self._gctx = None
 
-    def _phase_g(self, x_real: Tensor, update_d: bool = True, reduce: bool = False) -> list:
+    def _phase_g(self, x_real: Tensor, update_d: bool = True, reduce: bool = False, defer_last: bool = False) -> list:
         """Phase G; with reduce=True the all-reduce of each generator-gradient bucket is issued as soon as the bucket is
-        final (it then overlaps the backward of the buckets in front of it).  Returns the pending all-reduce handles."""
+        final (it then overlaps the backward of the buckets in front of it).  Returns the pending all-reduce handles
+        (own communicator: events).  defer_last: the last bucket is NOT exchanged here (see _opt_g_head)."""
         handles = []
         self._phase_g_head(x_real, update_d)
-        for i in range(len(self.g_buckets)):
+        n = len(self.g_buckets)
+        for i in range(n):
             if i > 0:
                 self._g_bucket(i)
-            if reduce:
+            if reduce and not (defer_last and i == n - 1):
                 handles += self._reduce_g_bucket(i)
         return handles
 
     def _reduce_g_bucket(self, i: int) -> list:
         lo, hi = self.g_buckets[i][4]
+        if self._inline:
+            return [self._reduce(self.G.grad[lo:hi])]
         return self.reducer.all_reduce_async(self.G.grad[lo:hi]) if hi > lo else []
+
+    def _wait_handles(self, handles) -> None:
+        if self._inline:
+            self._wait_events(handles)
+        else:
+            self.reducer.wait(handles)
 
     def _phase_opt_g(self) -> None:
         self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale)       # train.py:267
+
+    def _opt_g_head(self) -> None:
+        """Fused graph: the generator update that the PREVIOUS replay left pending - exchange of the last gradient bucket
+        (deferred so that it, too, runs beside work that does not depend on the generator), then AdamW under the device
+        flag `_pend` (a no-op on the first replay and after flush(), which runs the same two launches on its own)."""
+        if self._inline:
+            self._wait_events(self._reduce_g_bucket(len(self.g_buckets) - 1))
+        self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale, enable=self._pend)
+
+    def _fused_step(self, s: dict) -> None:
+        """The whole train step as ONE capturable sequence (no host-side seam): pending generator update of the previous
+        step beside the discriminator folds / real pass -> phase D -> phase G; leaves the generator update pending."""
+        self._phase_d(s["su"], s["sess"], s["mode"], s["x_real"], head=self._opt_g_head)
+        self._wait_handles(self._phase_g(s["x_real"], reduce=self.reducer.enabled, defer_last=True))
+        self._pend.fill_(1)
 
     # ------------------------------------------------------------------ public API
     def step(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,
@@ -440,8 +509,9 @@ class GanTrainer:
         su = speech_units.contiguous().float()
         xr = x_real.contiguous().float()
         self._phase_d(su, session_ids, speaking_mode_ids, xr)
-        self.reducer.all_reduce(self.D.grad)
-        self.reducer.wait(self._phase_g(xr, reduce=True))
+        if not self._inline:
+            self.reducer.all_reduce(self.D.grad)
+        self._wait_handles(self._phase_g(xr, reduce=True))
         self._phase_opt_g()
         return self.slots
 
@@ -455,23 +525,33 @@ class GanTrainer:
         return self._g_losses(x_real, update_d=True)
 
     def capture(self, batch: int, frames: int, unit_dim: int = 256, hop: int = 16, channels: int = 8,
-                pipelined: Optional[bool] = None) -> None:
-        """Capture the step as CUDA graphs over static input buffers (NCCL stays outside the graphs).  Two eager
+                pipelined: Optional[bool] = None, fused: Optional[bool] = None) -> None:
+        """Capture the step as CUDA graphs over static input buffers.  Two eager
         warm-up steps run first (allocator / lazy-initialisation warm-up, on all-zero inputs); the trainer's state -
         parameters, AdamW moments and step counters, spectral-norm u / v, loss slots - is snapshotted before and
         restored after them, so capture() leaves the training state exactly as it found it (resume-then-capture is
         safe, and `steps` in the next checkpoint still counts real steps only).
 
-        pipelined (default: whenever the discriminator passes run concurrently): phase D is captured as its five
-        pieces (see _d_folds) and step_graph() software-pipelines consecutive steps: the all-reduce of the generator
-        gradient and the generator's AdamW of step k run WHILE step k+1's discriminator folds and real pass - which
-        depend on neither - are already executing.  The generator parameters of the last step are final after flush()
-        (the eager step(), state_dict users and the inference engine call it)."""
+        fused (the default; STG_FUSED_GRAPH=0 or an explicit `pipelined` switch it off): the WHOLE step is ONE graph
+        (_fused_step) - with the own NCCL communicator the gradient all-reduces are graph nodes too, so a replay has no
+        host-side seam.  The generator update of step k is left pending on the device (flag `_pend`) and runs at the head
+        of replay k+1, beside that step's discriminator folds and real pass, which depend on neither the generator nor its
+        gradient; flush() applies a pending update on its own (the eager step(), checkpointing, `lr` changes and the
+        inference engine call it).  Measured on one B200 (tools/piece_times.py): the five-plus-two graphs of the
+        pipelined form cost ~0.2 ms per step in launch seams (pieces 3.80 ms, step 4.02 ms).
+
+        pipelined (round-1 form): phase D is captured as its five pieces (see _d_folds) and step_graph()
+        software-pipelines consecutive steps on the host: the all-reduce of the generator gradient and the generator's
+        AdamW of step k run WHILE step k+1's discriminator folds and real pass are already executing; pipelined=False:
+        three graphs (phase D, phase G per bucket, generator AdamW) replayed back to back."""
         dev = self.device
+        import os
+        if fused is None:
+            fused = pipelined is None and os.environ.get("STG_FUSED_GRAPH", "1") != "0"
         if pipelined is None:
-            import os
             pipelined = self.concurrent_d and self.use_adv and os.environ.get("STG_PIPELINE", "1") != "0"
         self.flush()
+        self._fused = None
         self._static = dict(
             su=torch.zeros(batch, frames, unit_dim, device=dev), sess=torch.zeros(batch, device=dev, dtype=torch.int64),
             x_real=torch.zeros(batch, frames * hop, channels, device=dev),
@@ -489,6 +569,18 @@ class GanTrainer:
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
         G = torch.cuda.CUDAGraph
+        # (data parallel: the process group's watchdog thread may touch the CUDA API while we capture)
+        gkw = dict(capture_error_mode="thread_local") if self.reducer.enabled else {}
+        if fused:
+            step_g, flush_g = G(), G()
+            self._pend.zero_()
+            with torch.cuda.graph(step_g, pool=pool, **gkw):
+                self._fused_step(s)
+            with torch.cuda.graph(flush_g, pool=pool, **gkw):
+                self._opt_g_head()
+            self._pend.zero_()
+            self._fused, self._graphs, self._d_graphs, self._pending_host = (step_g, flush_g), None, None, False
+            return
         # graphs that replay beside a gradient all-reduce leave a few SMs to the communicator (STG_NCCL_SMS, default 0 =
         # off: the persistent conv kernels otherwise hold every SM and the NCCL CTAs only get in between launches)
         import contextlib, os
@@ -511,15 +603,15 @@ class GanTrainer:
             pool_a = torch.cuda.graph_pool_handle()
             a1, a2, b1, b2, b3 = G(), G(), G(), G(), G()
             with beside_allreduce():      # (the deferred last bucket of the previous step)
-                with torch.cuda.graph(a1, pool=pool_a):
+                with torch.cuda.graph(a1, pool=pool_a, **gkw):
                     self._d_folds()
-                with torch.cuda.graph(a2, pool=pool_a):
+                with torch.cuda.graph(a2, pool=pool_a, **gkw):
                     self._d_real(s["x_real"])
-            with torch.cuda.graph(b1, pool=pool):
+            with torch.cuda.graph(b1, pool=pool, **gkw):
                 self._g_forward(s["su"], s["sess"], s["mode"])
-            with torch.cuda.graph(b2, pool=pool):
+            with torch.cuda.graph(b2, pool=pool, **gkw):
                 self._d_fake()
-            with torch.cuda.graph(b3, pool=pool):
+            with torch.cuda.graph(b3, pool=pool, **gkw):
                 self._d_update()
             self._d_graphs = (a1, a2, b1, b2, b3)
             self._pipe = torch.cuda.Stream(device=dev)
@@ -528,17 +620,17 @@ class GanTrainer:
         else:
             self._d_graphs = None
             g1 = G()
-            with torch.cuda.graph(g1, pool=pool):
+            with torch.cuda.graph(g1, pool=pool, **gkw):
                 self._phase_d(s["su"], s["sess"], s["mode"], s["x_real"])
         # phase G: one graph per generator-gradient bucket (the bucket's all-reduce is issued between them)
         g2 = [G() for _ in self.g_buckets]
-        with torch.cuda.graph(g2[0], pool=pool):
+        with torch.cuda.graph(g2[0], pool=pool, **gkw):
             self._phase_g_head(s["x_real"])
         for i in range(1, len(g2)):
-            with beside_allreduce(), torch.cuda.graph(g2[i], pool=pool):
+            with beside_allreduce(), torch.cuda.graph(g2[i], pool=pool, **gkw):
                 self._g_bucket(i)
         g3 = G()
-        with torch.cuda.graph(g3, pool=pool):
+        with torch.cuda.graph(g3, pool=pool, **gkw):
             self._phase_opt_g()
         self._graphs = (g1, g2, g3)
 
@@ -556,6 +648,8 @@ class GanTrainer:
         for b, val in snap["sn"]:
             b.copy_(val)
         self.slots.copy_(snap["slots"])
+        self._pend.zero_()
+        self._pending_host = False
         self.refold()
 
     def refold(self) -> None:
@@ -567,9 +661,13 @@ class GanTrainer:
         self._d_folded = True
 
     def flush(self) -> None:
-        """Complete a pipelined step: wait for the generator-gradient all-reduce and run the generator optimiser."""
+        """Complete a deferred generator update (fused graph: the device flag `_pend` is set; pipelined graphs: wait for
+        the generator-gradient all-reduce, then the optimiser graph)."""
+        if self._pending_host and self._fused is not None:
+            self._pending_host = False
+            self._fused[1].replay()           # (exchange of the last bucket +) AdamW under the flag, which it clears
         if self._pending_g is not None:
-            self.reducer.wait(self._pending_g)
+            self._wait_handles(self._pending_g)
             self._pending_g = None
             self._graphs[2].replay()
 
@@ -585,6 +683,10 @@ class GanTrainer:
             if speaking_mode_ids is None:
                 raise ValueError("step_graph: this generator uses speaking-mode embeddings - pass speaking_mode_ids")
             s["mode"].copy_(speaking_mode_ids, non_blocking=True)
+        if self._fused is not None:
+            self._fused[0].replay()
+            self._pending_host = True
+            return self.slots
         g1, g2, g3 = self._graphs
         def phase_g() -> list:
             handles = []
@@ -594,8 +696,9 @@ class GanTrainer:
             return handles
         if self._d_graphs is None:
             g1.replay()
-            self.reducer.all_reduce(self.D.grad)
-            self.reducer.wait(phase_g())
+            if not self._inline:
+                self.reducer.all_reduce(self.D.grad)
+            self._wait_handles(phase_g())
             g3.replay()
             return self.slots
         a1, a2, b1, b2, b3 = self._d_graphs
@@ -612,7 +715,8 @@ class GanTrainer:
         b2.replay()
         cur.wait_event(ev_r)
         b3.replay()
-        self.reducer.all_reduce(self.D.grad)
+        if not self._inline:
+            self.reducer.all_reduce(self.D.grad)
         self._pending_g = phase_g()
         return self.slots
 

@@ -252,3 +252,11 @@ def test_synthetic_batch_matches_oracle_generator():
     for kw in (dict(batch=3, frames=7, seed=5), dict(batch=2, frames=4, seed=9, unit_dim=25, hop=8)):
         for a, b in zip(synthetic_batch(**kw), O.synthetic_batch(**kw)):
             assert torch.equal(a, b)
+
+
+def test_nccl_library_binding_loads():
+    """ste_gan_b200/nccl.py binds the NCCL library PyTorch ships (no GPU needed for the version query)."""
+    from ste_gan_b200 import nccl
+    assert nccl.version() >= 21800
+    for sym in ("ncclGetUniqueId", "ncclCommInitRank", "ncclAllReduce", "ncclCommDestroy"):
+        assert hasattr(nccl.load_library(), sym)

@@ -3,7 +3,7 @@ with and without the multi-stream schedule.  python tools/phase_times.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import ste_gan_oracle as O
+from ste_gan_b200 import synthetic as O
 from ste_gan_b200.models.discriminator import DiscriminatorSmall
 from ste_gan_b200.models.generator import EMGGeneratorGanTTS
 from ste_gan_b200.trainer import GanTrainer
