@@ -54,8 +54,10 @@ class GradReducer:
     Buckets are issued back to front - the order backward completes them - asynchronously on the
     communicator's stream and waited for before the optimiser kernel, which applies 1/world."""
 
-    def __init__(self, group=None, bucket_mb: float = 32.0):
-        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    def __init__(self, group=None, bucket_mb: float = 32.0, enabled: bool = True):
+        """enabled=False: a reducer that does nothing even inside an initialised process group (a single-process reference
+        run on one rank; creating the communicator is a collective, so it must not happen on a subset of the ranks)."""
+        self.enabled = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.bucket = max(1, int(bucket_mb * (1 << 20) // 4))

@@ -93,7 +93,7 @@ def generator_grad_buckets(offsets: Dict[str, int], numel: int, nblk: int) -> li
 class GanTrainer:
     def __init__(self, net_g, net_d, precision: str = "bf16", lr: float = 2e-4, w_td: float = W_TD_DEFAULT,
                  w_fm: float = W_FM_DEFAULT, loss_adversarial: bool = True, loss_multi_td: bool = True,
-                 loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None):
+                 loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None, data_parallel: bool = True):
         self.net_g, self.net_d = net_g, net_d
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.w_td, self.w_fm = w_td, w_fm
@@ -103,7 +103,7 @@ class GanTrainer:
         self.g_plan = passes.FoldPlan(passes.generator_convs(net_g), self.dtype)
         self.d_plan = passes.FoldPlan(passes.discriminator_convs(net_d), self.dtype)
         self._d_folded = False                  # d_plan packs match the current D weights
-        self.reducer = GradReducer(group)
+        self.reducer = GradReducer(group, enabled=data_parallel)
         # data parallel with the own NCCL communicator: the all-reduces are stream-ordered launches issued INSIDE the phases
         # (and therefore inside the captured graphs); without it (STG_OWN_NCCL=0) torch.distributed calls between the graphs
         self._inline = self.reducer.comm is not None

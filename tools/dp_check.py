@@ -32,8 +32,7 @@ for su, sess, xr in batches:
 tr.flush()
 torch.cuda.synchronize()
 if rank == 0:
-    ref = GanTrainer(*nets(), precision="fp32")
-    ref.reducer.enabled, ref.reducer.world = False, 1          # single process, global batch
+    ref = GanTrainer(*nets(), precision="fp32", data_parallel=False)          # single process, global batch
     for su, sess, xr in batches:
         ref.step(su.to(dev), sess.to(dev), xr.to(dev))
     torch.cuda.synchronize()
