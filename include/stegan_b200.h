@@ -290,10 +290,13 @@ int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int d
  * captured graph.
  * enable (device int32[1], or NULL = always): when *enable == 0 the whole update - step counter included - is skipped;
  * after an executed update the flag is cleared.  This lets ONE captured graph hold "apply the previous step's generator
- * gradient, if there is one" at its head (where it overlaps work that does not depend on the generator). */
+ * gradient, if there is one" at its head (where it overlaps work that does not depend on the generator).
+ * flags & STG_ADAMW_KEEP_STEP: do not increment step_count - the update of a SLICE of a network whose first slice already
+ * counted this optimiser step (gradient buckets are updated one by one, each right behind its all-reduce). */
+enum { STG_ADAMW_KEEP_STEP = 1 };
 int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
               float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, int32_t* enable,
-              stg_stream_t stream);
+              int flags, stg_stream_t stream);
 
 /* diagnostics */
 const char* stg_strerror(int code);

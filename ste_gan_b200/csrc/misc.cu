@@ -314,10 +314,12 @@ extern "C" int stg_axpy_f32(float* y, const void* x, int x_dtype, float alpha, i
 
 extern "C" int stg_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float beta1,
                          float beta2, float eps, float weight_decay, int64_t* step_count, float grad_scale, int32_t* enable,
-                         stg_stream_t stream) {
+                         int flags, stg_stream_t stream) {
   if (!p || !g || !m || !v || !step_count) return STG_EINVAL;
-  step_inc_kernel<<<1, 1, 0, S_>>>(step_count, enable);
-  STG_LAUNCH_CHECK();
+  if (!(flags & STG_ADAMW_KEEP_STEP)) {
+    step_inc_kernel<<<1, 1, 0, S_>>>(step_count, enable);
+    STG_LAUNCH_CHECK();
+  }
   adamw_kernel<<<grid_for(n), 256, 0, S_>>>(p, g, m, v, n, lr, lr_dev, beta1, beta2, eps, weight_decay, step_count, grad_scale, enable);
   STG_LAUNCH_CHECK();
   if (enable) {                    // consumed: the next replay is a no-op until somebody sets the flag again

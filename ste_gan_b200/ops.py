@@ -513,9 +513,11 @@ def mse_const_multi(xs, targets, slots: Tensor, slot_idx, grad_scale: float, dx_
 
 
 def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, lr, beta1: float = 0.8, beta2: float = 0.99,
-          eps: float = 1e-8, weight_decay: float = 0.01, grad_scale: float = 1.0, enable: Optional[Tensor] = None) -> None:
+          eps: float = 1e-8, weight_decay: float = 0.01, grad_scale: float = 1.0, enable: Optional[Tensor] = None,
+          keep_step: bool = False) -> None:
     """lr: a Python float, or a device fp32[1] tensor read by the kernel when it RUNS (graph-safe schedules).
-    enable: optional device int32[1]; 0 skips the update (step counter included), an executed update clears it."""
+    enable: optional device int32[1]; 0 skips the update (step counter included), an executed update clears it.
+    keep_step: do not increment `step` (a later slice of a network whose first slice counted this optimiser step)."""
     _need(enable, 1, torch.int32, "enable")
     n = p.numel()
     lr_dev = None
@@ -526,4 +528,4 @@ def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, lr, beta1: f
         _need(t, n, torch.float32, nm)
     _need(step, 1, torch.int64, "step")
     check(_lib.load().stg_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, float(lr), _ptr(lr_dev), beta1, beta2, eps, weight_decay,
-                                _ptr(step), grad_scale, _ptr(enable), _stream()), "stg_adamw")
+                                _ptr(step), grad_scale, _ptr(enable), int(keep_step), _stream()), "stg_adamw")

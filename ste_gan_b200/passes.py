@@ -158,6 +158,19 @@ class FoldPlan:
             return ws.get(torch.cuda.current_stream().cuda_stream)
         return ws
 
+    def join_wgrads_of(self, compute_streams) -> None:
+        """Make the current stream wait for the weight-gradient side streams of these compute streams only (one backward
+        branch is through while others still run); the mapping and the kept operands stay until join_wgrads()."""
+        ws = self.wgrad_stream
+        if not isinstance(ws, dict):
+            return
+        for cs in compute_streams:
+            st = ws.get(cs.cuda_stream)
+            if st is not None:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream().wait_event(ev)
+
     def join_wgrads(self) -> None:
         ws = self.wgrad_stream
         for st in (ws.values() if isinstance(ws, dict) else ([ws] if ws is not None else [])):

@@ -66,10 +66,14 @@ class FlatParams:
         self.grad.zero_()
 
     def adamw(self, lr, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 1e-2,
-              grad_scale: float = 1.0, enable: Optional[Tensor] = None) -> None:
+              grad_scale: float = 1.0, enable: Optional[Tensor] = None, lo: int = 0, hi: Optional[int] = None,
+              keep_step: bool = False) -> None:
         """torch.optim.AdamW(lr=2e-4, betas=(.8,.99)) - ste_gan/constants.py:57.  grad_scale = 1/world
-        turns the all-reduced gradient SUM into the data-parallel mean inside the kernel."""
-        ops.adamw(self.flat, self.grad, self.m, self.v, self.step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, enable)
+        turns the all-reduced gradient SUM into the data-parallel mean inside the kernel.  [lo, hi): update only this
+        slice of the flat buffers (one gradient bucket); every slice but the first of a step passes keep_step."""
+        hi = self.numel if hi is None else hi
+        ops.adamw(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.step, lr, betas[0], betas[1], eps,
+                  weight_decay, grad_scale, enable, keep_step)
 
 
 def generator_grad_buckets(offsets: Dict[str, int], numel: int, nblk: int) -> list:
@@ -139,12 +143,16 @@ class GanTrainer:
         self._pending_host = False
         self._d_reduce_ev = None
         self.concurrent_d = True
+        import os
+        self._d_slices = self._disc_grad_slices() if os.environ.get("STG_D_BUCKETS", "1") != "0" else None
         # Gradient buckets of the generator, back to front (= the order its backward completes them).  GBlocks
         # [k2, n) + last_conv | [k1, k2) | [0, k1) + gblocks.0 + embeddings, cut where the parameter count from the
         # front passes 1/3 and 2/3 (base model: GB3..GB8 | GB2 | GB1, ~8 M parameters each).  Each entry:
         # (first GBlock, end GBlock, first conv, end conv of passes.generator_convs, flat-gradient slice).
         self.g_buckets = generator_grad_buckets(self.G.offsets, self.G.numel, len(list(net_g.gblocks)) - 1)
         # without a data-parallel group there is nothing to overlap: one bucket (one fold-backward launch, one graph)
+        if grad_buckets is None and os.environ.get("STG_G_BUCKETS"):
+            grad_buckets = int(os.environ["STG_G_BUCKETS"])
         if (grad_buckets if grad_buckets is not None else (3 if self.reducer.enabled else 1)) == 1:
             nblk = len(list(net_g.gblocks)) - 1
             self.g_buckets = [(0, nblk, 0, 5 * nblk + 2, (0, self.G.numel))]
@@ -163,6 +171,45 @@ class GanTrainer:
         """One ExponentialLR step (train.py:98-104: gamma .999, stepped once per epoch at train.py:470-472)."""
         self.lr = self._lr * gamma
         return self._lr
+
+    def _disc_grad_slices(self):
+        """Discriminator gradient as three exchange pieces in the order its backward completes them: period stacks | coarse
+        scale stacks (both "early") | the full-rate scale stack ("late": spectral norm, half of the backward work).  Each:
+        (range of weight-normed convs in d_plan's table, slice of the flat gradient).  None when the discriminator does not
+        have that shape (no spectral-norm stack between the period stacks and the remaining scale stacks)."""
+        subs = passes.disc_subnets(self.net_d)
+        heavy, rest = passes._heavy_split(subs)
+        if len(heavy) != 1 or any(i > heavy[0] for i in rest if subs[i][0] == "P") or any(i < heavy[0] for i in rest if subs[i][0] == "S"):
+            return None
+        wn = self.d_plan.wn
+        def item_range(mods):
+            ids = [k for k, m in enumerate(wn) if any(m is c for d_ in mods for c in list(d_.layers) + [d_.output])]
+            return (ids[0], ids[-1] + 1) if ids and ids == list(range(ids[0], ids[-1] + 1)) else None
+        def grad_range(prefixes):
+            offs = [o for nm, o in self.D.offsets.items() if nm.startswith(tuple(prefixes))]
+            nxt = [o for nm, o in self.D.offsets.items() if o > max(offs) and not nm.startswith(tuple(prefixes))]
+            return min(offs), (min(nxt) if nxt else self.D.numel)
+        p_mods = [subs[i][1] for i in rest if subs[i][0] == "P"]
+        s_mods = [subs[i][1] for i in rest if subs[i][0] == "S"]
+        h_mods = [subs[heavy[0]][1]]
+        names = {id(m): nm for nm, m in self.net_d.named_modules()}
+        pre = lambda mods: [names[id(m)] + "." for m in mods]
+        out = dict(early=[], late=None)
+        for mods in (p_mods, s_mods):
+            if mods:
+                ir = item_range(mods)
+                if ir is None:
+                    return None
+                out["early"].append((ir, grad_range(pre(mods))))
+        ir = item_range(h_mods)
+        if ir is None:
+            return None
+        out["late"] = (ir, grad_range(pre(h_mods)))
+        # the three slices must tile the flat gradient exactly
+        cover = sorted([g for _, g in out["early"]] + [out["late"][1]])
+        if cover[0][0] != 0 or cover[-1][1] != self.D.numel or any(a[1] != b[0] for a, b in zip(cover, cover[1:])):
+            return None
+        return out
 
     def _s2(self, i: int):
         return self._side2[i] if self.concurrent_d else None
@@ -315,8 +362,22 @@ class GanTrainer:
             passes.fork_join(self._s2(0), lambda: bwd(ch_r, only(dl_r, heavy)), lambda: bwd(ch_f, only(dl_f, heavy)))
         # current: P stacks, batched | its side: S stacks, batched
         passes.fork_join(self._s2(1), lambda: bwd(cs, only(dl_b, s_idx)), lambda: bwd(cp, only(dl_b, p_idx)))
+        early = []
+        if self._inline and heavy and self._d_slices is not None:
+            # data parallel: the period stacks and the two coarse scale stacks are through (the spectral-norm stack, half
+            # of the work, still runs on the side stream): make THEIR gradients final and exchange them now, so that only
+            # the spectral-norm stack's share of the 47 MB is left exposed behind the backward pass
+            self.d_plan.join_wgrads_of([cur, self._side2[1], *self._ps, *self._ss])
+            for (i_lo, i_hi), (g_lo, g_hi) in self._d_slices["early"]:
+                self.d_plan.backward_range(i_lo, i_hi, accumulate=False)
+                early.append(self._reduce(self.D.grad[g_lo:g_hi]))
         self._join()
         self.d_plan.join_wgrads()
+        if early:
+            (i_lo, i_hi), (g_lo, g_hi) = self._d_slices["late"]
+            self.d_plan.backward_range(i_lo, i_hi, accumulate=False)
+            self._wait_events(early + [self._reduce(self.D.grad[g_lo:g_hi])])
+            return
         self.d_plan.backward(accumulate=False)    # the only contribution since zero_grad: overwrite
         self._reduce_d()
 
@@ -486,18 +547,43 @@ class GanTrainer:
         self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale)       # train.py:267
 
     def _opt_g_head(self) -> None:
-        """Fused graph: the generator update that the PREVIOUS replay left pending - exchange of the last gradient bucket
-        (deferred so that it, too, runs beside work that does not depend on the generator), then AdamW under the device
-        flag `_pend` (a no-op on the first replay and after flush(), which runs the same two launches on its own)."""
+        """Fused graph: the part of the generator update that the PREVIOUS replay left pending - exchange of the LAST
+        gradient bucket (deferred so that it, too, runs beside work that does not depend on the generator), then AdamW of
+        that bucket's slice under the device flag `_pend` (a no-op on the first replay and after flush(), which runs the
+        same launches on its own).  The other buckets were updated inside the previous replay, each right behind its
+        all-reduce (_fused_step), so what is left here is short enough to hide behind the discriminator folds."""
+        n = len(self.g_buckets)
+        lo, hi = self.g_buckets[n - 1][4]
         if self._inline:
-            self._wait_events(self._reduce_g_bucket(len(self.g_buckets) - 1))
-        self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale, enable=self._pend)
+            self._wait_events(self._reduce_g_bucket(n - 1))
+        self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale, enable=self._pend, lo=lo, hi=hi, keep_step=n > 1)
 
     def _fused_step(self, s: dict) -> None:
         """The whole train step as ONE capturable sequence (no host-side seam): pending generator update of the previous
-        step beside the discriminator folds / real pass -> phase D -> phase G; leaves the generator update pending."""
+        step beside the discriminator folds / real pass -> phase D -> phase G.  Every generator-gradient bucket but the
+        last is exchanged AND applied (AdamW on its slice of the flat buffers) on the communication stream while the
+        buckets in front of it are still in their backward pass - the backward reads the packed operands, not the fp32
+        master weights, so updating them early is safe; the last bucket is left pending (_opt_g_head)."""
         self._phase_d(s["su"], s["sess"], s["mode"], s["x_real"], head=self._opt_g_head)
-        self._wait_handles(self._phase_g(s["x_real"], reduce=self.reducer.enabled, defer_last=True))
+        self._phase_g_head(s["x_real"])
+        n, evs = len(self.g_buckets), []
+        for i in range(n - 1):
+            if i > 0:
+                self._g_bucket(i)
+            lo, hi = self.g_buckets[i][4]
+            ev = self._reduce(self.G.grad[lo:hi])
+            if ev is None:                      # no data-parallel group: the slice is final now, fork the side stream here
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._comm.wait_event(ev)
+            with torch.cuda.stream(self._comm):
+                self.G.adamw(self.lr_dev, grad_scale=self.reducer.grad_scale, lo=lo, hi=hi, keep_step=i > 0)
+                done = torch.cuda.Event()
+                done.record(self._comm)
+            evs.append(done)
+        if n > 1:
+            self._g_bucket(n - 1)
+        self._wait_events(evs)
         self._pend.fill_(1)
 
     # ------------------------------------------------------------------ public API
