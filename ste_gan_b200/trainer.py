@@ -658,10 +658,25 @@ class GanTrainer:
         # (data parallel: the process group's watchdog thread may touch the CUDA API while we capture)
         gkw = dict(capture_error_mode="thread_local") if self.reducer.enabled else {}
         if fused:
+            # Data parallel: the persistent conv / wgrad kernels take one CTA per SM with (nearly) the whole register file,
+            # so a concurrent NCCL kernel only finds room on SMs that a launch leaves idle - measured at N = 8, the
+            # all-reduces then cost their full stand-alone time (0.67 ms for the 141 MB of a step) however they are
+            # overlapped.  STG_NCCL_SMS=R keeps R SMs free of them for the communicator inside this graph.
+            from . import _lib as _l
+            # Measured at N = 2 (bench.py, ms per step): R = 0: 4.32, 8: 4.70 (with 8 NCCL channels), 16: 4.25, 24: 4.31; capping
+            # NCCL's channel count to R always lost.  Default 16.
+            reserve = int(os.environ.get("STG_NCCL_SMS", "16")) if self.reducer.enabled else 0
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             step_g, flush_g = G(), G()
             self._pend.zero_()
-            with torch.cuda.graph(step_g, pool=pool, **gkw):
-                self._fused_step(s)
+            if reserve > 0:
+                _l.load().stg_set_sm_limit(n_sm - reserve)
+            try:
+                with torch.cuda.graph(step_g, pool=pool, **gkw):
+                    self._fused_step(s)
+            finally:
+                if reserve > 0:
+                    _l.load().stg_set_sm_limit(0)
             with torch.cuda.graph(flush_g, pool=pool, **gkw):
                 self._opt_g_head()
             self._pend.zero_()
