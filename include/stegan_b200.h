@@ -283,6 +283,38 @@ int stg_l1_mean_multi(const StgL1Item* items, int n_items, int dtype, float* out
 int stg_mse_const_multi(const StgMseItem* items, int n_items, int x_dtype, int dx_dtype, float* slots, float grad_scale,
                         stg_stream_t stream);
 
+/*
+ * EMG-encoder perceptual losses: the pieces of the frozen encoder that are not convolutions / GEMMs.
+ * The encoder is frozen (losses/emg_encoder_loss.py:61), so only input gradients exist.
+ *
+ * nn.LayerNorm over the last axis (layers/transformer.py:37-38,56,59): x, y [rows][D] in `dtype`; stats [rows][2] = (mean,
+ * rstd) for the backward, which returns d/dx from dy, the PRE-norm input x and the stats.
+ */
+int stg_layernorm_fwd(const void* x, int dtype, const float* gamma, const float* beta, int rows, int D, float eps, void* y,
+                      float* stats, stg_stream_t stream);
+int stg_layernorm_bwd(const void* dy, const void* x, int dtype, const float* stats, const float* gamma, int rows, int D,
+                      void* dx, stg_stream_t stream);
+/*
+ * MultiHeadAttention with LearnedRelativePositionalEmbedding (layers/transformer.py:87-113,163-306; unmasked, per-head
+ * embeddings added to the keys): qkv [B][L][3*H*d] = (q | k | v), each [H][d] per row, in `dtype`; emb [H][2*max_rel-1][d]
+ * float32; logit(i,j) = scale * q_i.k_j + (|j-i| < max_rel ? q_i.emb[h][j-i+max_rel-1] : -1e8); probs [B][H][L][L] float32
+ * (softmax, kept for the backward); o [B][L][H*d] = probs * v.  The backward returns dqkv from dout = d/do.
+ * One CTA per (sample, head) with its operands in shared memory: L up to ~140 frames at d = 96 (STG_EUNSUPPORTED beyond;
+ * the train step has 100-128 frames: chunk_size 1600-2048 EMG samples / 16).
+ */
+int stg_relattn_fwd(const void* qkv, int dtype, const float* emb, int B, int L, int H, int d, int max_rel, float scale, void* o,
+                    float* probs, stg_stream_t stream);
+int stg_relattn_bwd(const void* qkv, int dtype, const float* emb, const float* probs, const void* dout, int B, int L, int H,
+                    int d, int max_rel, float scale, void* dqkv, stg_stream_t stream);
+/*
+ * EMGEncoderLoss (losses/emg_encoder_loss.py:63-84) over N = B*T rows: slots[0] += mean_r ||target_r - pred_r + 1e-6||_2
+ * (F.pairwise_distance), slots[1] += mean_r cross_entropy(logits_r, phoneme_r); d_units / d_logits (`grad_dtype`, may be
+ * NULL) = gs_units * d slots[0] / d pred and gs_phonemes * d slots[1] / d logits.
+ */
+int stg_encoder_losses(const float* unit_pred, const float* unit_target, const float* phoneme_logits,
+                       const int64_t* phoneme_target, int N, int Du, int P, float* slots, float gs_units, float gs_phonemes,
+                       void* d_units, void* d_logits, int grad_dtype, stg_stream_t stream);
+
 /* torch.optim.AdamW (ste_gan/constants.py:57; train.py:80-81,199,267) over one flat fp32 buffer.
  * step_count is a device int64 (incremented by the kernel) so the update is CUDA-graph capturable.
  * lr_dev (device float[1], or NULL to use the host value `lr`): the learning rate is read on the device at execution

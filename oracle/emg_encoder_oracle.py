@@ -14,7 +14,8 @@ Every function restates the reference algorithm with explicit tensor formulas an
 Pinned by tests/golden/emg_encoder_tiny.pt (oracle/make_golden.py; the reference pins torch 2.0.1 - under this
 container's torch 2.11 `nn.TransformerEncoder.forward` no longer accepts the reference's custom layer, so the fixture
 generator applies `encoder.transformer.layers` one after the other, which is what the 2.0.1 container does for a stack
-without masks and without a final norm).  No CUDA implementation exists yet: parity for this row is "oracle pinned".
+without masks and without a final norm).  The CUDA implementation (ste_gan_b200/passes_encoder.py, csrc/encoder.cu) is
+checked against this oracle and the fixture by tests/test_encoder_gpu.py.
 """
 from __future__ import annotations
 
@@ -35,15 +36,25 @@ def _bn_eval(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return (x - sd[p + ".running_mean"][None, :, None]) * scale[None, :, None] + sd[p + ".bias"][None, :, None]
 
 
-def res_block(sd: StateDict, p: str, x: Tensor, stride: int) -> Tensor:
+def _relu(x: Tensor, mask) -> Tensor:
+    """ReLU; with `mask` (bool, same shape) the BACKWARD uses its sign pattern (ste_gan_oracle._ActWithMask: parity tests
+    feed the implementation-under-test's own pattern so that both differentiate the same piecewise-linear branch)."""
+    if mask is None:
+        return F.relu(x)
+    from oracle.ste_gan_oracle import _act
+    return _act(x, 0.0, mask)
+
+
+def res_block(sd: StateDict, p: str, x: Tensor, stride: int, masks=None) -> Tensor:
     """conv.py:122-132: relu(bn2(conv2(relu(bn1(conv1 x)))) + res), res = res_norm(1x1 strided conv x) or x."""
-    y = F.relu(_bn_eval(sd, p + ".bn1", F.conv1d(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], stride=stride, padding=1)))
+    m = masks if masks is not None else (None, None)
+    y = _relu(_bn_eval(sd, p + ".bn1", F.conv1d(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], stride=stride, padding=1)), m[0])
     y = _bn_eval(sd, p + ".bn2", F.conv1d(y, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1))
     if p + ".residual_path.weight" in sd:
         res = _bn_eval(sd, p + ".res_norm", F.conv1d(x, sd[p + ".residual_path.weight"], sd[p + ".residual_path.bias"], stride=stride))
     else:
         res = x
-    return F.relu(y + res)
+    return _relu(y + res, m[1])
 
 
 def relative_logits(q: Tensor, emb: Tensor) -> Tensor:
@@ -72,25 +83,26 @@ def attention(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return torch.einsum("bhta,haf->btf", torch.einsum("bhqk,bhka->bhqa", probs, v), w_o)
 
 
-def encoder_layer(sd: StateDict, p: str, x: Tensor) -> Tensor:
+def encoder_layer(sd: StateDict, p: str, x: Tensor, mask=None) -> Tensor:
     """transformer.py:54-60 (dropout is the identity in eval mode)."""
     D = x.shape[-1]
     x = F.layer_norm(x + attention(sd, p + ".self_attn", x), (D,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], LN_EPS)
-    ff = F.linear(F.relu(F.linear(x, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])), sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+    ff = F.linear(_relu(F.linear(x, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"]), mask), sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
     return F.layer_norm(x + ff, (D,), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], LN_EPS)
 
 
-def emg_encoder_forward(sd: StateDict, emg: Tensor) -> Tuple[Tensor, Tensor]:
-    """emg_encoder.py:71-88 in eval mode: emg [B,T,C] -> (speech-unit prediction [B,T/16,256], phoneme logits [B,T/16,P])."""
+def emg_encoder_forward(sd: StateDict, emg: Tensor, masks=None) -> Tuple[Tensor, Tensor]:
+    """emg_encoder.py:71-88 in eval mode: emg [B,T,C] -> (speech-unit prediction [B,T/16,256], phoneme logits [B,T/16,P]).
+    masks (parity tests): dict(blocks=[(inner ReLU [B,C,T], output ReLU [B,C,T]) per ResBlock], layers=[FFN ReLU [B,L,F]])."""
     x = emg.transpose(1, 2)
     i = 0
     while f"conv_blocks.{i}.conv1.weight" in sd:
-        x = res_block(sd, f"conv_blocks.{i}", x, stride=2)                      # every block is built with stride 2 (:50-53)
+        x = res_block(sd, f"conv_blocks.{i}", x, stride=2, masks=masks["blocks"][i] if masks else None)   # every block: stride 2 (:50-53)
         i += 1
     x = F.linear(x.transpose(1, 2), sd["w_raw_in.weight"], sd["w_raw_in.bias"])
     i = 0
     while f"transformer.layers.{i}.linear1.weight" in sd:
-        x = encoder_layer(sd, f"transformer.layers.{i}", x)
+        x = encoder_layer(sd, f"transformer.layers.{i}", x, masks["layers"][i] if masks else None)
         i += 1
     return F.linear(x, sd["w_out.weight"], sd["w_out.bias"]), F.linear(x, sd["w_aux.weight"], sd["w_aux.bias"])
 

@@ -17,7 +17,8 @@ Fixtures (all fp32, seed 0):
                       forwards, so the spectral-norm power iteration is pinned).
   train_step_b1.pt    BASELINE.json configs[0]: G + small D fwd/bwd, B=1, T=100:
                       losses, G output, per-parameter gradient norms and samples.
-  emg_encoder_tiny.pt (no CUDA path yet) a model_size=32, 2-layer EMG encoder in eval
+  emg_encoder_init.pt per-key checksums of the seed-0 initialisation of that encoder (pins the drop-in module's init).
+  emg_encoder_tiny.pt a model_size=32, 2-layer EMG encoder in eval
                       mode: state_dict, two inputs (25 and 111 frames), both outputs, the speech-unit and
                       phoneme losses and the gradient of their sum w.r.t. the EMG input.
 """
@@ -180,6 +181,8 @@ def emg_encoder_fixture():
     from ste_gan.models.emg_encoder import EMGEncoderTransformer
     torch.manual_seed(0)
     enc = EMGEncoderTransformer(8, 256, 48, model_size=32, num_extra_res_blocks=3, num_transformer_layers=2).eval()
+    # seed-0 initialisation checksums (key order included): pins that the drop-in module consumes the RNG identically
+    torch.save({k: tensor_summary(v.float()) for k, v in enc.state_dict().items()}, os.path.join(OUT, "emg_encoder_init.pt"))
     for mod in enc.modules():           # non-trivial BatchNorm statistics (a trained checkpoint has them)
         if isinstance(mod, torch.nn.BatchNorm1d):
             mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)

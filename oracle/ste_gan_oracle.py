@@ -316,14 +316,16 @@ def is_buffer_key(sd: StateDict, k: str) -> bool:
 def losses_and_grads(sd_g: StateDict, sd_d: StateDict, speech_units: Tensor, session_ids: Tensor,
                      x_real: Tensor, small: bool = True, speech_feature_type: str = "SPEECH_UNITS",
                      d_lr_step=None, masks: Optional[Dict[str, object]] = None,
-                     speaking_mode_ids: Optional[Tensor] = None) -> Dict[str, object]:
+                     speaking_mode_ids: Optional[Tensor] = None, encoder: Optional[Dict[str, object]] = None) -> Dict[str, object]:
     """One iteration of train.py:165-268 up to (and excluding) the optimizer
     arithmetic, returning every consumed quantity.  `d_lr_step(sd_d, grads)` -
     if given - is applied between the D and G phases (train.py:199) so that
     the G phase sees the updated discriminator, as in the reference.
     Spectral-norm buffers in `sd_d` advance 4 times (4 training forwards).
     masks (parity tests, see _ActWithMask): optional sign patterns under the keys "g" (generator_forward),
-    "d_fake_det", "d_real", "d_fake" (discriminator_forward of that pass)."""
+    "d_fake_det", "d_real", "d_fake" (discriminator_forward of that pass).
+    encoder: optional dict(sd=<EMG-encoder state_dict>, phoneme_targets=[B, frames] int64, w_su=1.0, w_ph=1.0) - adds the
+    two perceptual losses of train.py:219-230 (oracle/emg_encoder_oracle.py) to the generator loss."""
     masks = masks or {}
     g = {k: (v.detach().clone().requires_grad_(True)) for k, v in sd_g.items()}
     d = {k: (v if is_buffer_key(sd_d, k) else v.detach().clone().requires_grad_(True)) for k, v in sd_d.items()}
@@ -348,6 +350,12 @@ def losses_and_grads(sd_g: StateDict, sd_d: StateDict, speech_units: Tensor, ses
     td, td_parts = multi_td_loss(x_real, x_pred)                                            # :215
     fm = feature_matching_loss(d_fake, d_real2)                                             # :257-262
     loss_g = loss_adv + W_TD * td + W_FM * fm                                               # :216,263
+    if encoder is not None:                                                                 # :219-230
+        from oracle import emg_encoder_oracle as E
+        units, logits = E.emg_encoder_forward(encoder["sd"], x_pred, masks.get("encoder"))
+        su_loss, ph_loss = E.encoder_losses(units, logits, speech_units, encoder["phoneme_targets"])
+        loss_g = loss_g + encoder.get("w_su", 1.0) * su_loss + encoder.get("w_ph", 1.0) * ph_loss
+        out.update(loss_speech_unit=su_loss.detach(), loss_phoneme=ph_loss.detach())
     gparams = list(g.keys())
     x_pred.retain_grad()
     ggrads = torch.autograd.grad(loss_g, [g[k] for k in gparams] + [x_pred])                # :266

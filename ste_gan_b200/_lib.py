@@ -92,6 +92,11 @@ _SIGS = {
     "stg_average_filter": [_P, _L, _I, _I, _I, _P, _P],
     "stg_mse_const": [_P, _I, _L, _F, _P, _F, _P, _I, _P],
     "stg_l1_mean": [_P, _P, _I, _L, _P, _F, _P, _P],
+    "stg_layernorm_fwd": [_P, _I, _P, _P, _I, _I, _F, _P, _P, _P],
+    "stg_layernorm_bwd": [_P, _P, _I, _P, _P, _I, _I, _P, _P],
+    "stg_relattn_fwd": [_P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    "stg_relattn_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
+    "stg_encoder_losses": [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _I, _P],
     "stg_adamw": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _F, _P, _I, _P],
 }
 EXPORTS = sorted(list(_SIGS) + ["stg_strerror", "stg_last_cuda_error", "stg_version", "stg_launch_count", "stg_set_sm_limit"])

@@ -135,6 +135,47 @@ class MultiTdLossFn:
         return TdLossFn.apply(x_real, x_gen, _TD_RES, True, 9)
 
 
+class EncoderFn(torch.autograd.Function):
+    """(speech units, phoneme logits) = frozen EMG encoder(x) - models/emg_encoder.py:71-88 in eval mode; differentiable
+    w.r.t. the EMG input only (the encoder's weights are frozen, losses/emg_encoder_loss.py:61)."""
+
+    @staticmethod
+    def forward(ctx, enc, x):
+        from . import passes_encoder as pe
+        _require_cuda(x, "EMGEncoderTransformer.forward")
+        plan = enc.plan(act_dtype())
+        units, logits, ectx = pe.encoder_forward(plan, x.detach(), need_ctx=ctx.needs_input_grad[1])
+        ctx.plan, ctx.ectx, ctx.in_dtype = plan, ectx, x.dtype
+        return units, logits
+
+    @staticmethod
+    def backward(ctx, g_units, g_logits):
+        from . import passes_encoder as pe
+        dx = pe.encoder_backward(ctx.plan, ctx.ectx, g_units, g_logits)
+        ctx.ectx = None
+        return None, dx.to(ctx.in_dtype)
+
+
+class EncoderLossFn(torch.autograd.Function):
+    """(speech-unit loss, phoneme loss) of losses/emg_encoder_loss.py:63-84 from the encoder's two heads, value and gradient
+    in one fused kernel (the upstream gradients reach it as device scalars: no host synchronisation)."""
+
+    @staticmethod
+    def forward(ctx, unit_pred, unit_target, logits, phoneme_target):
+        _require_cuda(unit_pred, "EMGEncoderLoss")
+        up, lg = unit_pred.detach().contiguous().float(), logits.detach().contiguous().float()
+        slots = torch.zeros(2, device=up.device, dtype=torch.float32)
+        # gradients for unit upstream scales (they are linear in the upstream gradient: scaled in backward)
+        du, dl = ops.encoder_losses(up, unit_target.detach(), lg, phoneme_target, slots, 1.0, 1.0, torch.float32)
+        ctx.save_for_backward(du, dl)
+        return slots[0], slots[1]
+
+    @staticmethod
+    def backward(ctx, g_su, g_ph):
+        du, dl = ctx.saved_tensors
+        return du * g_su, None, dl * g_ph, None
+
+
 class SingleConvFn(torch.autograd.Function):
     """One normalised conv layer in the reference layout ([B,C,T] or [B,C,H,W]) - layers/conv.py:16-17,89-101."""
 

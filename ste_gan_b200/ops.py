@@ -529,3 +529,65 @@ def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, lr, beta1: f
     _need(step, 1, torch.int64, "step")
     check(_lib.load().stg_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, float(lr), _ptr(lr_dev), beta1, beta2, eps, weight_decay,
                                 _ptr(step), grad_scale, _ptr(enable), int(keep_step), _stream()), "stg_adamw")
+
+
+# ---- EMG-encoder perceptual losses
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+    """nn.LayerNorm over the last axis of a contiguous [..., D] tensor -> (y, stats [rows, 2] = mean, rstd)."""
+    D = x.shape[-1]
+    rows = x.numel() // D
+    _need(x, rows * D, None, "x"); _need(gamma, D, torch.float32, "gamma"); _need(beta, D, torch.float32, "beta")
+    y = torch.empty_like(x)
+    stats = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+    check(_lib.load().stg_layernorm_fwd(_ptr(x), code_of(x.dtype), _ptr(gamma), _ptr(beta), rows, D, float(eps), _ptr(y), _ptr(stats),
+                                        _stream()), "stg_layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, stats: Tensor, gamma: Tensor) -> Tensor:
+    D = x.shape[-1]
+    rows = x.numel() // D
+    _need(dy, rows * D, x.dtype, "dy"); _need(x, rows * D, None, "x"); _need(stats, rows * 2, torch.float32, "stats")
+    dx = torch.empty_like(x)
+    check(_lib.load().stg_layernorm_bwd(_ptr(dy), _ptr(x), code_of(x.dtype), _ptr(stats), _ptr(gamma), rows, D, _ptr(dx), _stream()),
+          "stg_layernorm_bwd")
+    return dx
+
+
+def relattn_fwd(qkv: Tensor, emb: Tensor, n_head: int, max_rel: int) -> Tuple[Tensor, Tensor]:
+    """qkv [B, L, 3*H*d] -> (o [B, L, H*d], probs fp32 [B, H, L, L]); emb fp32 [H, 2*max_rel-1, d]."""
+    B, L, C3 = qkv.shape
+    d = C3 // (3 * n_head)
+    _need(qkv, B * L * C3, None, "qkv"); _need(emb, n_head * (2 * max_rel - 1) * d, torch.float32, "emb")
+    o = torch.empty((B, L, n_head * d), device=qkv.device, dtype=qkv.dtype)
+    probs = torch.empty((B, n_head, L, L), device=qkv.device, dtype=torch.float32)
+    check(_lib.load().stg_relattn_fwd(_ptr(qkv), code_of(qkv.dtype), _ptr(emb), B, L, n_head, d, max_rel, float(d) ** -0.5, _ptr(o),
+                                      _ptr(probs), _stream()), "stg_relattn_fwd")
+    return o, probs
+
+
+def relattn_bwd(qkv: Tensor, emb: Tensor, probs: Tensor, dout: Tensor, n_head: int, max_rel: int) -> Tensor:
+    B, L, C3 = qkv.shape
+    d = C3 // (3 * n_head)
+    _need(qkv, B * L * C3, None, "qkv"); _need(dout, B * L * n_head * d, qkv.dtype, "dout")
+    _need(probs, B * n_head * L * L, torch.float32, "probs")
+    dqkv = torch.empty_like(qkv)
+    check(_lib.load().stg_relattn_bwd(_ptr(qkv), code_of(qkv.dtype), _ptr(emb), _ptr(probs), _ptr(dout), B, L, n_head, d, max_rel,
+                                      float(d) ** -0.5, _ptr(dqkv), _stream()), "stg_relattn_bwd")
+    return dqkv
+
+
+def encoder_losses(unit_pred: Tensor, unit_target: Tensor, logits: Tensor, phoneme_target: Tensor, slots: Tensor,
+                   gs_units: float = 0.0, gs_phonemes: float = 0.0, grad_dtype: Optional[torch.dtype] = None):
+    """slots[0] += speech-unit loss, slots[1] += phoneme loss; returns (d_units, d_logits) in grad_dtype (None: no gradients)."""
+    N, Du = unit_pred.numel() // unit_pred.shape[-1], unit_pred.shape[-1]
+    P_ = logits.shape[-1]
+    _need(unit_pred, N * Du, torch.float32, "unit_pred"); _need(unit_target, N * Du, torch.float32, "unit_target")
+    _need(logits, N * P_, torch.float32, "logits"); _need(phoneme_target, N, torch.int64, "phoneme_target")
+    _need(slots, 2, torch.float32, "slots")
+    du = torch.empty(unit_pred.shape, device=unit_pred.device, dtype=grad_dtype) if grad_dtype is not None else None
+    dl = torch.empty(logits.shape, device=logits.device, dtype=grad_dtype) if grad_dtype is not None else None
+    check(_lib.load().stg_encoder_losses(_ptr(unit_pred), _ptr(unit_target), _ptr(logits), _ptr(phoneme_target), N, Du, P_, _ptr(slots),
+                                         float(gs_units), float(gs_phonemes), _ptr(du), _ptr(dl),
+                                         code_of(grad_dtype) if grad_dtype is not None else F32, _stream()), "stg_encoder_losses")
+    return du, dl

@@ -29,7 +29,8 @@ from .dist import GradReducer
 Tensor = torch.Tensor
 
 W_TD_DEFAULT, W_FM_DEFAULT = 15.0, 7.0         # configs/ste_gan_base_gantts.yaml:33,37
-LOSS_NAMES = ["loss_d", "loss_adv", "loss_fm", "loss_td_20_8", "loss_td_51_13", "loss_td_80_16"]
+LOSS_NAMES = ["loss_d", "loss_adv", "loss_fm", "loss_td_20_8", "loss_td_51_13", "loss_td_80_16", "loss_speech_unit", "loss_phoneme"]
+W_SU_DEFAULT, W_PH_DEFAULT = 1.0, 1.0          # configs/ste_gan_base_gantts.yaml: loss_speech_unit_weight / loss_phoneme_weight
 
 
 class FlatParams:
@@ -97,11 +98,28 @@ def generator_grad_buckets(offsets: Dict[str, int], numel: int, nblk: int) -> li
 class GanTrainer:
     def __init__(self, net_g, net_d, precision: str = "bf16", lr: float = 2e-4, w_td: float = W_TD_DEFAULT,
                  w_fm: float = W_FM_DEFAULT, loss_adversarial: bool = True, loss_multi_td: bool = True,
-                 loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None, data_parallel: bool = True):
+                 loss_feat_match: bool = True, group=None, grad_buckets: Optional[int] = None, data_parallel: bool = True,
+                 emg_encoder=None, loss_speech_unit: Optional[bool] = None, loss_phoneme: Optional[bool] = None,
+                 w_su: float = W_SU_DEFAULT, w_ph: float = W_PH_DEFAULT):
+        """emg_encoder: a frozen ste_gan_b200.models.emg_encoder.EMGEncoderTransformer (eval mode) - switches on the two
+        perceptual losses of the generator step (train.py:219-230: speech-unit distance and phoneme cross-entropy of the
+        encoder's predictions on the GENERATED EMG; both default to on when an encoder is given, as in the YAML)."""
         self.net_g, self.net_d = net_g, net_d
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.w_td, self.w_fm = w_td, w_fm
         self.use_adv, self.use_td, self.use_fm = loss_adversarial, loss_multi_td, loss_feat_match
+        self.emg_encoder = emg_encoder
+        self.use_su = (emg_encoder is not None) if loss_speech_unit is None else bool(loss_speech_unit)
+        self.use_ph = (emg_encoder is not None) if loss_phoneme is None else bool(loss_phoneme)
+        if (self.use_su or self.use_ph) and emg_encoder is None:
+            raise ValueError("loss_speech_unit / loss_phoneme need an emg_encoder")
+        self.w_su, self.w_ph = w_su, w_ph
+        self._enc_plan = None
+        if emg_encoder is not None:
+            if emg_encoder.training:
+                raise ValueError("the EMG encoder of the perceptual losses is frozen: call emg_encoder.eval() (emg_encoder_loss.py:61)")
+            self._enc_plan = emg_encoder.plan(self.dtype)
+        self._cur_su = self._cur_ph = None
         self.G, self.D = FlatParams(net_g), FlatParams(net_d)
         # packed operands, gradient arenas and multi-tensor fold tables at fixed addresses (after the re-homing above)
         self.g_plan = passes.FoldPlan(passes.generator_convs(net_g), self.dtype)
@@ -137,6 +155,7 @@ class GanTrainer:
         self._ss = [torch.cuda.Stream(device=dev)]                                    # the same for the batched scale stacks
         self._sn = [torch.cuda.Stream(device=dev) for _ in range(4)]                  # spectral-norm fold chains, one per layer
         self._aux = torch.cuda.Stream(device=dev)                                     # time-domain loss beside the D passes
+        self._enc = torch.cuda.Stream(device=dev)                                     # EMG-encoder losses beside the D passes
         self._comm = torch.cuda.Stream(device=dev)                                    # gradient all-reduces (own NCCL communicator)
         self._pend = torch.zeros(1, device=dev, dtype=torch.int32)                    # device flag: a generator AdamW is pending (fused graph)
         self._fused = None                                                            # (step graph, flush graph) of the fused capture
@@ -287,6 +306,7 @@ class GanTrainer:
         self.slots.zero_()
         self.G.zero_grad(); self.D.zero_grad()
         self._gctx = None
+        self._cur_su = su
         if x_pred is not None:            # discriminator-only workload (disc_losses_step): the fake batch is an input
             self.x_pred = x_pred
             return
@@ -434,6 +454,23 @@ class GanTrainer:
         x_pred = self.x_pred
         dx_pred = torch.zeros_like(x_pred)
         td_ev = None
+        enc_ev, dx_enc = None, None
+        if self.use_su or self.use_ph:
+            # EMG-encoder perceptual losses (train.py:219-230): frozen encoder forward on x_pred, speech-unit distance to the
+            # step's own input units and phoneme cross-entropy, gradient w.r.t. x_pred.  Independent of the discriminator:
+            # on its own stream beside the discriminator passes.
+            from . import passes_encoder as pe
+            if self._cur_ph is None:
+                raise ValueError("the phoneme loss needs phoneme_targets ([B, frames] int64) in step() / step_graph()")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._enc.wait_event(ev)
+            with torch.cuda.stream(self._enc if self.concurrent_d else torch.cuda.current_stream()):
+                dx_enc, self._enc_units, self._enc_logits = pe.encoder_losses(
+                    self._enc_plan, x_pred, self._cur_su, self._cur_ph, self.slots[6:8], self.w_su, self.w_ph, True,
+                    self.use_su, self.use_ph)
+                enc_ev = torch.cuda.Event()
+                enc_ev.record(torch.cuda.current_stream())
         if self.use_td and self.use_adv and self.concurrent_d:
             # the time-domain loss needs only x_real / x_pred: it runs on its own stream beside the discriminator passes
             ev = torch.cuda.Event()
@@ -504,6 +541,9 @@ class GanTrainer:
             ops.axpy_f32(dx_pred, dx_d, 1.0)
         if self.use_td and td_ev is None:
             ops.td_loss(x_real, x_pred, self.slots[3:6], [self.w_td] * 3, dx_pred)   # train.py:215-216
+        if dx_enc is not None:
+            torch.cuda.current_stream().wait_event(enc_ev)
+            ops.axpy_f32(dx_pred, dx_enc, 1.0)
         return dx_pred
 
     def _g_bucket(self, i: int) -> None:
@@ -588,12 +628,13 @@ class GanTrainer:
 
     # ------------------------------------------------------------------ public API
     def step(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,
-             speaking_mode_ids: Optional[Tensor] = None) -> Tensor:
+             speaking_mode_ids: Optional[Tensor] = None, phoneme_targets: Optional[Tensor] = None) -> Tensor:
         """One train step on device tensors (eager launches).  Returns the loss-slot tensor (device, fp32[8]):
         see LOSS_NAMES; no host synchronisation happens here."""
         self.flush()
         su = speech_units.contiguous().float()
         xr = x_real.contiguous().float()
+        self._cur_ph = phoneme_targets
         self._phase_d(su, session_ids, speaking_mode_ids, xr)
         if not self._inline:
             self.reducer.all_reduce(self.D.grad)
@@ -641,14 +682,16 @@ class GanTrainer:
         self._static = dict(
             su=torch.zeros(batch, frames, unit_dim, device=dev), sess=torch.zeros(batch, device=dev, dtype=torch.int64),
             x_real=torch.zeros(batch, frames * hop, channels, device=dev),
-            mode=torch.zeros(batch, device=dev, dtype=torch.int64) if self.net_g.use_speaking_mode_embedding else None)
+            mode=torch.zeros(batch, device=dev, dtype=torch.int64) if self.net_g.use_speaking_mode_embedding else None,
+            ph=torch.zeros(batch, frames, device=dev, dtype=torch.int64) if (self.use_su or self.use_ph) else None)
         s = self._static
+        self._cur_ph = s["ph"]
         snap = self._snapshot_state()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.step(s["su"], s["sess"], s["x_real"], s["mode"])
+                self.step(s["su"], s["sess"], s["x_real"], s["mode"], s["ph"])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._restore_state(snap)
@@ -773,7 +816,7 @@ class GanTrainer:
             self._graphs[2].replay()
 
     def step_graph(self, speech_units: Tensor, session_ids: Tensor, x_real: Tensor,
-                   speaking_mode_ids: Optional[Tensor] = None) -> Tensor:
+                   speaking_mode_ids: Optional[Tensor] = None, phoneme_targets: Optional[Tensor] = None) -> Tensor:
         """Replay the captured step; inputs may be pinned-host or device tensors (copied into the static buffers).
         With a pipelined capture the generator optimiser of this step is deferred into the next call (or flush())."""
         s = self._static
@@ -784,6 +827,10 @@ class GanTrainer:
             if speaking_mode_ids is None:
                 raise ValueError("step_graph: this generator uses speaking-mode embeddings - pass speaking_mode_ids")
             s["mode"].copy_(speaking_mode_ids, non_blocking=True)
+        if s["ph"] is not None:
+            if phoneme_targets is None:
+                raise ValueError("step_graph: the EMG-encoder losses are on - pass phoneme_targets")
+            s["ph"].copy_(phoneme_targets, non_blocking=True)
         if self._fused is not None:
             self._fused[0].replay()
             self._pending_host = True
@@ -836,7 +883,8 @@ class GanTrainer:
     def losses(self) -> Dict[str, float]:
         """Host read of the loss slots (synchronises)."""
         v = self.slots.tolist()
-        out = dict(zip(LOSS_NAMES, v[:6]))
+        out = dict(zip(LOSS_NAMES, v[:8]))
         out["loss_td"] = v[3] + v[4] + v[5]
-        out["loss_g"] = v[1] + self.w_td * out["loss_td"] + self.w_fm * v[2]
+        out["loss_g"] = v[1] + self.w_td * out["loss_td"] + self.w_fm * v[2] + \
+            (self.w_su * v[6] if self.use_su else 0.0) + (self.w_ph * v[7] if self.use_ph else 0.0)
         return out

@@ -177,7 +177,7 @@ def gen_masks(gctx):
     return out
 
 
-def run_step_vs_oracle(g, d, batch, prec, small=True, speaking_mode_ids=None, speech_feature_type="SPEECH_UNITS"):
+def run_step_vs_oracle(g, d, batch, prec, small=True, speaking_mode_ids=None, speech_feature_type="SPEECH_UNITS", encoder=None):
     """One fused train step against the flip-aware oracle: G output, every feature map of the three discriminator
     passes that carry gradients, every loss term, and the gradient of EVERY parameter tensor of G and D."""
     from ste_gan_b200 import passes
@@ -185,7 +185,14 @@ def run_step_vs_oracle(g, d, batch, prec, small=True, speaking_mode_ids=None, sp
     sd_g, sd_d = cpu_sd(g), cpu_sd(d)
     su, sess, x_real = batch
     tol = TOL[prec]
-    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec)
+    enc_arg = None
+    if encoder is not None:                       # (frozen EMG encoder module in eval mode, phoneme targets [B, frames])
+        enc_mod, ph = encoder
+        enc_sd = {k: (v.detach().cpu().double() if v.is_floating_point() else v.detach().cpu().clone()) for k, v in enc_mod.state_dict().items()}
+        enc_arg = dict(sd=enc_sd, phoneme_targets=ph, w_su=1.0, w_ph=1.0)
+    tr = GanTrainer(g.cuda(), d.cuda(), precision=prec, emg_encoder=enc_mod.cuda() if encoder is not None else None)
+    if encoder is not None:
+        tr._cur_ph = ph.cuda()
     mode = speaking_mode_ids.cuda() if speaking_mode_ids is not None else None
     tr._phase_d(su.cuda(), sess.cuda(), mode, x_real.cuda())
     gd = {n: p.grad.detach().cpu().clone() for n, p in d.named_parameters()}
@@ -194,10 +201,14 @@ def run_step_vs_oracle(g, d, batch, prec, small=True, speaking_mode_ids=None, sp
     fm_fake = tr._last_g_fmaps[0]
     masks = dict(g=gen_masks(tr._last_gctx), d_fake_det=disc_masks(fm_fake_det, d), d_real=disc_masks(fm_real, d),
                  d_fake=disc_masks(fm_fake, d))
+    if encoder is not None:                       # the encoder's ReLU sign patterns on THIS x_pred (a second forward of the frozen net)
+        from ste_gan_b200 import passes_encoder as pe
+        from tests.test_encoder_gpu import _enc_masks
+        masks["encoder"] = _enc_masks(pe.encoder_forward(tr._enc_plan, tr.x_pred)[2])
     # the oracle is evaluated in float64: both the reference (fp32) and this library approximate the same function
     f64 = lambda sd: {k: v.double() for k, v in sd.items()}
     ref = O.losses_and_grads(f64(sd_g), f64(sd_d), su.double(), sess, x_real.double(), small=small, masks=masks,
-                             speaking_mode_ids=speaking_mode_ids, speech_feature_type=speech_feature_type)
+                             speaking_mode_ids=speaking_mode_ids, speech_feature_type=speech_feature_type, encoder=enc_arg)
     assert O.rel_l2(tr.x_pred, ref["x_pred"]) < tol
     subs = passes.disc_subnets(d)
     n_flip = 0
