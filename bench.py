@@ -472,6 +472,33 @@ def run_ours(args):
 
     roofline = roofline_block()
 
+    # ---- the train step WITH the EMG-encoder perceptual losses (train.py:219-230): random-init frozen
+    # 768-d encoder (no checkpoint ships with the reference), same batch shape; + 35.0 GFLOP per sample (encoder forward +
+    # input gradient: 4 ResBlocks 8.6 + 6 transformer layers 8.9 GFLOP forward)
+    encoder_step = None
+    if solo and not args.quick:
+        from ste_gan_b200.models.emg_encoder import EMGEncoderTransformer
+        torch.manual_seed(0); g2 = EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8).to(dev)
+        torch.manual_seed(0); d2 = DiscriminatorSmall(8).to(dev)
+        torch.manual_seed(0); enc = EMGEncoderTransformer(8, 256, 48).eval().to(dev)
+        tr2 = GanTrainer(g2, d2, precision="bf16", emg_encoder=enc)
+        tr2.capture(BATCH_PER_GPU, FRAMES, UNIT_DIM, HOP, CHANNELS)
+        ph = torch.randint(0, 48, (BATCH_PER_GPU, FRAMES), generator=torch.Generator().manual_seed(3)).to(dev)
+        for i in range(3):
+            tr2.step_graph(*devb[i % nb], phoneme_targets=ph)
+        ms_enc, _ = timed_region(lambda i: tr2.step_graph(*devb[i % nb], phoneme_targets=ph), tr2.flush, 10, 3, barrier, max_over_ranks)
+        L2 = tr2.losses()
+        gf = STEP_GFLOP_PER_SAMPLE + 35.0
+        encoder_step = {"workload": "configs[1] + speech-unit and phoneme losses through the frozen EMG encoder (768-d, 4 ResBlocks, 6 rel-pos "
+                                    "transformer layers; random init), bf16, batch 16",
+                        "ms_per_step": round(ms_enc, 4), "value": round(BATCH_PER_GPU / (ms_enc / 1e3), 1), "unit": "samples/s",
+                        "roofline": {"bound": "tensor", "achieved": round(gf * BATCH_PER_GPU / ms_enc, 1), "peak": peaks["tflops"],
+                                     "unit": "TFLOP/s", "frac": round(gf * BATCH_PER_GPU / ms_enc / peaks["tflops"], 4)},
+                        "finite": all(v == v and abs(v) < 1e30 for v in L2.values()),
+                        "loss_speech_unit": round(L2["loss_speech_unit"], 4), "loss_phoneme": round(L2["loss_phoneme"], 4)}
+        del tr2, g2, d2, enc
+        torch.cuda.empty_cache()
+
     # ---- the same reference step on THIS GPU through torch + cuDNN: context, not the target
     context = None
     if solo and not args.quick and not args.no_cpu_baseline:
@@ -484,6 +511,7 @@ def run_ours(args):
                 "timed_repeats": repeats, "ms_per_step_all_repeats": [round(x, 4) for x in ms_all],
                 "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
                 "parity_gate": gate, "roofline": roofline, "cpu_baseline": cpu, "inference": inference, "disc_losses": disc_losses,
+                "encoder_step": encoder_step,
                 "context": context, "losses_last_step": {k: round(v, 5) for k, v in final_losses.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -79,18 +79,31 @@ __device__ __forceinline__ void load_rows(const T* __restrict__ base, int64_t ro
     dst[r * ds + c] = to_f(base[(int64_t)r * row_stride + c]);
   }
 }
-
-// shared memory (floats): K [L][ds] | V [L][ds] | E [nE][ds] | per warp: q [d] + p [L]      ds = d + 1 (bank-conflict-free rows)
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+__device__ __forceinline__ void axpy4(float s, const float4& v, float4& acc) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
 template <typename T>
-__global__ void __launch_bounds__(256) relattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb, AttnP p,
+__device__ __forceinline__ void store4(T* p, const float4& v, float s) {
+  p[0] = from_f<T>(v.x * s); p[1] = from_f<T>(v.y * s); p[2] = from_f<T>(v.z * s); p[3] = from_f<T>(v.w * s);
+}
+
+// Operand rows in shared memory are ds = d + 4 floats long: 16-byte aligned, and for d = 96 (ds = 100 = 4 mod 32 banks) the
+// LDS.128 of 8 lanes that read 8 different rows hit 32 different banks - every dot product below reads float4s (3 LDS.128 per 8
+// FMAs instead of 3 LDS.32 per 2; the first version of these kernels was shared-memory-issue-bound at 3 % of the FMA rate).
+// shared memory (floats): K [L][ds] | V [L][ds] | E [nE][ds] | per warp: q [d] + p [Lp]      (d % 4 == 0, Lp = roundup4(L))
+template <typename T>
+__global__ void __launch_bounds__(512) relattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb, AttnP p,
                                                           T* __restrict__ o, float* __restrict__ probs) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const int L = p.L, d = p.d, ds = d + 1, M = p.M, HD = p.H * d;
+  const int L = p.L, d = p.d, ds = d + 4, d4 = d >> 2, M = p.M, HD = p.H * d, Lp = (L + 3) & ~3;
   const int e_lo = max(0, M - L), nE = 2 * M - 1 - 2 * e_lo;          // embedding rows any (i, j) of this length can touch
   float* Ks = sm; float* Vs = Ks + L * ds; float* Es = Vs + L * ds; float* wq = Es + nE * ds;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* myq = wq + warp * (d + L); float* myp = myq + d;
+  float* myq = wq + warp * (d + Lp); float* myp = myq + d;
   const T* base = qkv + (int64_t)b * L * 3 * HD + h * d;
   load_rows(base + HD, 3 * HD, L, d, ds, Ks);
   load_rows(base + 2 * HD, 3 * HD, L, d, ds, Vs);
@@ -102,14 +115,16 @@ __global__ void __launch_bounds__(256) relattn_fwd_kernel(const T* __restrict__ 
   for (int i = warp; i < L; i += nw) {
     for (int c = lane; c < d; c += 32) myq[c] = to_f(base[(int64_t)i * 3 * HD + c]);
     __syncwarp();
+    const float4* q4 = reinterpret_cast<const float4*>(myq);
     float mx = -INFINITY;
     for (int j = lane; j < L; j += 32) {
       const int rel = j - i;
-      float qk = 0.f, qe = 0.f;
-      const float* kr = Ks + j * ds;
       const bool in = rel > -M && rel < M;
-      const float* er = Es + (in ? (rel + M - 1 - e_lo) : 0) * ds;
-      for (int c = 0; c < d; ++c) { qk = fmaf(myq[c], kr[c], qk); qe = fmaf(myq[c], er[c], qe); }
+      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * ds);
+      const float4* e4 = reinterpret_cast<const float4*>(Es + (in ? (rel + M - 1 - e_lo) : 0) * ds);
+      float qk = 0.f, qe = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < d4; ++c) { const float4 q = q4[c]; qk = dot4(q, k4[c], qk); qe = dot4(q, e4[c], qe); }
       const float lg = qk * p.scale + (in ? qe : -1e8f);
       myp[j] = lg;
       mx = fmaxf(mx, lg);
@@ -122,29 +137,30 @@ __global__ void __launch_bounds__(256) relattn_fwd_kernel(const T* __restrict__ 
     float* pr = probs + (((int64_t)b * p.H + h) * L + i) * L;
     for (int j = lane; j < L; j += 32) { const float pv = myp[j] * inv; myp[j] = pv; pr[j] = pv; }
     __syncwarp();
-    for (int c = lane; c < d; c += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < L; ++j) acc = fmaf(myp[j], Vs[j * ds + c], acc);
-      o[((int64_t)b * L + i) * HD + h * d + c] = from_f<T>(acc);
+    for (int c = lane; c < d4; c += 32) {          // 4 output channels per lane
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int j = 0; j < L; ++j) axpy4(myp[j], *reinterpret_cast<const float4*>(Vs + j * ds + 4 * c), acc);
+      store4(o + ((int64_t)b * L + i) * HD + h * d + 4 * c, acc, 1.f);
     }
     __syncwarp();
   }
 }
 
-// shared memory (floats): Q | K | V | dO [L][ds] each | Dr [L] | per warp: row [L]   (the embedding rows are read through L1:
-// four fp32 operand tiles of 100-128 frames leave no room for the 76 KB table of a head)
+// shared memory (floats): Q | K | V | dO [L][ds] each | Dr [Lp] | per warp: row [Lp] + prow [Lp]   (the embedding rows are read
+// through L1: four fp32 operand tiles of 100-128 frames leave no room for the 76 KB table of a head)
 template <typename T>
-__global__ void __launch_bounds__(256) relattn_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb,
+__global__ void __launch_bounds__(512) relattn_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb,
                                                           const float* __restrict__ probs, const T* __restrict__ dout, AttnP p,
                                                           T* __restrict__ dqkv) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const int L = p.L, d = p.d, ds = d + 1, M = p.M, HD = p.H * d;
+  const int L = p.L, d = p.d, ds = d + 4, d4 = d >> 2, M = p.M, HD = p.H * d, Lp = (L + 3) & ~3;
   float* Qs = sm; float* Ks = Qs + L * ds; float* Vs = Ks + L * ds; float* Gs = Vs + L * ds;
-  float* Dr = Gs + L * ds; float* wrow = Dr + L;
+  float* Dr = Gs + L * ds; float* wrow = Dr + Lp;
   const float* Eh = emb + (int64_t)h * (2 * M - 1) * d;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* row = wrow + warp * L;
+  float* row = wrow + warp * 2 * Lp; float* prow = row + Lp;
   const T* base = qkv + (int64_t)b * L * 3 * HD + h * d;
   load_rows(base, 3 * HD, L, d, ds, Qs);
   load_rows(base + HD, 3 * HD, L, d, ds, Ks);
@@ -156,48 +172,59 @@ __global__ void __launch_bounds__(256) relattn_bwd_kernel(const T* __restrict__ 
   // pass 1, a warp per query row i: dP_ij = dO_i . V_j ; D_i = sum_j dP_ij P_ij ; dS_ij = P_ij (dP_ij - D_i) ;
   //                                 dq_i = sum_j dS_ij (scale K_j + E[j - i])
   for (int i = warp; i < L; i += nw) {
+    const float4* g4 = reinterpret_cast<const float4*>(Gs + i * ds);
     float dsum = 0.f;
     for (int j = lane; j < L; j += 32) {
+      const float4* v4 = reinterpret_cast<const float4*>(Vs + j * ds);
       float dp = 0.f;
-      const float* gr = Gs + i * ds; const float* vr = Vs + j * ds;
-      for (int c = 0; c < d; ++c) dp = fmaf(gr[c], vr[c], dp);
+#pragma unroll 4
+      for (int c = 0; c < d4; ++c) dp = dot4(g4[c], v4[c], dp);
+      const float pij = P[(int64_t)i * L + j];
+      prow[j] = pij;
       row[j] = dp;
-      dsum = fmaf(dp, P[(int64_t)i * L + j], dsum);
+      dsum = fmaf(dp, pij, dsum);
     }
     dsum = warp_sum_f(dsum);
     if (lane == 0) Dr[i] = dsum;
-    for (int j = lane; j < L; j += 32) row[j] = P[(int64_t)i * L + j] * (row[j] - dsum);
+    for (int j = lane; j < L; j += 32) row[j] = prow[j] * (row[j] - dsum);
     __syncwarp();
-    for (int c = lane; c < d; c += 32) {
-      float acc = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), ae = ak;
+#pragma unroll 2
       for (int j = 0; j < L; ++j) {
+        const float w = row[j];
+        axpy4(w, *reinterpret_cast<const float4*>(Ks + j * ds + 4 * c), ak);
         const int rel = j - i;
-        float w = Ks[j * ds + c] * p.scale;
-        if (rel > -M && rel < M) w += Eh[(int64_t)(rel + M - 1) * d + c];
-        acc = fmaf(row[j], w, acc);
+        if (rel > -M && rel < M) axpy4(w, *reinterpret_cast<const float4*>(Eh + (int64_t)(rel + M - 1) * d + 4 * c), ae);
       }
-      dbase[(int64_t)i * 3 * HD + c] = from_f<T>(acc);
+      ak.x = ak.x * p.scale + ae.x; ak.y = ak.y * p.scale + ae.y; ak.z = ak.z * p.scale + ae.z; ak.w = ak.w * p.scale + ae.w;
+      store4(dbase + (int64_t)i * 3 * HD + 4 * c, ak, 1.f);
     }
     __syncwarp();
   }
   __syncthreads();
   // pass 2, a warp per key row j: dS_ij recomputed from D_i ; dk_j = scale sum_i dS_ij q_i ; dv_j = sum_i P_ij dO_i
   for (int j = warp; j < L; j += nw) {
+    const float4* v4 = reinterpret_cast<const float4*>(Vs + j * ds);
     for (int i = lane; i < L; i += 32) {
+      const float4* g4 = reinterpret_cast<const float4*>(Gs + i * ds);
       float dp = 0.f;
-      const float* gr = Gs + i * ds; const float* vr = Vs + j * ds;
-      for (int c = 0; c < d; ++c) dp = fmaf(gr[c], vr[c], dp);
-      row[i] = P[(int64_t)i * L + j] * (dp - Dr[i]);
+#pragma unroll 4
+      for (int c = 0; c < d4; ++c) dp = dot4(g4[c], v4[c], dp);
+      const float pij = P[(int64_t)i * L + j];
+      prow[i] = pij;
+      row[i] = pij * (dp - Dr[i]);
     }
     __syncwarp();
-    for (int c = lane; c < d; c += 32) {
-      float dk = 0.f, dv = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+#pragma unroll 2
       for (int i = 0; i < L; ++i) {
-        dk = fmaf(row[i], Qs[i * ds + c], dk);
-        dv = fmaf(P[(int64_t)i * L + j], Gs[i * ds + c], dv);
+        axpy4(row[i], *reinterpret_cast<const float4*>(Qs + i * ds + 4 * c), dk);
+        axpy4(prow[i], *reinterpret_cast<const float4*>(Gs + i * ds + 4 * c), dv);
       }
-      dbase[(int64_t)j * 3 * HD + HD + c] = from_f<T>(dk * p.scale);
-      dbase[(int64_t)j * 3 * HD + 2 * HD + c] = from_f<T>(dv);
+      store4(dbase + (int64_t)j * 3 * HD + HD + 4 * c, dk, p.scale);
+      store4(dbase + (int64_t)j * 3 * HD + 2 * HD + 4 * c, dv, 1.f);
     }
     __syncwarp();
   }
@@ -270,23 +297,26 @@ extern "C" int stg_layernorm_bwd(const void* dy, const void* x, int dtype, const
   return STG_OK;
 }
 
-static size_t attn_smem(int L, int d, int M, int n_rows_sets, bool with_emb, int per_warp, int extra) {
-  const int ds = d + 1, e_lo = M - L > 0 ? M - L : 0, nE = with_emb ? 2 * M - 1 - 2 * e_lo : 0;
-  return sizeof(float) * ((size_t)n_rows_sets * L * ds + (size_t)nE * ds + extra + 8 * (size_t)per_warp);
+static size_t attn_smem(int L, int d, int M, int n_tiles, bool with_emb, int per_warp, int extra, int n_warps) {
+  const int ds = d + 4, e_lo = M - L > 0 ? M - L : 0, nE = with_emb ? 2 * M - 1 - 2 * e_lo : 0;
+  return sizeof(float) * ((size_t)n_tiles * L * ds + (size_t)nE * ds + extra + (size_t)n_warps * per_warp);
 }
 
 extern "C" int stg_relattn_fwd(const void* qkv, int dtype, const float* emb, int B, int L, int H, int d, int max_rel, float scale,
                                void* o, float* probs, stg_stream_t stream) {
-  if (!qkv || !emb || !o || !probs || B < 1 || L < 1 || H < 1 || d < 1 || max_rel < 1) return STG_EINVAL;
-  const size_t smem = attn_smem(L, d, max_rel, 2, true, d + L, 0);
-  if (smem > 220 * 1024) return STG_EUNSUPPORTED;      // sequence too long for the one-CTA-per-head kernel (L <= ~230 at d = 96)
+  if (!qkv || !emb || !o || !probs || B < 1 || L < 1 || H < 1 || d < 4 || (d & 3) || max_rel < 1) return STG_EINVAL;
+  const int Lp = (L + 3) & ~3;
+  int nw = 16;                                          // 16 warps when their scratch fits beside the operand tiles, else 8
+  size_t smem = attn_smem(L, d, max_rel, 2, true, d + Lp, 0, nw);
+  if (smem > 220 * 1024) { nw = 8; smem = attn_smem(L, d, max_rel, 2, true, d + Lp, 0, nw); }
+  if (smem > 220 * 1024) return STG_EUNSUPPORTED;      // sequence too long for the one-CTA-per-head kernel
   AttnP p{B, L, H, d, max_rel, scale};
   if (dtype == STG_F32) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    relattn_fwd_kernel<float><<<B * H, 256, smem, S_>>>((const float*)qkv, emb, p, (float*)o, probs);
+    relattn_fwd_kernel<float><<<B * H, 32 * nw, smem, S_>>>((const float*)qkv, emb, p, (float*)o, probs);
   } else if (dtype == STG_BF16) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    relattn_fwd_kernel<bf16><<<B * H, 256, smem, S_>>>((const bf16*)qkv, emb, p, (bf16*)o, probs);
+    relattn_fwd_kernel<bf16><<<B * H, 32 * nw, smem, S_>>>((const bf16*)qkv, emb, p, (bf16*)o, probs);
   } else return STG_EINVAL;
   STG_LAUNCH_CHECK();
   return STG_OK;
@@ -294,16 +324,19 @@ extern "C" int stg_relattn_fwd(const void* qkv, int dtype, const float* emb, int
 
 extern "C" int stg_relattn_bwd(const void* qkv, int dtype, const float* emb, const float* probs, const void* dout, int B, int L,
                                int H, int d, int max_rel, float scale, void* dqkv, stg_stream_t stream) {
-  if (!qkv || !emb || !probs || !dout || !dqkv || B < 1 || L < 1 || H < 1 || d < 1 || max_rel < 1) return STG_EINVAL;
-  const size_t smem = attn_smem(L, d, max_rel, 4, false, L, L);
+  if (!qkv || !emb || !probs || !dout || !dqkv || B < 1 || L < 1 || H < 1 || d < 4 || (d & 3) || max_rel < 1) return STG_EINVAL;
+  const int Lp = (L + 3) & ~3;
+  int nw = 16;
+  size_t smem = attn_smem(L, d, max_rel, 4, false, 2 * Lp, Lp, nw);
+  if (smem > 220 * 1024) { nw = 8; smem = attn_smem(L, d, max_rel, 4, false, 2 * Lp, Lp, nw); }
   if (smem > 220 * 1024) return STG_EUNSUPPORTED;
   AttnP p{B, L, H, d, max_rel, scale};
   if (dtype == STG_F32) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    relattn_bwd_kernel<float><<<B * H, 256, smem, S_>>>((const float*)qkv, emb, probs, (const float*)dout, p, (float*)dqkv);
+    relattn_bwd_kernel<float><<<B * H, 32 * nw, smem, S_>>>((const float*)qkv, emb, probs, (const float*)dout, p, (float*)dqkv);
   } else if (dtype == STG_BF16) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    relattn_bwd_kernel<bf16><<<B * H, 256, smem, S_>>>((const bf16*)qkv, emb, probs, (const bf16*)dout, p, (bf16*)dqkv);
+    relattn_bwd_kernel<bf16><<<B * H, 32 * nw, smem, S_>>>((const bf16*)qkv, emb, probs, (const bf16*)dout, p, (bf16*)dqkv);
   } else return STG_EINVAL;
   STG_LAUNCH_CHECK();
   return STG_OK;
