@@ -626,3 +626,45 @@ def test_time_domain_feature_loss_any_setting(win, shift, pad, aw):
     assert O.rel_l2(td.frame_power(xg.cuda()), (ws.double() ** 2).sum(-1)) < 1e-6
     low = O.average_filter(O.average_filter(xg.double().transpose(1, 2), aw), aw).transpose(1, 2)
     assert O.rel_l2(td.double_average(xg.cuda()), low) < 1e-6
+
+
+def test_disc_losses_step_matches_reference_port():
+    """GanTrainer.disc_losses_step (BASELINE.json configs[4]: D stacks + TD + FM + LSGAN isolated, fwd + bwd incl. the D AdamW
+    step) against the same sequence on the CPU (baseline/ref_runner.PortTrainer = the oracle's functions): the gradient w.r.t.
+    the fake batch that phase G hands to the generator, small and full discriminator, fp32."""
+    from baseline import ref_runner as R
+    from ste_gan_b200.trainer import GanTrainer
+    for small in (True, False):
+        g, d = _fresh_nets(small=small)
+        gen = torch.Generator().manual_seed(40)
+        x_pred = torch.tanh(torch.randn(2, 1024, 8, generator=gen))
+        _, _, x_real = O.synthetic_batch(2, 64, seed=41)
+        ref = R.PortTrainer("cpu", small=small)
+        dx_ref = ref.disc_losses_step(x_pred, x_real)
+        tr = GanTrainer(g.cuda(), d.cuda(), precision="fp32")
+        dx = tr.disc_losses_step(x_pred.cuda(), x_real.cuda())
+        # (the D AdamW step between the phases turns noise-level gradient elements into +-lr updates: 1e-3, not 1e-4)
+        assert O.rel_l2(dx, dx_ref) < 1e-3, (small, O.rel_l2(dx, dx_ref))
+        assert int(tr.D.step) == 1 and int(tr.G.step) == 0
+
+
+def test_utterance_generator_graph_cache_and_speaking_mode():
+    """The serving engine: LRU-bounded per-shape graph cache, speaking-mode ids through the captured graph, flush of a
+    trainer's pending generator update before the weights are packed."""
+    import ste_gan_b200
+    from ste_gan_b200.inference import UtteranceGenerator
+    from ste_gan_b200.models.generator import EMGGeneratorGanTTS
+    g = seeded(lambda: EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8, use_speaking_mode_embedding=True, channels=64)).cuda()
+    ug = UtteranceGenerator(g, "fp32", max_graphs=2)
+    outs = {}
+    for T in (20, 24, 28, 20):
+        su, sess, _ = O.synthetic_batch(1, T, seed=T)
+        mode = torch.tensor([T % 3])
+        y = ug.generate_graph(su.cuda(), sess.cuda(), mode.cuda()).clone()
+        with torch.no_grad():
+            ref = O.generator_forward(cpu_sd(g), su, sess, mode)
+        assert O.rel_l2(y, ref) < 1e-4, T
+        outs[T] = y
+    assert len(ug._graphs) == 2 and (1, 20) in ug._graphs and (1, 28) in ug._graphs      # (1, 24) was the least recently used
+    with pytest.raises(ValueError):
+        ug.generate_graph(*[t.cuda() for t in O.synthetic_batch(1, 20, seed=1)[:2]])     # speaking-mode ids are required
