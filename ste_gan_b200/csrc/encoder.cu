@@ -91,76 +91,111 @@ __device__ __forceinline__ void store4(T* p, const float4& v, float s) {
 }
 
 // Operand rows in shared memory are ds = d + 4 floats long: 16-byte aligned, and for d = 96 (ds = 100 = 4 mod 32 banks) the
-// LDS.128 of 8 lanes that read 8 different rows hit 32 different banks - every dot product below reads float4s (3 LDS.128 per 8
-// FMAs instead of 3 LDS.32 per 2; the first version of these kernels was shared-memory-issue-bound at 3 % of the FMA rate).
-// shared memory (floats): K [L][ds] | V [L][ds] | E [nE][ds] | per warp: q [d] + p [Lp]      (d % 4 == 0, Lp = roundup4(L))
+// LDS.128 of 8 lanes that read 8 different rows hit 32 different banks.  Every product is register-blocked over AR = 4 rows of
+// the side that is NOT spread over the lanes: a K / V / E / Q / dO row costs a lane one LDS.128 (4 shared-memory wavefronts)
+// and is then used against 4 broadcast rows (1 wavefront each), i.e. 16 FMAs per ~8 wavefronts instead of 4 per ~9.
+// History at B = 16, L = 100, d = 96 (per layer): scalar dots 203 us forward / 568 us backward -> float4 dots, 16 warps 115 / 241
+// -> 4-row blocks: see DESIGN.md section 3.5.
+constexpr int AR = 4;
+
+// shared memory (floats): K [L][ds] | V [L][ds] | per warp: q [AR][d] + logits/probs [AR][Lp] + positional logits [AR][Lt]
+// (d % 4 == 0, Lp = roundup4(L), Lt = roundup4(L + AR)); the head's embedding rows are read through L1.
 template <typename T>
-__global__ void __launch_bounds__(512) relattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb, AttnP p,
+__global__ void __launch_bounds__(512, 1) relattn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb, AttnP p,
                                                           T* __restrict__ o, float* __restrict__ probs) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const int L = p.L, d = p.d, ds = d + 4, d4 = d >> 2, M = p.M, HD = p.H * d, Lp = (L + 3) & ~3;
-  const int e_lo = max(0, M - L), nE = 2 * M - 1 - 2 * e_lo;          // embedding rows any (i, j) of this length can touch
-  float* Ks = sm; float* Vs = Ks + L * ds; float* Es = Vs + L * ds; float* wq = Es + nE * ds;
+  const int L = p.L, d = p.d, ds = d + 4, d4 = d >> 2, M = p.M, HD = p.H * d, Lp = (L + 3) & ~3, Lt = (L + AR + 3) & ~3;
+  float* Ks = sm; float* Vs = Ks + L * ds; float* wsc = Vs + L * ds;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* myq = wq + warp * (d + Lp); float* myp = myq + d;
+  float* qs = wsc + warp * (AR * d + AR * Lp + AR * Lt); float* lg = qs + AR * d; float* ts = lg + AR * Lp;
+  const float* Eh = emb + (int64_t)h * (2 * M - 1) * d;
   const T* base = qkv + (int64_t)b * L * 3 * HD + h * d;
   load_rows(base + HD, 3 * HD, L, d, ds, Ks);
   load_rows(base + 2 * HD, 3 * HD, L, d, ds, Vs);
-  for (int i = threadIdx.x; i < nE * d; i += blockDim.x) {
-    const int r = i / d, c = i - r * d;
-    Es[r * ds + c] = emb[((int64_t)h * (2 * M - 1) + e_lo + r) * d + c];
-  }
   __syncthreads();
-  for (int i = warp; i < L; i += nw) {
-    for (int c = lane; c < d; c += 32) myq[c] = to_f(base[(int64_t)i * 3 * HD + c]);
-    __syncwarp();
-    const float4* q4 = reinterpret_cast<const float4*>(myq);
-    float mx = -INFINITY;
-    for (int j = lane; j < L; j += 32) {
-      const int rel = j - i;
-      const bool in = rel > -M && rel < M;
-      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * ds);
-      const float4* e4 = reinterpret_cast<const float4*>(Es + (in ? (rel + M - 1 - e_lo) : 0) * ds);
-      float qk = 0.f, qe = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < d4; ++c) { const float4 q = q4[c]; qk = dot4(q, k4[c], qk); qe = dot4(q, e4[c], qe); }
-      const float lg = qk * p.scale + (in ? qe : -1e8f);
-      myp[j] = lg;
-      mx = fmaxf(mx, lg);
+  for (int ib = warp * AR; ib < L; ib += nw * AR) {
+    const int nr = min(AR, L - ib);
+    for (int x = lane; x < AR * d; x += 32) {
+      const int r = x / d, c = x - r * d;
+      qs[x] = r < nr ? to_f(base[(int64_t)(ib + r) * 3 * HD + c]) : 0.f;
     }
-    mx = warp_max_f(mx);
-    float sum = 0.f;
-    for (int j = lane; j < L; j += 32) { const float e = __expf(myp[j] - mx); myp[j] = e; sum += e; }
-    sum = warp_sum_f(sum);
-    const float inv = 1.f / sum;
-    float* pr = probs + (((int64_t)b * p.H + h) * L + i) * L;
-    for (int j = lane; j < L; j += 32) { const float pv = myp[j] * inv; myp[j] = pv; pr[j] = pv; }
     __syncwarp();
-    for (int c = lane; c < d4; c += 32) {          // 4 output channels per lane
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int j = 0; j < L; ++j) axpy4(myp[j], *reinterpret_cast<const float4*>(Vs + j * ds + 4 * c), acc);
-      store4(o + ((int64_t)b * L + i) * HD + h * d + 4 * c, acc, 1.f);
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    for (int j = lane; j < L; j += 32) {                          // q . k
+      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * ds);
+      float acc[AR] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int c = 0; c < d4; ++c) {
+        const float4 k = k4[c];
+#pragma unroll
+        for (int r = 0; r < AR; ++r) acc[r] = dot4(q4[r * d4 + c], k, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < AR; ++r) lg[r * Lp + j] = acc[r] * p.scale;
+    }
+    // q . emb[rel] for every relative position the block can meet: rel = mi - (ib + AR - 1), i.e. j - i = rel for row i = ib + r
+    // at j = mi - (AR - 1) + r
+    for (int mi = lane; mi < L + AR - 1; mi += 32) {
+      const int rel = mi - (ib + AR - 1);
+      const bool in = rel > -M && rel < M;
+      float acc[AR] = {0.f, 0.f, 0.f, 0.f};
+      if (in) {
+        const float4* e4 = reinterpret_cast<const float4*>(Eh + (int64_t)(rel + M - 1) * d);
+#pragma unroll 2
+        for (int c = 0; c < d4; ++c) {
+          const float4 e = e4[c];
+#pragma unroll
+          for (int r = 0; r < AR; ++r) acc[r] = dot4(q4[r * d4 + c], e, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < AR; ++r) ts[r * Lt + mi] = in ? acc[r] : -1e8f;
+    }
+    __syncwarp();
+    for (int r = 0; r < nr; ++r) {                                // softmax of row ib + r
+      float* row = lg + r * Lp;
+      const float* tr = ts + r * Lt + (AR - 1 - r);               // tr[j] = positional logit of (ib + r, j)
+      float mx = -INFINITY;
+      for (int j = lane; j < L; j += 32) { const float v = row[j] + tr[j]; row[j] = v; mx = fmaxf(mx, v); }
+      mx = warp_max_f(mx);
+      float sum = 0.f;
+      for (int j = lane; j < L; j += 32) { const float e = __expf(row[j] - mx); row[j] = e; sum += e; }
+      sum = warp_sum_f(sum);
+      const float inv = 1.f / sum;
+      float* pr = probs + (((int64_t)b * p.H + h) * L + ib + r) * L;
+      for (int j = lane; j < L; j += 32) { const float pv = row[j] * inv; row[j] = pv; pr[j] = pv; }
+    }
+    __syncwarp();
+    for (int c = lane; c < d4; c += 32) {                         // probs . v, 4 output channels per lane
+      float4 acc[AR];
+#pragma unroll
+      for (int r = 0; r < AR; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int j = 0; j < L; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(Vs + j * ds + 4 * c);
+#pragma unroll
+        for (int r = 0; r < AR; ++r) axpy4(lg[r * Lp + j], v, acc[r]);
+      }
+      for (int r = 0; r < nr; ++r) store4(o + ((int64_t)b * L + ib + r) * HD + h * d + 4 * c, acc[r], 1.f);
     }
     __syncwarp();
   }
 }
 
-// shared memory (floats): Q | K | V | dO [L][ds] each | Dr [Lp] | per warp: row [Lp] + prow [Lp]   (the embedding rows are read
-// through L1: four fp32 operand tiles of 100-128 frames leave no room for the 76 KB table of a head)
+// shared memory (floats): Q | K | V | dO [L][ds] each | Dr [Lp] | per warp: dS block [AR][Lp]   (embedding rows through L1)
 template <typename T>
-__global__ void __launch_bounds__(512) relattn_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb,
+__global__ void __launch_bounds__(512, 1) relattn_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ emb,
                                                           const float* __restrict__ probs, const T* __restrict__ dout, AttnP p,
                                                           T* __restrict__ dqkv) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
   const int L = p.L, d = p.d, ds = d + 4, d4 = d >> 2, M = p.M, HD = p.H * d, Lp = (L + 3) & ~3;
   float* Qs = sm; float* Ks = Qs + L * ds; float* Vs = Ks + L * ds; float* Gs = Vs + L * ds;
-  float* Dr = Gs + L * ds; float* wrow = Dr + Lp;
+  float* Dr = Gs + L * ds; float* wsc = Dr + Lp;
   const float* Eh = emb + (int64_t)h * (2 * M - 1) * d;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* row = wrow + warp * 2 * Lp; float* prow = row + Lp;
+  float* dS = wsc + warp * AR * Lp;
   const T* base = qkv + (int64_t)b * L * 3 * HD + h * d;
   load_rows(base, 3 * HD, L, d, ds, Qs);
   load_rows(base + HD, 3 * HD, L, d, ds, Ks);
@@ -169,62 +204,100 @@ __global__ void __launch_bounds__(512) relattn_bwd_kernel(const T* __restrict__ 
   __syncthreads();
   const float* P = probs + ((int64_t)b * p.H + h) * L * L;
   T* dbase = dqkv + (int64_t)b * L * 3 * HD + h * d;
-  // pass 1, a warp per query row i: dP_ij = dO_i . V_j ; D_i = sum_j dP_ij P_ij ; dS_ij = P_ij (dP_ij - D_i) ;
-  //                                 dq_i = sum_j dS_ij (scale K_j + E[j - i])
-  for (int i = warp; i < L; i += nw) {
-    const float4* g4 = reinterpret_cast<const float4*>(Gs + i * ds);
-    float dsum = 0.f;
+  // pass 1, a warp per block of AR query rows: dP_ij = dO_i . V_j ; D_i = sum_j dP_ij P_ij ; dS_ij = P_ij (dP_ij - D_i) ;
+  //                                             dq_i = sum_j dS_ij (scale K_j + E[j - i])
+  for (int ib = warp * AR; ib < L; ib += nw * AR) {
+    const int nr = min(AR, L - ib);
+    float dsum[AR] = {0.f, 0.f, 0.f, 0.f};
     for (int j = lane; j < L; j += 32) {
       const float4* v4 = reinterpret_cast<const float4*>(Vs + j * ds);
-      float dp = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < d4; ++c) dp = dot4(g4[c], v4[c], dp);
-      const float pij = P[(int64_t)i * L + j];
-      prow[j] = pij;
-      row[j] = dp;
-      dsum = fmaf(dp, pij, dsum);
+      float acc[AR] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int c = 0; c < d4; ++c) {
+        const float4 v = v4[c];
+#pragma unroll
+        for (int r = 0; r < AR; ++r)
+          acc[r] = dot4(*reinterpret_cast<const float4*>(Gs + min(ib + r, L - 1) * ds + 4 * c), v, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < AR; ++r) {
+        dS[r * Lp + j] = acc[r];
+        if (r < nr) dsum[r] = fmaf(acc[r], P[(int64_t)(ib + r) * L + j], dsum[r]);
+      }
     }
-    dsum = warp_sum_f(dsum);
-    if (lane == 0) Dr[i] = dsum;
-    for (int j = lane; j < L; j += 32) row[j] = prow[j] * (row[j] - dsum);
+#pragma unroll
+    for (int r = 0; r < AR; ++r) dsum[r] = warp_sum_f(dsum[r]);
+    if (lane == 0)
+      for (int r = 0; r < nr; ++r) Dr[ib + r] = dsum[r];
+    for (int j = lane; j < L; j += 32)
+#pragma unroll
+      for (int r = 0; r < AR; ++r) dS[r * Lp + j] = r < nr ? P[(int64_t)(ib + r) * L + j] * (dS[r * Lp + j] - dsum[r]) : 0.f;
     __syncwarp();
     for (int c = lane; c < d4; c += 32) {
-      float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), ae = ak;
+      float4 ak[AR], ae[AR];
+#pragma unroll
+      for (int r = 0; r < AR; ++r) { ak[r] = make_float4(0.f, 0.f, 0.f, 0.f); ae[r] = ak[r]; }
 #pragma unroll 2
       for (int j = 0; j < L; ++j) {
-        const float w = row[j];
-        axpy4(w, *reinterpret_cast<const float4*>(Ks + j * ds + 4 * c), ak);
-        const int rel = j - i;
-        if (rel > -M && rel < M) axpy4(w, *reinterpret_cast<const float4*>(Eh + (int64_t)(rel + M - 1) * d + 4 * c), ae);
+        const float4 k = *reinterpret_cast<const float4*>(Ks + j * ds + 4 * c);
+#pragma unroll
+        for (int r = 0; r < AR; ++r) axpy4(dS[r * Lp + j], k, ak[r]);
       }
-      ak.x = ak.x * p.scale + ae.x; ak.y = ak.y * p.scale + ae.y; ak.z = ak.z * p.scale + ae.z; ak.w = ak.w * p.scale + ae.w;
-      store4(dbase + (int64_t)i * 3 * HD + 4 * c, ak, 1.f);
+      for (int mi = 0; mi < L + AR - 1; ++mi) {                  // relative position rel meets row ib + r at j = mi - (AR - 1) + r
+        const int rel = mi - (ib + AR - 1);
+        if (rel <= -M || rel >= M) continue;
+        const float4 e = *reinterpret_cast<const float4*>(Eh + (int64_t)(rel + M - 1) * d + 4 * c);
+#pragma unroll
+        for (int r = 0; r < AR; ++r) {
+          const int j = mi - (AR - 1) + r;
+          if (j >= 0 && j < L) axpy4(dS[r * Lp + j], e, ae[r]);
+        }
+      }
+      for (int r = 0; r < nr; ++r) {
+        float4 q = ak[r];
+        q.x = q.x * p.scale + ae[r].x; q.y = q.y * p.scale + ae[r].y; q.z = q.z * p.scale + ae[r].z; q.w = q.w * p.scale + ae[r].w;
+        store4(dbase + (int64_t)(ib + r) * 3 * HD + 4 * c, q, 1.f);
+      }
     }
     __syncwarp();
   }
   __syncthreads();
-  // pass 2, a warp per key row j: dS_ij recomputed from D_i ; dk_j = scale sum_i dS_ij q_i ; dv_j = sum_i P_ij dO_i
-  for (int j = warp; j < L; j += nw) {
-    const float4* v4 = reinterpret_cast<const float4*>(Vs + j * ds);
+  // pass 2, a warp per block of AR key rows: dS_ij recomputed from D_i ; dk_j = scale sum_i dS_ij q_i ; dv_j = sum_i P_ij dO_i
+  for (int jb = warp * AR; jb < L; jb += nw * AR) {
+    const int nr = min(AR, L - jb);
     for (int i = lane; i < L; i += 32) {
       const float4* g4 = reinterpret_cast<const float4*>(Gs + i * ds);
-      float dp = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < d4; ++c) dp = dot4(g4[c], v4[c], dp);
-      const float pij = P[(int64_t)i * L + j];
-      prow[i] = pij;
-      row[i] = pij * (dp - Dr[i]);
+      float acc[AR] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int c = 0; c < d4; ++c) {
+        const float4 g = g4[c];
+#pragma unroll
+        for (int r = 0; r < AR; ++r)
+          acc[r] = dot4(g, *reinterpret_cast<const float4*>(Vs + min(jb + r, L - 1) * ds + 4 * c), acc[r]);
+      }
+      const float di = Dr[i];
+#pragma unroll
+      for (int r = 0; r < AR; ++r) dS[r * Lp + i] = r < nr ? P[(int64_t)i * L + jb + r] * (acc[r] - di) : 0.f;
     }
     __syncwarp();
     for (int c = lane; c < d4; c += 32) {
-      float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+      float4 dk[AR], dv[AR];
+#pragma unroll
+      for (int r = 0; r < AR; ++r) { dk[r] = make_float4(0.f, 0.f, 0.f, 0.f); dv[r] = dk[r]; }
 #pragma unroll 2
       for (int i = 0; i < L; ++i) {
-        axpy4(row[i], *reinterpret_cast<const float4*>(Qs + i * ds + 4 * c), dk);
-        axpy4(prow[i], *reinterpret_cast<const float4*>(Gs + i * ds + 4 * c), dv);
+        const float4 q = *reinterpret_cast<const float4*>(Qs + i * ds + 4 * c);
+        const float4 g = *reinterpret_cast<const float4*>(Gs + i * ds + 4 * c);
+#pragma unroll
+        for (int r = 0; r < AR; ++r) {
+          axpy4(dS[r * Lp + i], q, dk[r]);
+          axpy4(r < nr ? P[(int64_t)i * L + jb + r] : 0.f, g, dv[r]);
+        }
       }
-      store4(dbase + (int64_t)j * 3 * HD + HD + 4 * c, dk, p.scale);
-      store4(dbase + (int64_t)j * 3 * HD + 2 * HD + 4 * c, dv, 1.f);
+      for (int r = 0; r < nr; ++r) {
+        store4(dbase + (int64_t)(jb + r) * 3 * HD + HD + 4 * c, dk[r], p.scale);
+        store4(dbase + (int64_t)(jb + r) * 3 * HD + 2 * HD + 4 * c, dv[r], 1.f);
+      }
     }
     __syncwarp();
   }
@@ -297,19 +370,21 @@ extern "C" int stg_layernorm_bwd(const void* dy, const void* x, int dtype, const
   return STG_OK;
 }
 
-static size_t attn_smem(int L, int d, int M, int n_tiles, bool with_emb, int per_warp, int extra, int n_warps) {
-  const int ds = d + 4, e_lo = M - L > 0 ? M - L : 0, nE = with_emb ? 2 * M - 1 - 2 * e_lo : 0;
-  return sizeof(float) * ((size_t)n_tiles * L * ds + (size_t)nE * ds + extra + (size_t)n_warps * per_warp);
+static size_t attn_smem(int L, int d, int n_tiles, int per_warp, int extra, int n_warps) {
+  const int ds = d + 4;
+  return sizeof(float) * ((size_t)n_tiles * L * ds + extra + (size_t)n_warps * per_warp);
 }
+constexpr size_t ATTN_SMEM_MAX = 226 * 1024;
 
 extern "C" int stg_relattn_fwd(const void* qkv, int dtype, const float* emb, int B, int L, int H, int d, int max_rel, float scale,
                                void* o, float* probs, stg_stream_t stream) {
   if (!qkv || !emb || !o || !probs || B < 1 || L < 1 || H < 1 || d < 4 || (d & 3) || max_rel < 1) return STG_EINVAL;
   const int Lp = (L + 3) & ~3;
+  const int Lt = (L + 4 + 3) & ~3, pw = 4 * d + 4 * Lp + 4 * Lt;      // per-warp scratch (AR = 4 rows)
   int nw = 16;                                          // 16 warps when their scratch fits beside the operand tiles, else 8
-  size_t smem = attn_smem(L, d, max_rel, 2, true, d + Lp, 0, nw);
-  if (smem > 220 * 1024) { nw = 8; smem = attn_smem(L, d, max_rel, 2, true, d + Lp, 0, nw); }
-  if (smem > 220 * 1024) return STG_EUNSUPPORTED;      // sequence too long for the one-CTA-per-head kernel
+  size_t smem = attn_smem(L, d, 2, pw, 0, nw);
+  if (smem > ATTN_SMEM_MAX) { nw = 8; smem = attn_smem(L, d, 2, pw, 0, nw); }
+  if (smem > ATTN_SMEM_MAX) return STG_EUNSUPPORTED;    // sequence too long for the one-CTA-per-head kernel
   AttnP p{B, L, H, d, max_rel, scale};
   if (dtype == STG_F32) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -327,9 +402,9 @@ extern "C" int stg_relattn_bwd(const void* qkv, int dtype, const float* emb, con
   if (!qkv || !emb || !probs || !dout || !dqkv || B < 1 || L < 1 || H < 1 || d < 4 || (d & 3) || max_rel < 1) return STG_EINVAL;
   const int Lp = (L + 3) & ~3;
   int nw = 16;
-  size_t smem = attn_smem(L, d, max_rel, 4, false, 2 * Lp, Lp, nw);
-  if (smem > 220 * 1024) { nw = 8; smem = attn_smem(L, d, max_rel, 4, false, 2 * Lp, Lp, nw); }
-  if (smem > 220 * 1024) return STG_EUNSUPPORTED;
+  size_t smem = attn_smem(L, d, 4, 4 * Lp, Lp, nw);
+  if (smem > ATTN_SMEM_MAX) { nw = 8; smem = attn_smem(L, d, 4, 4 * Lp, Lp, nw); }
+  if (smem > ATTN_SMEM_MAX) return STG_EUNSUPPORTED;
   AttnP p{B, L, H, d, max_rel, scale};
   if (dtype == STG_F32) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(relattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
