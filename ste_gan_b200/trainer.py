@@ -160,7 +160,6 @@ class GanTrainer:
         self._pend = torch.zeros(1, device=dev, dtype=torch.int32)                    # device flag: a generator AdamW is pending (fused graph)
         self._fused = None                                                            # (step graph, flush graph) of the fused capture
         self._pending_host = False
-        self._d_reduce_ev = None
         self.concurrent_d = True
         import os
         self._d_slices = self._disc_grad_slices() if os.environ.get("STG_D_BUCKETS", "1") != "0" else None
