@@ -138,11 +138,12 @@ int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float
  * spectral_norm (legacy torch.nn.utils.spectral_norm, layers/conv.py:94,101): when
  * `training`, one power iteration updating u[c_out], v[cin_g*k] in place (eps 1e-12), then
  * sigma = u^T W v, packs of W/sigma as above.  `sigma_out[0]` receives sigma.
- * scratch: float[c_out + cin_g*k + 8].
+ * scratch: float[c_out + cin_g*k + 8].  u_used / v_used (optional, [c_out] / [cin_g*k]): copies of the u, v THIS forward used,
+ * for its backward (the module's buffers move on with the next forward's power iteration).
  */
 int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
                           int pack_groups, int flags, int training, int dtype, void* wf, void* wd, float* sigma_out,
-                          float* scratch, stg_stream_t stream);
+                          float* scratch, float* u_used, float* v_used, stg_stream_t stream);
 /* d w_orig = dw/sigma - (sum(dw .* w_orig)/sigma^2) u v^T ; u, v, sigma are the values used by that forward. */
 int stg_spectralnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, const float* w_orig, const float* u, const float* v,
                               const float* sigma, int c_out, int cin_g, int k, int groups, float* dw_orig, int accumulate,

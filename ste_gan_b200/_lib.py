@@ -58,7 +58,7 @@ _SIGS = {
     "stg_weightnorm_fold": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "stg_weightnorm_fold_bwd": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     "stg_wgrad_layout": [C.POINTER(StgWgrad), C.POINTER(C.c_int), C.POINTER(C.c_int)],
-    "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "stg_spectralnorm_fold": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "stg_spectralnorm_fold_bwd": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
     "stg_tc_pack_groups": [_I, _I, _I],
     "stg_l1_mean_multi": [_P, _I, _I, _P, _F, _P],

@@ -157,6 +157,48 @@ __global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W
   s = block_sum(s, red);
   if (threadIdx.x == 0) out[row] = s;
 }
+// Fused forms (the power iteration of a layer is a chain of dependent launches on the step's critical path: 7 -> 4):
+// raw_u[row] = sum_col W[row][col] * v[col] with v = raw_v / max(||raw_v||, eps) normalised ON THE FLY (every block re-derives the
+// norm of the <= 2560-element vector); block 0 also stores v (the module's buffer) and the copy the backward will use.
+__global__ void __launch_bounds__(256) sn_w_v_norm_kernel(const float* __restrict__ W, const float* __restrict__ raw_v, int n,
+                                                          float eps, float* __restrict__ out, float* __restrict__ v_dst,
+                                                          float* __restrict__ v_copy) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fmaf(raw_v[i], raw_v[i], ss);
+  ss = block_sum(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), eps);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float vi = raw_v[i] / nrm;
+    s = fmaf(W[(int64_t)row * n + i], vi, s);
+    if (row == 0) { v_dst[i] = vi; if (v_copy) v_copy[i] = vi; }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[row] = s;
+}
+// u = raw / max(||raw||, eps), sigma = ||raw||^2 / max(||raw||, eps), scale[0..c_out) = 1 / sigma, optional copy of u - one launch
+// instead of normalise + fill-scale + a device-to-device copy.
+__global__ void __launch_bounds__(1024) sn_finish_u_kernel(const float* __restrict__ raw, int n, float eps, float* __restrict__ u,
+                                                           float* __restrict__ u_copy, float* __restrict__ sigma,
+                                                           float* __restrict__ scale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(raw[i], raw[i], s);
+  s = block_sum(s, red);
+  const float nrm = fmaxf(sqrtf(s), eps), sg = s / nrm;
+  __syncthreads();      // every thread has read raw[] (scale aliases it) before anyone overwrites
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ui = raw[i] / nrm;
+    u[i] = ui;
+    if (u_copy) u_copy[i] = ui;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) scale[i] = 1.f / sg;
+  if (threadIdx.x == 0) *sigma = sg;
+}
 __global__ void __launch_bounds__(1024) sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
                                                       float* __restrict__ out) {
   __shared__ float red[32];
@@ -614,7 +656,7 @@ extern "C" int stg_weightnorm_fold_bwd(const float* dw, int dw_ld, int dw_span, 
 
 extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, int c_out, int cin_g, int k, int groups,
                                      int pack_groups, int flags, int training, int dtype, void* wf, void* wd,
-                                     float* sigma_out, float* scratch, stg_stream_t stream) {
+                                     float* sigma_out, float* scratch, float* u_used, float* v_used, stg_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w_orig || !u || !v || !sigma_out || !scratch) return STG_EINVAL;
   const int n = cin_g * k;
@@ -627,21 +669,22 @@ extern "C" int stg_spectralnorm_fold(const float* w_orig, float* u, float* v, in
     dim3 g1(ceil_div(n, 256), ceil_div(c_out, 32));
     sn_wt_u_kernel<<<g1, 256, 0, s>>>(w_orig, u, c_out, n, raw_v);
     STG_LAUNCH_CHECK();
-    sn_normalize_kernel<<<1, 1024, 0, s>>>(raw_v, n, eps, v, nullptr);
+    // v = normalize(W^T u) folded into the W v product; u = raw/max(||raw||,eps), sigma = <u, W v> = ||raw||^2 / max(||raw||, eps),
+    // the per-channel scale 1/sigma and the (u, v) copies that the backward of THIS forward needs: four launches in all
+    sn_w_v_norm_kernel<<<c_out, 256, 0, s>>>(w_orig, raw_v, n, eps, raw_u, v, v_used);
     STG_LAUNCH_CHECK();
-    sn_w_v_kernel<<<c_out, 256, 0, s>>>(w_orig, v, n, raw_u);
-    STG_LAUNCH_CHECK();
-    // u = raw/max(||raw||,eps) ; sigma = <u, W v> = ||raw||^2 / max(||raw||, eps)
-    sn_normalize_kernel<<<1, 1024, 0, s>>>(raw_u, c_out, eps, u, sigma_out);
+    sn_finish_u_kernel<<<1, 1024, 0, s>>>(raw_u, c_out, eps, u, u_used, sigma_out, scale);
     STG_LAUNCH_CHECK();
   } else {
     sn_w_v_kernel<<<c_out, 256, 0, s>>>(w_orig, v, n, raw_u);
     STG_LAUNCH_CHECK();
     sn_dot_kernel<<<1, 1024, 0, s>>>(u, raw_u, c_out, sigma_out);
     STG_LAUNCH_CHECK();
+    sn_fill_scale_kernel<<<ceil_div(c_out, 256), 256, 0, s>>>(sigma_out, c_out, scale);
+    STG_LAUNCH_CHECK();
+    if (u_used) STG_CUDA_CHECK(cudaMemcpyAsync(u_used, u, sizeof(float) * c_out, cudaMemcpyDeviceToDevice, s));
+    if (v_used) STG_CUDA_CHECK(cudaMemcpyAsync(v_used, v, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   }
-  sn_fill_scale_kernel<<<ceil_div(c_out, 256), 256, 0, s>>>(sigma_out, c_out, scale);
-  STG_LAUNCH_CHECK();
   if (dtype == STG_F32) return launch_packs<float>(w_orig, scale, c_out, cin_g, k, groups, pack_groups, flags, (float*)wf, (float*)wd, s);
   if (dtype == STG_BF16) return launch_packs<bf16>(w_orig, scale, c_out, cin_g, k, groups, pack_groups, flags, (bf16*)wf, (bf16*)wd, s);
   return STG_EINVAL;

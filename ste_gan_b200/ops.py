@@ -210,8 +210,9 @@ def weightnorm_fold_bwd(dw: Tensor, v: Tensor, g: Tensor, dv: Tensor, dg: Tensor
 
 
 def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, training: bool, dtype: torch.dtype,
-                      want_dgrad: bool = True, pack_groups: Optional[int] = None, unfold: bool = False):
-    """In-place power iteration on u, v when training.  Returns (wf, wd, sigma[1])."""
+                      want_dgrad: bool = True, pack_groups: Optional[int] = None, unfold: bool = False, keep_uv: bool = False):
+    """In-place power iteration on u, v when training.  Returns (wf, wd, sigma[1]) - with keep_uv also copies of the u, v this
+    forward used (written by the same kernels), for its backward."""
     c_out, cin_g, k = w_orig.shape[0], w_orig.shape[1], w_orig.shape[2]
     n = cin_g * k
     pg = groups if pack_groups is None else pack_groups
@@ -221,9 +222,14 @@ def spectralnorm_fold(w_orig: Tensor, u: Tensor, v: Tensor, groups: int, trainin
     wd = torch.empty(sd, device=u.device, dtype=dtype) if want_dgrad else None
     sigma = torch.empty((1,), device=u.device, dtype=torch.float32)
     scratch = torch.empty((c_out + n + 8,), device=u.device, dtype=torch.float32)
+    u_used = torch.empty_like(u) if keep_uv else None
+    v_used = torch.empty_like(v) if keep_uv else None
     check(_lib.load().stg_spectralnorm_fold(_ptr(w_orig), _ptr(u), _ptr(v), c_out, cin_g, k, groups, pg,
                                             _lib.PACK_UNFOLD if unfold else 0, int(training), code_of(dtype), _ptr(wf),
-                                            _ptr(wd), _ptr(sigma), _ptr(scratch), _stream()), "stg_spectralnorm_fold")
+                                            _ptr(wd), _ptr(sigma), _ptr(scratch), _ptr(u_used), _ptr(v_used), _stream()),
+          "stg_spectralnorm_fold")
+    if keep_uv:
+        return wf, wd, sigma, u_used, v_used
     return wf, wd, sigma
 
 

@@ -82,9 +82,9 @@ def fold(mod, dtype: torch.dtype, training: bool = True, want_dgrad: bool = True
         if persist is not None:
             persist[id(mod)] = f
         return f
-    wf, wd, sigma = ops.spectralnorm_fold(_w3(mod.weight_orig.data), mod.weight_u, mod.weight_v, mod.groups, training,
-                                          dtype, want_dgrad, pack_groups=pg, unfold=unf)
-    return Folded(mod, wf, wd, dtype, u=mod.weight_u.clone(), v=mod.weight_v.clone(), sigma=sigma, pg=pg, unfold=unf, kp=kp)
+    wf, wd, sigma, u_used, v_used = ops.spectralnorm_fold(_w3(mod.weight_orig.data), mod.weight_u, mod.weight_v, mod.groups,
+                                                          training, dtype, want_dgrad, pack_groups=pg, unfold=unf, keep_uv=True)
+    return Folded(mod, wf, wd, dtype, u=u_used, v=v_used, sigma=sigma, pg=pg, unfold=unf, kp=kp)
 
 
 def _grad_of(p: torch.nn.Parameter) -> Tensor:
