@@ -593,6 +593,24 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
   }
 }
 
+// the same transposition for ONE conv (per-layer folds: the spectral-norm layers re-pack on every forward)
+template <typename T>
+__global__ void __launch_bounds__(256) wd_from_wf_direct_kernel(const T* __restrict__ wf, T* __restrict__ wd, int c_out, int c_in,
+                                                                int pg) {
+  __shared__ T slab[8192];
+  const int j = blockIdx.x / pg, u = blockIdx.x - j * pg;
+  const int cin_gp = c_in / pg, cout_gp = c_out / pg, n = cin_gp * cout_gp;
+  const T* src = wf + ((int64_t)j * c_out + (int64_t)u * cout_gp) * cin_gp;
+  T* dst = wd + ((int64_t)j * c_in + (int64_t)u * cin_gp) * cout_gp;
+  if (n <= 8192) {
+    for (int i = threadIdx.x; i < n; i += 256) slab[i] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) { const int c = i / cout_gp, r = i - c * cout_gp; dst[i] = slab[r * cin_gp + c]; }
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) { const int c = i / cout_gp, r = i - c * cout_gp; dst[i] = src[(int64_t)r * cin_gp + c]; }
+  }
+}
+
 template <typename T>
 int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k, int groups, int pg, int flags, T* wf,
                  T* wd, cudaStream_t s) {
@@ -617,7 +635,12 @@ int launch_packs(const float* v, const float* scale, int c_out, int cin_g, int k
     pack_fwd_kernel<T><<<g1, 256, 0, s>>>(v, scale, c_out, cin_g, k, groups, pg, wf);
     STG_LAUNCH_CHECK();
   }
-  if (wd) {
+  if (wd && wf && sizeof(T) == 2 && groups > 1) {
+    // grouped convs on the tensor engine (bf16): the K-major data-gradient pack is the per-group transposition of the forward
+    // pack just written - contiguous slabs in, contiguous slabs out (the spectral-norm layers re-pack on every forward)
+    wd_from_wf_direct_kernel<T><<<k * pg, 256, 0, s>>>(wf, wd, c_out, c_in, pg);
+    STG_LAUNCH_CHECK();
+  } else if (wd) {
     dim3 g2(ceil_div(cout_gp, 32), ceil_div(cin_gp, 32), k * pg);
     pack_dgrad_kernel<T><<<g2, 256, 0, s>>>(v, scale, c_out, cin_g, k, groups, pg, wd);
     STG_LAUNCH_CHECK();
