@@ -360,6 +360,14 @@ int stg_debug_group_mma(const void* x, const void* w, int cin_g, int cout_g, flo
  * tail tiles that gather one row slice of several samples).  out[3c..3c+2] = rows per sample, first row, tiles per sample
  * (0: one tile per 128/rows samples); returns the number of classes (<= 4).  No GPU needed. */
 int stg_debug_row_classes(int t_dst, int* out);
+/* debug hardware probe (csrc/debug_probe.cu): bytes per clock one SM ingests through TMA while `grid` SMs pull
+ * [box_rows][64] bf16 boxes of an L2-resident buffer [n_rows][64] at once, from disjoint rows (mode 0) or all from the same
+ * rows (mode 1), through a `stages`-deep ring; clk[cta] = clocks for n_iters boxes. */
+int stg_debug_tma_bw(const void* buf, long long n_rows, int box_rows, int n_iters, int mode, int stages, int grid, long long* clk,
+                     stg_stream_t stream);
+/* debug accounting (host side): bytes the tcgen05 launches since the last reset were planned to pull into shared memory
+ * through TMA (main-loop operands + epilogue operands). */
+double stg_debug_ingest_bytes(int reset);
 
 #ifdef __cplusplus
 }

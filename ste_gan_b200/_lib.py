@@ -70,6 +70,7 @@ _SIGS = {
     "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_debug_row_classes": [_I, _P],
     "stg_debug_group_mma": [_P, _P, _I, _I, _P, _P],
+    "stg_debug_tma_bw": [_P, C.c_longlong, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_period_first_layer": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, _P, _P],
@@ -99,7 +100,8 @@ _SIGS = {
     "stg_encoder_losses": [_P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _P, _P, _I, _P],
     "stg_adamw": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _F, _P, _I, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["stg_strerror", "stg_last_cuda_error", "stg_version", "stg_launch_count", "stg_set_sm_limit"])
+EXPORTS = sorted(list(_SIGS) + ["stg_strerror", "stg_last_cuda_error", "stg_version", "stg_launch_count", "stg_set_sm_limit",
+                                   "stg_debug_ingest_bytes"])
 
 _lib = None
 
@@ -132,6 +134,8 @@ def load(build_if_missing: bool = True):
     lib.stg_version.restype = C.c_int
     lib.stg_set_sm_limit.argtypes = [C.c_int]
     lib.stg_set_sm_limit.restype = None
+    lib.stg_debug_ingest_bytes.argtypes = [C.c_int]
+    lib.stg_debug_ingest_bytes.restype = C.c_double
     lib.stg_launch_count.argtypes = []
     lib.stg_launch_count.restype = C.c_ulonglong
     _lib = lib

@@ -1,4 +1,5 @@
 // extern "C" entry points that dispatch between the engines, plus diagnostics.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -9,7 +10,8 @@ namespace stg {
 
 static thread_local std::string g_last_error;
 unsigned long long g_launch_count = 0;
-int g_sm_limit = 0;   // stg_set_sm_limit: SMs the persistent tcgen05 kernels may occupy (0 = all)
+double g_ingest_bytes = 0.0;
+int g_sm_limit = getenv("STG_SM_LIMIT") ? atoi(getenv("STG_SM_LIMIT")) : 0;   // stg_set_sm_limit: SMs the persistent tcgen05 kernels may occupy (0 = all)
 
 void set_cuda_error(cudaError_t e, const char* where) {
   g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
@@ -113,6 +115,8 @@ extern "C" const char* stg_last_cuda_error(void) { return g_last_error.c_str(); 
 extern "C" int stg_version(void) { return 100; }
 extern "C" unsigned long long stg_launch_count(void) { return g_launch_count; }
 extern "C" void stg_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+/* debug: bytes the tcgen05 launches since the last reset were planned to pull into shared memory through TMA */
+extern "C" double stg_debug_ingest_bytes(int reset) { const double v = g_ingest_bytes; if (reset) g_ingest_bytes = 0.0; return v; }
 
 /* debug: device buffer of 1 + 3*4000 int64 receiving a timeline of CTA 0 of every following stg_conv tcgen05 launch */
 extern "C" int stg_debug_set_trace(void* buf) { conv_tc_set_trace(static_cast<long long*>(buf)); return STG_OK; }

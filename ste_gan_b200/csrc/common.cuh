@@ -20,6 +20,7 @@ void set_cuda_error(cudaError_t e, const char* where);
   } while (0)
 
 extern unsigned long long g_launch_count;  // kernels launched by this library (process-wide)
+extern double g_ingest_bytes;              // debug accounting: shared-memory ingest (TMA loads) planned by the tcgen05 launches since the last reset
 extern int g_sm_limit;                     // SMs the persistent tcgen05 kernels may occupy (0 = all), stg_set_sm_limit
 #define STG_LAUNCH_CHECK()                 \
   do {                                     \

@@ -51,6 +51,7 @@ constexpr int MAX_RES = 8;     // residues of a strided data-gradient (= stride)
 struct TcEpi {
   int rows, c_dst, post_shift, mask_mode, act, dup_rows, out_f32, pair_sum;  // rows: output rows per sample (all phases)
   int n_in, n_out, has_pre, has_mask, has_post, has_raw, has_act;            // staged: slot bookkeeping
+  int in_sh;                    // staged: the epilogue-operand ring holds 1 << in_sh sub-tiles (2, 4 or 8) in flight
   float act_slope, mask_slope;  // act(v) = max(v, act_slope*v) ; act'(m) = m > 0 ? 1 : mask_slope   (none 1, relu 0, leaky 0.1)
   const float* bias;
   const bf16 *add_pre, *mask, *add_post;
@@ -177,6 +178,16 @@ struct Tracer {
     base[3 * n] = tag; base[3 * n + 1] = val; base[3 * n + 2] = t; ++n;
   }
 };
+
+// life-cycle events of CTA 0 (entry / set-up done / dependency released / exit), appended across launches through the
+// counter in trace[0] so that back-to-back launches show their period and overlap
+__device__ __forceinline__ void life_ev(long long* tr, int tag) {
+  if (tr == nullptr || blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const int slot = (int)atomicAdd(reinterpret_cast<unsigned long long*>(tr), 1ull);
+  if (slot < 1300) { long long* b = tr + 1 + 3 * 1300 * 3 + 3 * slot; b[0] = tag; b[1] = slot; b[2] = t; }
+}
 
 // ---------------------------------------------------------------------------------------------- tiles
 struct Tile {
@@ -308,29 +319,29 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
   const int rank = kPair ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;
   const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: 2*(n_in+n_out) slots + bias
-  const uint32_t bias_base = epi_base + (kStaged ? (2 * e.n_in + 3 * e.n_out) * SLOT : 0);
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: (n_in << in_sh) + 3 n_out slots + bias
+  const uint32_t bias_base = epi_base + (kStaged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT : 0);
   const uint32_t bar_base = bias_base + (kStaged ? 2048 : 0);   // one bias copy per epilogue team
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
-  auto in_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 6);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto in_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 6 + a); };   // a < 8
 
   // broadcast from lane 0: the compiler can prove the warp index (hence every role branch) warp-uniform, so the
   // single-issuer instructions (TMA, tcgen05.mma / commit) take their operands straight from uniform registers
   // instead of a per-instruction ELECT + R2UR "waterfall" (MMA issue: 410 -> 82 clk per stage)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+  life_ev(p.trace, 30);
   pdl_trigger();   // the next kernel of the stream may start its prologue now (it still waits for this grid to complete)
   if (warp == 0 && lane == 0) {
     for (int c = 0; c < p.n_cls; ++c) prefetch_tmap(&tmA4.m[c]);
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), kPair ? 2 * EPI_WARPS : EPI_WARPS); mbar_init(in_bar(a), 1);
-    }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), kPair ? 2 * EPI_WARPS : EPI_WARPS); }
+    for (int a = 0; a < 8; ++a) mbar_init(in_bar(a), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -341,7 +352,9 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
   if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   else __syncthreads();
   tc_fence_after();
+  life_ev(p.trace, 31);
   pdl_wait();      // everything above overlapped the previous kernel's tail; no global memory is touched before this line
+  life_ev(p.trace, 32);
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   // pair: stage-full barriers and the accumulator-drained barriers that count live in the LEADER's shared memory
@@ -602,8 +615,9 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
     //   FULL[q%3]  math arrives after writing the output slots (which implies it has consumed the input slots)
     //   FREE[q%3]  DMA arrives once the stores that last read output buffer q%3 (sub-tile q-3) have drained
     const int n_sub = p.bn / SUB;
+    const int in_mask = (1 << e.in_sh) - 1;
     auto in_slot = [&](int buf, int i) { return epi_base + (uint32_t)((buf * e.n_in + i) * SLOT); };
-    auto out_slot = [&](int buf, int o) { return epi_base + (uint32_t)((2 * e.n_in + buf * e.n_out + o) * SLOT); };  // buf: q % 3
+    auto out_slot = [&](int buf, int o) { return epi_base + (uint32_t)(((e.n_in << e.in_sh) + buf * e.n_out + o) * SLOT); };  // buf: q % 3
     auto bar_full = [&](int b3) { return 2 + b3; };
     auto bar_free = [&](int b3) { return 5 + b3; };
     const int my_tiles = (p.n_tiles - tile0 + tstep - 1) / tstep;
@@ -619,12 +633,13 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
       const int rows_in = e.pair_sum ? 64 : p.mrows;                     // rows of a pre/mask/output box
       const uint32_t in_bytes = (uint32_t)((e.has_pre + e.has_mask) * rows_in * SUB * 2 + e.has_post * (rows_in >> e.post_shift) * SUB * 2);
       const int rsh = e.pair_sum ? 1 : 0;
-      // iterator over (tile, sub-tile) pairs for the operand loads, which run two sub-tiles ahead of the math
+      // iterator over (tile, sub-tile) pairs for the operand loads, which run 1 << in_sh sub-tiles ahead of the math (a load
+      // takes 0.6-0.8 us to land, a team turns a sub-tile around in ~0.25 us: two in flight left the math waiting)
       int ld_t = tile0, ld_s = 0, ld_q = 0;
       Tile lx = decode_tile<kPair>(p, ld_t < p.n_tiles ? ld_t : tile0, rank);
       auto issue_loads = [&]() {
         if (e.n_in == 0 || ld_t >= p.n_tiles) return;
-        const int buf = ld_q & 1;
+        const int buf = ld_q & in_mask;
         const int col = lx.col0 + ld_s * SUB;
         const int r0 = lx.h0 >> rsh;                                     // first h row of the tile in its residue class
         mbar_expect_tx_el(in_bar(buf), in_bytes);
@@ -639,7 +654,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           if (ld_t < p.n_tiles) lx = decode_tile<kPair>(p, ld_t, rank);
         }
       };
-      issue_loads(); issue_loads();
+      for (int i = 0; i <= in_mask; ++i) issue_loads();
       int q = 0;
       for (int t = tile0; t < p.n_tiles; t += tstep) {
         const Tile x = decode_tile<kPair>(p, t, rank);
@@ -655,7 +670,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
             if (e.dup_rows) tma_store_4d_el(&em.act[x.cls], out_slot(obuf, o), col, 1, r0_out, x.b);
           }
           bulk_commit_el();
-          issue_loads();                         // operands of sub-tile q+2 into the input slots just consumed
+          issue_loads();                         // operands of sub-tile q + (1 << in_sh) into the input slots just consumed
           bulk_wait_read_el<1>();                // stores of sub-tile q-1 have read their slots -> buffer (q+2)%3 is free
           __syncwarp();
           if (q >= 1 && q + 2 < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free((q + 2) % 3)) : "memory");
@@ -706,7 +721,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
 #pragma unroll 1
         for (int s = (qbase & 1) == team ? 0 : 1; s < n_sub; s += 2) {
           const int q = qbase + s;
-          const int buf = q & 1;
+          const int buf = q & in_mask;
           float v[32];
           if (x.n_iters > 0) {
             tmem_ld16(t_addr + (uint32_t)(s * SUB), *reinterpret_cast<float(*)[16]>(&v[0]));
@@ -735,7 +750,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           }
           trc.ev(20, s);
           if (e.n_in > 0) {
-            mbar_wait(in_bar(buf), (q >> 1) & 1);
+            mbar_wait(in_bar(buf), (q >> e.in_sh) & 1);
             trc.ev(21, s);
             int i = 0;
             if (e.has_pre) {
@@ -860,6 +875,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  life_ev(p.trace, 33);
 }
 
 }  // namespace
@@ -910,14 +926,23 @@ static int sm_count() {
 // producers' issue floor), epilogues hide behind the next tile's main loop except the last one (bn / 32 sub-tiles of
 // ~200 clk with two teams).  Picks the divisor of cd_g with the smallest makespan; ties go to the wider tile.
 static int pick_bn_model(int cd_g, int groups, int64_t row_tiles, int n_stages, int step) {
+  // STG_BN_FEED (B/clk an SM ingests through TMA, 0 = not modelled) and STG_BN_ALPHA (weight of the SM-time objective
+  // against the launch's own makespan): see the note on work conservation in DESIGN.md 3.x
+  static const double feed = getenv("STG_BN_FEED") ? atof(getenv("STG_BN_FEED")) : 0.0;
+  static const double alpha = getenv("STG_BN_ALPHA") ? atof(getenv("STG_BN_ALPHA")) : 0.0;
   int best = 0;
   double best_t = 0;
   for (int bn = 256; bn >= step; bn -= step) {
     if (cd_g % bn) continue;
     const int64_t tiles = row_tiles * (cd_g / bn) * groups;
     const double waves = (double)((tiles + sm_count() - 1) / sm_count());
-    const double stage = (2.0 * bn > 200.0 ? 2.0 * bn : 200.0) + 60.0;   // + barrier round trip / commit latency per stage
-    const double t = waves * n_stages * stage + (bn / 32.0) * 200.0;
+    double mma = 2.0 * bn > 200.0 ? 2.0 * bn : 200.0;
+    if (feed > 0.0) { const double ld = (TM * KC * 2 + bn * KC * 2) / feed; if (ld > mma) mma = ld; }
+    const double stage = mma + 60.0;   // + barrier round trip / commit latency per stage
+    const double epi = (bn / 32.0) * 200.0;
+    const double makespan = waves * n_stages * stage + epi;
+    const double smtime = (double)tiles * (n_stages * stage + epi) / sm_count();
+    const double t = alpha * smtime + (1.0 - alpha) * makespan;
     if (best == 0 || t < best_t * 0.999) { best = bn; best_t = t; }
   }
   return best;
@@ -1167,7 +1192,21 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   bool pair = env_pair != 0 && p.cu_k == 0 && n_rc == 0 && n_mt >= 2 && (p.b_mn ? (p.cd_g % 64 == 0 && p.bn % 128 == 0) : (p.bn % 32 == 0));
   p.pairs_per_res = (n_mt + 1) / 2;
   int b_bytes = p.cu_k ? p.cu_fpc * p.cu_n * p.cu_k * 2 : (pair ? p.bn / 2 : p.bn) * KC * 2;
-  const int epi_bytes = staged ? (2 * e.n_in + 3 * e.n_out) * SLOT + 2048 : 0;
+  // epilogue-operand ring: as deep as a column tile has sub-tiles (<= 8) while the main loop keeps >= 4 stages of the
+  // one-tap-per-stage plan (or all the stages a tile has), else 4, else 2
+  static const int env_insh = getenv("STG_IN_DEPTH_SH") ? atoi(getenv("STG_IN_DEPTH_SH")) : -1;
+  e.in_sh = 1;
+  if (staged && e.n_in > 0) {
+    const int stage1 = TM * KC * 2 + (p.cu_k ? p.cu_fpc * p.cu_n * p.cu_k * 2 : p.bn * KC * 2);
+    const int want = n_stages_est < 4 ? n_stages_est : 4;
+    for (int sh = 3; sh >= 2; --sh) {
+      if ((1 << (sh - 1)) >= p.bn / SUB) continue;                       // the ring need not exceed the tile
+      const int epi = ((e.n_in << sh) + 3 * e.n_out) * SLOT + 2048;
+      if ((212 * 1024 - epi) / stage1 >= want) { e.in_sh = sh; break; }
+    }
+    if (env_insh >= 1 && env_insh <= 3) e.in_sh = env_insh;
+  }
+  const int epi_bytes = staged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT + 2048 : 0;
   const int avail = 212 * 1024 - epi_bytes;
   struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
   auto build = [&](int ng, TcP* out) {
@@ -1227,7 +1266,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   const int cands[] = {1, 2, 3, 4, 5, 6, 8, 10};
   for (int ci = 0; ci < 8; ++ci) {
     const int ng = cands[ci];
-    if (env_ng > 0 && ng != env_ng) continue;
+    if (env_ng > 0 && ng != env_ng && d->k >= env_ng) continue;
     if (ng > d->k && ng != 1) continue;
     Plan pl = build(ng, nullptr);
     if (!pl.ok) continue;
@@ -1243,7 +1282,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     best = Plan{0, 0, 0, 0, 0, 0, 0, false};
     for (int ci = 0; ci < 8; ++ci) {
       const int ng = cands[ci];
-      if (env_ng > 0 && ng != env_ng) continue;
+      if (env_ng > 0 && ng != env_ng && d->k >= env_ng) continue;
       if (ng > d->k && ng != 1) continue;
       Plan pl = build(ng, nullptr);
       if (!pl.ok) continue;
@@ -1262,7 +1301,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   build(best.ng, &p);
   p.hb = best.hb; p.a_boxes = best.a_boxes; p.a_bytes = best.a_bytes; p.max_ntaps = best.ng; p.stages = best.stages;
   const int stage_bytes = p.a_bytes + p.max_ntaps * b_bytes;
-  const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 8) + sizeof(TapTables) + 16;
+  const size_t smem = (size_t)p.stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * MAX_STAGES + 16) + sizeof(TapTables) + 16;
   static const bool dbg_plan = getenv("STG_DEBUG_PLAN") != nullptr;
   if (dbg_plan)
     fprintf(stderr, "[conv_tc] c %d->%d k%d s%d d%d g%d ph%d T %d->%d tr%d | bn %d staged %d ng %d stages %d hb %d a_boxes %d a_bytes %d "
@@ -1370,7 +1409,10 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   const int64_t n_tiles = n_rc ? (int64_t)p.cls_mt0[p.n_cls] * p.tiles_n : (int64_t)d->n_samples * p.n_res * p.tiles_m * p.tiles_n;
   if (n_tiles > 0x7fffffff) return STG_EINVAL;
   p.n_tiles = (int)n_tiles;
-  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  g_ingest_bytes += (double)n_tiles * ((double)best.traffic * p.k_chunks / p.n_res + (staged ? (double)e.n_in * p.mrows * p.bn * 2 : 0.0));
+  static const int env_cap = getenv("STG_GRID_CAP") ? atoi(getenv("STG_GRID_CAP")) : 0;   // tuning: CTAs per launch
+  int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  if (env_cap > 0 && grid > env_cap) grid = env_cap;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];

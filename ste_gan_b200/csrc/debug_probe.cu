@@ -84,10 +84,67 @@ group_mma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before(); __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
+// Third probe: what one SM can ingest through TMA when `gridDim.x` SMs pull [box_rows x 64] bf16 boxes (128-byte rows,
+// SWIZZLE_128B) at once - from disjoint rows (mode 0: activation-like) or all from the same rows (mode 1: weight-like).
+// One producer thread and one consumer thread per CTA around a `stages`-deep ring; nothing else runs.  clk[cta] = clocks
+// for n_iters boxes.
+__global__ void __launch_bounds__(64, 1)
+tma_bw_probe_kernel(const __grid_constant__ CUtensorMap tm, long long n_rows, int box_rows, int n_iters, int mode, int stages,
+                    long long* clk) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t box_bytes = (uint32_t)box_rows * 128u;
+  const uint32_t bars = base + (uint32_t)stages * box_bytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (16 + s); };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long n_boxes = n_rows / box_rows;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    int s = 0; uint32_t ph = 0;
+    const int wrap = (int)(n_boxes * box_rows);
+    int row = mode == 1 ? 0 : (int)((((long long)blockIdx.x * n_iters) % n_boxes) * box_rows);   // no division inside the loop
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(empty(s), ph ^ 1);
+      mbar_expect_tx(full(s), box_bytes);
+      tma_load_3d(base + (uint32_t)s * box_bytes, &tm, full(s), 0, row, 0);
+      row += box_rows; if (row >= wrap) row = 0;
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+    // all boxes landed: wait until the consumer has released the last one
+    const int ls = (n_iters - 1) % stages; const uint32_t lph = (uint32_t)(((n_iters - 1) / stages) & 1);
+    mbar_wait(empty(ls), lph);
+    clk[blockIdx.x] = clock64() - t0;
+  } else if (threadIdx.x == 32) {
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(full(s), ph);
+      mbar_arrive(empty(s));
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+  }
+}
 }  // namespace
 }  // namespace stg
 
 using namespace stg;
+/* buf: bf16 [n_rows][64]; clk: int64 [grid] */
+extern "C" int stg_debug_tma_bw(const void* buf, long long n_rows, int box_rows, int n_iters, int mode, int stages, int grid,
+                                long long* clk, stg_stream_t stream) {
+  if (box_rows < 8 || box_rows > 256 || stages < 1 || stages > 16 || stages * box_rows * 128 > 200 * 1024 || grid < 1) return STG_EINVAL;
+  CUtensorMap tm;
+  { const uint64_t dims[3] = {64, (uint64_t)n_rows, 1}; const uint64_t st[2] = {128, (uint64_t)n_rows * 128};
+    const uint32_t box[3] = {64, (uint32_t)box_rows, 1}; int r = make_tmap_bf16(&tm, buf, 3, dims, st, box, nullptr); if (r) return r; }
+  STG_CUDA_CHECK(cudaFuncSetAttribute(tma_bw_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const size_t smem = (size_t)stages * box_rows * 128 + 1024 + 512;
+  tma_bw_probe_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(tm, n_rows, box_rows, n_iters, mode, stages, clk);
+  STG_LAUNCH_CHECK();
+  return STG_OK;
+}
 /* x: bf16 [128][64], w: bf16 [(64/cin_g)*cout_g][cin_g], out: float [128][(64/cin_g)*cout_g]; cin_g in {16,32,64}, cout_g % 16 == 0 */
 extern "C" int stg_debug_group_mma(const void* x, const void* w, int cin_g, int cout_g, float* out, stg_stream_t stream) {
   if ((cin_g != 16 && cin_g != 32 && cin_g != 64) || cout_g % 16 || cout_g < 16 || (64 / cin_g) * cout_g > 256) return STG_EINVAL;

@@ -334,6 +334,7 @@ int wgrad_tc(const StgWgrad* d, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(gx, gy, nsplit);
+  g_ingest_bytes += (double)gx * gy * nsplit * p.chunks_per_split * stage_bytes;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];

@@ -107,7 +107,13 @@ def conv(src: Tensor, w: Tensor, *, n_samples: int, t_src: int, t_dst: int, c_sr
     e0.record()
     check(lib.stg_conv(C.byref(d), _stream()), "stg_conv")
     e1.record()
-    profile.append(dict(rec, events=(e0, e1)))
+    rec["ingest"] = _ingest(lib)
+    profile.append(dict(rec, events=(e0, e1), desc=d, fn="stg_conv", keep=(src, w, bias, add_pre, mask, add_post, y_raw, y_act)))
+
+
+def _ingest(lib) -> float:
+    """Bytes the launch just issued was planned to pull into shared memory (debug accounting of the tcgen05 engines)."""
+    return float(lib.stg_debug_ingest_bytes(1))
 
 
 def conv_tc_supported(**kw) -> bool:
@@ -157,7 +163,8 @@ def wgrad(x: Tensor, dy: Tensor, dw: Optional[Tensor], dbias: Optional[Tensor], 
     e0.record()
     check(lib.stg_conv_wgrad(C.byref(d), _stream()), "stg_conv_wgrad")
     e1.record()
-    profile.append(dict(rec, events=(e0, e1)))
+    rec["ingest"] = _ingest(lib)
+    profile.append(dict(rec, events=(e0, e1), desc=d, fn="stg_conv_wgrad", keep=(x, dy, dw, dbias)))
 
 
 def tc_pack_groups(c_in: int, c_out: int, groups: int) -> int:

@@ -27,8 +27,21 @@ torch.cuda.synchronize()
 buf = torch.zeros(1 + 3 * 5300, device="cuda", dtype=torch.int64)
 lib = _lib.load()
 lib.stg_debug_set_trace(buf.data_ptr())
-run(); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for _ in range(4):
+        run()
+buf.zero_(); torch.cuda.synchronize()
+g.replay(); torch.cuda.synchronize()
 lib.stg_debug_set_trace(None)
+life = [e for e in buf[1 + 3 * 3900:1 + 3 * 3900 + 3 * 16].view(-1, 3).cpu().tolist() if e[0] != 0]
+lt0 = life[0][2]
+ln = {30: "entry", 31: "set-up done", 32: "dependency released", 33: "exit"}
+print("life cycle of CTA 0 over 4 back-to-back launches (one CUDA graph, PDL):")
+for tag, val, t in life:
+    print(f"{(t - lt0) / 1e3:9.2f} us  {ln.get(tag, tag)}")
+print("last launch, CTA 0:")
+buf[1 + 3 * 3900:1 + 3 * 3900 + 3 * 16] = 0
 ev = [e for e in buf[1:1 + 3 * 3990].view(-1, 3).cpu().tolist() if e[0] != 0]
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
 names = {4: "  stage free (producer)", 5: "  stage landed (mma)", 1: "producer tile", 2: "mma start", 3: "mma issued", 10: "epi tile start", 11: "epi acc ready", 12: "epi sub done", 20: "  sub: acc in regs", 21: "  sub: inputs landed", 22: "  sub: smem written", 23: "  sub: out slot free", 24: "  sub: barrier passed"}

@@ -4,7 +4,7 @@ Prints the library's launch counter after every step so the ncu skip count can b
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import ste_gan_oracle as O
+from ste_gan_b200.synthetic import synthetic_batch
 from ste_gan_b200 import _lib
 from ste_gan_b200.models.discriminator import DiscriminatorSmall
 from ste_gan_b200.models.generator import EMGGeneratorGanTTS
@@ -15,7 +15,7 @@ lib = _lib.load(build_if_missing=False)
 torch.manual_seed(0); g = EMGGeneratorGanTTS("SPEECH_UNITS", 256, 17, 8).cuda()
 torch.manual_seed(0); d = DiscriminatorSmall(8).cuda()
 tr = GanTrainer(g, d, precision="bf16")
-batch = [t.cuda() for t in O.synthetic_batch(16, 100, seed=0)]
+batch = [t.cuda() for t in synthetic_batch(16, 100, seed=0)]
 import json
 from ste_gan_b200 import ops
 for i in range(n):
