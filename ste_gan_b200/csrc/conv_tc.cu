@@ -43,7 +43,7 @@ using namespace tc;
 constexpr int TM = 128;        // rows per CTA tile
 constexpr int KC = 64;         // channels per K chunk (128 B of bf16)
 constexpr int MAX_STAGES = 8;
-constexpr int ACC_COLS = 256;  // TMEM column distance between the two accumulator buffers
+constexpr int ACC_COLS = 256;  // TMEM column distance between the two accumulator buffers (TcP::acc_cols; 128 when two CTAs share an SM)
 constexpr int SUB = 32;        // staged epilogue: columns per sub-tile (64-byte rows, SWIZZLE_64B)
 constexpr int SLOT = TM * SUB * 2;  // bytes of one 128 x 32 bf16 sub-tile
 constexpr int MAX_RES = 8;     // residues of a strided data-gradient (= stride)
@@ -69,6 +69,7 @@ struct TapTables {
 
 struct TcP {
   int phases, t_dst, stride, k_chunks, bn, stages, a_boxes, tmem_cols;
+  int acc_cols, out_ring;  // TMEM distance between the two accumulator buffers; depth of the staged epilogue's output ring (3, or 2 when two CTAs share an SM)
   int pack, nh, mrows;     // phases packed per tile, h rows per tile, used accumulator rows = nh * pack
   int cs_g, cd_g;          // source / destination channels per (packed) group
   int n_res, tiles_m;      // output-row residues (1 unless transposed && stride > 1), row tiles per residue
@@ -304,7 +305,7 @@ __device__ __forceinline__ void epi_store(const TcEpi& e, int b, int row, int co
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool kStaged, bool kPair>
-__global__ void __launch_bounds__(kStaged ? 384 : 352, 1)
+__global__ void __launch_bounds__(kStaged ? 384 : 352, (kStaged && !kPair) ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ EpiMaps em, const TcP p) {
   constexpr int EPI_WARPS = 8;   // warps that read the accumulator (arrivals on tmem_empty)
@@ -320,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
   const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;           // staged: (n_in << in_sh) + 3 n_out slots + bias
-  const uint32_t bias_base = epi_base + (kStaged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT : 0);
+  const uint32_t bias_base = epi_base + (kStaged ? ((e.n_in << e.in_sh) + p.out_ring * e.n_out) * SLOT : 0);
   const uint32_t bar_base = bias_base + (kStaged ? 2048 : 0);   // one bias copy per epilogue team
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -469,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
       mbar_wait(tmem_empty_bar(as), aph ^ 1);  // epilogue(s) have drained this accumulator buffer
       tc_fence_after();
       trc.ev(2, t);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_cols);
       int cu_chunk = 0;
       for (int it = 0; it < x.n_iters; ++it) {
 #ifdef STG_PROF_LOOP
@@ -569,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
       const int as = acc_i & 1, aph = (acc_i >> 1) & 1;
       mbar_wait(tmem_empty_bar(as), aph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_cols);
       int g = x.g0, chunk = 0;
       for (int it = 0; it < x.n_iters; ++it) {
         const int nt = p.tt.g_ntaps[g], t0 = p.tt.g_tfirst[g];
@@ -616,6 +617,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
     //   FREE[q%3]  DMA arrives once the stores that last read output buffer q%3 (sub-tile q-3) have drained
     const int n_sub = p.bn / SUB;
     const int in_mask = (1 << e.in_sh) - 1;
+    auto ring = [&](int q) { return p.out_ring == 2 ? (q & 1) : q % 3; };   // output-ring slot of sub-tile q
     auto in_slot = [&](int buf, int i) { return epi_base + (uint32_t)((buf * e.n_in + i) * SLOT); };
     auto out_slot = [&](int buf, int o) { return epi_base + (uint32_t)(((e.n_in << e.in_sh) + buf * e.n_out + o) * SLOT); };  // buf: q % 3
     auto bar_full = [&](int b3) { return 2 + b3; };
@@ -660,7 +662,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
         const Tile x = decode_tile<kPair>(p, t, rank);
         const int r0_out = x.h0 >> rsh;
         for (int s = 0; s < n_sub; ++s, ++q) {
-          const int obuf = q % 3;
+          const int obuf = ring(q);
           asm volatile("bar.sync %0, 160;" ::"r"(bar_full(obuf)) : "memory");   // output slots written, input slots consumed
           const int col = x.col0 + s * SUB;
           int o = 0;
@@ -671,9 +673,10 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           }
           bulk_commit_el();
           issue_loads();                         // operands of sub-tile q + (1 << in_sh) into the input slots just consumed
-          bulk_wait_read_el<1>();                // stores of sub-tile q-1 have read their slots -> buffer (q+2)%3 is free
+          bulk_wait_read_el<1>();                // stores of sub-tile q-1 have read their slots -> its buffer is free
           __syncwarp();
-          if (q >= 1 && q + 2 < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free((q + 2) % 3)) : "memory");
+          // ... which sub-tile q - 1 + out_ring will write
+          if (q >= 1 && q - 1 + p.out_ring < q_total) asm volatile("bar.arrive %0, 160;" ::"r"(bar_free(ring(q - 1))) : "memory");
         }
       }
       bulk_wait_read_el<0>();   // the stores have READ their shared-memory slots; their global writes complete by the end of the grid
@@ -708,7 +711,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
           tc_fence_after();
         }
         trc.ev(11, t);
-        const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * ACC_COLS);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * p.acc_cols);
         const int r_in = e.pair_sum ? (m >> 1) : m;      // my row inside pre / mask / output sub-tiles
         const bool writer = !e.pair_sum || (lane & 1) == 0;
         // last sub-tile of this tile that belongs to my team (-1: none - possible only for one-sub-tile tiles)
@@ -782,8 +785,8 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
               }
             }
           }
-          const int obuf = q % 3;
-          if (q >= 3) asm volatile("bar.sync %0, 160;" ::"r"(bar_free(obuf)) : "memory");  // stores of sub-tile q-3 drained
+          const int obuf = ring(q);
+          if (q >= p.out_ring) asm volatile("bar.sync %0, 160;" ::"r"(bar_free(obuf)) : "memory");  // stores of sub-tile q - out_ring drained
           trc.ev(23, s);
           if (writer) {
             int o = 0;
@@ -829,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ TmA4 tmA4, const __grid_constant__ CUtens
         mbar_wait(tmem_full_bar(as), aph);
         tc_fence_after();
       }
-      const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * ACC_COLS);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(as * p.acc_cols);
       auto process = [&](int c, const EpiIn& in) {
         float v[16];
         if (x.n_iters > 0) {
@@ -1206,8 +1209,24 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     }
     if (env_insh >= 1 && env_insh <= 3) e.in_sh = env_insh;
   }
-  const int epi_bytes = staged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT + 2048 : 0;
-  const int avail = 212 * 1024 - epi_bytes;
+  int epi_bytes = staged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT + 2048 : 0;
+  int avail = 212 * 1024 - epi_bytes;
+  // Two CTAs per SM: the staged single-CTA kernel fits twice on an SM when a CTA stays below ~113 KB of shared memory and
+  // 256 TMEM columns (bn <= 128: two accumulator buffers 128 columns apart; epilogue rings two deep).  Measured
+  // (tools/conv_bench.py, profiles/r2_occ2_conv_bench.txt): the halved pipelines cost the dense layers 5-35 % (the bytes
+  // in flight per SM stay the same, the rings get shallower), but the issue-bound data-gradients of the compact-group layers
+  // gain 10-25 % (two issuing threads per SM) and grouped layers whose tiles hold few rows (1024 channels in 16 groups,
+  // T = 25: 256 mostly empty tiles) run in one wave instead of two (2.0x).  So: those two classes only.
+  // STG_OCC2=0 never, 1 whenever it fits.
+  static const int env_occ2 = getenv("STG_OCC2") ? atoi(getenv("STG_OCC2")) : -1;
+  const bool occ2_class = (p.cu_k != 0 && d->transposed) || (tile_groups > 1 && p.cu_k == 0 && p.bn <= 64);
+  bool occ2 = false;
+  if ((env_occ2 > 0 || (env_occ2 < 0 && occ2_class)) && staged && !pair && p.bn <= 128) {
+    const int epi2 = ((e.n_in << 1) + 2 * e.n_out) * SLOT + 2048;
+    const int avail2 = 110 * 1024 - epi2;
+    if (avail2 / (TM * KC * 2 + b_bytes) >= 2) { occ2 = true; e.in_sh = 1; epi_bytes = epi2; avail = avail2; }
+  }
+  p.out_ring = occ2 ? 2 : 3; p.acc_cols = occ2 ? 128 : ACC_COLS; p.tmem_cols = occ2 ? 256 : 512;
   struct Plan { int ng, stages, hb, a_boxes, a_bytes, n_groups; long long traffic; bool ok; };
   auto build = [&](int ng, TcP* out) {
     Plan pl{ng, 0, 0, 0, 0, 0, 0, false};
@@ -1305,9 +1324,9 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   static const bool dbg_plan = getenv("STG_DEBUG_PLAN") != nullptr;
   if (dbg_plan)
     fprintf(stderr, "[conv_tc] c %d->%d k%d s%d d%d g%d ph%d T %d->%d tr%d | bn %d staged %d ng %d stages %d hb %d a_boxes %d a_bytes %d "
-            "groups %d tiles_m %d res %d smem %zu\n", d->c_src, d->c_dst, d->k, d->stride, d->dilation, d->groups, d->phases, d->t_src,
+            "groups %d tiles_m %d res %d smem %zu occ2 %d\n", d->c_src, d->c_dst, d->k, d->stride, d->dilation, d->groups, d->phases, d->t_src,
             d->t_dst, d->transposed, p.bn, (int)staged, p.max_ntaps, p.stages, p.hb, p.a_boxes, p.a_bytes, p.res_gfirst[p.n_res],
-            p.tiles_m, p.n_res, smem);
+            p.tiles_m, p.n_res, smem, (int)occ2);
 
   CUtensorMap tmW;
   TmA4 tmA;
@@ -1385,6 +1404,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     STG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1411,7 +1431,8 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   p.n_tiles = (int)n_tiles;
   g_ingest_bytes += (double)n_tiles * ((double)best.traffic * p.k_chunks / p.n_res + (staged ? (double)e.n_in * p.mrows * p.bn * 2 : 0.0));
   static const int env_cap = getenv("STG_GRID_CAP") ? atoi(getenv("STG_GRID_CAP")) : 0;   // tuning: CTAs per launch
-  int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  const int slots = (occ2 ? 2 : 1) * sm_count();
+  int grid = p.n_tiles < slots ? p.n_tiles : slots;
   if (env_cap > 0 && grid > env_cap) grid = env_cap;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(staged ? 384 : 352); cfg.dynamicSmemBytes = smem; cfg.stream = s;
