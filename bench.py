@@ -17,7 +17,7 @@ JSON line (rank 0).
   roofline  dominant kernel (tcgen05 implicit-GEMM conv): ALGORITHMIC FLOPs of the launches recorded while the timed
             graphs were captured (module groups, not pack groups) / the kernel's busy time in a CUPTI timeline of replays
             of the SAME graphs (torch.profiler, outside the timed regions) vs MEASURED_PEAKS.json; `alone` = the same
-            launches timed one by one with CUDA events on a single stream; `hbm` = the HBM-bound kernels
+            launches replayed one shape at a time, 10x back to back in a CUDA graph of their own; `hbm` = the HBM-bound kernels
   cpu_baseline  the reference's own modules (baseline/_ref, kind "reference"; the oracle port otherwise) on the host cores
   inference / disc_losses / context.torch_gpu  BASELINE.json configs[3], configs[4] and the same reference step on the
             B200 through torch + cuDNN
@@ -26,6 +26,7 @@ JSON line (rank 0).
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import re
@@ -386,16 +387,13 @@ def run_ours(args):
         roofline = None
         timeline, span = cupti_by_kernel(lambda: tr.step_graph(*devb[0]), 3)
         tr.flush(); torch.cuda.synchronize()
-        # "alone": every conv / wgrad launch of an eager step bracketed by CUDA events on ONE stream (a 60 ms device-side sleep
-        # ahead of the step lets the host enqueue everything first, so the events time back-to-back kernels, not launch gaps)
-        tr.concurrent_d = False
+        # "alone": every distinct conv / wgrad launch of the timed schedule (one eager step with the same batching records the
+        # descriptors), replayed 10x back to back in its own CUDA graph - the kernel by itself on the chip, no launch gaps,
+        # its operands L2-warm; time per step = sum over launches of (replay time of its shape)
         tr.step(*devb[0])
         ops.profile = []
-        for j in (1, 2):
-            torch.cuda._sleep(int(0.06 * 1.9e9))
-            tr.step(*devb[j])
+        tr.step(*devb[1])
         torch.cuda.synchronize()
-        tr.concurrent_d = True
         prof, ops.profile = ops.profile, None
         if rank == 0:
             kname = {("tcgen05", "fwd"): "conv_tc_kernel", ("tcgen05", "dgrad"): "conv_tc_kernel", ("tcgen05", "wgrad"): "wgrad_tc_kernel",
@@ -405,10 +403,23 @@ def run_ours(args):
             for p in flop_log:                       # what the timed graphs launch
                 a = sched.setdefault(kname[(p["engine"], p["kind"])], dict(launches=0, flops=0.0, bytes=0.0))
                 a["launches"] += 1; a["flops"] += p["flops"]; a["bytes"] += p["bytes"]
-            alone = {}
+            alone, replay_us = {}, {}
+            st = torch.cuda.Stream()
             for p in prof:
+                key = (p["kind"], p["engine"], p["shape"])
+                if key not in replay_us:
+                    fn = getattr(lib, p["fn"])
+                    with torch.cuda.stream(st):
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr, stream=st):
+                            for _ in range(10):
+                                fn(ctypes.byref(p["desc"]), ctypes.c_void_p(st.cuda_stream))
+                        gr.replay(); torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(st); gr.replay(); e1.record(st); torch.cuda.synchronize()
+                    replay_us[key] = e0.elapsed_time(e1) * 1e3 / 10
                 a = alone.setdefault(kname[(p["engine"], p["kind"])], dict(launches=0, ms=0.0, flops=0.0))
-                a["launches"] += 1; a["ms"] += p["events"][0].elapsed_time(p["events"][1]); a["flops"] += p["flops"]
+                a["launches"] += 1; a["ms"] += replay_us[key] * 1e-3; a["flops"] += p["flops"]
             by_kernel = []
             for k, a in sched.items():
                 row = {"kernel": k, "launches_per_step": a["launches"], "gflop_per_step": round(a["flops"] / 1e9, 2),
@@ -419,7 +430,7 @@ def run_ours(args):
                                tflops=round(a["flops"] / (us * 1e-6) / 1e12, 2))
                 if k in alone:
                     row["alone_tflops"] = round(alone[k]["flops"] / (alone[k]["ms"] * 1e-3) / 1e12, 2)
-                    row["alone_ms_per_step"] = round(alone[k]["ms"] / 2, 4)
+                    row["alone_ms_per_step"] = round(alone[k]["ms"], 4)
                 by_kernel.append(row)
             by_kernel.sort(key=lambda x: -x.get("busy_us_per_step", x.get("alone_ms_per_step", 0) * 1e3))
             traffic = None
@@ -433,7 +444,7 @@ def run_ours(args):
                                                    "regions): busy time of every launch of the kernel as scheduled, concurrent streams included")
                 avg_us = top["busy_us_per_step"] / top["launches_per_step"]
             else:
-                achieved, timing = top.get("alone_tflops"), f"{span}; fell back to CUDA events around every launch of two eager steps on one stream"
+                achieved, timing = top.get("alone_tflops"), f"{span}; fell back to the stand-alone graph replay of every launch"
                 avg_us = 1e3 * top.get("alone_ms_per_step", 0.0) / max(1, top["launches_per_step"])
             # HBM-bound kernels of the same timeline: algorithmic bytes / busy time vs the measured copy bandwidth
             hbm = []
@@ -461,7 +472,7 @@ def run_ours(args):
                         "algorithmic_bytes_per_launch": int(top["algorithmic_mb_per_step"] * 1e6 / top["launches_per_step"]),
                         "flops_accounting": "2*B*T_out*C_out*k*C_in/groups with the MODULE's groups (redundant MMAs of merged pack groups are not work)",
                         "alone": {"tflops": top.get("alone_tflops"), "frac": round(top["alone_tflops"] / peaks["tflops"], 4) if top.get("alone_tflops") else None,
-                                  "timing": "CUDA events around every launch of two eager steps on one stream (kernel alone on the chip)"},
+                                  "timing": "every distinct launch of the timed schedule replayed 10x back to back in its own CUDA graph (kernel alone on the chip, L2-warm), summed over the step's launches"},
                         "timeline_span_us_per_step": round(span, 1) if isinstance(span, float) else None,
                         "step_tflops": round(STEP_GFLOP_PER_SAMPLE * BATCH_PER_GPU / ms_step, 2),
                         "step_frac": round(STEP_GFLOP_PER_SAMPLE * BATCH_PER_GPU / ms_step / peaks["tflops"], 4),
