@@ -70,6 +70,7 @@ _SIGS = {
     "stg_debug_rowshift": [_P, _P, _I, _I, _I, _P, _P],
     "stg_debug_row_classes": [_I, _P],
     "stg_debug_group_mma": [_P, _P, _I, _I, _P, _P],
+    "stg_debug_conv_plan": [_P, _P],
     "stg_debug_tma_bw": [_P, C.c_longlong, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "stg_unfold_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -118,5 +118,13 @@ extern "C" void stg_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 /* debug: bytes the tcgen05 launches since the last reset were planned to pull into shared memory through TMA */
 extern "C" double stg_debug_ingest_bytes(int reset) { const double v = g_ingest_bytes; if (reset) g_ingest_bytes = 0.0; return v; }
 
+/* debug, host-only: the launch plan of the tcgen05 convolution engine for a descriptor (pointers only need to be non-NULL) */
+extern "C" int stg_debug_conv_plan(const StgConv* d, int* out) {
+  if (!out) return STG_EINVAL;
+  const int r = validate_conv(d);
+  if (r != STG_OK) return r;
+  return conv_tc_plan(d, out);
+}
+
 /* debug: device buffer of 1 + 3*4000 int64 receiving a timeline of CTA 0 of every following stg_conv tcgen05 launch */
 extern "C" int stg_debug_set_trace(void* buf) { conv_tc_set_trace(static_cast<long long*>(buf)); return STG_OK; }

@@ -100,6 +100,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // engines
 int conv_simt(const StgConv* d, cudaStream_t s);
 int conv_tc(const StgConv* d, cudaStream_t s);
+int conv_tc_plan(const StgConv* d, int* out);   // host-only: the plan conv_tc would launch (16 ints, see stg_debug_conv_plan)
 bool conv_tc_supported(const StgConv* d);
 int wgrad_simt(const StgWgrad* d, cudaStream_t s);
 int wgrad_tc(const StgWgrad* d, cudaStream_t s);

@@ -1105,6 +1105,13 @@ static int epi_map(CUtensorMap* m, const void* base, int C, int P, int T, int B,
 
 static long long* g_trace = nullptr;
 void conv_tc_set_trace(long long* buf) { g_trace = buf; }
+static int* g_plan_out = nullptr;   // stg_debug_conv_plan: conv_tc() fills this with its plan and returns before touching the device
+int conv_tc_plan(const StgConv* d, int* out) {
+  g_plan_out = out;
+  const int r = conv_tc(d, nullptr);
+  g_plan_out = nullptr;
+  return r;
+}
 
 int conv_tc(const StgConv* d, cudaStream_t s) {
   if (!conv_tc_supported(d)) return STG_EUNSUPPORTED;
@@ -1198,6 +1205,10 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
   // epilogue-operand ring: as deep as a column tile has sub-tiles (<= 8) while the main loop keeps >= 4 stages of the
   // one-tap-per-stage plan (or all the stages a tile has), else 4, else 2
   static const int env_insh = getenv("STG_IN_DEPTH_SH") ? atoi(getenv("STG_IN_DEPTH_SH")) : -1;
+  // shared memory for main-loop stages + epilogue staging (the launch adds ~1.5 KB of alignment slack, barriers and tap tables;
+  // the SM gives one CTA 227 KB)
+  static const int smem_budget = (getenv("STG_SMEM_BUDGET_KB") ? atoi(getenv("STG_SMEM_BUDGET_KB")) : 224) * 1024;
+  static const int win_min_stages = getenv("STG_WIN_MIN_STAGES") ? atoi(getenv("STG_WIN_MIN_STAGES")) : 3;
   e.in_sh = 1;
   if (staged && e.n_in > 0) {
     const int stage1 = TM * KC * 2 + (p.cu_k ? p.cu_fpc * p.cu_n * p.cu_k * 2 : p.bn * KC * 2);
@@ -1205,12 +1216,12 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     for (int sh = 3; sh >= 2; --sh) {
       if ((1 << (sh - 1)) >= p.bn / SUB) continue;                       // the ring need not exceed the tile
       const int epi = ((e.n_in << sh) + 3 * e.n_out) * SLOT + 2048;
-      if ((212 * 1024 - epi) / stage1 >= want) { e.in_sh = sh; break; }
+      if ((smem_budget - epi) / stage1 >= want) { e.in_sh = sh; break; }
     }
     if (env_insh >= 1 && env_insh <= 3) e.in_sh = env_insh;
   }
   int epi_bytes = staged ? ((e.n_in << e.in_sh) + 3 * e.n_out) * SLOT + 2048 : 0;
-  int avail = 212 * 1024 - epi_bytes;
+  int avail = smem_budget - epi_bytes;
   // Two CTAs per SM: the staged single-CTA kernel fits twice on an SM when a CTA stays below ~113 KB of shared memory and
   // 256 TMEM columns (bn <= 128: two accumulator buffers 128 columns apart; epilogue rings two deep).  Measured
   // (tools/conv_bench.py, profiles/r2_occ2_conv_bench.txt): the halved pipelines cost the dense layers 5-35 % (the bytes
@@ -1292,7 +1303,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
     if (!best.ok) { best = pl; continue; }           // ng = 1 comes first: the baseline
     // a window plan replaces the one-tap-per-stage baseline only if it still pipelines (>= 3 stages) and moves
     // at least 35 % fewer bytes: for k = 3 the saving is ~25 % and the coarser stages cost more than that
-    if (pl.stages >= 3 && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
+    if (pl.stages >= win_min_stages && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
   }
   if (!best.ok) return STG_EUNSUPPORTED;
   if (pair && best.ng != 1) {   // tap windows keep the single-CTA pipeline: plan again with whole W tiles
@@ -1306,7 +1317,7 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
       Plan pl = build(ng, nullptr);
       if (!pl.ok) continue;
       if (!best.ok) { best = pl; continue; }
-      if (pl.stages >= 3 && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
+      if (pl.stages >= win_min_stages && pl.traffic * 100 <= base_traffic * 65 && pl.traffic < best.traffic) best = pl;
     }
     if (!best.ok) return STG_EUNSUPPORTED;
   }
@@ -1327,6 +1338,17 @@ int conv_tc(const StgConv* d, cudaStream_t s) {
             "groups %d tiles_m %d res %d smem %zu occ2 %d\n", d->c_src, d->c_dst, d->k, d->stride, d->dilation, d->groups, d->phases, d->t_src,
             d->t_dst, d->transposed, p.bn, (int)staged, p.max_ntaps, p.stages, p.hb, p.a_boxes, p.a_bytes, p.res_gfirst[p.n_res],
             p.tiles_m, p.n_res, smem, (int)occ2);
+  if (g_plan_out) {   // host-only query (no tensor maps, no launch): see stg_debug_conv_plan in include/stegan_b200.h
+    const int tiles_n = ceil_div(d->c_dst, p.bn);
+    const int64_t nt = pair ? (int64_t)p.n_res * p.pairs_per_res * tiles_n
+                     : n_rc ? (int64_t)p.cls_mt0[p.n_cls] * tiles_n : (int64_t)d->n_samples * p.n_res * p.tiles_m * tiles_n;
+    const int64_t slots = pair ? sm_count() / 2 : (occ2 ? 2 : 1) * sm_count();
+    int* o = g_plan_out;
+    o[0] = p.bn; o[1] = staged; o[2] = p.max_ntaps; o[3] = p.stages; o[4] = (int)smem; o[5] = occ2; o[6] = pair; o[7] = p.n_cls;
+    o[8] = (int)nt; o[9] = (int)((nt < slots ? nt : slots) * (pair ? 2 : 1)); o[10] = p.cu_k; o[11] = p.k_chunks; o[12] = p.tmem_cols;
+    o[13] = staged && e.n_in > 0 ? 1 << e.in_sh : 0; o[14] = p.out_ring; o[15] = p.n_res;
+    return STG_OK;
+  }
 
   CUtensorMap tmW;
   TmA4 tmA;

@@ -179,6 +179,79 @@ def test_conv_row_classes_cover_every_row_once():
         assert tiles == want, (T, tiles)
 
 
+def _conv_plan(**kw):
+    import ctypes as C
+    import torch
+    from ste_gan_b200 import _lib, ops
+    names = ("bn", "staged", "taps_per_stage", "stages", "smem", "occ2", "pair", "row_classes", "tiles", "grid", "compact_k",
+             "k_chunks", "tmem_cols", "in_ring", "out_ring", "residues")
+    ptrs = {k: 8 for k in ("src", "w")}
+    ptrs.update({k: 8 for k in kw.pop("ptrs", ("y_raw",))})
+    d = ops.StgConv(dtype=ops.code_of(torch.bfloat16), engine=ops.ENGINE_AUTO, **ptrs, **kw)
+    out = (C.c_int * 16)()
+    rc = _lib.load().stg_debug_conv_plan(C.byref(d), out)
+    return rc, dict(zip(names, out))
+
+
+def test_conv_engine_plans_of_the_bench_shapes():
+    """Host-only check of the tcgen05 convolution planner (stg_debug_conv_plan) on every layer class of the benchmarked
+    configurations (SURVEY.md 8 a7 / a8 / a9 / a11, B = 16 and the batched 32): the plan fits the hardware (227 KB of shared
+    memory, 512 TMEM columns, <= 2 x 148 CTAs), pipelines (>= 2 stages, >= 3 with a tap window), tiles the channels exactly,
+    uses compact per-group MMAs for groups narrower than a 64-channel chunk, and shares an SM between two CTAs exactly for
+    the two classes it was measured to pay for."""
+    from ste_gan_b200 import ops
+    G = [(768, 768, 3, d, 100) for d in (1, 3, 9, 27)] + [(768, 768, 1, 1, 100), (768, 384, 3, 1, 200), (384, 384, 3, 9, 400),
+         (384, 384, 3, 27, 800), (384, 192, 3, 1, 1600), (192, 192, 3, 3, 1600), (192, 192, 1, 1, 1600), (320, 768, 1, 1, 100)]
+    cases = []
+    for ci, co, k, dil, T in G:                                           # generator: forward (residual, raw + act) and data-gradient
+        geo = dict(n_samples=16, phases=1, t_src=T, t_dst=T, groups=1, k=k, dilation=dil, stride=1, pad=dil * (k - 1) // 2)
+        cases.append(("g fwd", dict(geo, c_src=ci, c_dst=co, act=ops.ACT_RELU, ptrs=("y_raw", "y_act", "add_post", "bias"))))
+        cases.append(("g dgrad", dict(geo, c_src=co, c_dst=ci, transposed=1, w_fwd_pack=1, mask_mode=ops.ACT_RELU, ptrs=("y_raw", "mask"))))
+    S = [(128, 256, 37, 2, 4, 1600), (256, 512, 37, 2, 16, 800), (512, 1024, 5, 1, 1, 400),                 # DiscriminatorSmallerS
+         (128, 128, 41, 2, 4, 1600), (128, 256, 41, 2, 16, 800), (256, 512, 41, 4, 16, 400), (512, 1024, 41, 4, 16, 100),
+         (1024, 1024, 41, 1, 16, 25), (1024, 1024, 5, 1, 1, 25)]                                              # DiscriminatorS (full)
+    for ci, co, k, st, g, T in S:
+        for B in (16, 32):
+            To = (T + 2 * (k // 2) - (k - 1) - 1) // st + 1
+            pg = ops.tc_pack_groups(ci, co, g)
+            geo = dict(n_samples=B, phases=1, k=k, dilation=1, stride=st, pad=k // 2, groups=pg)
+            cases.append(("s fwd", dict(geo, t_src=T, t_dst=To, c_src=ci, c_dst=co, act=ops.ACT_LEAKY, ptrs=("y_act", "bias"))))
+            cases.append(("s dgrad", dict(geo, t_src=To, t_dst=T, c_src=co, c_dst=ci, transposed=1, w_fwd_pack=int(g == 1),
+                                          mask_mode=ops.ACT_LEAKY, ptrs=("y_raw", "mask"))))
+    for p_, H in ((2, 803), (3, 536), (5, 323), (7, 231), (11, 148)):     # DiscriminatorSmallerP: 32 -> 256 -> 512, (3,1) stride 3
+        for ci, co in ((32, 256), (256, 512)):
+            Ho = (H + 4 - 2 - 1) // 3 + 1
+            geo = dict(n_samples=32, phases=p_, k=3, dilation=1, stride=3, pad=2, groups=1)
+            cases.append(("p fwd", dict(geo, t_src=H, t_dst=Ho, c_src=ci, c_dst=co, act=ops.ACT_LEAKY, ptrs=("y_act", "bias"))))
+            cases.append(("p dgrad", dict(geo, t_src=Ho, t_dst=H, c_src=co, c_dst=ci, transposed=1, w_fwd_pack=1,
+                                          mask_mode=ops.ACT_LEAKY, ptrs=("y_raw", "mask"))))
+            H = Ho
+    n_occ2 = 0
+    for what, kw in cases:
+        rc, pl = _conv_plan(**dict(kw))
+        tag = (what, {k: v for k, v in kw.items() if k != "ptrs"}, pl)
+        assert rc == 0, tag
+        cd_g = kw["c_dst"] // kw["groups"]
+        assert pl["smem"] <= 227 * 1024 and pl["stages"] >= 2 and pl["taps_per_stage"] >= 1, tag
+        assert pl["taps_per_stage"] == 1 or pl["stages"] >= 3, tag
+        assert pl["bn"] % 16 == 0 and 16 <= pl["bn"] <= 256, tag
+        assert pl["compact_k"] or cd_g % pl["bn"] == 0 or pl["bn"] >= cd_g, tag
+        assert 1 <= pl["grid"] <= pl["tiles"] and pl["grid"] <= (2 if pl["occ2"] else 1) * 148, tag
+        cs_g = kw["c_src"] // kw["groups"]
+        assert (pl["compact_k"] == cs_g) == (kw["groups"] > 1 and cs_g < 64), tag
+        if pl["occ2"]:
+            n_occ2 += 1
+            assert pl["staged"] and pl["smem"] <= 113 * 1024 and pl["bn"] <= 128 and pl["tmem_cols"] == 256 and pl["out_ring"] == 2, tag
+            assert (pl["compact_k"] and kw.get("transposed")) or (kw["groups"] > 1 and not pl["compact_k"] and pl["bn"] <= 64), tag
+        else:
+            assert pl["tmem_cols"] == 512 and pl["out_ring"] == 3, tag
+        if what.startswith("g "):
+            assert not pl["occ2"], tag                                      # dense layers: one CTA per SM (measured)
+        if pl["staged"] and what.endswith("dgrad"):
+            assert pl["in_ring"] in (2, 4, 8), tag
+    assert n_occ2 >= 8      # the compact-group data-gradients and the 1024-channel grouped layers of the full discriminator
+
+
 def test_checkpoint_interchange_with_torch_adamw(tmp_path):
     """SURVEY.md 8f rank 3 (host side, CPU): the fused trainer's flat AdamW moments <-> the state_dict of the reference's
     torch.optim.AdamW (ste_gan/utils/common.py:23-61, train.py:421-436) - both directions, file naming and the choice of
